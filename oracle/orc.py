@@ -1,0 +1,233 @@
+"""ctypes loader for oracle/liborc.so - the CPU restatement and the synthetic FQB generator.
+
+TEST INFRASTRUCTURE ONLY (see the header of h10x_oracle.c): imported by tests/, by
+__graft_entry__.smoke() and by bench.py's CPU-baseline legs.  Never imported by hash10x_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liborc.so")
+REF_DIR = os.path.join(_HERE, "_ref")
+
+STATUS = {0: "ok", 1: "hashTableSize is too small", 2: "chunkSize too small", 3: "bad parameter",
+          4: "out of memory", 5: "io"}
+
+DEFAULT_FACTOR1 = 0x49308BB9003CB3AD  # seed 17, SURVEY.md Appendix E
+
+
+def build_lib(force=False):
+    """(Re)build liborc.so (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(_LIB):
+        subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+class OrcIndex(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("B", C.c_int32), ("status", C.c_int32),
+                ("factor1", C.c_uint64), ("hashNumber", C.c_uint32), ("nBlocksMax", C.c_uint32),
+                ("nReads", C.c_uint64), ("nHashes", C.c_uint64),
+                ("hashIndex", C.POINTER(C.c_uint32)), ("hashValue", C.POINTER(C.c_uint64)),
+                ("hashDepth", C.POINTER(C.c_uint32)), ("blkNRead", C.POINTER(C.c_uint32)),
+                ("blkNHash", C.POINTER(C.c_uint32)), ("blkOff", C.POINTER(C.c_uint64)),
+                ("clus", C.POINTER(C.c_uint64)), ("codeOff", C.POINTER(C.c_uint64)),
+                ("codes", C.POINTER(C.c_uint32))]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genomeLen", C.c_uint64), ("nBarcodes", C.c_uint32),
+                ("pairsMin", C.c_uint32), ("pairsMax", C.c_uint32), ("molPerBarcode", C.c_uint32),
+                ("molLen", C.c_uint32), ("snpPeriod", C.c_uint32), ("errThresh", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_lib()
+        L = C.CDLL(_LIB)
+        L.orc_factor1.restype = C.c_uint64
+        L.orc_factor1.argtypes = [C.c_int]
+        L.orc_build.restype = C.POINTER(OrcIndex)
+        L.orc_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                C.c_int64, C.c_int, C.c_int, C.c_int]
+        L.orc_free.argtypes = [C.POINTER(OrcIndex)]
+        L.orc_write_hash.argtypes = [C.POINTER(OrcIndex), C.c_char_p]
+        L.orc_record_moshes.restype = C.c_int
+        L.orc_record_moshes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_seq_moshes.restype = C.c_int
+        L.orc_seq_moshes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_kmer_hashes.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.synth_layout.restype = C.c_uint64
+        L.synth_layout.argtypes = [C.POINTER(SynthParams), C.c_void_p]
+        L.synth_fill.argtypes = [C.POINTER(SynthParams), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def factor1(seed=17):
+    return int(lib().orc_factor1(seed))
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Index:
+    """Plain-numpy view of a built index (same fields for the oracle and the GPU build)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def status_text(self):
+        return STATUS.get(self.status, "status %d" % self.status)
+
+
+def build(recs, k=21, w=31, factor1_=DEFAULT_FACTOR1, B=24, N=0, chunk=100000, minB=20, maxB=30,
+          keep_table=True):
+    """Run the oracle on an in-memory FQB (uint32 array of 30*n words)."""
+    recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+    n = recs.size // 30
+    L = lib()
+    p = L.orc_build(recs.ctypes.data, n, k, w, factor1_, B, N, chunk, minB, maxB)
+    try:
+        ix = p.contents
+        out = Index(k=ix.k, w=ix.w, B=ix.B, status=ix.status, factor1=ix.factor1,
+                    hashNumber=ix.hashNumber, nBlocksMax=ix.nBlocksMax, nReads=ix.nReads,
+                    nHashes=ix.nHashes)
+        if ix.status in (0,):
+            hn, nb = ix.hashNumber, ix.nBlocksMax
+            out.hashIndex = _np(ix.hashIndex, 1 << ix.B, np.uint32) if keep_table else None
+            out.hashValue = _np(ix.hashValue, hn, np.uint64)
+            out.hashDepth = _np(ix.hashDepth, hn, np.uint32)
+            out.blkNRead = _np(ix.blkNRead, nb, np.uint32)
+            out.blkNHash = _np(ix.blkNHash, nb, np.uint32)
+            out.blkOff = _np(ix.blkOff, nb + 1, np.uint64)
+            out.clus = _np(ix.clus, ix.nHashes, np.uint64)
+            out.codeOff = _np(ix.codeOff, hn + 1, np.uint64)
+            out.codes = _np(ix.codes, ix.nHashes, np.uint32)
+        return out
+    finally:
+        L.orc_free(p)
+
+
+def build_and_write(recs, path, **kw):
+    """Oracle build written as a .hash file by the oracle's own writer; returns status."""
+    recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+    L = lib()
+    p = L.orc_build(recs.ctypes.data, recs.size // 30, kw.get("k", 21), kw.get("w", 31),
+                    kw.get("factor1_", DEFAULT_FACTOR1), kw.get("B", 24), kw.get("N", 0),
+                    kw.get("chunk", 100000), kw.get("minB", 20), kw.get("maxB", 30))
+    try:
+        st = p.contents.status
+        if st == 0:
+            st = L.orc_write_hash(p, path.encode())
+        return st
+    finally:
+        L.orc_free(p)
+
+
+def time_build(recs, repeat=1, **kw):
+    """Wall-clock seconds of the oracle build alone (arrays are not copied out)."""
+    import time
+    recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+    L = lib()
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        p = L.orc_build(recs.ctypes.data, recs.size // 30, kw.get("k", 21), kw.get("w", 31),
+                        kw.get("factor1_", DEFAULT_FACTOR1), kw.get("B", 24), kw.get("N", 0),
+                        kw.get("chunk", 100000), 20, 30)
+        dt = time.perf_counter() - t0
+        st = p.contents.status
+        L.orc_free(p)
+        if st:
+            raise RuntimeError("oracle build failed: " + STATUS.get(st, str(st)))
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def record_moshes(rec, k=21, w=31, factor1_=DEFAULT_FACTOR1):
+    """(hash, pos, which) arrays for one 30-word record, in processBlock's generation order."""
+    rec = np.ascontiguousarray(rec, dtype=np.uint32)
+    cap = 320
+    h = np.zeros(cap, np.uint64); pos = np.zeros(cap, np.int32); which = np.zeros(cap, np.uint8)
+    n = lib().orc_record_moshes(rec.ctypes.data, k, w, factor1_, h.ctypes.data, pos.ctypes.data,
+                                which.ctypes.data, cap)
+    return h[:n], pos[:n], which[:n]
+
+
+def seq_moshes(codes, k=21, w=31, factor1_=DEFAULT_FACTOR1):
+    """(hash, pos, isForward) for a base string given as 2-bit codes (uint8)."""
+    s = np.ascontiguousarray(codes, dtype=np.uint8)
+    cap = max(1, s.size)
+    h = np.zeros(cap, np.uint64); pos = np.zeros(cap, np.int32); fwd = np.zeros(cap, np.uint8)
+    n = lib().orc_seq_moshes(s.ctypes.data, s.size, k, w, factor1_, h.ctypes.data, pos.ctypes.data,
+                             fwd.ctypes.data, cap)
+    return h[:n], pos[:n], fwd[:n]
+
+
+def kmer_hashes(h, hrc, k=21, factor1_=DEFAULT_FACTOR1):
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().orc_kmer_hashes(h, hrc, factor1_, k, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+# ------------------------------------------------------------------ synthetic FQB (CPU)
+
+def synth_params(seed=1, genome_len=200_000, n_barcodes=40, pairs_min=20, pairs_max=120,
+                 mol_per_barcode=4, mol_len=20_000, snp_period=500, err_rate=0.002):
+    return SynthParams(seed, genome_len, n_barcodes, pairs_min, pairs_max, mol_per_barcode,
+                       mol_len, snp_period, int(err_rate * 2 ** 32), 0)
+
+
+def synth_layout(p):
+    off = np.zeros(p.nBarcodes + 1, np.uint64)
+    n = lib().synth_layout(C.byref(p), off.ctypes.data)
+    return int(n), off
+
+
+def synth_fqb(p, r0=0, r1=None):
+    """Records r0..r1-1 of the synthetic data set as a (n,30) uint32 array."""
+    n, off = synth_layout(p)
+    if r1 is None:
+        r1 = n
+    out = np.zeros((r1 - r0, 30), np.uint32)
+    lib().synth_fill(C.byref(p), off.ctypes.data, r0, r1, out.ctypes.data)
+    return out
+
+
+# ------------------------------------------------------------------ the compiled reference
+
+def ref_binary(name="hash10x"):
+    p = os.path.join(REF_DIR, name)
+    return p if os.path.exists(p) else None
+
+
+def run_reference(fqb_path, hash_path=None, B=24, extra=(), k=None, w=None, r=None, N=None,
+                  chunk=None, binary="hash10x", timeout=600):
+    """Run oracle/_ref/hash10x on an FQB file; returns CompletedProcess (stdout text)."""
+    exe = ref_binary(binary)
+    if exe is None:
+        raise FileNotFoundError("oracle/_ref/%s not built" % binary)
+    cmd = [exe]
+    for flag, v in (("-k", k), ("-w", w), ("-r", r), ("-N", N), ("-c", chunk)):
+        if v is not None:
+            cmd += [flag, str(v)]
+    cmd += ["-B", str(B), "--readFQB", fqb_path]
+    if hash_path:
+        cmd += ["--writeHash", hash_path]
+    cmd += list(extra)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
