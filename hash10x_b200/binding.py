@@ -1,0 +1,253 @@
+"""ctypes binding of include/h10x_gpu.h (the C ABI of libh10xgpu.so).
+
+Mirrors the reference's seam for this path - `initialise(); readFQB(); fillHashTable();`
+(hash10x.c:1200-1205) - with the same parameter names (-k -w -r -B -N -c) and the same error
+texts ("hashTableSize is too small", "chunkSize too small", "hashTableBits %d out of range").
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_FACTOR1 = 0x49308BB9003CB3AD  # -r 17
+
+H10X_NSTAGES = 12
+FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES, FLAG_GENERIC_ONLY = 1, 2, 4, 8
+
+
+class H10xError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("h10x error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("factor1", C.c_uint64), ("B", C.c_int32),
+                ("chunkSize", C.c_int32), ("N", C.c_int64), ("device", C.c_int32),
+                ("flags", C.c_uint32)]
+
+
+class CIndex(C.Structure):
+    _fields_ = [("B", C.c_int32), ("hashNumber", C.c_uint32), ("nBlocksMax", C.c_uint32),
+                ("reserved", C.c_uint32), ("nReads", C.c_uint64), ("nHashes", C.c_uint64),
+                ("hashIndex", C.c_void_p), ("hashValue", C.c_void_p), ("hashDepth", C.c_void_p),
+                ("blkNRead", C.c_void_p), ("blkNHash", C.c_void_p), ("blkOff", C.c_void_p),
+                ("clusHash", C.c_void_p), ("codeOff", C.c_void_p), ("codes", C.c_void_p),
+                ("onDevice", C.c_int32), ("pinned", C.c_int32)]
+
+
+class CStats(C.Structure):
+    _fields_ = [("msTotal", C.c_double), ("msStage", C.c_double * H10X_NSTAGES),
+                ("nRecords", C.c_uint64), ("nMoshes", C.c_uint64), ("nHashes", C.c_uint64),
+                ("nBins", C.c_uint64), ("nBlocks", C.c_uint64), ("algorithmicBytes", C.c_uint64),
+                ("kernelLaunches", C.c_uint64), ("fusedBlocks", C.c_uint64),
+                ("genericBlocks", C.c_uint64), ("peakDeviceBytes", C.c_uint64)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libh10xgpu.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libh10xgpu.so; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise H10xError(7, "libh10xgpu.so is not built (run `make -C hash10x_b200/csrc` or "
+                           "__graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(p)
+    vp, u64, sz, cp = C.c_void_p, C.c_uint64, C.c_size_t, C.c_char_p
+    L.h10x_abi_version.restype = C.c_int
+    L.h10x_gpu_device_count.restype = C.c_int
+    L.h10x_strerror.restype = cp
+    L.h10x_strerror.argtypes = [C.c_int]
+    L.h10x_stage_name.restype = cp
+    L.h10x_stage_name.argtypes = [C.c_int]
+    L.h10x_factor1_from_seed.restype = u64
+    L.h10x_factor1_from_seed.argtypes = [C.c_int]
+    L.h10x_gpu_create.restype = vp
+    L.h10x_gpu_create.argtypes = [C.POINTER(Params), cp, sz]
+    L.h10x_gpu_destroy.argtypes = [vp]
+    L.h10x_gpu_build_device.argtypes = [vp, vp, u64, vp, cp, sz]
+    L.h10x_gpu_index_device.argtypes = [vp, C.POINTER(CIndex)]
+    L.h10x_gpu_download.argtypes = [vp, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_build_host.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_build_file.argtypes = [vp, cp, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_stats.argtypes = [vp, C.POINTER(CStats)]
+    L.h10x_index_free.argtypes = [C.POINTER(CIndex)]
+    L.h10x_host_alloc.restype = vp
+    L.h10x_host_alloc.argtypes = [sz]
+    L.h10x_host_free.argtypes = [vp]
+    L.h10x_gpu_record_moshes.argtypes = [vp, vp, u64, vp, vp, u64, cp, sz]
+    L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
+    L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
+    _lib = L
+    return L
+
+
+def factor1_from_seed(seed=17):
+    return int(load_library().h10x_factor1_from_seed(seed))
+
+
+def _arr(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class Index:
+    """Host copy of the state `--readFQB` leaves behind (see h10x_index in include/h10x_gpu.h)."""
+
+    def __init__(self, ci, lib, keep_c=False):
+        self.B, self.hashNumber, self.nBlocksMax = ci.B, ci.hashNumber, ci.nBlocksMax
+        self.nReads, self.nHashes = ci.nReads, ci.nHashes
+        hn, nb, H = ci.hashNumber, ci.nBlocksMax, ci.nHashes
+        self.hashIndex = _arr(ci.hashIndex, 1 << ci.B, np.uint32) if ci.hashIndex else None
+        self.hashValue = _arr(ci.hashValue, hn, np.uint64)
+        self.hashDepth = _arr(ci.hashDepth, hn, np.uint32)
+        self.blkNRead = _arr(ci.blkNRead, nb, np.uint32)
+        self.blkNHash = _arr(ci.blkNHash, nb, np.uint32)
+        self.blkOff = _arr(ci.blkOff, nb + 1, np.uint64)
+        self.clus = _arr(ci.clusHash, H, np.uint64)
+        self.codeOff = _arr(ci.codeOff, hn + 1, np.uint64) if ci.codeOff else None
+        self.codes = _arr(ci.codes, H, np.uint32) if ci.codes else None
+        self.status = 0
+
+
+class Hash10xGPU:
+    """One build context on one GPU = the reference's initialise() (hash10x.c:1099-1118)."""
+
+    def __init__(self, k=21, w=31, r=17, B=28, N=0, chunkSize=100000, device=0, flags=0,
+                 factor1=None):
+        self.lib = load_library()
+        if factor1 is None:
+            factor1 = DEFAULT_FACTOR1 if r == 17 else factor1_from_seed(r)
+        self.params = Params(k, w, factor1, B, chunkSize, N, device, flags)
+        err = C.create_string_buffer(512)
+        self.ctx = self.lib.h10x_gpu_create(C.byref(self.params), err, len(err))
+        if not self.ctx:
+            msg = err.value.decode()
+            code = 7 if "no CUDA device" in msg else (2 if "chunkSize" in msg else 3)
+            raise H10xError(code, msg)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.h10x_gpu_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st, err):
+        if st != 0:
+            raise H10xError(st, err.value.decode() or self.lib.h10x_strerror(st).decode())
+
+    # --- the seam with host buffers (what the C host program calls) ---
+    def build_host(self, recs, want_index=True):
+        """recs: uint32 array of 30*n words (n FQB records) in host memory."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+        return self.build_host_ptr(recs.ctypes.data, recs.size // 30, want_index)
+
+    def build_host_ptr(self, ptr, n, want_index=True):
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_build_host(self.ctx, ptr, n, C.byref(ci), err, len(err))
+        self._check(st, err)
+        try:
+            return Index(ci, self.lib) if want_index else (ci.hashNumber, ci.nHashes, ci.nBlocksMax)
+        finally:
+            self.lib.h10x_index_free(C.byref(ci))
+
+    def build_file(self, path):
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_build_file(self.ctx, path.encode(), C.byref(ci), err, len(err))
+        self._check(st, err)
+        try:
+            return Index(ci, self.lib)
+        finally:
+            self.lib.h10x_index_free(C.byref(ci))
+
+    def build_file_to_hash(self, fqb_path, hash_path):
+        """--readFQB fqb --writeHash hash, entirely through the C ABI."""
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_build_file(self.ctx, fqb_path.encode(), C.byref(ci), err, len(err))
+        self._check(st, err)
+        try:
+            st = self.lib.h10x_write_hash(C.byref(ci), hash_path.encode())
+            if st:
+                raise H10xError(st, "write fail")
+            return ci.hashNumber, ci.nHashes, ci.nBlocksMax
+        finally:
+            self.lib.h10x_index_free(C.byref(ci))
+
+    # --- device-resident build (inputs already in HBM; results stay in HBM) ---
+    def build_device(self, dev_ptr, n_records, stream=0):
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_build_device(self.ctx, dev_ptr, n_records, stream, err, len(err))
+        self._check(st, err)
+
+    def download(self):
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_download(self.ctx, C.byref(ci), err, len(err))
+        self._check(st, err)
+        try:
+            return Index(ci, self.lib)
+        finally:
+            self.lib.h10x_index_free(C.byref(ci))
+
+    def device_index(self):
+        ci = CIndex()
+        st = self.lib.h10x_gpu_index_device(self.ctx, C.byref(ci))
+        if st:
+            raise H10xError(st, "no index resident")
+        return ci
+
+    def stats(self):
+        cs = CStats()
+        self.lib.h10x_gpu_stats(self.ctx, C.byref(cs))
+        d = {f: getattr(cs, f) for f, _ in CStats._fields_ if f != "msStage"}
+        d["msStage"] = {self.lib.h10x_stage_name(i).decode(): cs.msStage[i] for i in range(H10X_NSTAGES)}
+        return d
+
+    def record_moshes(self, recs):
+        """K1 alone: per-record mosh hashes in generation order -> (offsets[n+1], hashes)."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+        n = recs.size // 30
+        off = np.zeros(n + 1, np.uint64)
+        cap = max(1, n * 237)
+        out = np.zeros(cap, np.uint64)
+        err = C.create_string_buffer(512)
+        st = self.lib.h10x_gpu_record_moshes(self.ctx, recs.ctypes.data, n, off.ctypes.data,
+                                             out.ctypes.data, cap, err, len(err))
+        self._check(st, err)
+        return off, out[:int(off[n])]
+
+
+def write_hash(index_arrays, path):
+    """h10x_write_hash on numpy arrays (B, hashNumber, ... as in Index)."""
+    L = load_library()
+    ix = index_arrays
+    keep = [np.ascontiguousarray(a) for a in (ix.hashIndex, ix.hashValue, ix.hashDepth, ix.blkNRead,
+                                              ix.blkNHash, ix.blkOff, ix.clus)]
+    ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
+                keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+                keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0)
+    st = L.h10x_write_hash(C.byref(ci), path.encode())
+    if st:
+        raise H10xError(st, "write fail")

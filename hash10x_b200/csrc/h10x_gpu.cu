@@ -1,0 +1,915 @@
+/* h10x_gpu.cu - device pipeline and C ABI of libh10xgpu.so (sm_100a).
+ *
+ * Replaces, on one B200, the reference's `--readFQB` branch (hash10x.c:1200-1205):
+ *   readFQB (hash10x.c:188-236)  ->  stage "runs"     barcode-run detection over word 0
+ *   processBlock (:154-186)      ->  stages "moshes"  k-mer hash + modulo selection (seqhash.c:58-80,154-195)
+ *                                              "blocksort"/"dedup"  per-barcode sort + first-occurrence dedup
+ *   hashIndexFind (:139-152)     ->  stages "hashsort"/"binids"  bin ids in (first block, hash) order,
+ *                                              per-bin depth = number of blocks holding the hash
+ *   clusHash sort (:176-183)     ->  stage  "clusters" per-block (bin id, read16) lists sorted by bin id
+ *   fillHashTable (:317-347)     ->  stage  "codes"    hash->barcode CSR, ascending block numbers
+ *   hashIndex[] layout (:142-148)->  stage  "table"    min-id displacement insertion = the sequential layout
+ *
+ * Data layout in HBM: see DESIGN.md.  No CPU fallback: every entry point fails without a device.
+ */
+#include "../../include/h10x_gpu.h"
+#include "h10x_common.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+/* ------------------------------------------------------------------ errors / memory */
+
+struct H10xError : std::runtime_error {
+  int code ;
+  H10xError (int c, const std::string &m) : std::runtime_error (m), code (c) {}
+} ;
+
+#define CK(call) do { cudaError_t e_ = (call) ; if (e_ != cudaSuccess) \
+  throw H10xError (e_ == cudaErrorMemoryAllocation ? H10X_ERR_NOMEM : H10X_ERR_CUDA, \
+		   std::string (#call) + ": " + cudaGetErrorString (e_) + " (" __FILE__ ":" + std::to_string (__LINE__) + ")") ; } while (0)
+
+struct MemTrack { size_t cur = 0, peak = 0 ; } ;
+
+template <class T> struct DBuf {
+  T *p = nullptr ; size_t n = 0 ; cudaStream_t s = 0 ; MemTrack *mt = nullptr ;
+  DBuf () {}
+  DBuf (size_t n_, cudaStream_t s_, MemTrack *mt_) { alloc (n_, s_, mt_) ; }
+  DBuf (const DBuf&) = delete ; DBuf &operator= (const DBuf&) = delete ;
+  void alloc (size_t n_, cudaStream_t s_, MemTrack *mt_)
+  { release () ; n = n_ ; s = s_ ; mt = mt_ ;
+    size_t bytes = (n ? n : 1) * sizeof (T) ;
+    CK (cudaMallocAsync ((void**)&p, bytes, s)) ;
+    if (mt) { mt->cur += bytes ; if (mt->cur > mt->peak) mt->peak = mt->cur ; }
+  }
+  void release ()
+  { if (p) { cudaFreeAsync (p, s) ; if (mt) mt->cur -= (n ? n : 1) * sizeof (T) ; p = nullptr ; n = 0 ; } }
+  void swap (DBuf &o) { std::swap (p, o.p) ; std::swap (n, o.n) ; std::swap (s, o.s) ; std::swap (mt, o.mt) ; }
+  ~DBuf () { release () ; }
+} ;
+
+static const char *kStageNames[H10X_NSTAGES] = {
+  "runs", "moshes", "blocksort", "dedup", "hashsort", "binids", "entryids", "codes",
+  "clusters", "table", "fused", "other" } ;
+enum { ST_RUNS = 0, ST_MOSHES, ST_BLOCKSORT, ST_DEDUP, ST_HASHSORT, ST_BINIDS, ST_ENTRYIDS, ST_CODES,
+       ST_CLUSTERS, ST_TABLE, ST_FUSED, ST_OTHER } ;
+
+struct h10x_ctx {
+  h10x_params P ;
+  HashParams hp ;
+  cudaStream_t own = 0 ;
+  MemTrack mt ;
+  /* resident result of the last build */
+  DBuf<uint32_t> hashIndex, hashDepth, blkNRead, blkNHash, codes ;
+  DBuf<uint64_t> hashValue, blkOff, codeOff, clus ;
+  uint32_t hashNumber = 1, nBlocksMax = 2 ;
+  uint64_t nReads = 0, nHashes = 0 ;
+  bool haveIndex = false ;
+  h10x_stats stats ;
+  /* stage timing */
+  std::vector<cudaEvent_t> evPool ; size_t evUsed = 0 ;
+  struct Span { int stage ; cudaEvent_t a, b ; } ;
+  std::vector<Span> spans ;
+  uint64_t launches = 0 ;
+} ;
+
+static cudaEvent_t ctx_event (h10x_ctx *c)
+{ if (c->evUsed == c->evPool.size ()) { cudaEvent_t e ; CK (cudaEventCreate (&e)) ; c->evPool.push_back (e) ; }
+  return c->evPool[c->evUsed++] ;
+}
+
+struct StageTimer {
+  h10x_ctx *c ; cudaStream_t s ; int stage ; cudaEvent_t a ;
+  StageTimer (h10x_ctx *c_, cudaStream_t s_, int st) : c (c_), s (s_), stage (st)
+  { a = ctx_event (c) ; cudaEventRecord (a, s) ; }
+  ~StageTimer () { cudaEvent_t b = ctx_event (c) ; cudaEventRecord (b, s) ; c->spans.push_back ({stage, a, b}) ; }
+} ;
+
+#define LAUNCH(c, kernel, grid, block, smem, stream, ...) do { \
+  kernel<<<(grid), (block), (smem), (stream)>>> (__VA_ARGS__) ; ++(c)->launches ; CK (cudaGetLastError ()) ; } while (0)
+
+static inline unsigned gridFor (uint64_t n, unsigned block) { return (unsigned) std::max<uint64_t> (1, (n + block - 1) / block) ; }
+
+template <class F> static void cubCall (h10x_ctx *c, cudaStream_t s, F f)
+{ size_t bytes = 0 ;
+  CK (f (nullptr, bytes)) ;
+  DBuf<char> tmp (bytes, s, &c->mt) ;
+  CK (f ((void*) tmp.p, bytes)) ;
+  c->launches += 1 ;	/* counted as one library call */
+}
+
+struct CastU64 { __host__ __device__ uint64_t operator() (uint32_t x) const { return (uint64_t) x ; } } ;
+
+/* ------------------------------------------------------------------ kernels: runs */
+
+/* flag[i] = 1 when record i starts a new barcode run (hash10x.c:213-220); notes whether any
+   record carries barcode word 0, the only case in which the reference's chunk loop can merge runs */
+__global__ void k_run_flags (const uint32_t *__restrict__ fqb, uint32_t n, uint32_t *__restrict__ flag,
+			     int *__restrict__ anyZero)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= n) return ;
+  uint32_t w0 = fqb[(size_t) H10X_REC_WORDS * i] ;
+  uint32_t prev = i ? fqb[(size_t) H10X_REC_WORDS * (i - 1)] : ~w0 ;
+  flag[i] = (w0 != prev) ? 1u : 0u ;
+  if (w0 == 0) *anyZero = 1 ;
+}
+
+/* blkStart[b] = first record of 0-based run b; blkStart[nRuns] = n */
+__global__ void k_run_starts (const uint32_t *__restrict__ flag, const uint32_t *__restrict__ incl, uint32_t n,
+			      uint32_t *__restrict__ blkStart)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= n) return ;
+  if (flag[i]) blkStart[incl[i] - 1] = i ;
+  if (i == n - 1) blkStart[incl[i]] = n ;
+}
+
+__global__ void k_flags_from_starts (const uint32_t *__restrict__ blkStart, uint32_t nBlk, uint32_t *__restrict__ flag)
+{ uint32_t b = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (b < nBlk) flag[blkStart[b]] = 1u ;
+}
+
+__global__ void k_gather_word0 (const uint32_t *__restrict__ fqb, const uint32_t *__restrict__ blkStart, uint32_t nBlk,
+				uint32_t *__restrict__ out)
+{ uint32_t b = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (b < nBlk) out[b] = fqb[(size_t) H10X_REC_WORDS * blkStart[b]] ;
+}
+
+/* ------------------------------------------------------------------ kernels: generic mosh path */
+
+/* one thread per read (2 per record).  EMIT=false counts, EMIT=true writes (hash, record) pairs at
+   the offsets the scan of the counts produced, so generation order (read index ascending, read 1
+   before read 2, position ascending - hash10x.c:160-164) is the memory order. */
+template <bool EMIT>
+__global__ void k_moshes (const uint32_t *__restrict__ fqb, uint32_t r0, uint32_t nb, HashParams hp,
+			  uint32_t *__restrict__ cnt2, const uint32_t *__restrict__ blkIncl, uint32_t p0,
+			  const uint32_t *__restrict__ phOff, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{ uint32_t t = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (t >= 2 * nb) return ;
+  uint32_t rec = r0 + (t >> 1) ; int rd = t & 1 ;
+  const uint32_t *src = fqb + (size_t) H10X_REC_WORDS * rec + 15 * rd ;
+  uint32_t u[10] ;
+#pragma unroll
+  for (int i = 0 ; i < 10 ; ++i) u[i] = src[i] ;
+  uint32_t n = 0 ;
+  uint32_t base = 0 ;
+  if (EMIT) base = cnt2[t] + phOff[blkIncl[rec] - 1 - p0] ;
+  h10x_scan_read (u, rd ? H10X_R2_START : H10X_R1_START, rd ? H10X_R2_LEN : H10X_R1_LEN, hp,
+		  [&] (uint64_t x) { if (EMIT) { keys[base + n] = x ; vals[base + n] = rec ; } ++n ; }) ;
+  if (!EMIT) cnt2[t] = n ;
+}
+
+/* per block of the batch: number of moshes; ph = 1 for a block with none (it gets the phantom
+   {hash 0, read 0} entry of hash10x.c:167-168) */
+__global__ void k_blk_moshes (const uint32_t *__restrict__ blkStart, uint32_t p0, uint32_t nblk, uint32_t r0,
+			      const uint32_t *__restrict__ off2, uint32_t *__restrict__ ph)
+{ uint32_t p = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (p > nblk) return ;
+  if (p == nblk) { ph[p] = 0 ; return ; }
+  uint32_t a = off2[2 * (blkStart[p0 + p] - r0)], b = off2[2 * (blkStart[p0 + p + 1] - r0)] ;
+  ph[p] = (a == b) ? 1u : 0u ;
+}
+
+__global__ void k_seg_off (const uint32_t *__restrict__ blkStart, uint32_t p0, uint32_t nblk, uint32_t r0,
+			   const uint32_t *__restrict__ off2, const uint32_t *__restrict__ phOff,
+			   const uint32_t *__restrict__ ph, uint32_t *__restrict__ segOff,
+			   uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{ uint32_t p = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (p > nblk) return ;
+  uint32_t so = off2[2 * (blkStart[p0 + p] - r0)] + phOff[p] ;
+  segOff[p] = so ;
+  if (keys && p < nblk && ph[p]) { keys[so] = 0 ; vals[so] = blkStart[p0 + p] ; }
+}
+
+/* first occurrence of each hash within its block, after the stable sort by hash */
+__global__ void k_uniq_flag (const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t m,
+			     const uint32_t *__restrict__ blkIncl, uint32_t *__restrict__ flag)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= m) return ;
+  bool f = (i == 0) || keys[i] != keys[i-1] || blkIncl[vals[i]] != blkIncl[vals[i-1]] ;
+  flag[i] = f ? 1u : 0u ;
+}
+
+__global__ void k_compact (const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t m,
+			   const uint32_t *__restrict__ flag, const uint32_t *__restrict__ incl, uint64_t eBase,
+			   uint64_t *__restrict__ eHash, uint32_t *__restrict__ eRec)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= m || !flag[i]) return ;
+  uint64_t e = eBase + incl[i] - 1 ;
+  eHash[e] = keys[i] ; eRec[e] = vals[i] ;
+}
+
+__global__ void k_blk_off (const uint32_t *__restrict__ segOff, const uint32_t *__restrict__ incl, uint32_t nblk,
+			   uint64_t eBase, uint64_t *__restrict__ blkOffProc)
+{ uint32_t p = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (p < nblk) blkOffProc[p] = eBase + incl[segOff[p]] - 1 ;
+}
+
+/* ------------------------------------------------------------------ kernels: bins */
+
+__global__ void k_iota (uint32_t *__restrict__ a, uint64_t n)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ; if (i < n) a[i] = (uint32_t) i ; }
+
+__global__ void k_head_flag (const uint64_t *__restrict__ sh, uint64_t n, uint32_t *__restrict__ head)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i < n) head[i] = (i == 0 || sh[i] != sh[i-1]) ? 1u : 0u ;
+}
+
+/* entries are stored in (block, hash) order, so the reference's insertion order of bins
+   (hash10x.c:147: first block that holds the hash, then hash value) is the order of each bin's
+   smallest entry index.  isFirst marks those entries. */
+__global__ void k_seg_start (const uint32_t *__restrict__ head, const uint32_t *__restrict__ segIncl, uint64_t n,
+			     const uint32_t *__restrict__ se, uint32_t *__restrict__ segStart,
+			     uint32_t *__restrict__ isFirst)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= n) return ;
+  if (head[i]) { segStart[segIncl[i] - 1] = (uint32_t) i ; isFirst[se[i]] = 1u ; }
+  if (i == n - 1) segStart[segIncl[i]] = (uint32_t) n ;
+}
+
+__global__ void k_bins (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ se,
+			const uint64_t *__restrict__ sh, const uint32_t *__restrict__ rank,
+			uint32_t *__restrict__ idOfSeg, uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
+{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (s >= nSeg) return ;
+  uint32_t i = segStart[s] ;
+  uint32_t id = 1u + rank[se[i]] ;
+  idOfSeg[s] = id ;
+  hashValue[id] = sh[i] ;
+  hashDepth[id] = segStart[s+1] - i ;	/* one entry per (block, hash): hash10x.c:178 */
+}
+
+__global__ void k_entry_ids (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ idOfSeg,
+			     const uint32_t *__restrict__ se, uint32_t *__restrict__ entryId)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i < n) entryId[se[i]] = idOfSeg[segIncl[i] - 1] ;
+}
+
+/* fillHashTable (hash10x.c:317-347): within a bin the sorted order is ascending entry index, i.e.
+   ascending block number */
+__global__ void k_codes (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ segStart,
+			 const uint32_t *__restrict__ idOfSeg, const uint32_t *__restrict__ se,
+			 const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
+			 const uint64_t *__restrict__ codeOff, uint32_t *__restrict__ codes)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= n) return ;
+  uint32_t s = segIncl[i] - 1 ;
+  codes[codeOff[idOfSeg[s]] + (i - segStart[s])] = blkIncl[eRec[se[i]]] ;
+}
+
+__global__ void k_clus_prep (uint64_t n, const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
+			     const uint32_t *__restrict__ blkStart, uint16_t *__restrict__ read16)
+{ uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (e >= n) return ;
+  uint32_t rec = eRec[e] ;
+  read16[e] = (uint16_t) (rec - blkStart[blkIncl[rec] - 1]) ;	/* U16 truncation: hash10x.c:37,180 */
+}
+
+__global__ void k_clus_pack (uint64_t n, const uint32_t *__restrict__ ids, const uint16_t *__restrict__ read16,
+			     uint64_t *__restrict__ clus)
+{ uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (e < n) clus[e] = (uint64_t) ids[e] | ((uint64_t) read16[e] << 32) ;
+}
+
+__global__ void k_shift_offsets (const uint64_t *__restrict__ in, uint64_t base, uint32_t n, uint32_t *__restrict__ out)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i < n) out[i] = (uint32_t) (in[i] - base) ;
+}
+
+/* hashIndex[] (hash10x.c:139-152).  Sequential insertion puts bin n at the first slot of its probe
+   sequence not held by a smaller id.  That fixed point is unique, so it can be reached in parallel:
+   a bin claims a slot that is empty or holds a larger id (compare-and-swap); the displaced larger
+   id is re-inserted from the start of its own sequence. */
+__global__ void k_table_insert (uint32_t hashNumber, const uint64_t *__restrict__ hashValue,
+				uint32_t *table, int B)
+{ uint32_t id = 1u + blockIdx.x * blockDim.x + threadIdx.x ;
+  if (id >= hashNumber) return ;
+  const uint64_t mask = ((uint64_t) 1 << B) - 1 ;
+  uint32_t cur = id ;
+  for (;;)
+    { uint64_t hv = hashValue[cur] ;
+      uint64_t off = hv & mask, diff = ((hv >> B) & mask) | 1 ;
+      uint32_t displaced = 0 ;
+      for (;;)
+	{ uint32_t old = *(volatile uint32_t*) &table[off] ;
+	  for (;;)
+	    { if (old != 0 && old < cur) break ;		/* held by a smaller id: probe on */
+	      uint32_t prev = atomicCAS (&table[off], old, cur) ;
+	      if (prev == old) { displaced = old ; old = 0xffffffffu ; break ; }
+	      old = prev ;
+	    }
+	  if (old == 0xffffffffu) break ;
+	  off = (off + diff) & mask ;
+	}
+      if (!displaced) return ;
+      cur = displaced ;
+    }
+}
+
+/* ------------------------------------------------------------------ host: parameters */
+
+static uint64_t inv64 (uint64_t a)	/* inverse of odd a modulo 2^64 (Newton) */
+{ uint64_t x = a ; for (int i = 0 ; i < 6 ; ++i) x *= 2 - a * x ; return x ; }
+
+static void make_hash_params (const h10x_params &P, HashParams &hp)
+{ hp.k = P.k ; hp.w = P.w ; hp.factor1 = P.factor1 ;
+  hp.shift = 64 - 2 * P.k ;
+  hp.kmask = (((uint64_t) 1) << (2 * P.k)) - 1 ;
+  hp.rcShift = 2 * (P.k - 1) ;
+  uint64_t w = (uint64_t) P.w ; int tz = 0 ;
+  while (!(w & 1)) { w >>= 1 ; ++tz ; }
+  hp.wTz = tz ; hp.wTzMask = (((uint64_t) 1) << tz) - 1 ;
+  hp.wInv = inv64 (w) ; hp.wLim = ~(uint64_t) 0 / w ;
+}
+
+/* ------------------------------------------------------------------ host: the build */
+
+struct BlockTable {	/* 0-based barcode blocks of the consumed records */
+  std::vector<uint32_t> start ;	/* nBlk + 1 */
+  uint32_t nBlk = 0 ;
+} ;
+
+/* The reference's chunk loop (hash10x.c:202-223) at run granularity.  Needed only when some run
+   carries barcode word 0: `if (!barcode) barcode = u[0]` at a chunk start then re-seeds the barcode
+   and glues the open all-A run onto the run that follows.  Also decides "chunkSize too small". */
+static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::vector<uint32_t> &runWord,
+			    uint32_t nRuns, uint64_t nRec, int chunkSize, int64_t N, BlockTable &bt)
+{
+  bt.start.clear () ;
+  uint64_t pos = 0, nReads = 0, curStart = 0, curN = 0 ;
+  uint32_t barcode = 0, r = 0 ;	/* r = run containing pos */
+  bool open = false ;		/* block 1 exists from the start with nRead 0 */
+  bt.start.push_back (0) ;
+  (void) open ;
+  while (!N || nReads < (uint64_t) N)
+    { int64_t thisChunk = (int64_t) chunkSize - (int64_t) curN ;
+      if (thisChunk <= 0) return H10X_ERR_CHUNK_TOO_SMALL ;
+      if (N && nReads + (uint64_t) thisChunk > (uint64_t) N) thisChunk = N - (int64_t) nReads ;
+      uint64_t n = std::min<uint64_t> ((uint64_t) thisChunk, nRec - pos) ;
+      if (!n) break ;
+      if (!barcode) barcode = runWord[r] ;
+      uint64_t end = pos + n ;
+      while (pos < end)
+	{ uint64_t segEnd = std::min<uint64_t> (end, runStart[r+1]) ;
+	  uint64_t len = segEnd - pos ;
+	  if (runWord[r] == barcode) curN += len ;
+	  else { bt.start.push_back ((uint32_t) pos) ; curStart = pos ; curN = len ; barcode = runWord[r] ; }
+	  pos = segEnd ;
+	  if (pos == runStart[r+1] && r + 1 < nRuns) ++r ;
+	}
+      nReads += n ;
+    }
+  (void) curStart ;
+  bt.nBlk = (uint32_t) bt.start.size () ;
+  bt.start.push_back ((uint32_t) nRec) ;
+  return H10X_OK ;
+}
+
+static void reset_result (h10x_ctx *c)
+{ c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
+  c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
+  c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
+  c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ;
+  memset (&c->stats, 0, sizeof (c->stats)) ;
+}
+
+/* segmented sort of (key, val) pairs whose segments are the barcode blocks; batched so that each
+   CUB call stays inside its `int num_items` interface */
+template <class K, class V>
+static void segmented_sort_blocks (h10x_ctx *c, cudaStream_t s, const K *kin, K *kout, const V *vin, V *vout,
+				   const std::vector<uint64_t> &hOff /* nSeg+1, host */, const uint64_t *dOff,
+				   bool stable)
+{
+  const uint64_t maxItems = (uint64_t) 1 << 30 ;
+  size_t nSeg = hOff.size () - 1, a = 0 ;
+  while (a < nSeg)
+    { size_t b = a + 1 ;
+      while (b < nSeg && hOff[b+1] - hOff[a] <= maxItems) ++b ;
+      uint64_t base = hOff[a], items = hOff[b] - base ;
+      if (items > 0x7fffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "a single barcode block exceeds 2^31 entries") ;
+      if (items)
+	{ uint32_t ns = (uint32_t) (b - a) ;
+	  DBuf<uint32_t> rel (ns + 1, s, &c->mt) ;
+	  LAUNCH (c, k_shift_offsets, gridFor (ns + 1, 256), 256, 0, s, dOff + a, base, ns + 1, rel.p) ;
+	  cubCall (c, s, [&] (void *t, size_t &bytes)
+	    { return stable
+		? cub::DeviceSegmentedSort::StableSortPairs (t, bytes, kin + base, kout + base, vin + base, vout + base,
+							      (int) items, (int) ns, rel.p, rel.p + 1, s)
+		: cub::DeviceSegmentedSort::SortPairs (t, bytes, kin + base, kout + base, vin + base, vout + base,
+						       (int) items, (int) ns, rel.p, rel.p + 1, s) ; }) ;
+	}
+      a = b ;
+    }
+}
+
+static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s)
+{
+  const h10x_params &P = c->P ;
+  reset_result (c) ;
+  cudaEvent_t evA = ctx_event (c), evB = ctx_event (c) ;
+  CK (cudaEventRecord (evA, s)) ;
+
+  uint64_t nRec64 = (P.N > 0 && (uint64_t) P.N < nFile) ? (uint64_t) P.N : nFile ;
+  if (nRec64 >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 records on one device") ;
+  uint32_t nRec = (uint32_t) nRec64 ;
+  c->nReads = nRec ;
+  MemTrack *mt = &c->mt ;
+
+  /* ---------------- runs -> barcode blocks ---------------- */
+  BlockTable bt ;
+  DBuf<uint32_t> blkIncl (nRec, s, mt) ;	/* 1-based block number of every record */
+  DBuf<uint32_t> dBlkStart ;
+  if (nRec == 0)
+    { bt.nBlk = 1 ; bt.start = {0, 0} ; }	/* block 1 exists with nRead 0 (hash10x.c:200-201) */
+  else
+    { StageTimer tm (c, s, ST_RUNS) ;
+      DBuf<uint32_t> flag (nRec, s, mt) ;
+      DBuf<int> anyZero (1, s, mt) ;
+      CK (cudaMemsetAsync (anyZero.p, 0, sizeof (int), s)) ;
+      LAUNCH (c, k_run_flags, gridFor (nRec, 256), 256, 0, s, fqb, nRec, flag.p, anyZero.p) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, flag.p, blkIncl.p, nRec, s) ; }) ;
+      uint32_t nRuns = 0 ; int hAnyZero = 0 ;
+      CK (cudaMemcpyAsync (&nRuns, blkIncl.p + (nRec - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaMemcpyAsync (&hAnyZero, anyZero.p, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      dBlkStart.alloc ((size_t) nRuns + 1, s, mt) ;
+      LAUNCH (c, k_run_starts, gridFor (nRec, 256), 256, 0, s, flag.p, blkIncl.p, nRec, dBlkStart.p) ;
+      std::vector<uint32_t> runStart ((size_t) nRuns + 1) ;
+      CK (cudaMemcpyAsync (runStart.data (), dBlkStart.p, 4 * ((size_t) nRuns + 1), cudaMemcpyDeviceToHost, s)) ;
+      if (!hAnyZero)
+	{ CK (cudaStreamSynchronize (s)) ;
+	  /* blocks are the runs; "chunkSize too small" (hash10x.c:206) fires when one run fills the
+	     whole chunk buffer and the loop comes round again (chunk semantics) */
+	  for (uint32_t r = 0 ; r < nRuns ; ++r)
+	    { uint64_t st = runStart[r], len = runStart[r+1] - st ;
+	      if (len >= (uint64_t) P.chunkSize && (P.N == 0 || st + (uint64_t) P.chunkSize < (uint64_t) P.N))
+		throw H10xError (H10X_ERR_CHUNK_TOO_SMALL, "chunkSize too small") ;
+	    }
+	  bt.nBlk = nRuns ; bt.start.swap (runStart) ;
+	}
+      else
+	{ DBuf<uint32_t> dWord (nRuns, s, mt) ;
+	  LAUNCH (c, k_gather_word0, gridFor (nRuns, 256), 256, 0, s, fqb, dBlkStart.p, nRuns, dWord.p) ;
+	  std::vector<uint32_t> runWord (nRuns) ;
+	  CK (cudaMemcpyAsync (runWord.data (), dWord.p, 4 * (size_t) nRuns, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaStreamSynchronize (s)) ;
+	  int st = simulate_chunks (runStart, runWord, nRuns, nRec, P.chunkSize, P.N, bt) ;
+	  if (st) throw H10xError (st, h10x_strerror (st)) ;
+	  if (bt.nBlk != nRuns)	/* some runs were glued: rebuild the per-record block numbers */
+	    { dBlkStart.alloc ((size_t) bt.nBlk + 1, s, mt) ;
+	      CK (cudaMemcpyAsync (dBlkStart.p, bt.start.data (), 4 * ((size_t) bt.nBlk + 1), cudaMemcpyHostToDevice, s)) ;
+	      CK (cudaMemsetAsync (flag.p, 0, 4 * (size_t) nRec, s)) ;
+	      LAUNCH (c, k_flags_from_starts, gridFor (bt.nBlk, 256), 256, 0, s, dBlkStart.p, bt.nBlk, flag.p) ;
+	      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, flag.p, blkIncl.p, nRec, s) ; }) ;
+	      CK (cudaStreamSynchronize (s)) ;	/* bt.start is read by the async copy above */
+	    }
+	}
+    }
+
+  const uint32_t nBlk = bt.nBlk ;
+  const uint32_t nProcBlk = nBlk - 1 ;		/* the final run is never hashed (hash10x.c:209,216) */
+  const uint32_t nProc = bt.start[nProcBlk] ;	/* records of the processed blocks */
+  c->nBlocksMax = nBlk + 1 ;
+
+  /* ---------------- moshes -> per-block unique (hash, record) entries ---------------- */
+  DBuf<uint64_t> eHash ; DBuf<uint32_t> eRec ;
+  DBuf<uint64_t> blkOffProc ((size_t) nProcBlk + 1, s, mt) ;
+  std::vector<uint64_t> hBlkOff ((size_t) nProcBlk + 1, 0) ;
+  uint64_t H = 0, totalMoshes = 0 ;
+  size_t eCap = 0 ;
+  auto ensureE = [&] (uint64_t need)
+    { if (need <= eCap) return ;
+      size_t cap = std::max<size_t> ((size_t) need, eCap + eCap / 2) ;
+      DBuf<uint64_t> nh (cap, s, mt) ; DBuf<uint32_t> nr (cap, s, mt) ;
+      if (H) { CK (cudaMemcpyAsync (nh.p, eHash.p, 8 * H, cudaMemcpyDeviceToDevice, s)) ;
+	       CK (cudaMemcpyAsync (nr.p, eRec.p, 4 * H, cudaMemcpyDeviceToDevice, s)) ; }
+      eHash.swap (nh) ; eRec.swap (nr) ; eCap = cap ;
+    } ;
+  if (nProcBlk) ensureE ((uint64_t) nProc * 8 + 1024) ;
+
+  const uint32_t batchRecs = 8u << 20 ;		/* 8M records: at most 2^31 moshes even if every k-mer is one */
+  uint32_t p0 = 0 ;
+  while (p0 < nProcBlk)
+    { uint32_t p1 = p0 + 1 ;
+      while (p1 < nProcBlk && bt.start[p1+1] - bt.start[p0] <= batchRecs) ++p1 ;
+      uint32_t r0 = bt.start[p0], nb = bt.start[p1] - r0, nblk = p1 - p0 ;
+      if ((uint64_t) nb * 237 > 0x7fffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "barcode block too large for the generic path") ;
+      DBuf<uint32_t> cnt2 ((size_t) 2 * nb + 1, s, mt), off2 ((size_t) 2 * nb + 1, s, mt) ;
+      DBuf<uint32_t> ph ((size_t) nblk + 1, s, mt), phOff ((size_t) nblk + 1, s, mt), segOff ((size_t) nblk + 1, s, mt) ;
+      uint32_t Mb = 0 ;
+      { StageTimer tm (c, s, ST_MOSHES) ;
+	CK (cudaMemsetAsync (cnt2.p + 2 * (size_t) nb, 0, 4, s)) ;
+	LAUNCH (c, k_moshes<false>, gridFor (2 * (uint64_t) nb, 128), 128, 0, s, fqb, r0, nb, c->hp, cnt2.p,
+		(const uint32_t*) nullptr, p0, (const uint32_t*) nullptr, (uint64_t*) nullptr, (uint32_t*) nullptr) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, cnt2.p, off2.p, 2 * (size_t) nb + 1, s) ; }) ;
+	LAUNCH (c, k_blk_moshes, gridFor (nblk + 1, 256), 256, 0, s, dBlkStart.p, p0, nblk, r0, off2.p, ph.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, ph.p, phOff.p, (size_t) nblk + 1, s) ; }) ;
+	LAUNCH (c, k_seg_off, gridFor (nblk + 1, 256), 256, 0, s, dBlkStart.p, p0, nblk, r0, off2.p, phOff.p, ph.p, segOff.p,
+		(uint64_t*) nullptr, (uint32_t*) nullptr) ;
+	CK (cudaMemcpyAsync (&Mb, segOff.p + nblk, 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+      }
+      totalMoshes += Mb ;
+      DBuf<uint64_t> keys (Mb, s, mt), keysS (Mb, s, mt) ;
+      DBuf<uint32_t> vals (Mb, s, mt), valsS (Mb, s, mt) ;
+      { StageTimer tm (c, s, ST_MOSHES) ;
+	LAUNCH (c, k_moshes<true>, gridFor (2 * (uint64_t) nb, 128), 128, 0, s, fqb, r0, nb, c->hp, off2.p,
+		blkIncl.p, p0, phOff.p, keys.p, vals.p) ;
+	LAUNCH (c, k_seg_off, gridFor (nblk + 1, 256), 256, 0, s, dBlkStart.p, p0, nblk, r0, off2.p, phOff.p, ph.p, segOff.p,
+		keys.p, vals.p) ;
+      }
+      { StageTimer tm (c, s, ST_BLOCKSORT) ;
+	/* stable: among equal hashes the first generated (lowest read index) stays first, which is
+	   the entry glibc's stable qsort leaves first for the dedup of hash10x.c:166-172 */
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceSegmentedSort::StableSortPairs (t, b, keys.p, keysS.p, vals.p, valsS.p, (int) Mb, (int) nblk,
+							       segOff.p, segOff.p + 1, s) ; }) ;
+      }
+      uint32_t Hb = 0 ;
+      { StageTimer tm (c, s, ST_DEDUP) ;
+	keys.release () ; vals.release () ;
+	DBuf<uint32_t> uflag (Mb, s, mt), uincl (Mb, s, mt) ;
+	LAUNCH (c, k_uniq_flag, gridFor (Mb, 256), 256, 0, s, keysS.p, valsS.p, Mb, blkIncl.p, uflag.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, uflag.p, uincl.p, Mb, s) ; }) ;
+	CK (cudaMemcpyAsync (&Hb, uincl.p + (Mb - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	ensureE (H + Hb) ;
+	LAUNCH (c, k_compact, gridFor (Mb, 256), 256, 0, s, keysS.p, valsS.p, Mb, uflag.p, uincl.p, H, eHash.p, eRec.p) ;
+	LAUNCH (c, k_blk_off, gridFor (nblk, 256), 256, 0, s, segOff.p, uincl.p, nblk, H, blkOffProc.p + p0) ;
+      }
+      H += Hb ;
+      p0 = p1 ;
+    }
+  CK (cudaMemcpyAsync (blkOffProc.p + nProcBlk, &H, 8, cudaMemcpyHostToDevice, s)) ;
+  CK (cudaMemcpyAsync (hBlkOff.data (), blkOffProc.p, 8 * ((size_t) nProcBlk + 1), cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  hBlkOff[nProcBlk] = H ;
+  c->nHashes = H ;
+  c->stats.genericBlocks = nProcBlk ;
+  if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
+
+  /* ---------------- bins: ids, values, depths ---------------- */
+  uint32_t D = 0 ;
+  DBuf<uint32_t> entryId (H, s, mt) ;
+  DBuf<uint32_t> se (H, s, mt), segIncl (H, s, mt), segStart, idOfSeg ;
+  if (H)
+    { DBuf<uint64_t> sh (H, s, mt) ;
+      { StageTimer tm (c, s, ST_HASHSORT) ;
+	DBuf<uint32_t> iota (H, s, mt) ;
+	LAUNCH (c, k_iota, gridFor (H, 256), 256, 0, s, iota.p, H) ;
+	/* stable LSD radix sort over the 2k hash bits: inside a bin, entries keep ascending index */
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceRadixSort::SortPairs (t, b, eHash.p, sh.p, iota.p, se.p, H, 0, 2 * P.k, s) ; }) ;
+      }
+      { StageTimer tm (c, s, ST_BINIDS) ;
+	DBuf<uint32_t> head (H, s, mt) ;
+	LAUNCH (c, k_head_flag, gridFor (H, 256), 256, 0, s, sh.p, H, head.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, head.p, segIncl.p, H, s) ; }) ;
+	CK (cudaMemcpyAsync (&D, segIncl.p + (H - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	/* hash10x.c:149: die once hashNumber exceeds 2^(B-2) - 2 */
+	if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)
+	  throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+	segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
+	DBuf<uint32_t> isFirst (H, s, mt), rank (H, s, mt) ;
+	CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
+	LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, isFirst.p, rank.p, H, s) ; }) ;
+	c->hashNumber = D + 1 ;
+	c->hashValue.alloc ((size_t) D + 1, s, mt) ;
+	c->hashDepth.alloc ((size_t) D + 2, s, mt) ;	/* one spare 0 so the scan yields codeOff[hashNumber] */
+	CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
+	LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+      }
+      { StageTimer tm (c, s, ST_ENTRYIDS) ;
+	LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl.p, idOfSeg.p, se.p, entryId.p) ;
+      }
+    }
+  else
+    { c->hashNumber = 1 ;
+      c->hashValue.alloc (1, s, mt) ; c->hashDepth.alloc (2, s, mt) ;
+      CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ; CK (cudaMemsetAsync (c->hashDepth.p, 0, 8, s)) ;
+    }
+
+  /* ---------------- hash -> code CSR ---------------- */
+  if (!(P.flags & H10X_FLAG_NO_CODES))
+    { StageTimer tm (c, s, ST_CODES) ;
+      size_t hn = c->hashNumber ;
+      c->codeOff.alloc (hn + 1, s, mt) ;
+      c->codes.alloc (H, s, mt) ;
+      cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+      if (H)
+	LAUNCH (c, k_codes, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eRec.p, blkIncl.p,
+		c->codeOff.p, c->codes.p) ;
+    }
+  se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ;
+
+  /* ---------------- code -> hash lists ---------------- */
+  c->clus.alloc (H, s, mt) ;
+  if (H)
+    { StageTimer tm (c, s, ST_CLUSTERS) ;
+      DBuf<uint16_t> rd (H, s, mt), rdS (H, s, mt) ;
+      DBuf<uint32_t> idS (H, s, mt) ;
+      LAUNCH (c, k_clus_prep, gridFor (H, 256), 256, 0, s, H, eRec.p, blkIncl.p, dBlkStart.p, rd.p) ;
+      segmented_sort_blocks<uint32_t, uint16_t> (c, s, entryId.p, idS.p, rd.p, rdS.p, hBlkOff, blkOffProc.p, false) ;
+      LAUNCH (c, k_clus_pack, gridFor (H, 256), 256, 0, s, H, idS.p, rdS.p, c->clus.p) ;
+    }
+  entryId.release () ; eRec.release () ;
+
+  /* ---------------- hashIndex[] ---------------- */
+  if (!(P.flags & H10X_FLAG_NO_TABLE))
+    { StageTimer tm (c, s, ST_TABLE) ;
+      size_t tableSize = (size_t) 1 << P.B ;
+      c->hashIndex.alloc (tableSize, s, mt) ;
+      CK (cudaMemsetAsync (c->hashIndex.p, 0, 4 * tableSize, s)) ;
+      if (D) LAUNCH (c, k_table_insert, gridFor (D, 256), 256, 0, s, c->hashNumber, c->hashValue.p, c->hashIndex.p, P.B) ;
+    }
+
+  /* ---------------- block table in the reference's numbering ---------------- */
+  { StageTimer tm (c, s, ST_OTHER) ;
+    std::vector<uint32_t> nRead ((size_t) nBlk + 1, 0), nHash ((size_t) nBlk + 1, 0) ;
+    std::vector<uint64_t> off ((size_t) nBlk + 2, 0) ;
+    for (uint32_t b = 1 ; b <= nBlk ; ++b)
+      { nRead[b] = bt.start[b] - bt.start[b-1] ;
+	if (b <= nProcBlk) { nHash[b] = (uint32_t) (hBlkOff[b] - hBlkOff[b-1]) ; off[b] = hBlkOff[b-1] ; }
+	else off[b] = H ;
+      }
+    off[nBlk + 1] = H ;
+    c->blkNRead.alloc ((size_t) nBlk + 1, s, mt) ; c->blkNHash.alloc ((size_t) nBlk + 1, s, mt) ;
+    c->blkOff.alloc ((size_t) nBlk + 2, s, mt) ;
+    CK (cudaMemcpyAsync (c->blkNRead.p, nRead.data (), 4 * ((size_t) nBlk + 1), cudaMemcpyHostToDevice, s)) ;
+    CK (cudaMemcpyAsync (c->blkNHash.p, nHash.data (), 4 * ((size_t) nBlk + 1), cudaMemcpyHostToDevice, s)) ;
+    CK (cudaMemcpyAsync (c->blkOff.p, off.data (), 8 * ((size_t) nBlk + 2), cudaMemcpyHostToDevice, s)) ;
+    CK (cudaStreamSynchronize (s)) ;
+  }
+
+  CK (cudaEventRecord (evB, s)) ;
+  CK (cudaEventSynchronize (evB)) ;
+  float ms = 0 ; CK (cudaEventElapsedTime (&ms, evA, evB)) ;
+  h10x_stats &st = c->stats ;
+  st.msTotal = ms ;
+  for (auto &sp : c->spans) { float t = 0 ; cudaEventElapsedTime (&t, sp.a, sp.b) ; st.msStage[sp.stage] += t ; }
+  st.nRecords = nRec ; st.nMoshes = totalMoshes ; st.nHashes = H ; st.nBins = D ; st.nBlocks = nBlk ;
+  st.algorithmicBytes = 120ull * nRec + 12ull * H + 12ull * D + ((P.flags & H10X_FLAG_NO_TABLE) ? 0 : (4ull << P.B))
+    + 32ull * ((uint64_t) nBlk + 1) ;
+  st.kernelLaunches = c->launches ;
+  st.peakDeviceBytes = c->mt.peak ;
+  c->haveIndex = true ;
+}
+
+/* ------------------------------------------------------------------ C ABI */
+
+static void set_err (char *err, size_t errlen, const char *msg)
+{ if (err && errlen) { strncpy (err, msg, errlen - 1) ; err[errlen - 1] = 0 ; } }
+
+template <class F> static int guarded (char *err, size_t errlen, F f)
+{ try { f () ; set_err (err, errlen, "") ; return H10X_OK ; }
+  catch (const H10xError &e) { set_err (err, errlen, e.what ()) ; return e.code ; }
+  catch (const std::bad_alloc &) { set_err (err, errlen, "host out of memory") ; return H10X_ERR_NOMEM ; }
+  catch (const std::exception &e) { set_err (err, errlen, e.what ()) ; return H10X_ERR_CUDA ; }
+}
+
+extern "C" {
+
+int h10x_abi_version (void) { return H10X_ABI_VERSION ; }
+
+int h10x_gpu_device_count (void)
+{ int n = 0 ; if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError () ; return 0 ; } return n ; }
+
+const char *h10x_strerror (int code)
+{ switch (code)
+    { case H10X_OK: return "ok" ;
+    case H10X_ERR_TABLE_TOO_SMALL: return "hashTableSize is too small" ;	/* hash10x.c:149 */
+    case H10X_ERR_CHUNK_TOO_SMALL: return "chunkSize too small" ;		/* hash10x.c:206 */
+    case H10X_ERR_BAD_PARAM: return "bad parameter" ;
+    case H10X_ERR_NOMEM: return "out of memory" ;
+    case H10X_ERR_IO: return "file read problem" ;				/* hash10x.c:209 */
+    case H10X_ERR_CUDA: return "CUDA error" ;
+    case H10X_ERR_NO_DEVICE: return "no CUDA device: libh10xgpu has no CPU fallback" ;
+    case H10X_ERR_UNSUPPORTED: return "size not supported on one device" ;
+    }
+  return "unknown error" ;
+}
+
+const char *h10x_stage_name (int stage) { return (stage >= 0 && stage < H10X_NSTAGES) ? kStageNames[stage] : "" ; }
+
+uint64_t h10x_factor1_from_seed (int seed)
+{ srandom ((unsigned) seed) ;
+  uint64_t hi = (uint64_t) random () ; uint64_t lo = (uint64_t) random () ;
+  return (hi << 32) | lo | 1 ;
+}
+
+h10x_ctx *h10x_gpu_create (const h10x_params *p, char *err, size_t errlen)
+{
+  h10x_ctx *c = nullptr ;
+  int st = guarded (err, errlen, [&] ()
+    { if (!p) throw H10xError (H10X_ERR_BAD_PARAM, "null params") ;
+      if (p->k < 1 || p->k >= 32) throw H10xError (H10X_ERR_BAD_PARAM, "seqhash k " + std::to_string (p->k) + " must be between 1 and 32") ;
+      if (p->w < 1) throw H10xError (H10X_ERR_BAD_PARAM, "seqhash w " + std::to_string (p->w) + " must be positive") ;
+      int maxB = (p->flags & H10X_FLAG_WIDE_B) ? 34 : 30 ;
+      if (p->B < 20 || p->B > maxB)
+	throw H10xError (H10X_ERR_BAD_PARAM, "hashTableBits " + std::to_string (p->B) + " out of range 20-" + std::to_string (maxB)) ;
+      if (p->chunkSize < 1) throw H10xError (H10X_ERR_CHUNK_TOO_SMALL, "chunkSize too small") ;
+      if (p->N < 0) throw H10xError (H10X_ERR_BAD_PARAM, "negative N") ;
+      int n = h10x_gpu_device_count () ;
+      if (n <= 0 || p->device < 0 || p->device >= n) throw H10xError (H10X_ERR_NO_DEVICE, h10x_strerror (H10X_ERR_NO_DEVICE)) ;
+      CK (cudaSetDevice (p->device)) ;
+      c = new h10x_ctx () ;
+      c->P = *p ;
+      make_hash_params (*p, c->hp) ;
+      memset (&c->stats, 0, sizeof (c->stats)) ;
+      CK (cudaStreamCreateWithFlags (&c->own, cudaStreamNonBlocking)) ;
+      cudaMemPool_t pool ;
+      CK (cudaDeviceGetDefaultMemPool (&pool, p->device)) ;
+      uint64_t thr = ~0ull ;	/* keep freed blocks cached between builds */
+      CK (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &thr)) ;
+    }) ;
+  if (st != H10X_OK) { delete c ; return nullptr ; }
+  return c ;
+}
+
+void h10x_gpu_destroy (h10x_ctx *c)
+{ if (!c) return ;
+  cudaSetDevice (c->P.device) ;
+  reset_result (c) ;
+  for (auto e : c->evPool) cudaEventDestroy (e) ;
+  if (c->own) { cudaStreamSynchronize (c->own) ; cudaStreamDestroy (c->own) ; }
+  delete c ;
+}
+
+int h10x_gpu_build_device (h10x_ctx *c, const void *d_fqb, uint64_t nRecords, void *stream, char *err, size_t errlen)
+{ if (!c) { set_err (err, errlen, "null context") ; return H10X_ERR_BAD_PARAM ; }
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = stream ? (cudaStream_t) stream : c->own ;
+      build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s) ;
+    }) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (stream ? (cudaStream_t) stream : c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
+  return st ;
+}
+
+int h10x_gpu_index_device (h10x_ctx *c, h10x_index *out)
+{ if (!c || !out || !c->haveIndex) return H10X_ERR_BAD_PARAM ;
+  memset (out, 0, sizeof (*out)) ;
+  out->B = c->P.B ; out->hashNumber = c->hashNumber ; out->nBlocksMax = c->nBlocksMax ;
+  out->nReads = c->nReads ; out->nHashes = c->nHashes ;
+  out->hashIndex = c->hashIndex.p ; out->hashValue = c->hashValue.p ; out->hashDepth = c->hashDepth.p ;
+  out->blkNRead = c->blkNRead.p ; out->blkNHash = c->blkNHash.p ; out->blkOff = c->blkOff.p ;
+  out->clusHash = (h10x_cluster_hash*) c->clus.p ; out->codeOff = c->codeOff.p ; out->codes = c->codes.p ;
+  out->onDevice = 1 ;
+  return H10X_OK ;
+}
+
+static void *pinned_alloc (size_t bytes)
+{ void *p = nullptr ; CK (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault)) ; return p ; }
+
+void h10x_index_free (h10x_index *ix)
+{ if (!ix || ix->onDevice) return ;
+  void *ps[] = { ix->hashIndex, ix->hashValue, ix->hashDepth, ix->blkNRead, ix->blkNHash, ix->blkOff,
+		 ix->clusHash, ix->codeOff, ix->codes } ;
+  for (void *p : ps) if (p) { if (ix->pinned) cudaFreeHost (p) ; else free (p) ; }
+  ix->hashIndex = nullptr ; ix->hashValue = nullptr ; ix->hashDepth = nullptr ; ix->blkNRead = nullptr ;
+  ix->blkNHash = nullptr ; ix->blkOff = nullptr ; ix->clusHash = nullptr ; ix->codeOff = nullptr ; ix->codes = nullptr ;
+}
+
+int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
+{ if (!c || !out || !c->haveIndex) { set_err (err, errlen, "no index resident") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      out->B = c->P.B ; out->hashNumber = c->hashNumber ; out->nBlocksMax = c->nBlocksMax ;
+      out->nReads = c->nReads ; out->nHashes = c->nHashes ; out->pinned = 1 ;
+      size_t hn = c->hashNumber, nb = c->nBlocksMax, H = c->nHashes ;
+      auto pull = [&] (void **dst, const void *src, size_t bytes)
+	{ if (!src) { *dst = nullptr ; return ; }
+	  *dst = pinned_alloc (bytes) ;
+	  if (bytes) CK (cudaMemcpyAsync (*dst, src, bytes, cudaMemcpyDeviceToHost, s)) ;
+	} ;
+      pull ((void**) &out->hashIndex, c->hashIndex.p, c->hashIndex.p ? ((size_t) 4 << c->P.B) : 0) ;
+      pull ((void**) &out->hashValue, c->hashValue.p, 8 * hn) ;
+      pull ((void**) &out->hashDepth, c->hashDepth.p, 4 * hn) ;
+      pull ((void**) &out->blkNRead, c->blkNRead.p, 4 * nb) ;
+      pull ((void**) &out->blkNHash, c->blkNHash.p, 4 * nb) ;
+      pull ((void**) &out->blkOff, c->blkOff.p, 8 * (nb + 1)) ;
+      pull ((void**) &out->clusHash, c->clus.p, 8 * H) ;
+      pull ((void**) &out->codeOff, c->codeOff.p, c->codeOff.p ? 8 * (hn + 1) : 0) ;
+      pull ((void**) &out->codes, c->codes.p, c->codes.p ? 4 * H : 0) ;
+      CK (cudaStreamSynchronize (s)) ;
+    }) ;
+  if (st != H10X_OK) h10x_index_free (out) ;
+  return st ;
+}
+
+int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_index *out, char *err, size_t errlen)
+{ if (!c || !out || (!fqb && nRecords)) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      /* only the first N records are ever looked at (hash10x.c:202,207) */
+      uint64_t n = (c->P.N > 0 && (uint64_t) c->P.N < nRecords) ? (uint64_t) c->P.N : nRecords ;
+      DBuf<uint32_t> d ((size_t) n * H10X_REC_WORDS, s, &c->mt) ;
+      if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
+      build_device_impl (c, d.p, n, s) ;
+    }) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
+  return h10x_gpu_download (c, out, err, errlen) ;
+}
+
+int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *err, size_t errlen)
+{ if (!c || !path || !out) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  FILE *f = fopen (path, "rb") ;
+  if (!f) { set_err (err, errlen, "failed to open fqb file") ; return H10X_ERR_IO ; }
+  uint32_t *d_fqb = nullptr ; uint64_t n = 0 ;
+  void *stage[2] = { nullptr, nullptr } ;
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      if (fseeko (f, 0, SEEK_END)) throw H10xError (H10X_ERR_IO, "file read problem") ;
+      uint64_t bytes = (uint64_t) ftello (f) ; rewind (f) ;
+      n = bytes / 120 ;			/* fread(u,120,..) drops a trailing partial record */
+      if (c->P.N > 0 && (uint64_t) c->P.N < n) n = (uint64_t) c->P.N ;
+      CK (cudaMalloc ((void**) &d_fqb, std::max<uint64_t> (n * 120, 16))) ;
+      const size_t chunkRecs = 1u << 19 ;	/* 60 MB pinned staging, double buffered */
+      stage[0] = pinned_alloc (chunkRecs * 120) ; stage[1] = pinned_alloc (chunkRecs * 120) ;
+      cudaEvent_t done[2] ; CK (cudaEventCreate (&done[0])) ; CK (cudaEventCreate (&done[1])) ;
+      uint64_t pos = 0 ; int cur = 0 ; bool used[2] = { false, false } ;
+      while (pos < n)
+	{ size_t want = (size_t) std::min<uint64_t> (chunkRecs, n - pos) ;
+	  if (used[cur]) CK (cudaEventSynchronize (done[cur])) ;
+	  size_t got = fread (stage[cur], 120, want, f) ;
+	  if (got != want) throw H10xError (H10X_ERR_IO, "file read problem") ;
+	  CK (cudaMemcpyAsync ((char*) d_fqb + pos * 120, stage[cur], got * 120, cudaMemcpyHostToDevice, s)) ;
+	  CK (cudaEventRecord (done[cur], s)) ; used[cur] = true ;
+	  pos += got ; cur ^= 1 ;
+	}
+      CK (cudaStreamSynchronize (s)) ;
+      cudaEventDestroy (done[0]) ; cudaEventDestroy (done[1]) ;
+      build_device_impl (c, d_fqb, n, s) ;
+    }) ;
+  fclose (f) ;
+  if (stage[0]) cudaFreeHost (stage[0]) ;
+  if (stage[1]) cudaFreeHost (stage[1]) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
+  if (d_fqb) cudaFree (d_fqb) ;
+  if (st != H10X_OK) return st ;
+  return h10x_gpu_download (c, out, err, errlen) ;
+}
+
+int h10x_gpu_stats (h10x_ctx *c, h10x_stats *out)
+{ if (!c || !out) return H10X_ERR_BAD_PARAM ; *out = c->stats ; return H10X_OK ; }
+
+void *h10x_host_alloc (size_t bytes)
+{ void *p = nullptr ; if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError () ; return nullptr ; } return p ; }
+
+void h10x_host_free (void *p) { if (p) cudaFreeHost (p) ; }
+
+int h10x_gpu_record_moshes (h10x_ctx *c, const void *fqb, uint64_t nRecords, uint64_t *outOff, uint64_t *outHash,
+			    uint64_t cap, char *err, size_t errlen)
+{ if (!c || !outOff || (!fqb && nRecords)) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      if (nRecords > (8u << 20)) throw H10xError (H10X_ERR_UNSUPPORTED, "record_moshes: at most 8M records per call") ;
+      uint32_t nb = (uint32_t) nRecords ;
+      outOff[0] = 0 ;
+      if (!nb) return ;
+      DBuf<uint32_t> d ((size_t) nb * H10X_REC_WORDS, s, &c->mt) ;
+      CK (cudaMemcpyAsync (d.p, fqb, (size_t) nb * 120, cudaMemcpyHostToDevice, s)) ;
+      DBuf<uint32_t> cnt2 ((size_t) 2 * nb + 1, s, &c->mt), off2 ((size_t) 2 * nb + 1, s, &c->mt) ;
+      DBuf<uint32_t> ones (nb, s, &c->mt), zero (1, s, &c->mt) ;
+      CK (cudaMemsetAsync (cnt2.p + 2 * (size_t) nb, 0, 4, s)) ;
+      CK (cudaMemsetAsync (zero.p, 0, 4, s)) ;
+      LAUNCH (c, k_moshes<false>, gridFor (2 * (uint64_t) nb, 128), 128, 0, s, d.p, 0u, nb, c->hp, cnt2.p,
+	      (const uint32_t*) nullptr, 0u, (const uint32_t*) nullptr, (uint64_t*) nullptr, (uint32_t*) nullptr) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, cnt2.p, off2.p, 2 * (size_t) nb + 1, s) ; }) ;
+      std::vector<uint32_t> h ((size_t) 2 * nb + 1) ;
+      CK (cudaMemcpyAsync (h.data (), off2.p, 4 * h.size (), cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      uint32_t M = h[2 * (size_t) nb] ;
+      for (uint32_t i = 0 ; i <= nb ; ++i) outOff[i] = h[2 * (size_t) i] ;
+      if (M > cap) throw H10xError (H10X_ERR_BAD_PARAM, "record_moshes: output capacity too small") ;
+      if (!M) return ;
+      /* blkIncl = all ones and p0 = 0 make every record "block 0" whose phantom offset is 0 */
+      CK (cudaMemsetAsync (ones.p, 0, 4 * (size_t) nb, s)) ;
+      DBuf<uint32_t> onesv (nb, s, &c->mt) ;
+      std::vector<uint32_t> hv (nb, 1u) ;
+      CK (cudaMemcpyAsync (onesv.p, hv.data (), 4 * (size_t) nb, cudaMemcpyHostToDevice, s)) ;
+      DBuf<uint64_t> keys (M, s, &c->mt) ; DBuf<uint32_t> vals (M, s, &c->mt) ;
+      LAUNCH (c, k_moshes<true>, gridFor (2 * (uint64_t) nb, 128), 128, 0, s, d.p, 0u, nb, c->hp, off2.p,
+	      onesv.p, 0u, zero.p, keys.p, vals.p) ;
+      CK (cudaMemcpyAsync (outHash, keys.p, 8 * (size_t) M, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+    }) ;
+}
+
+} /* extern "C" */

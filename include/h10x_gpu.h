@@ -1,0 +1,158 @@
+/* h10x_gpu.h - C ABI of libh10xgpu.so: hash10x's `--readFQB` minhash index build on one B200.
+ *
+ * The reference (richarddurbin/hash10x, plain C, /root/reference) has no plugin or FFI seam;
+ * the seam this library replaces is the `--readFQB` branch of its command loop
+ * (hash10x.c:1200-1205: initialise(); readFQB(); fillHashTable();) and the global state that
+ * branch leaves behind for every later command (hash10x.c:85-96).  Each entry
+ * point below names the reference code it stands in for.  Plain C types only; no CUDA, C++ or
+ * torch types cross this boundary (streams and device pointers travel as void* / integers).
+ *
+ * There is no CPU fallback: every build entry point returns H10X_ERR_NO_DEVICE when no CUDA
+ * device is usable.  INTEGRATION.md shows the change a hash10x maintainer would make to call it.
+ */
+#ifndef H10X_GPU_H
+#define H10X_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H10X_ABI_VERSION 1
+
+/* return codes; the host turns 1 and 2 into the reference's die() texts
+   ("hashTableSize is too small" hash10x.c:149, "chunkSize too small" hash10x.c:206) */
+enum {
+  H10X_OK = 0,
+  H10X_ERR_TABLE_TOO_SMALL = 1,
+  H10X_ERR_CHUNK_TOO_SMALL = 2,
+  H10X_ERR_BAD_PARAM = 3,
+  H10X_ERR_NOMEM = 4,
+  H10X_ERR_IO = 5,
+  H10X_ERR_CUDA = 6,
+  H10X_ERR_NO_DEVICE = 7,
+  H10X_ERR_UNSUPPORTED = 8
+};
+
+/* the `params` globals of hash10x.c:25-33 that the --readFQB path reads, plus the hasher
+   constant.  factor1 is computed by the HOST exactly as seqhash.c:29 does after srandom(r)
+   (hash10x.c:1101), so the libc RNG never enters device code; h10x_factor1_from_seed() does it. */
+typedef struct h10x_params {
+  int32_t k;			/* -k, 1..31 (seqhash.c:24) */
+  int32_t w;			/* -w, >= 1 (seqhash.c:25) */
+  uint64_t factor1;		/* Seqhash.factor1 (seqhash.h:20) */
+  int32_t B;			/* -B, hashTableBits; 20..30 unless H10X_FLAG_WIDE_B (hash10x.c:1107) */
+  int32_t chunkSize;		/* -c, only for the reference's chunk-boundary behaviour (hash10x.c:197-209) */
+  int64_t N;			/* -N, 0 = all records (hash10x.c:202,207) */
+  int32_t device;		/* CUDA device ordinal */
+  uint32_t flags;		/* H10X_FLAG_* */
+} h10x_params ;
+
+#define H10X_FLAG_WIDE_B	1u	/* accept B up to 34 as README.md:55 / moshset.c:17 describe */
+#define H10X_FLAG_NO_TABLE	2u	/* skip hashIndex[] materialisation (hashIndex stays NULL) */
+#define H10X_FLAG_NO_CODES	4u	/* skip the hash->code CSR (fillHashTable) */
+#define H10X_FLAG_GENERIC_ONLY	8u	/* force the generic (global-memory) sort path for every block */
+
+/* ClusterHash of hash10x.c:35-43, 8 bytes; subCluster and flags are written as 0 */
+typedef struct h10x_cluster_hash {
+  uint32_t hash ;		/* bin id, not the hash value */
+  uint16_t read ;		/* read-pair index within the barcode block, truncated to 16 bits */
+  uint8_t subCluster ;
+  uint8_t flags ;
+} h10x_cluster_hash ;
+
+/* The state --readFQB leaves behind (hash10x.c:85-96), as flat arrays.  Block numbering is the
+   reference's: entry 0 is the dummy, blocks 1..nBlocksMax-1 are the barcode runs in file order and
+   the last run has nHash 0 (hash10x.c:209,216).  Block i's ClusterHash list is
+   clusHash[blkOff[i] .. blkOff[i]+blkNHash[i]) sorted by bin id; bin x's barcode list
+   (hashCodes[x], hash10x.c:317-338) is codes[codeOff[x] .. codeOff[x+1]) ascending. */
+typedef struct h10x_index {
+  int32_t B ;
+  uint32_t hashNumber ;		/* bins are 1..hashNumber-1 */
+  uint32_t nBlocksMax ;		/* arrayMax(clusterBlocks) */
+  uint32_t reserved ;
+  uint64_t nReads ;		/* records consumed (readFQB's nReads) */
+  uint64_t nHashes ;		/* sum of nHash */
+  uint32_t *hashIndex ;		/* 2^B, layout identical to the reference's sequential insertion */
+  uint64_t *hashValue ;		/* hashNumber, [0] = 0 */
+  uint32_t *hashDepth ;		/* hashNumber, [0] = 0 */
+  uint32_t *blkNRead ;		/* nBlocksMax */
+  uint32_t *blkNHash ;		/* nBlocksMax */
+  uint64_t *blkOff ;		/* nBlocksMax + 1 */
+  h10x_cluster_hash *clusHash ;	/* nHashes */
+  uint64_t *codeOff ;		/* hashNumber + 1 */
+  uint32_t *codes ;		/* nHashes */
+  int32_t onDevice ;		/* 1: the pointers above are device pointers owned by the context */
+  int32_t pinned ;		/* 1: host arrays are cudaHostAlloc'ed (h10x_index_free knows) */
+} h10x_index ;
+
+/* per-build measurements for the roofline report */
+#define H10X_NSTAGES 12
+typedef struct h10x_stats {
+  double msTotal ;		/* CUDA-event time of the whole device build */
+  double msStage[H10X_NSTAGES] ;	/* per stage, names from h10x_stage_name() */
+  uint64_t nRecords, nMoshes, nHashes, nBins, nBlocks ;
+  uint64_t algorithmicBytes ;	/* 120 R + 12 H + 12 D + 4*2^B + 32 (nB+1)   */
+  uint64_t kernelLaunches ;	/* kernels launched by the last build (ours + CUB's) */
+  uint64_t fusedBlocks, genericBlocks ;	/* barcode blocks taken by each mosh path */
+  uint64_t peakDeviceBytes ;
+} h10x_stats ;
+
+typedef struct h10x_ctx h10x_ctx ;
+
+int h10x_abi_version (void) ;
+int h10x_gpu_device_count (void) ;
+const char *h10x_strerror (int code) ;
+const char *h10x_stage_name (int stage) ;
+
+/* seqhash.c:29 under srandom(seed) (hash10x.c:1101) - glibc TYPE_3 random(); host only */
+uint64_t h10x_factor1_from_seed (int seed) ;
+
+/* initialise() hash10x.c:1099-1118: checks k, w, B; binds the device */
+h10x_ctx *h10x_gpu_create (const h10x_params *p, char *err, size_t errlen) ;
+void h10x_gpu_destroy (h10x_ctx *ctx) ;
+
+/* readFQB() + fillHashTable() (hash10x.c:188-236, 317-347) on records already resident in device
+   memory: d_fqb = nRecords * 30 little-endian U32 (16-byte aligned).  `stream` is a cudaStream_t
+   (NULL = the context's own stream).  The index stays resident on the device, owned by ctx, until
+   the next build or destroy.  Asynchronous only up to the host decisions it needs; returns after
+   the last kernel is enqueued and counters are known. */
+int h10x_gpu_build_device (h10x_ctx *ctx, const void *d_fqb, uint64_t nRecords, void *stream,
+			   char *err, size_t errlen) ;
+
+/* device-pointer view of the resident index (onDevice = 1); valid until the next build */
+int h10x_gpu_index_device (h10x_ctx *ctx, h10x_index *out) ;
+
+/* copy the resident index to host memory (pinned); free with h10x_index_free */
+int h10x_gpu_download (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
+
+/* the whole seam with HOST buffers: H2D of the FQB records, build, D2H of the index */
+int h10x_gpu_build_host (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x_index *out,
+			 char *err, size_t errlen) ;
+
+/* same, reading `path` as readFQB's fread loop does (whole 120-byte records only) */
+int h10x_gpu_build_file (h10x_ctx *ctx, const char *path, h10x_index *out, char *err, size_t errlen) ;
+
+int h10x_gpu_stats (h10x_ctx *ctx, h10x_stats *out) ;
+void h10x_index_free (h10x_index *ix) ;
+
+/* pinned host staging for callers that want the H2D copy to run at full PCIe rate */
+void *h10x_host_alloc (size_t bytes) ;
+void h10x_host_free (void *p) ;
+
+/* moshes of each record without the index build (the K1 stage alone), for parity tests of
+   seqhash.c:154-195: outCount[i] = number of moshes of record i in generation order, written to
+   outHash[outOff[i]..]; arrays are HOST memory, outOff has nRecords+1 entries. */
+int h10x_gpu_record_moshes (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, uint64_t *outOff,
+			    uint64_t *outHash, uint64_t cap, char *err, size_t errlen) ;
+
+/* writeHashFile()/readHashFile() hash10x.c:244-315 on a host index (host code, no CUDA) */
+int h10x_write_hash (const h10x_index *ix, const char *path) ;
+int h10x_read_hash (const char *path, int32_t B, h10x_index *out, char *err, size_t errlen) ;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

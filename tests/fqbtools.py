@@ -1,0 +1,51 @@
+"""Hand-built FQB records for edge-case tests (packing as fq2b.c:33-61 of the reference)."""
+import numpy as np
+
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def pack_read(codes):
+    """151 2-bit codes -> 15 words (10 base words, 5 qual words of all-good quality)."""
+    codes = np.asarray(codes, dtype=np.uint32)
+    assert codes.size == 151
+    u = np.zeros(15, np.uint32)
+    for i in range(9):
+        v = 0
+        for c in codes[16 * i:16 * i + 16]:
+            v = (v << 2) | int(c)
+        u[i] = v
+    v = 0
+    for c in codes[144:151]:
+        v = (v << 2) | int(c)
+    u[9] = v                        # last 7 bases right-aligned (fq2b.c:41)
+    u[10:14] = 0xFFFFFFFF
+    u[14] = 0x7FFFFF
+    return u
+
+
+def barcode_codes(word):
+    return [(word >> (2 * (15 - i))) & 3 for i in range(16)]
+
+
+def make_record(barcode_word, r1_tail, r2):
+    """barcode word + 135 codes for read-1 positions 16..150 + 151 codes of read 2."""
+    r1 = np.concatenate([barcode_codes(barcode_word), np.asarray(r1_tail)]).astype(np.uint32)
+    rec = np.concatenate([pack_read(r1), pack_read(r2)])
+    assert rec[0] == barcode_word
+    return rec
+
+
+def random_records(rng, barcode_words, counts):
+    """counts[i] random records for barcode_words[i], grouped in that order."""
+    out = []
+    for w, n in zip(barcode_words, counts):
+        for _ in range(n):
+            out.append(make_record(int(w), rng.integers(0, 4, 135), rng.integers(0, 4, 151)))
+    return np.array(out, dtype=np.uint32).reshape(-1, 30)
+
+
+def const_records(barcode_word, n, base1, base2):
+    """n records whose read-1 tail is all base1 and read 2 all base2 (poly-A gives hash 0 moshes,
+    poly-C none: SURVEY.md Appendix E)."""
+    rec = make_record(barcode_word, np.full(135, base1), np.full(151, base2))
+    return np.tile(rec, (n, 1))

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA build (through the C ABI) against the CPU oracle, bit-exact.
+
+Strict mode: identical bin ids, hashValue order, depths, per-block (id, read)
+lists, hash->code CSR and a byte-identical hashIndex table.
+"""
+import numpy as np
+import pytest
+
+import fqbtools
+import hashfile
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(**kw):
+    import hash10x_b200
+    return hash10x_b200.Hash10xGPU(**kw)
+
+
+def _compare(orc, recs, B=20, k=21, w=31, r=17, N=0, chunk=100000, flags=0):
+    f1 = orc.factor1(r)
+    want = orc.build(recs, k=k, w=w, factor1_=f1, B=B, N=N, chunk=chunk)
+    assert want.status == 0, want.status_text
+    with _gpu(k=k, w=w, r=r, B=B, N=N, chunkSize=chunk, flags=flags, factor1=f1) as g:
+        got = g.build_host(recs)
+        st = g.stats()
+    a, b = hashfile.from_index(want), hashfile.from_index(got)
+    assert got.nReads == want.nReads and got.nHashes == want.nHashes
+    hashfile.assert_strict_equal(a, b, table=True)
+    assert np.array_equal(got.clus, want.clus)          # bytes 6-7 are zero on both sides
+    assert np.array_equal(got.blkOff, want.blkOff)
+    assert np.array_equal(got.codeOff, want.codeOff)
+    assert np.array_equal(got.codes, want.codes)
+    hashfile.check_table(b)
+    return want, got, st
+
+
+def test_record_moshes_match_oracle(orc, gpu_lib):
+    rng = np.random.default_rng(5)
+    recs = fqbtools.random_records(rng, [0x1234567, 0x89ABCDE], [40, 24])
+    recs = np.concatenate([recs, fqbtools.const_records(77, 3, 0, 0), fqbtools.const_records(78, 2, 1, 1)])
+    with _gpu(B=20) as g:
+        off, hashes = g.record_moshes(recs)
+    for i, rec in enumerate(recs):
+        h, _pos, _which = orc.record_moshes(rec)
+        assert np.array_equal(hashes[int(off[i]):int(off[i + 1])], h), i
+    # poly-A: every k-mer of both reads is a mosh with hash 0 (107 + 130); poly-C: none
+    assert int(off[65] - off[64]) == 237 and int(off[68] - off[67]) == 0
+
+
+@pytest.mark.parametrize("seed,nb,pmin,pmax", [(1, 30, 1, 40), (2, 200, 20, 300), (3, 12, 500, 1500)])
+def test_synthetic_strict(orc, gpu_lib, seed, nb, pmin, pmax):
+    p = orc.synth_params(seed=seed, n_barcodes=nb, pairs_min=pmin, pairs_max=pmax)
+    recs = orc.synth_fqb(p)
+    want, got, st = _compare(orc, recs, B=21)
+    assert st["nBins"] == want.hashNumber - 1
+
+
+@pytest.mark.parametrize("k,w,r", [(21, 31, 17), (16, 32, 17), (31, 7, 3), (11, 1, 9), (25, 12, 17), (5, 3, 1)])
+def test_parameters(orc, gpu_lib, k, w, r):
+    p = orc.synth_params(seed=11, n_barcodes=25, pairs_min=3, pairs_max=60, genome_len=50_000, mol_len=5_000)
+    recs = orc.synth_fqb(p)
+    _compare(orc, recs, B=22, k=k, w=w, r=r)
+
+
+def test_quirks_last_block_phantom_polyA(orc, gpu_lib):
+    rng = np.random.default_rng(9)
+    recs = np.concatenate([
+        fqbtools.random_records(rng, [11], [5]),
+        fqbtools.const_records(12, 4, 1, 1),      # poly-C block: no moshes -> phantom {hash 0, read 0}
+        fqbtools.random_records(rng, [13], [7]),
+        fqbtools.const_records(14, 3, 0, 0),      # poly-A block: hash 0 moshes, shares the phantom's bin
+        fqbtools.const_records(15, 2, 1, 1),      # second phantom block
+        fqbtools.random_records(rng, [16], [6]),  # last block: never hashed
+    ])
+    want, got, _ = _compare(orc, recs)
+    assert got.blkNHash[2] == 1 and got.blkNHash[4] == 1 and got.blkNHash[6] == 0
+    z = int(np.where(got.hashValue[1:] == 0)[0][0]) + 1
+    assert got.hashDepth[z] == 3
+
+
+def test_edge_sizes(orc, gpu_lib):
+    rng = np.random.default_rng(2)
+    one = fqbtools.random_records(rng, [5], [9])
+    for recs in (np.zeros((0, 30), np.uint32), one, one[:1],
+                 fqbtools.random_records(rng, [5, 6], [1, 1]),
+                 fqbtools.random_records(rng, [9, 8, 9, 8], [2, 3, 2, 1])):   # barcode recurs: separate runs
+        _compare(orc, recs)
+
+
+def test_read_index_wraps_at_16_bits(orc, gpu_lib):
+    # 66000 pairs in one barcode: read index > 65535 is stored truncated (hash10x.c:37,180)
+    p = orc.synth_params(seed=4, n_barcodes=3, pairs_min=66000, pairs_max=66000, genome_len=3_000_000,
+                         mol_per_barcode=50, mol_len=50_000)
+    recs = orc.synth_fqb(p)
+    _compare(orc, recs, B=22)
+
+
+def test_N_limit_and_chunks(orc, gpu_lib):
+    p = orc.synth_params(seed=6, n_barcodes=40, pairs_min=10, pairs_max=90)
+    recs = orc.synth_fqb(p)
+    for N in (1, 57, 1000, recs.shape[0], recs.shape[0] + 5):
+        _compare(orc, recs, N=N)
+    for chunk in (91, 100, 1000):
+        _compare(orc, recs, chunk=chunk)
+        _compare(orc, recs, chunk=chunk, N=777)
+
+
+def test_chunk_too_small(orc, gpu_lib):
+    import hash10x_b200
+    p = orc.synth_params(seed=6, n_barcodes=40, pairs_min=10, pairs_max=90)
+    recs = orc.synth_fqb(p)
+    n, off = orc.synth_layout(p)
+    big = int(np.diff(off.astype(np.int64)).max())
+    for chunk in (big, big - 1, 10):
+        want = orc.build(recs, B=20, chunk=chunk)
+        assert want.status == 2
+        with _gpu(B=20, chunkSize=chunk) as g:
+            with pytest.raises(hash10x_b200.H10xError) as e:
+                g.build_host(recs)
+            assert e.value.code == 2 and "chunkSize too small" in e.value.msg
+    # exactly at the -N limit the reference leaves the loop before the check (hash10x.c:202)
+    first = int(off[1])
+    for N in (first, first + 1):
+        want = orc.build(recs, B=20, chunk=first, N=N)
+        with _gpu(B=20, chunkSize=first, N=N) as g:
+            if want.status == 2:
+                with pytest.raises(hash10x_b200.H10xError):
+                    g.build_host(recs)
+            else:
+                got = g.build_host(recs)
+                hashfile.assert_strict_equal(hashfile.from_index(want), hashfile.from_index(got))
+
+
+def test_table_too_small(orc, gpu_lib):
+    import hash10x_b200
+    # B=20 holds at most 2^18-2 bins; ~330k distinct hashes overflow it
+    p = orc.synth_params(seed=8, n_barcodes=60, pairs_min=800, pairs_max=1000, genome_len=20_000_000,
+                         mol_len=100_000, mol_per_barcode=20)
+    recs = orc.synth_fqb(p)
+    want = orc.build(recs, B=20)
+    assert want.status == 1
+    with _gpu(B=20) as g:
+        with pytest.raises(hash10x_b200.H10xError) as e:
+            g.build_host(recs)
+        assert e.value.code == 1 and "hashTableSize is too small" in e.value.msg
+    _compare(orc, recs, B=21)
+
+
+def test_all_A_barcode_chunk_boundary(orc, gpu_lib):
+    # barcode word 0 ending exactly on a chunk boundary is glued to the next run by the reference's
+    # `if (!barcode) barcode = u[0]` (hash10x.c:212); elsewhere it is an ordinary run
+    rng = np.random.default_rng(21)
+    recs = fqbtools.random_records(rng, [7, 0, 9, 0, 5, 3], [6, 4, 5, 3, 4, 2])
+    for chunk in (10, 11, 12, 7, 8, 9, 15, 18, 100):
+        want = orc.build(recs, B=20, chunk=chunk)
+        if want.status == 0:
+            _compare(orc, recs, chunk=chunk)
+    starts0 = fqbtools.random_records(rng, [0, 4, 0, 2], [5, 5, 5, 5])
+    for chunk in (5, 6, 10, 11, 100):
+        want = orc.build(starts0, B=20, chunk=chunk)
+        if want.status == 0:
+            _compare(orc, starts0, chunk=chunk)
+
+
+def test_build_file_and_device_paths(orc, gpu_lib, tmp_path):
+    p = orc.synth_params(seed=12, n_barcodes=50, pairs_min=5, pairs_max=80)
+    recs = orc.synth_fqb(p)
+    path = str(tmp_path / "x.fqb")
+    with open(path, "wb") as f:
+        f.write(recs.tobytes())
+        f.write(b"\x01\x02\x03")           # trailing partial record is ignored (fread of whole records)
+    want = orc.build(recs, B=20)
+    with _gpu(B=20) as g:
+        got = g.build_file(path)
+        hashfile.assert_strict_equal(hashfile.from_index(want), hashfile.from_index(got))
+        hp = str(tmp_path / "x.hash")
+        g.build_file_to_hash(path, hp)
+    op = str(tmp_path / "o.hash")
+    assert orc.build_and_write(recs, op, B=20) == 0
+    a, b = open(hp, "rb").read(), open(op, "rb").read()
+    assert a == b                           # the two writers agree byte for byte
+    hf = hashfile.parse(hp)
+    hashfile.assert_strict_equal(hashfile.from_index(want), hf)
+
+
+def test_bad_parameters(gpu_lib):
+    import hash10x_b200
+    for kw in (dict(B=19), dict(B=31), dict(k=0), dict(k=32), dict(w=0)):
+        with pytest.raises(hash10x_b200.H10xError):
+            _gpu(**kw)
+    with _gpu(B=31, flags=1) as g:        # H10X_FLAG_WIDE_B models the "B bound relaxed" oracle
+        assert g.ctx
