@@ -18,6 +18,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <iterator>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,22 +38,57 @@ struct H10xError : std::runtime_error {
   throw H10xError (e_ == cudaErrorMemoryAllocation ? H10X_ERR_NOMEM : H10X_ERR_CUDA, \
 		   std::string (#call) + ": " + cudaGetErrorString (e_) + " (" __FILE__ ":" + std::to_string (__LINE__) + ")") ; } while (0)
 
-struct MemTrack { size_t cur = 0, peak = 0 ; } ;
+/* Device workspace: one cudaMalloc'ed slab per context with a first-fit free list kept on the host.
+   Every buffer of a build is carved out of it, so a build makes no driver allocation calls
+   (cudaMallocAsync pools were measured to cost 100s of ms per build while they grow and split).
+   All work of a build is enqueued on one stream, so a block freed on the host can be handed out
+   again at once: whatever used it was enqueued earlier on the same stream.  When the slab is too
+   small the build is abandoned (SlabFull), the slab is re-allocated larger and the build is re-run. */
+struct SlabFull { size_t need ; } ;
+
+struct MemTrack {
+  char *base = nullptr ; size_t cap = 0 ;
+  size_t cur = 0, peak = 0 ;
+  std::map<size_t, size_t> freeList ;	/* offset -> size, coalesced */
+  void reset () { freeList.clear () ; if (cap) freeList[0] = cap ; cur = 0 ; }
+  void *take (size_t bytes)
+  { bytes = (bytes + 511) & ~(size_t) 511 ;
+    for (auto it = freeList.begin () ; it != freeList.end () ; ++it)
+      if (it->second >= bytes)
+	{ size_t off = it->first, sz = it->second ;
+	  freeList.erase (it) ;
+	  if (sz > bytes) freeList[off + bytes] = sz - bytes ;
+	  cur += bytes ; if (cur > peak) peak = cur ;
+	  return base + off ;
+	}
+    throw SlabFull { cur + bytes } ;
+  }
+  void give (void *p, size_t bytes)
+  { bytes = (bytes + 511) & ~(size_t) 511 ;
+    size_t off = (size_t) ((char*) p - base) ;
+    cur -= bytes ;
+    auto nx = freeList.lower_bound (off) ;
+    if (nx != freeList.end () && off + bytes == nx->first) { bytes += nx->second ; nx = freeList.erase (nx) ; }
+    if (nx != freeList.begin ())
+      { auto pv = std::prev (nx) ;
+	if (pv->first + pv->second == off) { pv->second += bytes ; return ; }
+      }
+    freeList[off] = bytes ;
+  }
+} ;
 
 template <class T> struct DBuf {
-  T *p = nullptr ; size_t n = 0 ; cudaStream_t s = 0 ; MemTrack *mt = nullptr ;
+  T *p = nullptr ; size_t n = 0 ; MemTrack *mt = nullptr ;
   DBuf () {}
-  DBuf (size_t n_, cudaStream_t s_, MemTrack *mt_) { alloc (n_, s_, mt_) ; }
+  DBuf (size_t n_, cudaStream_t, MemTrack *mt_) { alloc (n_, 0, mt_) ; }
   DBuf (const DBuf&) = delete ; DBuf &operator= (const DBuf&) = delete ;
-  void alloc (size_t n_, cudaStream_t s_, MemTrack *mt_)
-  { release () ; n = n_ ; s = s_ ; mt = mt_ ;
-    size_t bytes = (n ? n : 1) * sizeof (T) ;
-    CK (cudaMallocAsync ((void**)&p, bytes, s)) ;
-    if (mt) { mt->cur += bytes ; if (mt->cur > mt->peak) mt->peak = mt->cur ; }
+  void alloc (size_t n_, cudaStream_t, MemTrack *mt_)
+  { release () ; mt = mt_ ; n = n_ ;
+    p = (T*) mt->take ((n ? n : 1) * sizeof (T)) ;
   }
   void release ()
-  { if (p) { cudaFreeAsync (p, s) ; if (mt) mt->cur -= (n ? n : 1) * sizeof (T) ; p = nullptr ; n = 0 ; } }
-  void swap (DBuf &o) { std::swap (p, o.p) ; std::swap (n, o.n) ; std::swap (s, o.s) ; std::swap (mt, o.mt) ; }
+  { if (p) { mt->give (p, (n ? n : 1) * sizeof (T)) ; p = nullptr ; n = 0 ; } }
+  void swap (DBuf &o) { std::swap (p, o.p) ; std::swap (n, o.n) ; std::swap (mt, o.mt) ; }
   ~DBuf () { release () ; }
 } ;
 
@@ -78,6 +115,9 @@ struct h10x_ctx {
   struct Span { int stage ; cudaEvent_t a, b ; } ;
   std::vector<Span> spans ;
   uint64_t launches = 0 ;
+  /* pinned host arena reused by h10x_gpu_download (one slot per index array) */
+  void *hostSlot[9] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } ;
+  size_t hostCap[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 } ;
 } ;
 
 static cudaEvent_t ctx_event (h10x_ctx *c)
@@ -375,7 +415,7 @@ static void reset_result (h10x_ctx *c)
 { c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
-  c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ;
+  c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
   memset (&c->stats, 0, sizeof (c->stats)) ;
 }
 
@@ -408,10 +448,10 @@ static void segmented_sort_blocks (h10x_ctx *c, cudaStream_t s, const K *kin, K 
     }
 }
 
-static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s)
+static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true)
 {
   const h10x_params &P = c->P ;
-  reset_result (c) ;
+  if (reset) reset_result (c) ;
   cudaEvent_t evA = ctx_event (c), evB = ctx_event (c) ;
   CK (cudaEventRecord (evA, s)) ;
 
@@ -666,6 +706,46 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   c->haveIndex = true ;
 }
 
+/* ------------------------------------------------------------------ slab sizing / retry */
+
+static void slab_free (h10x_ctx *c)
+{ reset_result (c) ;
+  if (c->mt.base) { cudaFree (c->mt.base) ; c->mt.base = nullptr ; }
+  c->mt.cap = 0 ; c->mt.reset () ;
+}
+
+static void slab_resize (h10x_ctx *c, size_t want)
+{ slab_free (c) ;
+  size_t freeB = 0, totalB = 0 ;
+  CK (cudaMemGetInfo (&freeB, &totalB)) ;
+  size_t limit = freeB - std::min<size_t> (freeB / 50, (size_t) 512 << 20) ;	/* leave a little headroom */
+  if (want > limit) want = limit ;
+  want &= ~(size_t) 511 ;
+  CK (cudaMalloc ((void**) &c->mt.base, want)) ;
+  c->mt.cap = want ; c->mt.reset () ;
+}
+
+/* run `body` (a complete build) inside the slab, growing the slab and re-running when it is too small */
+template <class F> static void with_slab (h10x_ctx *c, cudaStream_t s, size_t estimate, F body)
+{ if (c->mt.cap < estimate) { reset_result (c) ; slab_resize (c, estimate) ; }
+  for (int attempt = 0 ; ; ++attempt)
+    { try { body () ; return ; }
+      catch (const SlabFull &f)
+	{ cudaStreamSynchronize (s) ;
+	  size_t old = c->mt.cap ;
+	  size_t want = std::max<size_t> (f.need + f.need / 4, old + old / 2) ;
+	  slab_resize (c, want) ;
+	  if (c->mt.cap <= old || attempt > 12)
+	    throw H10xError (H10X_ERR_NOMEM, "device workspace: need " + std::to_string (f.need) + " bytes, have " + std::to_string (c->mt.cap)) ;
+	}
+    }
+}
+
+static size_t slab_estimate (const h10x_params &P, uint64_t nRec, bool withFqb)
+{ return (size_t) 420 * nRec + ((P.flags & H10X_FLAG_NO_TABLE) ? 0 : ((size_t) 4 << P.B)) + (withFqb ? 120 * nRec : 0)
+    + ((size_t) 64 << 20) ;
+}
+
 /* ------------------------------------------------------------------ C ABI */
 
 static void set_err (char *err, size_t errlen, const char *msg)
@@ -728,10 +808,6 @@ h10x_ctx *h10x_gpu_create (const h10x_params *p, char *err, size_t errlen)
       make_hash_params (*p, c->hp) ;
       memset (&c->stats, 0, sizeof (c->stats)) ;
       CK (cudaStreamCreateWithFlags (&c->own, cudaStreamNonBlocking)) ;
-      cudaMemPool_t pool ;
-      CK (cudaDeviceGetDefaultMemPool (&pool, p->device)) ;
-      uint64_t thr = ~0ull ;	/* keep freed blocks cached between builds */
-      CK (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &thr)) ;
     }) ;
   if (st != H10X_OK) { delete c ; return nullptr ; }
   return c ;
@@ -740,8 +816,10 @@ h10x_ctx *h10x_gpu_create (const h10x_params *p, char *err, size_t errlen)
 void h10x_gpu_destroy (h10x_ctx *c)
 { if (!c) return ;
   cudaSetDevice (c->P.device) ;
-  reset_result (c) ;
+  if (c->own) cudaStreamSynchronize (c->own) ;
+  slab_free (c) ;
   for (auto e : c->evPool) cudaEventDestroy (e) ;
+  for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
   if (c->own) { cudaStreamSynchronize (c->own) ; cudaStreamDestroy (c->own) ; }
   delete c ;
 }
@@ -751,7 +829,8 @@ int h10x_gpu_build_device (h10x_ctx *c, const void *d_fqb, uint64_t nRecords, vo
   int st = guarded (err, errlen, [&] ()
     { CK (cudaSetDevice (c->P.device)) ;
       cudaStream_t s = stream ? (cudaStream_t) stream : c->own ;
-      build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s) ;
+      with_slab (c, s, slab_estimate (c->P, nRecords, false),
+		 [&] () { build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s) ; }) ;
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (stream ? (cudaStream_t) stream : c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
   return st ;
@@ -773,7 +852,7 @@ static void *pinned_alloc (size_t bytes)
 { void *p = nullptr ; CK (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault)) ; return p ; }
 
 void h10x_index_free (h10x_index *ix)
-{ if (!ix || ix->onDevice) return ;
+{ if (!ix || ix->onDevice || ix->pinned == 2) return ;	/* pinned == 2: arrays live in the context's arena */
   void *ps[] = { ix->hashIndex, ix->hashValue, ix->hashDepth, ix->blkNRead, ix->blkNHash, ix->blkOff,
 		 ix->clusHash, ix->codeOff, ix->codes } ;
   for (void *p : ps) if (p) { if (ix->pinned) cudaFreeHost (p) ; else free (p) ; }
@@ -788,11 +867,18 @@ int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
     { CK (cudaSetDevice (c->P.device)) ;
       cudaStream_t s = c->own ;
       out->B = c->P.B ; out->hashNumber = c->hashNumber ; out->nBlocksMax = c->nBlocksMax ;
-      out->nReads = c->nReads ; out->nHashes = c->nHashes ; out->pinned = 1 ;
+      out->nReads = c->nReads ; out->nHashes = c->nHashes ; out->pinned = 2 ;
       size_t hn = c->hashNumber, nb = c->nBlocksMax, H = c->nHashes ;
+      int slot = 0 ;
       auto pull = [&] (void **dst, const void *src, size_t bytes)
-	{ if (!src) { *dst = nullptr ; return ; }
-	  *dst = pinned_alloc (bytes) ;
+	{ int i = slot++ ;
+	  if (!src) { *dst = nullptr ; return ; }
+	  if (c->hostCap[i] < bytes || !c->hostSlot[i])
+	    { if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
+	      c->hostSlot[i] = nullptr ; c->hostCap[i] = 0 ;
+	      c->hostSlot[i] = pinned_alloc (bytes) ; c->hostCap[i] = bytes ? bytes : 1 ;
+	    }
+	  *dst = c->hostSlot[i] ;
 	  if (bytes) CK (cudaMemcpyAsync (*dst, src, bytes, cudaMemcpyDeviceToHost, s)) ;
 	} ;
       pull ((void**) &out->hashIndex, c->hashIndex.p, c->hashIndex.p ? ((size_t) 4 << c->P.B) : 0) ;
@@ -806,7 +892,7 @@ int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
       pull ((void**) &out->codes, c->codes.p, c->codes.p ? 4 * H : 0) ;
       CK (cudaStreamSynchronize (s)) ;
     }) ;
-  if (st != H10X_OK) h10x_index_free (out) ;
+  if (st != H10X_OK) memset (out, 0, sizeof (*out)) ;
   return st ;
 }
 
@@ -817,9 +903,12 @@ int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_i
       cudaStream_t s = c->own ;
       /* only the first N records are ever looked at (hash10x.c:202,207) */
       uint64_t n = (c->P.N > 0 && (uint64_t) c->P.N < nRecords) ? (uint64_t) c->P.N : nRecords ;
-      DBuf<uint32_t> d ((size_t) n * H10X_REC_WORDS, s, &c->mt) ;
-      if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
-      build_device_impl (c, d.p, n, s) ;
+      with_slab (c, s, slab_estimate (c->P, n, true), [&] ()
+	{ reset_result (c) ;
+	  DBuf<uint32_t> d ((size_t) n * H10X_REC_WORDS, s, &c->mt) ;
+	  if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
+	  build_device_impl (c, d.p, n, s, false) ;
+	}) ;
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
   return h10x_gpu_download (c, out, err, errlen) ;
@@ -854,7 +943,7 @@ int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *e
 	}
       CK (cudaStreamSynchronize (s)) ;
       cudaEventDestroy (done[0]) ; cudaEventDestroy (done[1]) ;
-      build_device_impl (c, d_fqb, n, s) ;
+      with_slab (c, s, slab_estimate (c->P, n, false), [&] () { build_device_impl (c, d_fqb, n, s) ; }) ;
     }) ;
   fclose (f) ;
   if (stage[0]) cudaFreeHost (stage[0]) ;
@@ -883,10 +972,13 @@ int h10x_gpu_record_moshes (h10x_ctx *c, const void *fqb, uint64_t nRecords, uin
       uint32_t nb = (uint32_t) nRecords ;
       outOff[0] = 0 ;
       if (!nb) return ;
+      reset_result (c) ;
+      size_t est = (size_t) nb * (120 + 24 + 237 * 12) + ((size_t) 16 << 20) ;
+      if (c->mt.cap < est) slab_resize (c, est) ;
       DBuf<uint32_t> d ((size_t) nb * H10X_REC_WORDS, s, &c->mt) ;
       CK (cudaMemcpyAsync (d.p, fqb, (size_t) nb * 120, cudaMemcpyHostToDevice, s)) ;
       DBuf<uint32_t> cnt2 ((size_t) 2 * nb + 1, s, &c->mt), off2 ((size_t) 2 * nb + 1, s, &c->mt) ;
-      DBuf<uint32_t> ones (nb, s, &c->mt), zero (1, s, &c->mt) ;
+      DBuf<uint32_t> zero (1, s, &c->mt) ;
       CK (cudaMemsetAsync (cnt2.p + 2 * (size_t) nb, 0, 4, s)) ;
       CK (cudaMemsetAsync (zero.p, 0, 4, s)) ;
       LAUNCH (c, k_moshes<false>, gridFor (2 * (uint64_t) nb, 128), 128, 0, s, d.p, 0u, nb, c->hp, cnt2.p,
@@ -900,7 +992,6 @@ int h10x_gpu_record_moshes (h10x_ctx *c, const void *fqb, uint64_t nRecords, uin
       if (M > cap) throw H10xError (H10X_ERR_BAD_PARAM, "record_moshes: output capacity too small") ;
       if (!M) return ;
       /* blkIncl = all ones and p0 = 0 make every record "block 0" whose phantom offset is 0 */
-      CK (cudaMemsetAsync (ones.p, 0, 4 * (size_t) nb, s)) ;
       DBuf<uint32_t> onesv (nb, s, &c->mt) ;
       std::vector<uint32_t> hv (nb, 1u) ;
       CK (cudaMemcpyAsync (onesv.p, hv.data (), 4 * (size_t) nb, cudaMemcpyHostToDevice, s)) ;

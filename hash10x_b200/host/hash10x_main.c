@@ -1,0 +1,334 @@
+/* hash10x_main.c - `hash10x-b200`: hash10x's command loop over the B200 index build.
+ *
+ * Keeps the reference program's interface for the --readFQB pipeline (hash10x.c:1122-1305):
+ * positional, order-sensitive command chaining; -k -w -r -B -N -c -o set globals that the next
+ * operation uses; every command is echoed as "COMMAND ..." and followed by a resource line; fatal
+ * errors are "FATAL ERROR: ...\n" on stderr with exit(-1) (utils.c:18-29).  --readFQB runs on the
+ * GPU through libh10xgpu.so (include/h10x_gpu.h) - there is no CPU build in this program - and
+ * leaves the same state behind (hash table, values, depths, block table, ClusterHash lists,
+ * hash->code lists) for --writeHash, --hashStats, --codeStats and --hashDepthRange, which are O(bins)
+ * / O(hashes) host passes exactly as in the reference.  --readHash loads a .hash file written by
+ * either program.  The research probes (--cluster, --cribBuild, --hashExplore, ...) are out of scope
+ *  and die with a message saying so.
+ */
+#define _GNU_SOURCE
+#include "h10x_gpu.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/resource.h>
+
+static struct { int k, w, r, B, N, chunkSize, clusterThreshold ; } params ;
+static FILE *outFile ;
+static h10x_index ix ;		/* the state --readFQB / --readHash leave behind */
+static int haveIndex = 0, indexFromGpu = 0 ;
+static h10x_ctx *ctx = 0 ;
+static long totalAllocated = 0 ;
+
+static void die (const char *format, ...)
+{ va_list args ;
+  va_start (args, format) ;
+  fprintf (stderr, "FATAL ERROR: ") ; vfprintf (stderr, format, args) ; fprintf (stderr, "\n") ;
+  va_end (args) ;
+  exit (-1) ;
+}
+
+/* utils.c:122-150: rusage deltas since the previous call */
+static struct rusage rOld, rFirst ;
+static void timeUpdate (FILE *f)
+{ static int isFirst = 1 ;
+  struct rusage rNew ;
+  getrusage (RUSAGE_SELF, &rNew) ;
+  if (!isFirst)
+    { long secs = rNew.ru_utime.tv_sec - rOld.ru_utime.tv_sec, usecs = rNew.ru_utime.tv_usec - rOld.ru_utime.tv_usec ;
+      if (usecs < 0) { usecs += 1000000 ; secs -= 1 ; }
+      fprintf (f, "user\t%d.%06d", (int) secs, (int) usecs) ;
+      secs = rNew.ru_stime.tv_sec - rOld.ru_stime.tv_sec ; usecs = rNew.ru_stime.tv_usec - rOld.ru_stime.tv_usec ;
+      if (usecs < 0) { usecs += 1000000 ; secs -= 1 ; }
+      fprintf (f, "\tsystem\t%d.%06d", (int) secs, (int) usecs) ;
+      fprintf (f, "\tmax_RSS\t%ld", rNew.ru_maxrss - rOld.ru_maxrss) ;
+      fprintf (f, "\tmemory\t%li", totalAllocated) ;
+      fputc ('\n', f) ;
+    }
+  else { rFirst = rNew ; isFirst = 0 ; }
+  rOld = rNew ;
+}
+static void timeTotal (FILE *f) { rOld = rFirst ; timeUpdate (f) ; }
+
+static void usage (void)
+{ fprintf (stderr, "Usage: hash10x-b200 <commands>\n") ;
+  fprintf (stderr, "Commands can be parameter settings with -x, or operations:\n") ;
+  fprintf (stderr, "Be sure to set relevant parameters before invoking an operation!\n") ;
+  fprintf (stderr, "   -k <kmer size> [%d]\n", params.k) ;
+  fprintf (stderr, "   -w <window> [%d]\n", params.w) ;
+  fprintf (stderr, "   -r <random number seed> [%d]\n", params.r) ;
+  fprintf (stderr, "   -B <hash index table bitcount> [%d]\n", params.B) ;
+  fprintf (stderr, "   -N <num records to read: 0 for all> [%d]\n", params.N) ;
+  fprintf (stderr, "   -c <file chunkSize in readPairs> [%d]\n", params.chunkSize) ;
+  fprintf (stderr, "   -o | --output <output filename> : '-' for stdout\n") ;
+  fprintf (stderr, "   --readFQB <sorted fqb input file name>: must have this or readHash (runs on the GPU)\n") ;
+  fprintf (stderr, "   --readHash <hash input file name>\n") ;
+  fprintf (stderr, "   --writeHash <hash output file name>\n") ;
+  fprintf (stderr, "   --hashDepthRange <min> <max>: set limits for hash counts\n") ;
+  fprintf (stderr, "   --hashStats : distribution of hash counts and summary info\n") ;
+  fprintf (stderr, "   --codeStats : distribution of barcode/cluster sizes and summary info\n") ;
+  fprintf (stderr, "   --gpuStats : per-stage device times and roofline bytes of the last --readFQB\n") ;
+  fprintf (stderr, "   --help : print this usage message\n") ;
+}
+
+/* ---- initialise() hash10x.c:1099-1118 ---- */
+static void initialise (int k, int w, int r, int B)
+{ if (k <= 0 || w <= 0) die ("k %d, w %d must be > 0; run without args for usage", k, w) ;
+  if (k >= 32) die ("seqhash k %d must be between 1 and 32\n", k) ;
+  if (B < 20 || B > 30) die ("hashTableBits %d out of range 20-30", B) ;
+  if (haveIndex) { h10x_index_free (&ix) ; memset (&ix, 0, sizeof (ix)) ; haveIndex = 0 ; }
+  fprintf (outFile, "hash10x initialised with k = %d, w = %d, random seed = %d, hashtable bits = %d\n", k, w, r, B) ;
+}
+
+/* ---- --readFQB: readFQB() + fillHashTable(), hash10x.c:188-236,317-347, on the GPU ---- */
+static void readFQB (const char *path)
+{ char err[512] ;
+  h10x_params p ;
+  memset (&p, 0, sizeof (p)) ;
+  p.k = params.k ; p.w = params.w ; p.B = params.B ; p.N = params.N ; p.chunkSize = params.chunkSize ;
+  p.factor1 = h10x_factor1_from_seed (params.r) ;
+  p.device = getenv ("H10X_DEVICE") ? atoi (getenv ("H10X_DEVICE")) : 0 ;
+  printf ("  reading and processing sorted fqb file with chunkSize %d", params.chunkSize) ;
+  if (params.N) printf (", first %d records", params.N) ;
+  printf ("\n") ;
+  if (params.chunkSize <= 0) die ("chunkSize too small") ;
+  if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
+  if (!(ctx = h10x_gpu_create (&p, err, sizeof (err)))) die ("%s", err) ;
+  int st = h10x_gpu_build_file (ctx, path, &ix, err, sizeof (err)) ;
+  if (st == H10X_ERR_TABLE_TOO_SMALL) die ("hashTableSize is too small") ;
+  else if (st == H10X_ERR_CHUNK_TOO_SMALL) die ("chunkSize too small") ;
+  else if (st == H10X_ERR_IO) die ("file read problem") ;
+  else if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+  haveIndex = 1 ; indexFromGpu = 1 ;
+  totalAllocated += ((long) 4 << ix.B) + 12L * ix.hashNumber + 12L * (long) ix.nHashes ;
+
+  int nBarcodes = (int) ix.nBlocksMax - 1, i ;
+  /* the reference prints these twice when the output is stdout (hash10x.c:230 tests `!= stdin`) */
+  for (i = 0 ; i < 2 ; ++i)
+    { FILE *f = i ? stdout : outFile ;
+      fprintf (f, "  read %d read pair records for %d barcodes, mean %.2f read pairs per barcode\n",
+	       (int) ix.nReads, nBarcodes, (int) ix.nReads / (double) nBarcodes) ;
+      fprintf (f, "  created %ld hashes, mean %.2f hashes per read pair, %.2f per barcode\n",
+	       (long) ix.nHashes, ix.nHashes / (double) (int) ix.nReads, ix.nHashes / (double) nBarcodes) ;
+    }
+  fprintf (outFile, "  filled hash table: %ld hashes from %d barcodes in %d bins\n",
+	   (long) ix.nHashes, (int) ix.nBlocksMax, (int) ix.hashNumber) ;
+}
+
+/* ---- --readHash: readHashFile() hash10x.c:269-315; hash->code lists rebuilt as in fillHashTable ---- */
+static void readHash (const char *path)
+{ char err[512] ;
+  int st = h10x_read_hash (path, params.B, &ix, err, sizeof (err)) ;
+  if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+  haveIndex = 1 ; indexFromGpu = 0 ;
+  fprintf (outFile, "  read %ld hashes for %ld reads in %d barcode blocks\n", (long) ix.nHashes, (long) ix.nReads, (int) ix.nBlocksMax) ;
+  if (outFile != stdout)
+    printf ("  read %ld hashes for %ld reads in %d barcode blocks\n", (long) ix.nHashes, (long) ix.nReads, (int) ix.nBlocksMax) ;
+  /* fillHashTable: counting pass over the ClusterHash lists in block order keeps lists ascending */
+  uint32_t hn = ix.hashNumber, b ; uint64_t e ;
+  ix.codeOff = calloc ((size_t) hn + 1, 8) ; ix.codes = malloc ((ix.nHashes ? ix.nHashes : 1) * 4) ;
+  uint64_t *fill = calloc ((size_t) hn + 1, 8) ;
+  if (!ix.codeOff || !ix.codes || !fill) die ("myalloc failure") ;
+  long nHashes = 0 ;
+  for (b = 1 ; b < hn ; ++b) nHashes += ix.hashDepth[b] ;
+  for (b = 0 ; b < hn ; ++b) ix.codeOff[b+1] = ix.codeOff[b] + ix.hashDepth[b] ;
+  for (b = 1 ; b < ix.nBlocksMax ; ++b)
+    for (e = ix.blkOff[b] ; e < ix.blkOff[b] + ix.blkNHash[b] ; ++e)
+      { uint32_t x = ix.clusHash[e].hash ; ix.codes[ix.codeOff[x] + fill[x]++] = b ; }
+  free (fill) ;
+  fprintf (outFile, "  filled hash table: %ld hashes from %d barcodes in %d bins\n", nHashes, (int) ix.nBlocksMax, (int) ix.hashNumber) ;
+}
+
+static void writeHash (const char *path)
+{ if (!haveIndex) die ("write fail 1") ;
+  int st = h10x_write_hash (&ix, path) ;
+  if (st) die ("failed to open hash file %s", path) ;
+  fprintf (outFile, "  wrote %lld hash table entries and %d barcode blocks\n", 1LL << ix.B, (int) ix.nBlocksMax) ;
+  if (outFile != stdout) printf ("  wrote %lld hash table entries and %d barcode blocks\n", 1LL << ix.B, (int) ix.nBlocksMax) ;
+}
+
+/* ---- histogramReport hash10x.c:351-375: same arithmetic, including the int thresholds ---- */
+static void histogramReport (const char *prefix, const int *a, int max)
+{ uint64_t sum = 0, total = 0, partSum = 0, partTotal = 0, best = 0, massBest = 0 ;
+  int i, median = 0, massMedian = 0, n99 = 0, nMass99 = 0, mode = 0, massMode = 0 ;
+  for (i = 0 ; i < max ; ++i) { sum += a[i] ; total += i * a[i] ; }
+  int t50 = sum * 0.5, tMass50 = total * 0.5, t99 = sum * 0.99, tMass99 = total * 0.99 ;
+  for (i = 0 ; i < max ; ++i)
+    { int n = a[i] ;
+      partSum += n ; partTotal += i * n ;
+      fprintf (outFile, "%s_HIST %6d %d %.4f %.4f\n", prefix, i, n, partSum / (double) sum, partTotal / (double) total) ;
+      if ((uint64_t) n > best) { mode = i ; best = n ; }
+      if ((uint64_t) (i * n) > massBest) { massMode = i ; massBest = i * n ; }
+      if (partSum > (uint64_t) t50 && !median) median = i ;
+      if (partTotal > (uint64_t) tMass50 && !massMedian) massMedian = i ;
+      if (partSum > (uint64_t) t99 && !n99) n99 = i ;
+      if (partTotal > (uint64_t) tMass99 && !nMass99) nMass99 = i ;
+    }
+  fprintf (outFile, "%s_STATS MEAN %.1f", prefix, total / (double) sum) ;
+  fprintf (outFile, "  MODE %d  MEDIAN %d  PERCENT99 %d", mode, median, n99) ;
+  fprintf (outFile, "  MASS_MODE %d  N50 %d  N99 %d\n", massMode, massMedian, nMass99) ;
+}
+
+static int *countHist (const uint32_t *v, uint32_t n, int *maxOut)
+{ uint32_t i, top = 0 ;
+  for (i = 0 ; i < n ; ++i) if (v[i] > top) top = v[i] ;
+  int *a = calloc ((size_t) top + 1, sizeof (int)) ;
+  if (!a) die ("myalloc failure") ;
+  for (i = 0 ; i < n ; ++i) ++a[v[i]] ;
+  *maxOut = (int) top + 1 ;
+  return a ;
+}
+
+/* hashDepthHist hash10x.c:377-386: over all of hashDepth, dummy bin 0 included */
+static void hashStats (void)
+{ if (!haveIndex || ix.hashNumber <= 1) { fprintf (stderr, "  no hash list to print stats for\n") ; return ; }
+  int max ; int *a = countHist (ix.hashDepth, ix.hashNumber, &max) ;
+  histogramReport ("HASH_COUNT", a, max) ;
+  free (a) ;
+}
+
+/* codeSizeHist hash10x.c:388-402: over all blocks, dummy block 0 and the unhashed last one included */
+static void codeStats (void)
+{ if (!haveIndex || !ix.nBlocksMax) { fprintf (stderr, "  no barcodes to print stats for\n") ; return ; }
+  int max ; int *a = countHist (ix.blkNHash, ix.nBlocksMax, &max) ;
+  histogramReport ("CODE_SIZE", a, max) ;
+  free (a) ;
+}
+
+/* ---- --hashDepthRange: hashWithinRangeBuild + goodHashesBuild, hash10x.c:528-539,738-766 ---- */
+static unsigned char *hashWithinRange = 0 ;
+static int hashRangeMin = 0, hashRangeMax = 0 ;
+static uint16_t **goodHashes = 0 ;
+static int *nGoodHashes = 0 ;
+
+typedef struct { uint32_t depth ; uint16_t idx ; } GoodKey ;
+static int cmpGood (const void *a, const void *b)
+{ const GoodKey *x = a, *y = b ;
+  if (x->depth != y->depth) return x->depth < y->depth ? -1 : 1 ;
+  return (int) x->idx - (int) y->idx ;	/* glibc qsort is a stable merge sort: ties keep list order */
+}
+
+static void hashDepthRange (int min, int max)
+{ if (!haveIndex) die ("cluster code called without setting hashDepthRange") ;
+  uint32_t i, c ;
+  if (!(hashWithinRange && min == hashRangeMin && max == hashRangeMax))
+    { if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
+      for (i = 0 ; i < ix.hashNumber ; ++i)	/* flags are only ever set, as in the reference */
+	{ int n = (int) ix.hashDepth[i] ; if (n >= min && n < max) hashWithinRange[i] = 1 ; }
+      hashRangeMin = min ; hashRangeMax = max ;
+    }
+  goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;
+  nGoodHashes = calloc (ix.nBlocksMax, sizeof (int)) ;
+  GoodKey *keys = malloc (65536 * sizeof (GoodKey)) ;
+  for (c = 0 ; c < ix.nBlocksMax ; ++c)
+    { uint32_t nh = c ? ix.blkNHash[c] : 0 ;
+      if (nh > 65535)
+	{ nGoodHashes[c] = 0 ; goodHashes[c] = calloc (1, 2) ;
+	  fprintf (stderr, "ignoring barcode %d - too many hashes %d > %d\n", (int) c, (int) nh, 65535) ;
+	  continue ;
+	}
+      const h10x_cluster_hash *ch = ix.clusHash + ix.blkOff[c] ;
+      int n = 0 ;
+      for (i = 0 ; i < nh ; ++i)
+	if (hashWithinRange[ch[i].hash]) { keys[n].depth = ix.hashDepth[ch[i].hash] ; keys[n].idx = (uint16_t) i ; ++n ; }
+      qsort (keys, n, sizeof (GoodKey), cmpGood) ;
+      goodHashes[c] = malloc ((n ? n : 1) * 2) ;
+      for (i = 0 ; i < (uint32_t) n ; ++i) goodHashes[c][i] = keys[i].idx ;
+      nGoodHashes[c] = n ;
+    }
+  free (keys) ;
+  printf ("  made goodHashes arrays for hash range %d to %d\n  ", hashRangeMin, hashRangeMax) ;
+  timeUpdate (outFile) ; fflush (outFile) ;
+}
+
+static void gpuStats (void)
+{ h10x_stats s ; int i ;
+  if (!ctx || !indexFromGpu || h10x_gpu_stats (ctx, &s)) { fprintf (stderr, "  no GPU build to report\n") ; return ; }
+  fprintf (outFile, "GPU_BUILD records %llu moshes %llu hashes %llu bins %llu blocks %llu\n",
+	   (unsigned long long) s.nRecords, (unsigned long long) s.nMoshes, (unsigned long long) s.nHashes,
+	   (unsigned long long) s.nBins, (unsigned long long) s.nBlocks) ;
+  fprintf (outFile, "GPU_BUILD device_ms %.3f algorithmic_bytes %llu achieved_GBps %.1f launches %llu peak_device_bytes %llu\n",
+	   s.msTotal, (unsigned long long) s.algorithmicBytes, s.algorithmicBytes / (s.msTotal * 1e6),
+	   (unsigned long long) s.kernelLaunches, (unsigned long long) s.peakDeviceBytes) ;
+  for (i = 0 ; i < H10X_NSTAGES ; ++i)
+    if (s.msStage[i] > 0) fprintf (outFile, "GPU_STAGE %-10s %.3f ms\n", h10x_stage_name (i), s.msStage[i]) ;
+}
+
+int main (int argc, char *argv[])
+{
+  --argc ; ++argv ;
+  outFile = stdout ;
+  timeUpdate (stdout) ;
+  params.k = 21 ; params.w = 31 ; params.r = 17 ; params.B = 28 ; params.N = 0 ;
+  params.chunkSize = 100000 ; params.clusterThreshold = 5 ;
+  if (!argc) usage () ;
+
+  while (argc)
+    { if (**argv != '-') die ("option/command %s does not start with '-': run without arguments for usage", *argv) ;
+      { int i ;
+	fprintf (outFile, "COMMAND %s", *argv) ;
+	for (i = 1 ; i < argc && *argv[i] != '-' ; ++i) fprintf (outFile, " %s", argv[i]) ;
+	fputc ('\n', outFile) ;
+	if (outFile != stdout)
+	  { printf ("COMMAND %s", *argv) ;
+	    for (i = 1 ; i < argc && *argv[i] != '-' ; ++i) fprintf (outFile, " %s", argv[i]) ;	/* sic: hash10x.c:1169 */
+	    putchar ('\n') ;
+	  }
+      }
+#define ARGMATCH(x,n)	(!strcmp (*argv, x) && argc >= n && (argc -= n, argv += n))
+      if (ARGMATCH ("-k", 2)) params.k = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-w", 2)) params.w = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-r", 2)) params.r = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-B", 2)) params.B = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-N", 2)) params.N = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-c", 2)) params.chunkSize = atoi (argv[-1]) ;
+      else if (ARGMATCH ("-t", 2) || ARGMATCH ("--threads", 2))
+	fprintf (stderr, "  can't set thread number - not compiled with OMP\n") ;
+      else if (ARGMATCH ("-o", 2) || ARGMATCH ("--output", 2))
+	{ if (!strcmp (argv[-1], "-")) outFile = stdout ;
+	  else if (!(outFile = fopen (argv[-1], "w")))
+	    { fprintf (stderr, "can't open output file %s\n", argv[-1]) ; outFile = stdout ; }
+	}
+      else if (ARGMATCH ("--readFQB", 2))
+	{ FILE *f = fopen (argv[-1], "r") ;
+	  if (!f) die ("failed to open fqb file %s", argv[-1]) ;
+	  fclose (f) ;
+	  initialise (params.k, params.w, params.r, params.B) ;
+	  readFQB (argv[-1]) ;
+	}
+      else if (ARGMATCH ("--readHash", 2))
+	{ FILE *f = fopen (argv[-1], "r") ;
+	  if (!f) die ("failed to open hash file %s", argv[-1]) ;
+	  fclose (f) ;
+	  initialise (params.k, params.w, params.r, params.B) ;
+	  readHash (argv[-1]) ;
+	}
+      else if (ARGMATCH ("--writeHash", 2)) writeHash (argv[-1]) ;
+      else if (ARGMATCH ("--hashDepthRange", 3)) hashDepthRange (atoi (argv[-2]), atoi (argv[-1])) ;
+      else if (ARGMATCH ("--hashStats", 1)) hashStats () ;
+      else if (ARGMATCH ("--codeStats", 1)) codeStats () ;
+      else if (ARGMATCH ("--gpuStats", 1)) gpuStats () ;
+      else if (ARGMATCH ("--help", 1)) usage () ;
+      else if (ARGMATCH ("--quit", 1) || ARGMATCH ("--exit", 1)) break ;
+      else if (!strcmp (*argv, "--cluster") || !strcmp (*argv, "--clusterReport") || !strcmp (*argv, "--clusterSplit")
+	       || !strcmp (*argv, "--cribBuild") || !strcmp (*argv, "--cribSummary") || !strcmp (*argv, "--hashInfo")
+	       || !strcmp (*argv, "--hashExplore") || !strcmp (*argv, "--doubleShared") || !strcmp (*argv, "--codeExplore")
+	       || !strcmp (*argv, "--errorFix") || !strcmp (*argv, "--shareScan") || !strcmp (*argv, "--interactive"))
+	die ("command %s is outside the scope of hash10x-b200: write the index with --writeHash and run it in hash10x --readHash", *argv) ;
+      else die ("unknown option/command %s; run without arguments for usage", *argv) ;
+
+      printf ("  ") ; timeUpdate (stdout) ; fflush (stdout) ;
+    }
+
+  fprintf (outFile, "total resources used: ") ; timeTotal (outFile) ;
+  if (outFile != stdout) { printf ("total resources used: ") ; timeTotal (stdout) ; }
+  if (ctx) h10x_gpu_destroy (ctx) ;
+  return 0 ;
+}

@@ -85,7 +85,8 @@ typedef struct h10x_index {
   uint64_t *codeOff ;		/* hashNumber + 1 */
   uint32_t *codes ;		/* nHashes */
   int32_t onDevice ;		/* 1: the pointers above are device pointers owned by the context */
-  int32_t pinned ;		/* 1: host arrays are cudaHostAlloc'ed (h10x_index_free knows) */
+  int32_t pinned ;		/* 0 malloc, 1 cudaHostAlloc (both freed by h10x_index_free), 2 = the
+				   context's reusable pinned arena: valid until its next download */
 } h10x_index ;
 
 /* per-build measurements for the roofline report */
@@ -125,7 +126,8 @@ int h10x_gpu_build_device (h10x_ctx *ctx, const void *d_fqb, uint64_t nRecords, 
 /* device-pointer view of the resident index (onDevice = 1); valid until the next build */
 int h10x_gpu_index_device (h10x_ctx *ctx, h10x_index *out) ;
 
-/* copy the resident index to host memory (pinned); free with h10x_index_free */
+/* copy the resident index to pinned host memory owned by the context (pinned = 2): the arrays stay
+   valid until the next download/build_host/build_file on this context or its destruction */
 int h10x_gpu_download (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
 
 /* the whole seam with HOST buffers: H2D of the FQB records, build, D2H of the index */

@@ -1,0 +1,73 @@
+"""Drop-in check of the host program: `hash10x-b200` against the reference binary (oracle/_ref/hash10x)
+on the same FQB with the same command chain - same stdout apart from resource lines, same .hash."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import hashfile
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "hash10x_b200", "bin", "hash10x-b200")
+
+
+def _clean(text):
+    keep = []
+    for ln in text.splitlines():
+        if re.match(r"^\s*user\t", ln) or ln.startswith("total resources used"):
+            continue
+        keep.append(ln)
+    return keep
+
+
+def _run(exe, args, cwd):
+    return subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+@pytest.mark.parametrize("extra", [[], ["-N", "1500"], ["-c", "400"], ["-k", "17", "-w", "13", "-r", "5"]])
+def test_cli_matches_reference(orc, gpu_lib, tmp_path, extra):
+    ref = orc.ref_binary("hash10x")
+    if ref is None:
+        pytest.skip("oracle/_ref/hash10x not built")
+    assert os.path.exists(CLI), "hash10x-b200 not built"
+    p = orc.synth_params(seed=31, n_barcodes=40, pairs_min=10, pairs_max=200)
+    recs = orc.synth_fqb(p)
+    recs.tofile(str(tmp_path / "in.fqb"))
+    chain = extra + ["-B", "20", "--readFQB", "in.fqb", "--writeHash", "OUT.hash", "--hashStats", "--codeStats",
+                     "--hashDepthRange", "2", "12"]
+    a = _run(ref, [x.replace("OUT", "ref") for x in chain], str(tmp_path))
+    b = _run(CLI, [x.replace("OUT", "gpu") for x in chain], str(tmp_path))
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    la = [x.replace("ref.hash", "X.hash") for x in _clean(a.stdout)]
+    lb = [x.replace("gpu.hash", "X.hash") for x in _clean(b.stdout)]
+    assert la == lb
+    ha, hb = hashfile.parse(str(tmp_path / "ref.hash")), hashfile.parse(str(tmp_path / "gpu.hash"))
+    assert ha.size == hb.size and (ha.depthDim, ha.blkDim) == (hb.depthDim, hb.blkDim)
+    hashfile.assert_strict_equal(ha, hb, table=True)
+    # the GPU-written file goes back through the reference: --readHash then the same reports
+    c = _run(ref, ["-B", "20", "--readHash", "gpu.hash", "--hashStats", "--codeStats"], str(tmp_path))
+    d = _run(ref, ["-B", "20", "--readHash", "ref.hash", "--hashStats", "--codeStats"], str(tmp_path))
+    assert c.returncode == 0
+    assert [x.replace("gpu.hash", "X") for x in _clean(c.stdout)] == [x.replace("ref.hash", "X") for x in _clean(d.stdout)]
+    # and our own --readHash reads both
+    e = _run(CLI, ["-B", "20", "--readHash", "ref.hash", "--hashStats", "--codeStats"], str(tmp_path))
+    assert e.returncode == 0
+    assert [x.replace("ref.hash", "X") for x in _clean(e.stdout)] == [x.replace("ref.hash", "X") for x in _clean(d.stdout)]
+
+
+def test_cli_errors_match_reference(orc, gpu_lib, tmp_path):
+    ref = orc.ref_binary("hash10x")
+    if ref is None:
+        pytest.skip("oracle/_ref/hash10x not built")
+    p = orc.synth_params(seed=31, n_barcodes=40, pairs_min=10, pairs_max=200)
+    orc.synth_fqb(p).tofile(str(tmp_path / "in.fqb"))
+    for chain in (["-B", "19", "--readFQB", "in.fqb"], ["-B", "31", "--readFQB", "in.fqb"],
+                  ["-B", "20", "-c", "50", "--readFQB", "in.fqb"], ["-B", "20", "--readFQB", "missing.fqb"],
+                  ["-B", "20", "--bogus"], ["-B", "21", "--readHash", "in.fqb"]):
+        a, b = _run(ref, chain, str(tmp_path)), _run(CLI, chain, str(tmp_path))
+        assert a.returncode != 0 and b.returncode == a.returncode, chain
+        assert a.stderr.strip().splitlines()[-1] == b.stderr.strip().splitlines()[-1], chain
