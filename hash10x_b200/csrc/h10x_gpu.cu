@@ -14,10 +14,12 @@
  */
 #include "../../include/h10x_gpu.h"
 #include "h10x_common.cuh"
+#include "h10x_fused.cuh"
 
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <iterator>
 #include <map>
 #include <cstdio>
@@ -295,12 +297,12 @@ __global__ void k_entry_ids (uint64_t n, const uint32_t *__restrict__ segIncl, c
    ascending block number */
 __global__ void k_codes (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ segStart,
 			 const uint32_t *__restrict__ idOfSeg, const uint32_t *__restrict__ se,
-			 const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
+			 const uint32_t *__restrict__ entryBlk,
 			 const uint64_t *__restrict__ codeOff, uint32_t *__restrict__ codes)
 { uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
   if (i >= n) return ;
   uint32_t s = segIncl[i] - 1 ;
-  codes[codeOff[idOfSeg[s]] + (i - segStart[s])] = blkIncl[eRec[se[i]]] ;
+  codes[codeOff[idOfSeg[s]] + (i - segStart[s])] = entryBlk[se[i]] ;
 }
 
 __global__ void k_clus_prep (uint64_t n, const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
@@ -517,31 +519,88 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   const uint32_t nProc = bt.start[nProcBlk] ;	/* records of the processed blocks */
   c->nBlocksMax = nBlk + 1 ;
 
-  /* ---------------- moshes -> per-block unique (hash, record) entries ---------------- */
-  DBuf<uint64_t> eHash ; DBuf<uint32_t> eRec ;
+  /* ---------------- moshes -> per-block unique (hash, read) lists ---------------- */
   DBuf<uint64_t> blkOffProc ((size_t) nProcBlk + 1, s, mt) ;
+  DBuf<uint64_t> srcOff ((size_t) nProcBlk + 1, s, mt) ;
+  DBuf<uint32_t> blkCnt ((size_t) nProcBlk + 1, s, mt) ;
   std::vector<uint64_t> hBlkOff ((size_t) nProcBlk + 1, 0) ;
+  std::vector<uint32_t> hCnt ((size_t) nProcBlk + 1, H10X_BLK_FALLBACK) ;
   uint64_t H = 0, totalMoshes = 0 ;
-  size_t eCap = 0 ;
-  auto ensureE = [&] (uint64_t need)
-    { if (need <= eCap) return ;
-      size_t cap = std::max<size_t> ((size_t) need, eCap + eCap / 2) ;
-      DBuf<uint64_t> nh (cap, s, mt) ; DBuf<uint32_t> nr (cap, s, mt) ;
-      if (H) { CK (cudaMemcpyAsync (nh.p, eHash.p, 8 * H, cudaMemcpyDeviceToDevice, s)) ;
-	       CK (cudaMemcpyAsync (nr.p, eRec.p, 4 * H, cudaMemcpyDeviceToDevice, s)) ; }
-      eHash.swap (nh) ; eRec.swap (nr) ; eCap = cap ;
-    } ;
-  if (nProcBlk) ensureE ((uint64_t) nProc * 8 + 1024) ;
 
+  /* -- fused path: one CTA per block, everything in shared memory (h10x_fused.cuh) -- */
+  const int n1 = H10X_R1_LEN - P.k + 1, n2 = H10X_R2_LEN - P.k + 1 ;
+  const int c1 = (n1 + 7) / 8, c2 = (n2 + 7) / 8 ;
+  const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && nProcBlk > 0 ;
+  struct FusedClass { uint32_t cap, nbuck, lb, threads ; } ;
+  static const FusedClass kClasses[3] = { { 1024, 256, 8, 128 }, { 4096, 1024, 10, 256 }, { 12288, 4096, 12, 512 } } ;
+  DBuf<uint64_t> scratch ; DBuf<unsigned long long> cursor ;
+  uint64_t nFused = 0 ;
+  if (fusedOK)
+    { StageTimer tm (c, s, ST_FUSED) ;
+      std::vector<uint32_t> lists[3] ;
+      const double perPair = (double) (n1 + n2) / (double) P.w ;	/* expected moshes per read pair */
+      for (uint32_t p = 0 ; p < nProcBlk ; ++p)
+	{ uint32_t nRead = bt.start[p+1] - bt.start[p] ;
+	  double e = perPair * nRead, need = e * 1.12 + 6.0 * sqrt (e) + 16.0 ;
+	  int rbits = 0 ; while (((uint64_t) 1 << rbits) < nRead) ++rbits ;
+	  if (2 * P.k + rbits > 64) continue ;
+	  for (int ci = 0 ; ci < 3 ; ++ci)
+	    if (need <= kClasses[ci].cap && (int) kClasses[ci].lb <= 2 * P.k) { lists[ci].push_back (p) ; break ; }
+	}
+      uint64_t scratchCap = (uint64_t) (perPair * 1.15 * nProc) + (1u << 20) ;
+      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (1, s, mt) ;
+      CK (cudaMemsetAsync (cursor.p, 0, 8, s)) ;
+      CK (cudaMemsetAsync (blkCnt.p, 0xff, 4 * ((size_t) nProcBlk + 1), s)) ;
+      std::vector<DBuf<uint32_t>> dLists (3) ;
+      for (int ci = 0 ; ci < 3 ; ++ci)
+	{ if (lists[ci].empty ()) continue ;
+	  const FusedClass &fc = kClasses[ci] ;
+	  dLists[ci].alloc (lists[ci].size (), s, mt) ;
+	  CK (cudaMemcpyAsync (dLists[ci].p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
+	  FusedArgs fa ;
+	  fa.fqb = fqb ; fa.list = dLists[ci].p ; fa.blkStart = dBlkStart.p ; fa.scratch = scratch.p ; fa.cursor = cursor.p ;
+	  fa.scratchCap = scratchCap ; fa.srcOff = srcOff.p ; fa.blkCnt = blkCnt.p ; fa.nList = (uint32_t) lists[ci].size () ;
+	  fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ;
+	  size_t smem = (size_t) fc.cap * 16 + 4 * ((size_t) 2 * fc.nbuck + 1) + 16 ;
+	  const bool wodd = (c->hp.wTz == 0) ;
+#define FUSED_LAUNCH(T, W) do { \
+	    CK (cudaFuncSetAttribute (k_fused_block<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ; \
+	    LAUNCH (c, (k_fused_block<T, W>), fa.nList, T, smem, s, fa, c->hp) ; } while (0)
+	  if (fc.threads == 128) { if (wodd) FUSED_LAUNCH (128, true) ; else FUSED_LAUNCH (128, false) ; }
+	  else if (fc.threads == 256) { if (wodd) FUSED_LAUNCH (256, true) ; else FUSED_LAUNCH (256, false) ; }
+	  else { if (wodd) FUSED_LAUNCH (512, true) ; else FUSED_LAUNCH (512, false) ; }
+#undef FUSED_LAUNCH
+	}
+      CK (cudaMemcpyAsync (hCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies above */
+      for (uint32_t p = 0 ; p < nProcBlk ; ++p) if (hCnt[p] != H10X_BLK_FALLBACK) ++nFused ;
+    }
+  c->stats.fusedBlocks = nFused ; c->stats.genericBlocks = nProcBlk - nFused ;
+
+  /* -- generic path for whatever the fused path did not take: global-memory segmented sort -- */
+  DBuf<uint64_t> gHash ; DBuf<uint32_t> gRec ;
+  uint64_t G = 0 ; size_t gCap = 0 ;
+  auto ensureG = [&] (uint64_t need)
+    { if (need <= gCap) return ;
+      size_t cap = std::max<size_t> ((size_t) need, gCap + gCap / 2) ;
+      DBuf<uint64_t> nh (cap, s, mt) ; DBuf<uint32_t> nr (cap, s, mt) ;
+      if (G) { CK (cudaMemcpyAsync (nh.p, gHash.p, 8 * G, cudaMemcpyDeviceToDevice, s)) ;
+	       CK (cudaMemcpyAsync (nr.p, gRec.p, 4 * G, cudaMemcpyDeviceToDevice, s)) ; }
+      gHash.swap (nh) ; gRec.swap (nr) ; gCap = cap ;
+    } ;
   const uint32_t batchRecs = 8u << 20 ;		/* 8M records: at most 2^31 moshes even if every k-mer is one */
-  uint32_t p0 = 0 ;
-  while (p0 < nProcBlk)
-    { uint32_t p1 = p0 + 1 ;
-      while (p1 < nProcBlk && bt.start[p1+1] - bt.start[p0] <= batchRecs) ++p1 ;
+  uint32_t q0 = 0 ;
+  while (q0 < nProcBlk)
+    { if (hCnt[q0] != H10X_BLK_FALLBACK) { ++q0 ; continue ; }
+      /* a maximal run of consecutive generic blocks, cut into batches of at most batchRecs records */
+      uint32_t p0 = q0, p1 = p0 + 1 ;
+      while (p1 < nProcBlk && hCnt[p1] == H10X_BLK_FALLBACK && bt.start[p1+1] - bt.start[p0] <= batchRecs) ++p1 ;
+      q0 = p1 ;
       uint32_t r0 = bt.start[p0], nb = bt.start[p1] - r0, nblk = p1 - p0 ;
       if ((uint64_t) nb * 237 > 0x7fffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "barcode block too large for the generic path") ;
       DBuf<uint32_t> cnt2 ((size_t) 2 * nb + 1, s, mt), off2 ((size_t) 2 * nb + 1, s, mt) ;
       DBuf<uint32_t> ph ((size_t) nblk + 1, s, mt), phOff ((size_t) nblk + 1, s, mt), segOff ((size_t) nblk + 1, s, mt) ;
+      DBuf<uint64_t> gOff ((size_t) nblk + 1, s, mt) ;
       uint32_t Mb = 0 ;
       { StageTimer tm (c, s, ST_MOSHES) ;
 	CK (cudaMemsetAsync (cnt2.p + 2 * (size_t) nb, 0, 4, s)) ;
@@ -579,20 +638,38 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, uflag.p, uincl.p, Mb, s) ; }) ;
 	CK (cudaMemcpyAsync (&Hb, uincl.p + (Mb - 1), 4, cudaMemcpyDeviceToHost, s)) ;
 	CK (cudaStreamSynchronize (s)) ;
-	ensureE (H + Hb) ;
-	LAUNCH (c, k_compact, gridFor (Mb, 256), 256, 0, s, keysS.p, valsS.p, Mb, uflag.p, uincl.p, H, eHash.p, eRec.p) ;
-	LAUNCH (c, k_blk_off, gridFor (nblk, 256), 256, 0, s, segOff.p, uincl.p, nblk, H, blkOffProc.p + p0) ;
+	ensureG (G + Hb) ;
+	LAUNCH (c, k_compact, gridFor (Mb, 256), 256, 0, s, keysS.p, valsS.p, Mb, uflag.p, uincl.p, G, gHash.p, gRec.p) ;
+	LAUNCH (c, k_blk_off, gridFor (nblk, 256), 256, 0, s, segOff.p, uincl.p, nblk, G, gOff.p) ;
+	std::vector<uint64_t> hOff ((size_t) nblk + 1) ;
+	CK (cudaMemcpyAsync (hOff.data (), gOff.p, 8 * (size_t) nblk, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	hOff[nblk] = G + Hb ;
+	std::vector<uint64_t> src (nblk) ;
+	for (uint32_t i = 0 ; i < nblk ; ++i)
+	  { hCnt[p0 + i] = (uint32_t) (hOff[i+1] - hOff[i]) ; src[i] = hOff[i] | ((uint64_t) 1 << 63) ; }
+	CK (cudaMemcpyAsync (srcOff.p + p0, src.data (), 8 * (size_t) nblk, cudaMemcpyHostToDevice, s)) ;
+	CK (cudaMemcpyAsync (blkCnt.p + p0, hCnt.data () + p0, 4 * (size_t) nblk, cudaMemcpyHostToDevice, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
       }
-      H += Hb ;
-      p0 = p1 ;
+      G += Hb ;
     }
-  CK (cudaMemcpyAsync (blkOffProc.p + nProcBlk, &H, 8, cudaMemcpyHostToDevice, s)) ;
-  CK (cudaMemcpyAsync (hBlkOff.data (), blkOffProc.p, 8 * ((size_t) nProcBlk + 1), cudaMemcpyDeviceToHost, s)) ;
-  CK (cudaStreamSynchronize (s)) ;
+
+  /* -- final placement in block order: eHash / eRead / entryBlk -- */
+  for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
   hBlkOff[nProcBlk] = H ;
   c->nHashes = H ;
-  c->stats.genericBlocks = nProcBlk ;
   if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
+  DBuf<uint64_t> eHash (H, s, mt) ; DBuf<uint16_t> eRead (H, s, mt) ; DBuf<uint32_t> entryBlk (H, s, mt) ;
+  { StageTimer tm (c, s, ST_DEDUP) ;
+    CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
+    if (nProcBlk)
+      LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
+	      scratch.p, gHash.p, gRec.p, dBlkStart.p, eHash.p, eRead.p, entryBlk.p) ;
+    CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
+  }
+  scratch.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
+  if (!totalMoshes) totalMoshes = H ;
 
   /* ---------------- bins: ids, values, depths ---------------- */
   uint32_t D = 0 ;
@@ -648,22 +725,21 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
       cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
       if (H)
-	LAUNCH (c, k_codes, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eRec.p, blkIncl.p,
+	LAUNCH (c, k_codes, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, entryBlk.p,
 		c->codeOff.p, c->codes.p) ;
     }
-  se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ;
+  se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; entryBlk.release () ;
 
   /* ---------------- code -> hash lists ---------------- */
   c->clus.alloc (H, s, mt) ;
   if (H)
     { StageTimer tm (c, s, ST_CLUSTERS) ;
-      DBuf<uint16_t> rd (H, s, mt), rdS (H, s, mt) ;
+      DBuf<uint16_t> rdS (H, s, mt) ;
       DBuf<uint32_t> idS (H, s, mt) ;
-      LAUNCH (c, k_clus_prep, gridFor (H, 256), 256, 0, s, H, eRec.p, blkIncl.p, dBlkStart.p, rd.p) ;
-      segmented_sort_blocks<uint32_t, uint16_t> (c, s, entryId.p, idS.p, rd.p, rdS.p, hBlkOff, blkOffProc.p, false) ;
+      segmented_sort_blocks<uint32_t, uint16_t> (c, s, entryId.p, idS.p, eRead.p, rdS.p, hBlkOff, blkOffProc.p, false) ;
       LAUNCH (c, k_clus_pack, gridFor (H, 256), 256, 0, s, H, idS.p, rdS.p, c->clus.p) ;
     }
-  entryId.release () ; eRec.release () ;
+  entryId.release () ; eRead.release () ; entryBlk.release () ;
 
   /* ---------------- hashIndex[] ---------------- */
   if (!(P.flags & H10X_FLAG_NO_TABLE))

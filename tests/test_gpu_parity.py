@@ -79,6 +79,30 @@ def test_quirks_last_block_phantom_polyA(orc, gpu_lib):
     assert got.hashDepth[z] == 3
 
 
+def test_generic_only_flag_and_fallbacks(orc, gpu_lib):
+    # the fused shared-memory path and the generic global-memory path must agree: force the generic
+    # one (flag 8), and mix in blocks the fused path must hand back (poly-A flood, oversized block)
+    rng = np.random.default_rng(17)
+    p = orc.synth_params(seed=13, n_barcodes=30, pairs_min=5, pairs_max=400)
+    recs = orc.synth_fqb(p)
+    _, _, st = _compare(orc, recs, B=21, flags=8)
+    assert st["fusedBlocks"] == 0
+    _, _, st = _compare(orc, recs, B=21)
+    assert st["fusedBlocks"] == 29 and st["genericBlocks"] == 0
+    mixed = np.concatenate([
+        recs[:3000],
+        fqbtools.const_records(0x0AAAAAA1, 300, 0, 0),          # 300 poly-A pairs: 71100 identical moshes
+        fqbtools.random_records(rng, [0x0AAAAAA2], [3]),
+        np.concatenate([fqbtools.const_records(0x0AAAAAA3, 40, 0, 0), fqbtools.random_records(rng, [0x0AAAAAA3], [40])]),
+        recs[3000:],
+    ])
+    _, _, st = _compare(orc, mixed, B=21)
+    assert st["genericBlocks"] >= 1 and st["fusedBlocks"] >= 25
+    big = orc.synth_params(seed=14, n_barcodes=4, pairs_min=1500, pairs_max=2600, genome_len=2_000_000)
+    _, _, st = _compare(orc, orc.synth_fqb(big), B=21)
+    assert st["genericBlocks"] >= 1
+
+
 def test_edge_sizes(orc, gpu_lib):
     rng = np.random.default_rng(2)
     one = fqbtools.random_records(rng, [5], [9])
