@@ -52,11 +52,13 @@ class ClockSampler(threading.Thread):
     in-process through NVML: spawning nvidia-smi every 200 ms takes driver locks that stall
     cudaMallocAsync / stream synchronisation in the process being measured."""
 
-    def __init__(self, gpu=0, period=0.1):
+    def __init__(self, gpu=0, period=0.1, enabled=True):
         super().__init__(daemon=True)
         self.gpu, self.period, self.rows, self.stop_flag = gpu, period, [], threading.Event()
         self.nv = self.h = None
         self.max_sm = None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -78,14 +80,21 @@ class ClockSampler(threading.Thread):
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, rs))
+                self.rows.append((sm, rs, time.perf_counter()))
             except Exception:
                 pass
             self.stop_flag.wait(self.period)
 
+    def window(self):
+        """start of the timed region: the thread is already running (its first NVML calls are slow
+        and take driver locks, so they must not land inside the timed steps)"""
+        self.t_start = time.perf_counter()
+
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=3)
+        t0 = getattr(self, "t_start", 0.0)
+        self.rows = [r for r in self.rows if r[2] >= t0]
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "NVML unavailable"}
         nv = self.nv
@@ -211,11 +220,12 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     # --- value: device-resident build, CUDA events on the launching stream ---
+    sampler = ClockSampler(local, enabled=not args.no_clocks)
+    sampler.start()
     for _ in range(args.warmup):
         g.build_device(fqb.data_ptr(), n_rec, stream.cuda_stream)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.window()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = {}
     launches = 0
@@ -338,6 +348,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample NVML clocks during the timed region")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     name = args.workload or ("1gb" if world == 1 else "human8")

@@ -1,28 +1,33 @@
-/* h10x_fused.cuh - the hot kernel: one CTA per barcode block does the whole of processBlock's
- * first half (hash10x.c:154-172) on chip:
+/* h10x_fused.cuh - the hot kernel: persistent CTAs, each taking whole barcode blocks and doing
+ * the first half of processBlock (hash10x.c:154-172) on chip:
  *
- *   ingest     one warp per read pair; lane l loads word l of the 30-word FQB record (coalesced);
- *   windows    the pair's 237 k-mers are split into chunks of 8 consecutive start positions, one
- *              chunk per lane (14 chunks of read 1, 17 of read 2 for k=21); the three 32-bit words
- *              that hold a chunk's 8+k-1 bases come from the owning lanes by warp shuffle and are
- *              funnel-shifted into one 64-bit window W; its 2-bit-reversed complement WR gives the
- *              reverse-complement k-mers, so no per-base rolling state exists at all;
- *   hash       h_j = (W >> (64-2k-2j)) & mask, hRC_j = (WR >> 2j) & mask, both times factor1
- *              (seqhash.c:58-59), canonical = smaller of the two top-2k-bit products (seqhash.c:67),
- *              "mosh" iff divisible by w (seqhash.c:171,189) - tested without division on the
- *              unshifted product;
- *   collect    selected (hash << rb | readIndex) keys go to a shared-memory list and a bucket
- *              histogram on the top hash bits;
- *   sort       bucket scatter + per-bucket insertion sort (expected O(n): hashes are uniform);
- *   dedup      first of each run of equal hashes = lowest read index, which is what the reference's
- *              stable qsort + dedup loop keeps (hash10x.c:166-172); an empty block yields the
- *              phantom {hash 0, read 0} entry (hash10x.c:167-168);
+ *   ingest     one warp per read pair; lane l loads word l of the 30-word FQB record (coalesced,
+ *              prefetched one pair ahead);
+ *   windows    the pair's k-mers are split into chunks of 8 consecutive start positions, one chunk
+ *              per lane (14 chunks of read 1, 17 of read 2 for k=21; the last chunk of a read is
+ *              slid back to end at the last k-mer, its duplicates vanish in the dedup).  The three
+ *              32-bit words holding a chunk's 8+k-1 bases come from the owning lanes by warp
+ *              shuffle and are funnel-shifted into one 64-bit window W; its 2-bit-reversed
+ *              complement WR yields the reverse-complement k-mers, so there is no per-base rolling
+ *              state and no unpacked base array;
+ *   hash       h_j = (W >> (64-2k-2j)) & mask, hRC_j = (WR >> 2j) & mask, each times factor1
+ *              (seqhash.c:58-59); canonical = the smaller top-2k-bit product (seqhash.c:67); a
+ *              "mosh" iff divisible by w (seqhash.c:171,189), tested without division on the
+ *              unshifted product m = hash << (64-2k);
+ *   collect    a selected key (m | readIndex) is stored, predicated, to the lane's private column
+ *              of a per-CTA staging area in global memory that the persistent CTA reuses for every
+ *              block (so it lives in L2): no atomics and no divergence in the hash loop;
+ *   sort       keys are gathered into shared-memory buckets on their top hash bits (histogram,
+ *              scan, scatter) and each bucket is insertion-sorted: expected O(n), hashes are uniform;
+ *   dedup      first key of each run of equal hashes = lowest read index, which is what the
+ *              reference's stable qsort + dedup loop keeps (hash10x.c:166-172); an empty block
+ *              yields the phantom {hash 0, read 0} entry (hash10x.c:167-168);
  *   output     the block's sorted unique list goes to a global scratch slab at an atomically
  *              reserved offset; k_place later moves it to its final place in block order.
  *
- * A block whose keys do not fit (more moshes than `cap`, an over-full bucket from low-complexity
- * reads, scratch exhausted) is flagged H10X_BLK_FALLBACK and re-done by the generic global-memory
- * path, so results never depend on which path ran.
+ * A block whose keys do not fit (more moshes than `cap`, a lane column or a bucket over-full from
+ * low-complexity reads, scratch exhausted) is flagged H10X_BLK_FALLBACK and re-done by the generic
+ * global-memory path, so results never depend on which path ran.
  */
 #pragma once
 #include "h10x_common.cuh"
@@ -33,8 +38,17 @@
 __device__ __forceinline__ uint32_t h10x_swap_pairs (uint32_t x)
 { return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1) ; }
 
-/* exclusive scan in place of a[0..n) (n a multiple of nothing in particular) by the whole CTA;
-   returns the total to every thread.  warpTmp: 33 words of shared memory. */
+/* low 64 bits of (xhi:xlo) * (fhi:flo) in three multiply instructions */
+__device__ __forceinline__ uint64_t h10x_mul64 (uint32_t xlo, uint32_t xhi, uint32_t flo, uint32_t fhi)
+{ uint32_t plo, phi ;
+  asm ("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %4;\n\tmov.b64 {%0, %1}, t;\n\t"
+       "mad.lo.u32 %1, %2, %5, %1;\n\tmad.lo.u32 %1, %3, %4, %1;\n\t}"
+       : "=r" (plo), "=r" (phi) : "r" (xlo), "r" (xhi), "r" (flo), "r" (fhi)) ;
+  return ((uint64_t) phi << 32) | plo ;
+}
+
+/* exclusive scan in place of a[0..n) by the whole CTA; returns the total to every thread.
+   warpTmp: 33 words of shared memory. */
 template <int THREADS>
 __device__ __forceinline__ uint32_t cta_exclusive_scan (uint32_t *a, uint32_t n, uint32_t *warpTmp)
 {
@@ -68,155 +82,167 @@ struct FusedArgs {
   const uint32_t *fqb ;		/* records */
   const uint32_t *list ;	/* 0-based block numbers handled by this launch */
   const uint32_t *blkStart ;	/* first record of every block */
+  uint64_t *stage ;		/* per-CTA staging columns: gridDim * THREADS * rowCap keys */
   uint64_t *scratch ;		/* unique-key slab */
   unsigned long long *cursor ;	/* next free scratch slot */
+  unsigned int *work ;		/* ticket counter of this launch */
   uint64_t scratchCap ;
   uint64_t *srcOff ;		/* per block: where its list went */
   uint32_t *blkCnt ;		/* per block: unique count, or H10X_BLK_FALLBACK */
   uint32_t nList ;
-  uint32_t cap ;		/* key capacity of the shared-memory list */
-  uint32_t nbuck ;		/* buckets (power of two) */
+  uint32_t cap ;		/* key capacity of the shared-memory bucket array */
+  uint32_t nbuck ;		/* buckets (power of two, >= THREADS) */
   uint32_t lb ;			/* log2 (nbuck) */
+  uint32_t rowCap ;		/* keys per lane column of the staging area */
   uint32_t c1, c2 ;		/* 8-k-mer chunks of read 1 / read 2 */
   uint32_t n1, n2 ;		/* k-mers of read 1 / read 2 */
 } ;
 
-template <int THREADS, bool WODD>
+/* K > 0: k fixed at compile time (shifts and masks become immediates); K == 0: k from hp */
+template <int THREADS, bool WODD, int K>
 __global__ void __launch_bounds__ (THREADS)
 k_fused_block (FusedArgs a, HashParams hp)
 {
   extern __shared__ __align__ (16) unsigned char smemRaw[] ;
-  uint64_t *A = (uint64_t*) smemRaw ;
-  uint64_t *S = A + a.cap ;
-  uint32_t *start = (uint32_t*) (S + a.cap) ;	/* nbuck + 1 */
-  uint32_t *cur = start + a.nbuck + 1 ;		/* nbuck */
-  __shared__ uint32_t sCount, sBig, sUnique, warpTmp[33] ;
+  uint64_t *S = (uint64_t*) smemRaw ;			/* cap keys, bucketed */
+  uint32_t *start = (uint32_t*) (S + a.cap) ;		/* nbuck + 1 */
+  uint32_t *cur = start + a.nbuck + 1 ;			/* nbuck */
+  __shared__ uint32_t sCount, sBad, sTicket, warpTmp[33] ;
   __shared__ unsigned long long sBase ;
 
   const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5 ;
-  const uint32_t blk = a.list[blockIdx.x] ;
-  const uint32_t r0 = a.blkStart[blk], nRead = a.blkStart[blk + 1] - r0 ;
-  const uint32_t rb = (nRead > 1) ? 32 - __clz (nRead - 1) : 0 ;	/* bits of the read index */
-  const int k2 = 2 * hp.k ;
-  const int buckShift = k2 - (int) a.lb ;
-
-  for (uint32_t i = t ; i <= a.nbuck ; i += THREADS) start[i] = 0 ;
-  if (t == 0) { sCount = 0 ; sBig = 0 ; }
-  __syncthreads () ;
+  const int kk = K ? K : hp.k ;
+  const int SH = 64 - 2 * kk ;				/* low zero bits of a masked product */
+  const uint32_t HMASK = (kk > 16) ? ((1u << (2 * kk - 32)) - 1u) : 0u ;	/* high word of the k-mer mask */
+  const uint32_t LMASK = (kk >= 16) ? 0xffffffffu : ((1u << (2 * kk)) - 1u) ;	/* low word of the k-mer mask */
+  const uint32_t TOPLO = (SH >= 32) ? 0u : ~((1u << SH) - 1u) ;		/* low word of the product mask */
+  const uint32_t TOPHI = (SH > 32) ? ~((1u << (SH - 32)) - 1u) : 0xffffffffu ;
+  const uint32_t flo = (uint32_t) hp.factor1, fhi = (uint32_t) (hp.factor1 >> 32) ;
+  const uint32_t ilo = (uint32_t) hp.wInv, ihi = (uint32_t) (hp.wInv >> 32) ;
+  const uint64_t wLim = hp.wLim ;
+  const uint64_t tzMaskSh = hp.wTzMask << SH ;
+  const int buckShift = 64 - (int) a.lb ;
 
   /* ---- lane's chunk: which read, first k-mer start position, source lanes of its 3 words ---- */
   const bool isR2 = lane >= a.c1 ;
-  const uint32_t chunk = isR2 ? lane - a.c1 : lane ;
   const bool laneActive = lane < a.c1 + a.c2 ;
-  const uint32_t p0 = (isR2 ? H10X_R2_START : H10X_R1_START) + 8 * chunk ;	/* unpacked position */
-  const uint32_t nk = isR2 ? a.n2 : a.n1 ;		/* k-mers of this read */
-  const uint32_t first = 8 * chunk ;			/* k-mer number of j = 0 */
+  const uint32_t nk = isR2 ? a.n2 : a.n1 ;			/* k-mers of this read */
+  const uint32_t chunk = isR2 ? lane - a.c1 : lane ;
+  const uint32_t first = min (8u * chunk, nk - 8u) ;		/* the last chunk slides back: all 8 valid */
+  const uint32_t p0 = (isR2 ? H10X_R2_START : H10X_R1_START) + first ;	/* unpacked position of k-mer 0 */
   const uint32_t wi = p0 >> 4, sh = 2 * (p0 & 15) ;
   const uint32_t base = isR2 ? 15u : 0u ;
   const uint32_t src0 = base + wi, src1 = base + min (wi + 1, 9u), src2 = base + min (wi + 2, 9u) ;
   const bool has1 = wi + 1 <= 9, has2 = wi + 2 <= 9 ;
-  const uint64_t f = hp.factor1 ;
-  const uint64_t topMask = ~(((uint64_t) 1 << hp.shift) - 1) ;	/* the 2k hash bits of a product */
-  const uint64_t tzMaskSh = hp.wTzMask << hp.shift ;
+  uint64_t *const col = a.stage + ((size_t) blockIdx.x * THREADS) * a.rowCap + t ;	/* slot i at col[i*THREADS] */
 
-  for (uint32_t pr = wid ; pr < nRead ; pr += THREADS / 32)
-    { const uint32_t *rec = a.fqb + (size_t) H10X_REC_WORDS * (r0 + pr) ;
-      uint32_t word = (lane < H10X_REC_WORDS) ? __ldg (rec + lane) : 0u ;
-      uint32_t w0 = __shfl_sync (0xffffffffu, word, src0) ;
-      uint32_t w1 = __shfl_sync (0xffffffffu, word, src1) ;
-      uint32_t w2 = __shfl_sync (0xffffffffu, word, src2) ;
-      if (!has1) w1 = 0 ;
-      if (!has2) w2 = 0 ;
-      if (!laneActive) continue ;
-      uint32_t Whi = __funnelshift_l (w1, w0, sh), Wlo = __funnelshift_l (w2, w1, sh) ;
-      uint64_t W = ((uint64_t) Whi << 32) | Wlo ;		/* bases p0 .. p0+31, first base on top */
-      uint64_t WR = ((uint64_t) h10x_swap_pairs (__brev (~Wlo)) << 32) | h10x_swap_pairs (__brev (~Whi)) ;
+  for (;;)
+    { if (t == 0) { sTicket = atomicAdd (a.work, 1u) ; sCount = 0 ; sBad = 0 ; }
+      for (uint32_t i = t ; i <= a.nbuck ; i += THREADS) start[i] = 0 ;
+      __syncthreads () ;
+      const uint32_t ticket = sTicket ;
+      if (ticket >= a.nList) break ;
+      const uint32_t blk = a.list[ticket] ;
+      const uint32_t r0 = a.blkStart[blk], nRead = a.blkStart[blk + 1] - r0 ;
+      const uint32_t *rec0 = a.fqb + (size_t) H10X_REC_WORDS * r0 ;
+
+      /* ---- hash loop: no atomics, no divergence; selected keys go to the lane's column ---- */
+      uint32_t cnt = 0 ; bool over = false ;
+      uint32_t wordNext = (wid < nRead && lane < H10X_REC_WORDS) ? __ldcs (rec0 + (size_t) H10X_REC_WORDS * wid + lane) : 0u ;
+      for (uint32_t pr = wid ; pr < nRead ; pr += THREADS / 32)
+	{ const uint32_t word = wordNext ;
+	  const uint32_t nx = pr + THREADS / 32 ;
+	  if (nx < nRead && lane < H10X_REC_WORDS) wordNext = __ldcs (rec0 + (size_t) H10X_REC_WORDS * nx + lane) ;
+	  uint32_t w0 = __shfl_sync (0xffffffffu, word, src0) ;
+	  uint32_t w1 = __shfl_sync (0xffffffffu, word, src1) ;
+	  uint32_t w2 = __shfl_sync (0xffffffffu, word, src2) ;
+	  if (!has1) w1 = 0 ;
+	  if (!has2) w2 = 0 ;
+	  if (!laneActive) continue ;
+	  const uint32_t Whi = __funnelshift_l (w1, w0, sh), Wlo = __funnelshift_l (w2, w1, sh) ;	/* bases p0..p0+31 */
+	  const uint32_t WRhi = h10x_swap_pairs (__brev (~Wlo)), WRlo = h10x_swap_pairs (__brev (~Whi)) ;
+	  if (cnt + 8 > a.rowCap) { over = true ; cnt = 0 ; }
 #pragma unroll
-      for (int j = 0 ; j < 8 ; ++j)
-	{ uint64_t h = (W >> (hp.shift - 2 * j)) & hp.kmask ;
-	  uint64_t hrc = (WR >> (2 * j)) & hp.kmask ;
-	  uint64_t pf = (h * f) & topMask, prr = (hrc * f) & topMask ;
-	  uint64_t m = pf < prr ? pf : prr ;			/* canonical hash << shift */
-	  bool sel = (first + j < nk) && (m * hp.wInv <= hp.wLim) ;
-	  if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
-	  if (sel)
-	    { uint64_t hash = m >> hp.shift ;
-	      uint32_t pos = atomicAdd (&sCount, 1u) ;
-	      if (pos < a.cap) A[pos] = (hash << rb) | pr ;
-	      atomicAdd (&start[(uint32_t) (hash >> buckShift)], 1u) ;
+	  for (int j = 0 ; j < 8 ; ++j)
+	    { const int c = SH - 2 * j ;		/* (W >> c) & mask: k-mer j, first base on top */
+	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi = (Whi >> c) & HMASK ;
+	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi = (WRhi >> (2 * j)) & HMASK ;
+	      if (kk <= 16) { hhi = 0 ; rhi = 0 ; if (c >= 32) hlo = (Whi >> (c - 32)) & LMASK ; }
+	      uint64_t pf = h10x_mul64 (hlo, hhi, flo, fhi) & (((uint64_t) TOPHI << 32) | TOPLO) ;
+	      uint64_t pq = h10x_mul64 (rlo, rhi, flo, fhi) & (((uint64_t) TOPHI << 32) | TOPLO) ;
+	      uint64_t m = pf < pq ? pf : pq ;		/* canonical hash << SH */
+	      uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
+	      bool sel = q <= wLim ;
+	      if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
+	      if (sel) { col[(size_t) cnt * THREADS] = m | pr ; ++cnt ; }
 	    }
 	}
-    }
-  __syncthreads () ;
+      if (over) sBad = 1 ;
+      if (cnt) atomicAdd (&sCount, cnt) ;
+      __syncthreads () ;
 
-  uint32_t n = sCount ;
-  bool bad = n > a.cap ;
-  if (!bad && n == 0)		/* hash10x.c:167-168: the phantom entry of an empty block */
-    { if (t == 0) { A[0] = 0 ; start[0] = 1 ; }
-      n = 1 ;
-      __syncthreads () ;
-    }
-
-  uint32_t U = 0 ;
-  if (!bad)
-    { /* ---- bucket offsets ---- */
-      for (uint32_t i = t ; i < a.nbuck ; i += THREADS) if (start[i] > H10X_BUCKET_LIMIT) sBig = 1 ;
-      __syncthreads () ;
-      bad = sBig != 0 ;
-    }
-  if (!bad)
-    { cta_exclusive_scan<THREADS> (start, a.nbuck + 1, warpTmp) ;
-      for (uint32_t i = t ; i < a.nbuck ; i += THREADS) cur[i] = start[i] ;
-      __syncthreads () ;
-      /* ---- scatter to buckets ---- */
-      for (uint32_t i = t ; i < n ; i += THREADS)
-	{ uint64_t key = A[i] ;
-	  uint32_t b = (uint32_t) ((key >> rb) >> buckShift) ;
-	  S[atomicAdd (&cur[b], 1u)] = key ;
+      uint32_t n = sCount ;
+      bool bad = sBad != 0 || n > a.cap ;
+      if (!bad)
+	{ /* ---- bucket histogram on the top hash bits ---- */
+	  for (uint32_t i = 0 ; i < cnt ; ++i) atomicAdd (&start[(uint32_t) (col[(size_t) i * THREADS] >> buckShift)], 1u) ;
+	  if (n == 0 && t == 0) start[0] = 1 ;	/* hash10x.c:167-168: the phantom entry of an empty block */
+	  __syncthreads () ;
+	  for (uint32_t i = t ; i < a.nbuck ; i += THREADS) if (start[i] > H10X_BUCKET_LIMIT) sBad = 1 ;
+	  __syncthreads () ;
+	  bad = sBad != 0 ;
 	}
-      __syncthreads () ;
-      /* ---- insertion sort inside each bucket: buckets are in hash order, so S ends up sorted ---- */
-      for (uint32_t b = t ; b < a.nbuck ; b += THREADS)
-	{ uint32_t lo = start[b], hi = start[b + 1] ;
-	  for (uint32_t i = lo + 1 ; i < hi ; ++i)
-	    { uint64_t key = S[i] ; uint32_t j = i ;
-	      while (j > lo && S[j - 1] > key) { S[j] = S[j - 1] ; --j ; }
-	      S[j] = key ;
+      uint32_t U = 0 ;
+      if (!bad)
+	{ cta_exclusive_scan<THREADS> (start, a.nbuck + 1, warpTmp) ;
+	  for (uint32_t i = t ; i < a.nbuck ; i += THREADS) cur[i] = start[i] ;
+	  __syncthreads () ;
+	  /* ---- scatter to buckets ---- */
+	  for (uint32_t i = 0 ; i < cnt ; ++i)
+	    { uint64_t key = col[(size_t) i * THREADS] ;
+	      S[atomicAdd (&cur[(uint32_t) (key >> buckShift)], 1u)] = key ;
+	    }
+	  if (n == 0) { if (t == 0) S[0] = 0 ; n = 1 ; }
+	  __syncthreads () ;
+	  /* ---- insertion sort inside each bucket: buckets are in hash order, so S ends up sorted ---- */
+	  for (uint32_t b = t ; b < a.nbuck ; b += THREADS)
+	    { uint32_t lo = start[b], hi = start[b + 1] ;
+	      for (uint32_t i = lo + 1 ; i < hi ; ++i)
+		{ uint64_t key = S[i] ; uint32_t j = i ;
+		  while (j > lo && S[j - 1] > key) { S[j] = S[j - 1] ; --j ; }
+		  S[j] = key ;
+		}
+	    }
+	  __syncthreads () ;
+	  /* ---- dedup: keep the first key of every run of equal hashes (lowest read index) ---- */
+	  const uint32_t per = (n + THREADS - 1) / THREADS ;
+	  const uint32_t lo = min (t * per, n), hi = min (lo + per, n) ;
+	  uint32_t ucnt = 0 ;
+	  for (uint32_t i = lo ; i < hi ; ++i) ucnt += (i == 0 || (S[i] >> SH) != (S[i - 1] >> SH)) ? 1u : 0u ;
+	  cur[t] = ucnt ;			/* nbuck >= THREADS */
+	  __syncthreads () ;
+	  U = cta_exclusive_scan<THREADS> (cur, THREADS, warpTmp) ;
+	  if (t == 0) sBase = atomicAdd (a.cursor, (unsigned long long) U) ;
+	  __syncthreads () ;
+	  if (sBase + U > a.scratchCap) bad = true ;
+	  else
+	    { uint64_t *dst = a.scratch + sBase + cur[t] ;
+	      for (uint32_t i = lo ; i < hi ; ++i)
+		if (i == 0 || (S[i] >> SH) != (S[i - 1] >> SH)) *dst++ = S[i] ;
 	    }
 	}
-      __syncthreads () ;
-      /* ---- dedup: keep the first key of every run of equal hashes (lowest read index) ---- */
-      const uint32_t per = (n + THREADS - 1) / THREADS ;
-      const uint32_t lo = min (t * per, n), hi = min (lo + per, n) ;
-      uint32_t cnt = 0 ;
-      for (uint32_t i = lo ; i < hi ; ++i) cnt += (i == 0 || (S[i] >> rb) != (S[i - 1] >> rb)) ? 1u : 0u ;
-      uint32_t *perThread = cur ;		/* reuse: nbuck >= THREADS is guaranteed by the host */
-      perThread[t] = cnt ;
-      __syncthreads () ;
-      U = cta_exclusive_scan<THREADS> (perThread, THREADS, warpTmp) ;
-      uint32_t o = perThread[t] ;
-      for (uint32_t i = lo ; i < hi ; ++i)
-	if (i == 0 || (S[i] >> rb) != (S[i - 1] >> rb)) A[o++] = S[i] ;
       if (t == 0)
-	{ unsigned long long b0 = atomicAdd (a.cursor, (unsigned long long) U) ;
-	  sBase = b0 ;
+	{ if (bad) { a.blkCnt[blk] = H10X_BLK_FALLBACK ; a.srcOff[blk] = 0 ; }
+	  else { a.blkCnt[blk] = U ; a.srcOff[blk] = sBase | ((uint64_t) SH << 56) ; }
 	}
       __syncthreads () ;
-      if (sBase + U > a.scratchCap) bad = true ;
     }
-  if (bad)
-    { if (t == 0) { a.blkCnt[blk] = H10X_BLK_FALLBACK ; a.srcOff[blk] = 0 ; }
-      return ;
-    }
-  uint64_t *dst = a.scratch + sBase ;
-  for (uint32_t i = t ; i < U ; i += THREADS) dst[i] = A[i] ;
-  if (t == 0) { a.blkCnt[blk] = U ; a.srcOff[blk] = sBase | ((uint64_t) rb << 56) ; }
 }
 
 /* Moves every block's unique list to its final place, in block order, and splits it into the
    arrays the index stages use: eHash (hash value), eRead (read index, 16 bits: hash10x.c:37,180) and
-   entryBlk (1-based block number).  One CTA per block.  kind 0: fused scratch (key = hash<<rb|read);
-   kind 1: generic path arrays (gHash, gRec). */
+   entryBlk (1-based block number).  One CTA per block.  Source kind by bit 63 of srcOff:
+   0 = fused scratch (key = hash << sh | read, sh in bits 56..61); 1 = generic path arrays. */
 __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff, const uint32_t *__restrict__ blkCnt,
 			 const uint64_t *__restrict__ blkOff, const uint64_t *__restrict__ scratch,
 			 const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gRec,
@@ -226,19 +252,19 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
     { uint64_t so = srcOff[blk] ;
       uint32_t n = blkCnt[blk] ;
       uint64_t dst = blkOff[blk] ;
-      if (so >> 63)	/* generic source */
+      if (so >> 63)
 	{ uint64_t off = so & 0x7fffffffffffffffull ;
 	  uint32_t r0 = blkStart[blk] ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
 	    { eHash[dst + i] = gHash[off + i] ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blk + 1 ; }
 	}
       else
-	{ uint32_t rb = (uint32_t) (so >> 56) ;
+	{ uint32_t sh = (uint32_t) (so >> 56) ;
 	  uint64_t off = so & 0x00ffffffffffffffull ;
-	  uint64_t rmask = ((uint64_t) 1 << rb) - 1 ;
+	  uint64_t rmask = ((uint64_t) 1 << sh) - 1 ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
 	    { uint64_t key = scratch[off + i] ;
-	      eHash[dst + i] = key >> rb ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blk + 1 ;
+	      eHash[dst + i] = key >> sh ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blk + 1 ;
 	    }
 	}
     }

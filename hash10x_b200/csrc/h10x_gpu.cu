@@ -19,6 +19,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <iterator>
 #include <map>
@@ -450,9 +451,22 @@ static void segmented_sort_blocks (h10x_ctx *c, cudaStream_t s, const K *kin, K 
     }
 }
 
+/* H10X_TRACE=1: host wall-clock between checkpoints of a build, on stderr */
+struct HostTrace {
+  bool on ; std::chrono::steady_clock::time_point t0 ;
+  HostTrace () : on (getenv ("H10X_TRACE") != nullptr), t0 (std::chrono::steady_clock::now ()) {}
+  void mark (const char *what)
+  { if (!on) return ;
+    auto t1 = std::chrono::steady_clock::now () ;
+    fprintf (stderr, "h10x-trace %-14s %9.3f ms\n", what, std::chrono::duration<double, std::milli> (t1 - t0).count ()) ;
+    t0 = t1 ;
+  }
+} ;
+
 static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true)
 {
   const h10x_params &P = c->P ;
+  HostTrace tr ;
   if (reset) reset_result (c) ;
   cudaEvent_t evA = ctx_event (c), evB = ctx_event (c) ;
   CK (cudaEventRecord (evA, s)) ;
@@ -514,6 +528,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	}
     }
 
+  tr.mark ("runs") ;
   const uint32_t nBlk = bt.nBlk ;
   const uint32_t nProcBlk = nBlk - 1 ;		/* the final run is never hashed (hash10x.c:209,216) */
   const uint32_t nProc = bt.start[nProcBlk] ;	/* records of the processed blocks */
@@ -530,52 +545,74 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   /* -- fused path: one CTA per block, everything in shared memory (h10x_fused.cuh) -- */
   const int n1 = H10X_R1_LEN - P.k + 1, n2 = H10X_R2_LEN - P.k + 1 ;
   const int c1 = (n1 + 7) / 8, c2 = (n2 + 7) / 8 ;
-  const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && nProcBlk > 0 ;
-  struct FusedClass { uint32_t cap, nbuck, lb, threads ; } ;
-  static const FusedClass kClasses[3] = { { 1024, 256, 8, 128 }, { 4096, 1024, 10, 256 }, { 12288, 4096, 12, 512 } } ;
-  DBuf<uint64_t> scratch ; DBuf<unsigned long long> cursor ;
+  const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && n1 >= 8 && nProcBlk > 0 ;
+  struct FusedClass { uint32_t cap, nbuck, lb, threads, rowCap ; } ;
+  static const FusedClass kClasses[4] = { { 1024, 256, 8, 128, 32 }, { 4096, 1024, 10, 256, 48 },
+					  { 12288, 2048, 11, 512, 64 }, { 24576, 4096, 12, 1024, 64 } } ;
+  const int nClasses = 4 ;
+  DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
   uint64_t nFused = 0 ;
   if (fusedOK)
     { StageTimer tm (c, s, ST_FUSED) ;
-      std::vector<uint32_t> lists[3] ;
+      std::vector<uint32_t> lists[4] ;
       const double perPair = (double) (n1 + n2) / (double) P.w ;	/* expected moshes per read pair */
       for (uint32_t p = 0 ; p < nProcBlk ; ++p)
 	{ uint32_t nRead = bt.start[p+1] - bt.start[p] ;
 	  double e = perPair * nRead, need = e * 1.12 + 6.0 * sqrt (e) + 16.0 ;
-	  int rbits = 0 ; while (((uint64_t) 1 << rbits) < nRead) ++rbits ;
-	  if (2 * P.k + rbits > 64) continue ;
-	  for (int ci = 0 ; ci < 3 ; ++ci)
+	  if (((uint64_t) nRead >> (64 - 2 * P.k)) != 0) continue ;	/* read index must fit under the hash bits */
+	  for (int ci = 0 ; ci < nClasses ; ++ci)
 	    if (need <= kClasses[ci].cap && (int) kClasses[ci].lb <= 2 * P.k) { lists[ci].push_back (p) ; break ; }
 	}
       uint64_t scratchCap = (uint64_t) (perPair * 1.15 * nProc) + (1u << 20) ;
-      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (1, s, mt) ;
+      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (1, s, mt) ; work.alloc (nClasses, s, mt) ;
       CK (cudaMemsetAsync (cursor.p, 0, 8, s)) ;
+      CK (cudaMemsetAsync (work.p, 0, 4 * nClasses, s)) ;
       CK (cudaMemsetAsync (blkCnt.p, 0xff, 4 * ((size_t) nProcBlk + 1), s)) ;
-      std::vector<DBuf<uint32_t>> dLists (3) ;
-      for (int ci = 0 ; ci < 3 ; ++ci)
+      int nSM = 148 ;
+      CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, P.device)) ;
+      std::vector<DBuf<uint32_t>> dLists (nClasses) ;
+      const bool wodd = (c->hp.wTz == 0) ;
+      const bool k21 = (P.k == 21 && wodd) ;
+      /* pass 1: grids and the staging area they need (launches run one after another and share it) */
+      uint32_t grid[4] = { 0, 0, 0, 0 } ; size_t smemB[4] ; size_t stageKeys = 0 ;
+      const void *fn[4] ;
+      for (int ci = 0 ; ci < nClasses ; ++ci)
+	{ const FusedClass &fc = kClasses[ci] ;
+	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) 2 * fc.nbuck + 1) + 16 ;
+#define FUSED_FN(T) (k21 ? (const void*) k_fused_block<T, true, 21> : wodd ? (const void*) k_fused_block<T, true, 0> \
+		     : (const void*) k_fused_block<T, false, 0>)
+	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
+#undef FUSED_FN
+	  if (lists[ci].empty ()) continue ;
+	  CK (cudaFuncSetAttribute (fn[ci], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemB[ci])) ;
+	  int occ = 1 ;
+	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn[ci], (int) fc.threads, smemB[ci])) ;
+	  if (occ < 1) occ = 1 ;
+	  grid[ci] = (uint32_t) std::min<size_t> (lists[ci].size (), (size_t) nSM * occ) ;
+	  stageKeys = std::max<size_t> (stageKeys, (size_t) grid[ci] * fc.threads * fc.rowCap) ;
+	}
+      stage.alloc (stageKeys, s, mt) ;
+      for (int ci = 0 ; ci < nClasses ; ++ci)
 	{ if (lists[ci].empty ()) continue ;
 	  const FusedClass &fc = kClasses[ci] ;
 	  dLists[ci].alloc (lists[ci].size (), s, mt) ;
 	  CK (cudaMemcpyAsync (dLists[ci].p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
 	  FusedArgs fa ;
-	  fa.fqb = fqb ; fa.list = dLists[ci].p ; fa.blkStart = dBlkStart.p ; fa.scratch = scratch.p ; fa.cursor = cursor.p ;
-	  fa.scratchCap = scratchCap ; fa.srcOff = srcOff.p ; fa.blkCnt = blkCnt.p ; fa.nList = (uint32_t) lists[ci].size () ;
-	  fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ;
-	  size_t smem = (size_t) fc.cap * 16 + 4 * ((size_t) 2 * fc.nbuck + 1) + 16 ;
-	  const bool wodd = (c->hp.wTz == 0) ;
-#define FUSED_LAUNCH(T, W) do { \
-	    CK (cudaFuncSetAttribute (k_fused_block<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ; \
-	    LAUNCH (c, (k_fused_block<T, W>), fa.nList, T, smem, s, fa, c->hp) ; } while (0)
-	  if (fc.threads == 128) { if (wodd) FUSED_LAUNCH (128, true) ; else FUSED_LAUNCH (128, false) ; }
-	  else if (fc.threads == 256) { if (wodd) FUSED_LAUNCH (256, true) ; else FUSED_LAUNCH (256, false) ; }
-	  else { if (wodd) FUSED_LAUNCH (512, true) ; else FUSED_LAUNCH (512, false) ; }
-#undef FUSED_LAUNCH
+	  fa.fqb = fqb ; fa.list = dLists[ci].p ; fa.blkStart = dBlkStart.p ; fa.stage = stage.p ; fa.scratch = scratch.p ;
+	  fa.cursor = cursor.p ; fa.work = work.p + ci ; fa.scratchCap = scratchCap ; fa.srcOff = srcOff.p ; fa.blkCnt = blkCnt.p ;
+	  fa.nList = (uint32_t) lists[ci].size () ; fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.rowCap = fc.rowCap ;
+	  fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ;
+	  HashParams hpv = c->hp ;
+	  void *args[2] = { (void*) &fa, (void*) &hpv } ;
+	  CK (cudaLaunchKernel (fn[ci], dim3 (grid[ci]), dim3 (fc.threads), args, smemB[ci], s)) ;
+	  ++c->launches ;
 	}
       CK (cudaMemcpyAsync (hCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies above */
       for (uint32_t p = 0 ; p < nProcBlk ; ++p) if (hCnt[p] != H10X_BLK_FALLBACK) ++nFused ;
     }
   c->stats.fusedBlocks = nFused ; c->stats.genericBlocks = nProcBlk - nFused ;
+  tr.mark ("fused") ;
 
   /* -- generic path for whatever the fused path did not take: global-memory segmented sort -- */
   DBuf<uint64_t> gHash ; DBuf<uint32_t> gRec ;
@@ -655,6 +692,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       G += Hb ;
     }
 
+  tr.mark ("generic") ;
   /* -- final placement in block order: eHash / eRead / entryBlk -- */
   for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
   hBlkOff[nProcBlk] = H ;
@@ -668,9 +706,10 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	      scratch.p, gHash.p, gRec.p, dBlkStart.p, eHash.p, eRead.p, entryBlk.p) ;
     CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
   }
-  scratch.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
+  scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
   if (!totalMoshes) totalMoshes = H ;
 
+  tr.mark ("place") ;
   /* ---------------- bins: ids, values, depths ---------------- */
   uint32_t D = 0 ;
   DBuf<uint32_t> entryId (H, s, mt) ;
@@ -716,6 +755,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ; CK (cudaMemsetAsync (c->hashDepth.p, 0, 8, s)) ;
     }
 
+  tr.mark ("bins-enq") ;
   /* ---------------- hash -> code CSR ---------------- */
   if (!(P.flags & H10X_FLAG_NO_CODES))
     { StageTimer tm (c, s, ST_CODES) ;
@@ -750,6 +790,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       if (D) LAUNCH (c, k_table_insert, gridFor (D, 256), 256, 0, s, c->hashNumber, c->hashValue.p, c->hashIndex.p, P.B) ;
     }
 
+  tr.mark ("rest-enq") ;
   /* ---------------- block table in the reference's numbering ---------------- */
   { StageTimer tm (c, s, ST_OTHER) ;
     std::vector<uint32_t> nRead ((size_t) nBlk + 1, 0), nHash ((size_t) nBlk + 1, 0) ;
@@ -770,6 +811,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 
   CK (cudaEventRecord (evB, s)) ;
   CK (cudaEventSynchronize (evB)) ;
+  tr.mark ("final-sync") ;
   float ms = 0 ; CK (cudaEventElapsedTime (&ms, evA, evB)) ;
   h10x_stats &st = c->stats ;
   st.msTotal = ms ;
