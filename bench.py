@@ -29,14 +29,16 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: genome, barcodes, pairs/barcode range, molecules, mol len, snp period, err rate, B
     "1gb": dict(genome_len=1_000_000_000, n_barcodes=500_000, pairs_min=300, pairs_max=500,
-                mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=28,
-                desc="BASELINE configs[2]: synthetic 1 Gb diploid genome at 60x, ~200M 151+151bp read pairs, 24 GB FQB, -B 28"),
+                mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=28, read_len=160,
+                desc="BASELINE configs[2]: synthetic 1 Gb diploid genome at 60x, ~200M read pairs, 24 GB FQB, -B 28 "
+                     "(160+160 bp reads: with 151 bp the zero padding of the last packed word adds ~0.39 novel hashes "
+                     "per pair and the reference itself dies with 'hashTableSize is too small' at -B 28)"),
     "yeast": dict(genome_len=12_000_000, n_barcodes=10_000, pairs_min=150, pairs_max=350,
-                  mol_per_barcode=10, mol_len=50_000, snp_period=500, err_rate=0.004, B=24,
+                  mol_per_barcode=10, mol_len=50_000, snp_period=500, err_rate=0.004, B=24, read_len=151,
                   desc="BASELINE configs[1]: synthetic yeast-scale diploid (12 Mb, ~2.5M read pairs, 10k barcodes, 60x), -B 24"),
     "human8": dict(genome_len=3_100_000_000, n_barcodes=187_500, pairs_min=300, pairs_max=500,
-                   mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=30,
-                   desc="one eighth of BASELINE configs[3]: 3.1 Gb human-scale genome, 75M read pairs per GPU, -B 30"),
+                   mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=30, read_len=160,
+                   desc="one eighth of BASELINE configs[3]: 3.1 Gb human-scale genome, 75M read pairs per GPU, -B 30, 160+160 bp reads"),
 }
 
 
@@ -44,7 +46,7 @@ def synth_params(orc, wl, seed=3):
     return orc.synth_params(seed=seed, genome_len=wl["genome_len"], n_barcodes=wl["n_barcodes"],
                             pairs_min=wl["pairs_min"], pairs_max=wl["pairs_max"],
                             mol_per_barcode=wl["mol_per_barcode"], mol_len=wl["mol_len"],
-                            snp_period=wl["snp_period"], err_rate=wl["err_rate"])
+                            snp_period=wl["snp_period"], err_rate=wl["err_rate"], read_len=wl.get("read_len", 151))
 
 
 class ClockSampler(threading.Thread):

@@ -16,9 +16,12 @@
  * (haplotype B = A with a substitution every ~snpPeriod bases), nBarcodes
  * barcodes each holding molPerBarcode molecules of molLen bases drawn from a
  * random haplotype, a uniform number of read pairs per barcode, 151+151 bp
- * pairs (read 1 = 16 bp barcode + 7 bp spacer + 128 bp insert, read 2 = the
+ * pairs by default (read 1 = 16 bp barcode + 7 bp spacer + insert, read 2 = the
  * reverse-complement end of a 300-699 bp fragment), substitution errors with
- * probability errThresh / 2^32 per base.
+ * probability errThresh / 2^32 per base.  readLen = 160 fills the last packed
+ * word: with 151 bp the reference hashes the zero padding of word 9 (SURVEY.md
+ * Appendix C), which adds ~0.39 never-seen hashes per pair and overflows the
+ * reference's -B 28 table at the 200M-pair scale.
  */
 #ifndef H10X_SYNTH_FQB_H
 #define H10X_SYNTH_FQB_H
@@ -41,7 +44,7 @@ typedef struct {
   uint32_t molLen;         /* molecule length in bases (> 700)                  */
   uint32_t snpPeriod;      /* hap B differs from hap A at ~1/snpPeriod bases; 0 = haploid */
   uint32_t errThresh;      /* per-base substitution probability * 2^32          */
-  uint32_t reserved;
+  uint32_t readLen;        /* bases per read, 145..160 (0 = 151); 160 fills the last packed word */
 } synth_params;
 
 SY_HD uint64_t sy_mix (uint64_t x)        /* splitmix64 finaliser */
@@ -87,11 +90,13 @@ SY_HD void sy_record (const synth_params *p, uint32_t b, uint32_t j, uint64_t re
   uint64_t errKey = sy_mix (p->seed ^ (recGlobal * 0xA24BAED4963EE407ull)) ;
   uint32_t bc = sy_barcode (b) ;
   int rd, q, i ;
+  const int L = p->readLen ? (int) p->readLen : 151 ;
+  const int nFull = L / 16 ;
 
   for (i = 0 ; i < 30 ; ++i) rec[i] = 0 ;
   for (rd = 0 ; rd < 2 ; ++rd)
     { uint32_t *u = rec + 15*rd ;
-      for (q = 0 ; q < 151 ; ++q)
+      for (q = 0 ; q < L ; ++q)
 	{ uint32_t base ;
 	  if (rd == 0 && q < 16) base = (bc >> (2*(15-q))) & 3u ;             /* barcode */
 	  else if (rd == 0 && q < 23) base = (uint32_t)((r1 >> (2*q)) & 3u) ;   /* spacer */
@@ -104,16 +109,17 @@ SY_HD void sy_record (const synth_params *p, uint32_t b, uint32_t j, uint64_t re
 	      base = sy_genome_base (p, hap, x) ;
 	      if (rc) base = 3u - base ;
 	      if (p->errThresh)
-		{ uint64_t e = sy_mix (errKey + (uint64_t)(rd*151 + q)) ;
+		{ uint64_t e = sy_mix (errKey + (uint64_t)(rd*L + q)) ;
 		  if ((uint32_t)e < p->errThresh) base = (base + 1u + (uint32_t)((e >> 40) % 3u)) & 3u ;
 		}
 	    }
-	  /* fq2b.c:33-42 packing: full words MSB first, last 7 bases right-aligned in word 9 */
-	  if (q < 144) u[q >> 4] |= base << (2*(15 - (q & 15))) ;
-	  else u[9] |= base << (2*(150 - q)) ;
+	  /* fq2b.c:33-42 packing: full words MSB first, the last partial word right-aligned */
+	  if (q < 16*nFull) u[q >> 4] |= base << (2*(15 - (q & 15))) ;
+	  else u[nFull] |= base << (2*(L - 1 - q)) ;
 	}
       /* fq2b.c:52-61: 1 bit per base, all "good" quality; 151 = 4 full words + 23 bits */
-      u[10] = u[11] = u[12] = u[13] = 0xFFFFFFFFu ; u[14] = 0x7FFFFFu ;
+      for (i = 0 ; i < L/32 ; ++i) u[10 + i] = 0xFFFFFFFFu ;
+      if (L % 32) u[10 + L/32] = (1u << (L % 32)) - 1u ;
     }
 }
 

@@ -41,7 +41,7 @@ class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("genomeLen", C.c_uint64), ("nBarcodes", C.c_uint32),
                 ("pairsMin", C.c_uint32), ("pairsMax", C.c_uint32), ("molPerBarcode", C.c_uint32),
                 ("molLen", C.c_uint32), ("snpPeriod", C.c_uint32), ("errThresh", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("readLen", C.c_uint32)]
 
 
 _lib = None
@@ -188,9 +188,9 @@ def kmer_hashes(h, hrc, k=21, factor1_=DEFAULT_FACTOR1):
 # ------------------------------------------------------------------ synthetic FQB (CPU)
 
 def synth_params(seed=1, genome_len=200_000, n_barcodes=40, pairs_min=20, pairs_max=120,
-                 mol_per_barcode=4, mol_len=20_000, snp_period=500, err_rate=0.002):
+                 mol_per_barcode=4, mol_len=20_000, snp_period=500, err_rate=0.002, read_len=151):
     return SynthParams(seed, genome_len, n_barcodes, pairs_min, pairs_max, mol_per_barcode,
-                       mol_len, snp_period, int(err_rate * 2 ** 32), 0)
+                       mol_len, snp_period, int(err_rate * 2 ** 32), read_len)
 
 
 def synth_layout(p):
