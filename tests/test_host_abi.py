@@ -1,0 +1,115 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/h10x_gpu.h declares,
+fails loudly without a device, and its host-only parts (.hash writer/reader, factor1) are right."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import hashfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "h10x_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(h10x_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import hash10x_b200
+    L = hash10x_b200.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.h10x_abi_version() == 1
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "h10x_gpu.h"\nint main(void){ h10x_params p; h10x_index i; (void)p; (void)i; '
+                   'return sizeof(h10x_cluster_hash) == 8 ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_factor1_and_error_texts():
+    import hash10x_b200
+    L = hash10x_b200.load_library()
+    assert hash10x_b200.factor1_from_seed(17) == 0x49308BB9003CB3AD
+    assert L.h10x_strerror(1) == b"hashTableSize is too small"      # hash10x.c:149
+    assert L.h10x_strerror(2) == b"chunkSize too small"             # hash10x.c:206
+    assert [L.h10x_stage_name(i) for i in range(12)].count(b"") == 0
+
+
+def test_no_device_means_loud_failure_not_fallback():
+    import hash10x_b200
+    L = hash10x_b200.load_library()
+    if L.h10x_gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(hash10x_b200.H10xError) as e:
+        hash10x_b200.Hash10xGPU(B=20)
+    assert e.value.code == 7 and "no CPU fallback" in e.value.msg
+    cli = os.path.join(ROOT, "hash10x_b200", "bin", "hash10x-b200")
+    if os.path.exists(cli):
+        fq = os.path.join(ROOT, "tests", "golden", "synth_small.fqb")
+        r = subprocess.run([cli, "-B", "20", "--readFQB", fq], capture_output=True, text=True)
+        assert r.returncode != 0 and "FATAL ERROR: no CUDA device" in r.stderr
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _dirs, files in os.walk(os.path.join(ROOT, "hash10x_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")) and f != "synth_fqb.h":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle", "").replace("oracle/", "ORACLEDIR/") or \
+                    "import" not in text or "from oracle" not in text, f
+                assert "from oracle" not in text and "import oracle" not in text and "liborc" not in text, f
+
+
+def test_hash_writer_reader_roundtrip_and_reference_layout(orc, tmp_path):
+    """h10x_write_hash on an oracle-built index gives the same bytes as the oracle's own writer
+    (which is checked against the reference binary), and h10x_read_hash reads it back."""
+    import hash10x_b200
+    from hash10x_b200 import binding
+    p = orc.synth_params(seed=77, n_barcodes=40, pairs_min=2, pairs_max=70)
+    recs = orc.synth_fqb(p)
+    ix = orc.build(recs, B=20)
+    a = str(tmp_path / "a.hash")
+    b = str(tmp_path / "b.hash")
+    binding.write_hash(ix, a)
+    assert orc.build_and_write(recs, b, B=20) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+    L = hash10x_b200.load_library()
+    ci = binding.CIndex()
+    err = C.create_string_buffer(256)
+    assert L.h10x_read_hash(a.encode(), 21, C.byref(ci), err, 256) == 3 and b"rerun with -B 20" in err.value
+    assert L.h10x_read_hash(a.encode(), 20, C.byref(ci), err, 256) == 0
+    got = binding.Index(ci, L)
+    L.h10x_index_free(C.byref(ci))
+    assert got.hashNumber == ix.hashNumber and got.nHashes == ix.nHashes and got.nReads == ix.nReads
+    assert np.array_equal(got.hashValue, ix.hashValue) and np.array_equal(got.clus, ix.clus)
+    assert np.array_equal(got.hashDepth, ix.hashDepth) and np.array_equal(got.blkOff, ix.blkOff)
+    bad = str(tmp_path / "bad.hash")
+    open(bad, "wb").write(b"nope" + open(a, "rb").read()[4:])
+    assert L.h10x_read_hash(bad.encode(), 20, C.byref(ci), err, 256) != 0 and b"not a 10X hash file" in err.value
+
+
+def test_synth_generator_is_deterministic_and_well_formed(orc):
+    p = orc.synth_params(seed=5, n_barcodes=10, pairs_min=3, pairs_max=9)
+    a, b = orc.synth_fqb(p), orc.synth_fqb(p)
+    assert np.array_equal(a, b)
+    n, off = orc.synth_layout(p)
+    assert a.shape == (n, 30)
+    runs = np.flatnonzero(np.r_[True, a[1:, 0] != a[:-1, 0]])
+    assert np.array_equal(runs, off[:-1].astype(np.int64))           # grouped by barcode, distinct words
+    assert (a[:, 9] < (1 << 14)).all() and (a[:, 24] < (1 << 14)).all()   # 151 bp: last word right-aligned
+    assert (a[:, 14] == 0x7FFFFF).all() and (a[:, 10:14] == 0xFFFFFFFF).all()
+    part = orc.synth_fqb(p, 5, 17)
+    assert np.array_equal(part, a[5:17])

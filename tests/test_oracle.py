@@ -1,0 +1,154 @@
+"""CPU tests (no GPU): the oracle against (i) the known-answer vectors produced by the reference's
+seqhash.c, (ii) the golden digests generated from the reference binary
+(tests/golden/make_golden.py), (iii) the reference binary itself when oracle/_ref is present."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import fqbtools
+import hashfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+KAT_SEQ = ("CCCCACCACCAGGACACTTTCAGAGTTCTCCGTCATCGTTAGCAGCACGGTTAGCTTGTCTCTGTCTATTTCACGACTGGTGGAGTCGTATAGTC"
+           "ACGAGCTGGGTATGTCCTGAAGCTAGACATTGGAACTATGTAAGTCCTCTTCCGG")
+
+
+def test_factor1_from_glibc_random(orc):
+    # seqhash.c:29 after srandom(17): the constant every other vector depends on
+    assert orc.factor1(17) == 0x49308BB9003CB3AD
+    assert orc.DEFAULT_FACTOR1 == 0x49308BB9003CB3AD
+
+
+def test_kat_sequence_generator_matches_appendix_e():
+    x, out = 42, []
+    for _ in range(150):
+        x = (x * 1103515245 + 12345) & 0x7FFFFFFF
+        out.append("ACGT"[(x >> 16) & 3])
+    assert "".join(out) == KAT_SEQ
+
+
+def test_kat_kmer0_hashes(orc):
+    codes = [fqbtools.CODE[c] for c in KAT_SEQ]
+    h = 0
+    hrc = 0
+    for i, c in enumerate(codes[:21]):
+        h = (h << 2) | c
+        hrc |= (3 - c) << (2 * i)
+    assert h == 0x154514A11FD and hrc == 0x202ED7AEBAA
+    hf, hr = orc.kmer_hashes(h, hrc)
+    assert (hf, hr) == (0x32DB51C0BC3, 0x1FF0AB2C2AA)
+
+
+def test_kat_moshes(orc):
+    codes = np.array([fqbtools.CODE[c] for c in KAT_SEQ], np.uint8)
+    h, pos, fwd = orc.seq_moshes(codes)
+    want = [(4, 0x21C5F360BD8, 1), (25, 0x29099B43123, 0), (75, 0x10091E2CC3B, 1), (102, 0xEAAE4BA6A5, 1),
+            (106, 0xD50A11DD64, 1)]
+    assert [(int(p), int(x), int(f)) for x, p, f in zip(h, pos, fwd)] == want
+    # 30 x A -> 10 moshes, all hash 0; 30 x C -> none; shorter than k -> none
+    h, pos, _ = orc.seq_moshes(np.zeros(30, np.uint8))
+    assert list(pos) == list(range(10)) and not h.any()
+    assert orc.seq_moshes(np.ones(30, np.uint8))[0].size == 0
+    assert orc.seq_moshes(np.zeros(20, np.uint8))[0].size == 0
+
+
+def _digest_matches(hf, d):
+    def crc(a):
+        return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+    assert hf.hashNumber == d["hashNumber"] and hf.nBlocksMax == d["nBlocksMax"] and hf.nHashes == d["nHashes"]
+    assert crc(hf.hashValue) == d["crc_hashValue"]
+    assert crc(hf.hashDepth[:hf.depthMax]) == d["crc_hashDepth"]
+    assert crc(hf.hashIndex) == d["crc_hashIndex"]
+    assert crc(hf.blkNRead) == d["crc_blkNRead"] and crc(hf.blkNHash) == d["crc_blkNHash"]
+    assert crc(hf.clusIdx) == d["crc_clusIdx"] and crc(hf.clusRead) == d["crc_clusRead"]
+
+
+def _golden_cases():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        return sorted(json.load(f).items())
+
+
+@pytest.mark.parametrize("name,d", _golden_cases())
+def test_oracle_reproduces_reference_golden(orc, tmp_path, name, d):
+    recs = np.fromfile(os.path.join(GOLD, name + ".fqb"), np.uint32)
+    kw = d["params"]
+    f1 = orc.factor1(kw.get("r", 17))
+    path = str(tmp_path / "o.hash")
+    st = orc.build_and_write(recs, path, B=kw.get("B", 20), k=kw.get("k", 21), w=kw.get("w", 31), factor1_=f1,
+                             N=kw.get("N", 0), chunk=kw.get("chunk", 100000))
+    assert st == 0
+    hf = hashfile.parse(path)
+    _digest_matches(hf, d)
+    assert hf.size == d["fileSize"] and (hf.depthDim, hf.blkDim) == (d["depthDim"], d["blkDim"])
+    hashfile.check_table(hf)
+
+
+def test_golden_quirks_are_what_the_survey_says():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        g = json.load(f)
+    q = g["quirks"]
+    assert q["blkNHash_head"][2] == 1 and q["blkNHash_head"][4] == 1     # phantom entries
+    assert q["blkNHash_head"][6] == 0                                    # last run never hashed
+    assert g["single_run"]["hashNumber"] == 1 and g["single_run"]["nHashes"] == 0
+    # the all-A barcode run glued to its successor only when it ends on the chunk boundary
+    assert g["allA_barcode_c10"]["nBlocksMax"] == g["allA_barcode_c11"]["nBlocksMax"] - 1
+
+
+# ------------------------------------------------------------------ live reference (this container only)
+
+def _need_ref(orc):
+    if orc.ref_binary() is None:
+        pytest.skip("oracle/_ref/hash10x not built (no /root/reference on this machine)")
+
+
+@pytest.mark.parametrize("seed,nb,pmax,kw", [
+    (1, 30, 200, {}), (2, 80, 60, dict(N=1500)), (3, 50, 90, dict(chunk=97)), (4, 20, 300, dict(k=16, w=32, r=3)),
+    (5, 20, 300, dict(k=31, w=5, r=99)), (6, 15, 100, dict(k=11, w=2, r=1))])
+def test_oracle_equals_reference_binary(orc, tmp_path, seed, nb, pmax, kw):
+    _need_ref(orc)
+    p = orc.synth_params(seed=seed, n_barcodes=nb, pairs_min=2, pairs_max=pmax, genome_len=60_000, mol_len=8_000)
+    recs = orc.synth_fqb(p)
+    fqb = str(tmp_path / "a.fqb")
+    recs.tofile(fqb)
+    B = 21
+    r = orc.run_reference(fqb, str(tmp_path / "r.hash"), B=B, k=kw.get("k"), w=kw.get("w"), r=kw.get("r"),
+                          N=kw.get("N"), chunk=kw.get("chunk"))
+    assert r.returncode == 0, r.stderr
+    st = orc.build_and_write(recs, str(tmp_path / "o.hash"), B=B, k=kw.get("k", 21), w=kw.get("w", 31),
+                             factor1_=orc.factor1(kw.get("r", 17)), N=kw.get("N", 0), chunk=kw.get("chunk", 100000))
+    assert st == 0
+    a, b = hashfile.parse(str(tmp_path / "r.hash")), hashfile.parse(str(tmp_path / "o.hash"))
+    assert a.size == b.size
+    hashfile.assert_strict_equal(a, b, table=True)
+    hashfile.assert_canonical_equal(a, b)
+    ix = orc.build(recs, B=B, k=kw.get("k", 21), w=kw.get("w", 31), factor1_=orc.factor1(kw.get("r", 17)),
+                   N=kw.get("N", 0), chunk=kw.get("chunk", 100000))
+    co, cd = hashfile.hash_to_code_lists(a)
+    assert np.array_equal(co, ix.codeOff) and np.array_equal(cd, ix.codes)     # -DCHECK's invariant and more
+    assert np.array_equal(np.diff(ix.codeOff.astype(np.int64)), ix.hashDepth)
+
+
+def test_oracle_errors_equal_reference(orc, tmp_path):
+    _need_ref(orc)
+    p = orc.synth_params(seed=9, n_barcodes=30, pairs_min=20, pairs_max=90)
+    recs = orc.synth_fqb(p)
+    fqb = str(tmp_path / "a.fqb")
+    recs.tofile(fqb)
+    r = orc.run_reference(fqb, None, B=20, chunk=50)
+    assert r.returncode != 0 and "chunkSize too small" in r.stderr
+    assert orc.build(recs, B=20, chunk=50).status == 2
+    r = orc.run_reference(fqb, None, B=19)
+    assert r.returncode != 0 and "out of range 20-30" in r.stderr
+    assert orc.build(recs, B=19).status == 3
+    big = orc.synth_params(seed=8, n_barcodes=60, pairs_min=800, pairs_max=1000, genome_len=20_000_000,
+                           mol_len=100_000, mol_per_barcode=20)
+    recs = orc.synth_fqb(big)
+    recs.tofile(fqb)
+    r = orc.run_reference(fqb, None, B=20)
+    assert r.returncode != 0 and "hashTableSize is too small" in r.stderr
+    assert orc.build(recs, B=20).status == 1
