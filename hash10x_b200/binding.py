@@ -46,6 +46,13 @@ class CStats(C.Structure):
                 ("genericBlocks", C.c_uint64), ("peakDeviceBytes", C.c_uint64)]
 
 
+class CDistInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("blockBase", C.c_uint32),
+                ("nBlocksGlobal", C.c_uint32), ("nReadsGlobal", C.c_uint64), ("nHashesGlobal", C.c_uint64),
+                ("nLocalBins", C.c_uint32), ("reserved", C.c_uint32), ("localBinId", C.c_void_p),
+                ("localCodeOff", C.c_void_p), ("localCodes", C.c_void_p)]
+
+
 def lib_path():
     return os.path.join(_HERE, "libh10xgpu.so")
 
@@ -86,6 +93,11 @@ def load_library():
     L.h10x_host_alloc.argtypes = [sz]
     L.h10x_host_free.argtypes = [vp]
     L.h10x_gpu_record_moshes.argtypes = [vp, vp, u64, vp, vp, u64, cp, sz]
+    L.h10x_dist_unique_id.argtypes = [vp, cp, sz]
+    L.h10x_dist_init.argtypes = [vp, C.c_int, C.c_int, vp, cp, sz]
+    L.h10x_gpu_build_device_dist.argtypes = [vp, vp, u64, vp, cp, sz]
+    L.h10x_gpu_dist_info.argtypes = [vp, C.POINTER(CDistInfo)]
+    L.h10x_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -217,6 +229,46 @@ class Hash10xGPU:
         if st:
             raise H10xError(st, "no index resident")
         return ci
+
+    # --- multi-GPU: one context per rank, NCCL inside the library ---
+    @staticmethod
+    def dist_unique_id():
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        err = C.create_string_buffer(512)
+        st = L.h10x_dist_unique_id(buf, err, len(err))
+        if st:
+            raise H10xError(st, err.value.decode())
+        return buf.raw
+
+    def dist_init(self, rank, nranks, id_bytes):
+        err = C.create_string_buffer(512)
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        self._check(self.lib.h10x_dist_init(self.ctx, rank, nranks, buf, err, len(err)), err)
+
+    def build_device_dist(self, dev_ptr, n_records, stream=0):
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_build_device_dist(self.ctx, dev_ptr, n_records, stream, err, len(err)), err)
+
+    def dist_info(self, download=True):
+        di = CDistInfo()
+        if self.lib.h10x_gpu_dist_info(self.ctx, C.byref(di)):
+            raise H10xError(3, "no distributed build")
+        out = {f: getattr(di, f) for f, _ in CDistInfo._fields_ if not f.startswith("local") and f != "reserved"}
+        out["nLocalBins"] = di.nLocalBins
+        if download:
+            def pull(ptr, n):
+                a = np.zeros(n, np.uint32)
+                if n:
+                    st = self.lib.h10x_gpu_memcpy_d2h(self.ctx, a.ctypes.data, ptr, 4 * n)
+                    if st:
+                        raise H10xError(st, "d2h")
+                return a
+            off = pull(di.localCodeOff, di.nLocalBins + 1)
+            out["localBinId"] = pull(di.localBinId, di.nLocalBins)
+            out["localCodeOff"] = off
+            out["localCodes"] = pull(di.localCodes, int(off[-1]) if off.size else 0)
+        return out
 
     def stats(self):
         cs = CStats()

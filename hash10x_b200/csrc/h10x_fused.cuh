@@ -241,12 +241,12 @@ k_fused_block (FusedArgs a, HashParams hp)
 
 /* Moves every block's unique list to its final place, in block order, and splits it into the
    arrays the index stages use: eHash (hash value), eRead (read index, 16 bits: hash10x.c:37,180) and
-   entryBlk (1-based block number).  One CTA per block.  Source kind by bit 63 of srcOff:
+   entryBlk (1-based GLOBAL block number: blkBase is this rank's first block in a multi-GPU build).  One CTA per block.  Source kind by bit 63 of srcOff:
    0 = fused scratch (key = hash << sh | read, sh in bits 56..61); 1 = generic path arrays. */
 __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff, const uint32_t *__restrict__ blkCnt,
 			 const uint64_t *__restrict__ blkOff, const uint64_t *__restrict__ scratch,
 			 const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gRec,
-			 const uint32_t *__restrict__ blkStart,
+			 const uint32_t *__restrict__ blkStart, uint32_t blkBase,
 			 uint64_t *__restrict__ eHash, uint16_t *__restrict__ eRead, uint32_t *__restrict__ entryBlk)
 { for (uint32_t blk = blockIdx.x ; blk < nProcBlk ; blk += gridDim.x)
     { uint64_t so = srcOff[blk] ;
@@ -256,7 +256,7 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	{ uint64_t off = so & 0x7fffffffffffffffull ;
 	  uint32_t r0 = blkStart[blk] ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
-	    { eHash[dst + i] = gHash[off + i] ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blk + 1 ; }
+	    { eHash[dst + i] = gHash[off + i] ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blkBase + blk + 1 ; }
 	}
       else
 	{ uint32_t sh = (uint32_t) (so >> 56) ;
@@ -264,7 +264,7 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	  uint64_t rmask = ((uint64_t) 1 << sh) - 1 ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
 	    { uint64_t key = scratch[off + i] ;
-	      eHash[dst + i] = key >> sh ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blk + 1 ;
+	      eHash[dst + i] = key >> sh ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blkBase + blk + 1 ;
 	    }
 	}
     }

@@ -118,6 +118,9 @@ struct h10x_ctx {
   struct Span { int stage ; cudaEvent_t a, b ; } ;
   std::vector<Span> spans ;
   uint64_t launches = 0 ;
+  /* multi-GPU (h10x_dist.cuh) */
+  struct DistState *dist = nullptr ;
+  DBuf<uint32_t> localBinId, localCodeOff, localCodes ;	/* this rank's part of the hash->code lists */
   /* pinned host arena reused by h10x_gpu_download (one slot per index array) */
   void *hostSlot[9] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } ;
   size_t hostCap[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 } ;
@@ -149,6 +152,8 @@ template <class F> static void cubCall (h10x_ctx *c, cudaStream_t s, F f)
 }
 
 struct CastU64 { __host__ __device__ uint64_t operator() (uint32_t x) const { return (uint64_t) x ; } } ;
+
+#include "h10x_dist.cuh"
 
 /* ------------------------------------------------------------------ kernels: runs */
 
@@ -416,6 +421,7 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 
 static void reset_result (h10x_ctx *c)
 { c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
+  c->localBinId.release () ; c->localCodeOff.release () ; c->localCodes.release () ;
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
   c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
@@ -463,7 +469,13 @@ struct HostTrace {
   }
 } ;
 
-static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true)
+static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
+		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal) ;
+static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_t mine[4], std::vector<uint32_t> &all) ;
+
+static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true,
+			       bool dist = false)
 {
   const h10x_params &P = c->P ;
   HostTrace tr ;
@@ -481,6 +493,9 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   BlockTable bt ;
   DBuf<uint32_t> blkIncl (nRec, s, mt) ;	/* 1-based block number of every record */
   DBuf<uint32_t> dBlkStart ;
+  int sawZeroBarcode = 0 ;
+  auto doRuns = [&] ()
+  {
   if (nRec == 0)
     { bt.nBlk = 1 ; bt.start = {0, 0} ; }	/* block 1 exists with nRead 0 (hash10x.c:200-201) */
   else
@@ -494,6 +509,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       CK (cudaMemcpyAsync (&nRuns, blkIncl.p + (nRec - 1), 4, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaMemcpyAsync (&hAnyZero, anyZero.p, 4, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;
+      sawZeroBarcode = hAnyZero ;
       dBlkStart.alloc ((size_t) nRuns + 1, s, mt) ;
       LAUNCH (c, k_run_starts, gridFor (nRec, 256), 256, 0, s, flag.p, blkIncl.p, nRec, dBlkStart.p) ;
       std::vector<uint32_t> runStart ((size_t) nRuns + 1) ;
@@ -527,10 +543,40 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    }
 	}
     }
+  } ;
+
+  /* multi-GPU: ranks own consecutive barcode-run ranges; agree on errors and on global block numbers */
+  bool lastRank = true ; uint32_t blkBase = 0, nBlkGlobal = 0 ;
+  if (!dist) doRuns () ;
+  else
+    { int localErr = 0 ;
+      try { doRuns () ; }
+      catch (const H10xError &e) { localErr = e.code ; bt.nBlk = 1 ; bt.start = {0, nRec} ; }
+      uint32_t words[2] = { 0, 0 } ;
+      if (nRec)
+	{ CK (cudaMemcpyAsync (&words[0], fqb, 4, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaMemcpyAsync (&words[1], fqb + (size_t) H10X_REC_WORDS * (nRec - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaStreamSynchronize (s)) ;
+	}
+      if (!localErr && (nRec == 0 || P.N != 0 || sawZeroBarcode)) localErr = H10X_ERR_UNSUPPORTED ;
+      const uint32_t mine[4] = { bt.nBlk, words[0], words[1], nRec } ;
+      std::vector<uint32_t> all ;
+      dist_agree (c, s, localErr, mine, all) ;		/* throws the same error on every rank */
+      const int R = c->dist->rank, NR = c->dist->nranks ;
+      uint64_t readsGlobal = 0 ;
+      for (int r = 0 ; r < NR ; ++r)
+	{ if (r < R) blkBase += all[4*r] ;
+	  nBlkGlobal += all[4*r] ; readsGlobal += all[4*r + 3] ;
+	  if (r + 1 < NR && all[4*r + 2] == all[4*(r+1) + 1])
+	    throw H10xError (H10X_ERR_UNSUPPORTED, "multi-GPU shards must be cut at barcode-run boundaries") ;
+	}
+      lastRank = (R == NR - 1) ;
+      c->dist->blockBase = blkBase ; c->dist->nBlocksGlobal = nBlkGlobal ; c->dist->nReadsGlobal = readsGlobal ;
+    }
 
   tr.mark ("runs") ;
   const uint32_t nBlk = bt.nBlk ;
-  const uint32_t nProcBlk = nBlk - 1 ;		/* the final run is never hashed (hash10x.c:209,216) */
+  const uint32_t nProcBlk = nBlk - (lastRank ? 1 : 0) ;	/* the (globally) final run is never hashed (hash10x.c:209,216) */
   const uint32_t nProc = bt.start[nProcBlk] ;	/* records of the processed blocks */
   c->nBlocksMax = nBlk + 1 ;
 
@@ -703,7 +749,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
     if (nProcBlk)
       LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
-	      scratch.p, gHash.p, gRec.p, dBlkStart.p, eHash.p, eRead.p, entryBlk.p) ;
+	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, eHash.p, eRead.p, entryBlk.p) ;
     CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
   }
   scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
@@ -729,35 +775,63 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, head.p, segIncl.p, H, s) ; }) ;
 	CK (cudaMemcpyAsync (&D, segIncl.p + (H - 1), 4, cudaMemcpyDeviceToHost, s)) ;
 	CK (cudaStreamSynchronize (s)) ;
-	/* hash10x.c:149: die once hashNumber exceeds 2^(B-2) - 2 */
-	if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)
-	  throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
-	segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
-	DBuf<uint32_t> isFirst (H, s, mt), rank (H, s, mt) ;
-	CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
-	LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
-	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, isFirst.p, rank.p, H, s) ; }) ;
-	c->hashNumber = D + 1 ;
-	c->hashValue.alloc ((size_t) D + 1, s, mt) ;
-	c->hashDepth.alloc ((size_t) D + 2, s, mt) ;	/* one spare 0 so the scan yields codeOff[hashNumber] */
-	CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
-	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
-	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-	LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+	segStart.alloc ((size_t) D + 1, s, mt) ;
+	if (!dist)
+	  { /* hash10x.c:149: die once hashNumber exceeds 2^(B-2) - 2 */
+	    if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)
+	      throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+	    idOfSeg.alloc (D, s, mt) ;
+	    DBuf<uint32_t> isFirst (H, s, mt), rank (H, s, mt) ;
+	    CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
+	    LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
+	    cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, isFirst.p, rank.p, H, s) ; }) ;
+	    c->hashNumber = D + 1 ;
+	    c->hashValue.alloc ((size_t) D + 1, s, mt) ;
+	    c->hashDepth.alloc ((size_t) D + 2, s, mt) ;	/* one spare 0 so the scan yields codeOff[hashNumber] */
+	    CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+	    CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+	    CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
+	    LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+	  }
+	else
+	  { DBuf<uint32_t> isFirst (H, s, mt) ;	/* k_seg_start marks first entries; unused here */
+	    CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
+	    LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
+	  }
       }
-      { StageTimer tm (c, s, ST_ENTRYIDS) ;
-	LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl.p, idOfSeg.p, se.p, entryId.p) ;
-      }
+      if (!dist)
+	{ StageTimer tm (c, s, ST_ENTRYIDS) ;
+	  LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl.p, idOfSeg.p, se.p, entryId.p) ;
+	}
+      else
+	{ uint32_t Dl = D ;
+	  dist_bins (c, s, H, sh.p, se.p, segIncl.p, Dl, segStart.p, entryBlk.p, nBlkGlobal, entryId.p, D) ;
+	}
     }
-  else
+  else if (!dist)
     { c->hashNumber = 1 ;
       c->hashValue.alloc (1, s, mt) ; c->hashDepth.alloc (2, s, mt) ;
       CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ; CK (cudaMemsetAsync (c->hashDepth.p, 0, 8, s)) ;
     }
+  else
+    { segStart.alloc (1, s, mt) ; CK (cudaMemsetAsync (segStart.p, 0, 4, s)) ;
+      dist_bins (c, s, 0, nullptr, nullptr, nullptr, 0, segStart.p, nullptr, nBlkGlobal, nullptr, D) ;
+    }
 
   tr.mark ("bins-enq") ;
   /* ---------------- hash -> code CSR ---------------- */
-  if (!(P.flags & H10X_FLAG_NO_CODES))
+  if (dist)
+    { /* this rank's part of every bin's barcode list: bin localBinId[j] holds the (global) blocks
+	 localCodes[localCodeOff[j] .. localCodeOff[j+1]), ascending; the full list of a bin is the
+	 concatenation over ranks in rank order, because ranks own ascending block ranges */
+      StageTimer tm (c, s, ST_CODES) ;
+      c->localCodes.alloc (H, s, mt) ;
+      uint32_t Dl = c->dist->nLocalBins ;
+      c->localCodeOff.alloc ((size_t) Dl + 1, s, mt) ;
+      CK (cudaMemcpyAsync (c->localCodeOff.p, segStart.p, 4 * ((size_t) Dl + 1), cudaMemcpyDeviceToDevice, s)) ;
+      if (H) LAUNCH (c, k_gather_u32, gridFor (H, 256), 256, 0, s, H, se.p, entryBlk.p, c->localCodes.p) ;
+    }
+  else if (!(P.flags & H10X_FLAG_NO_CODES))
     { StageTimer tm (c, s, ST_CODES) ;
       size_t hn = c->hashNumber ;
       c->codeOff.alloc (hn + 1, s, mt) ;
@@ -782,7 +856,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   entryId.release () ; eRead.release () ; entryBlk.release () ;
 
   /* ---------------- hashIndex[] ---------------- */
-  if (!(P.flags & H10X_FLAG_NO_TABLE))
+  if (!(P.flags & H10X_FLAG_NO_TABLE) && c->hashValue.p)
     { StageTimer tm (c, s, ST_TABLE) ;
       size_t tableSize = (size_t) 1 << P.B ;
       c->hashIndex.alloc (tableSize, s, mt) ;
@@ -822,6 +896,188 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   st.kernelLaunches = c->launches ;
   st.peakDeviceBytes = c->mt.peak ;
   c->haveIndex = true ;
+}
+
+/* ------------------------------------------------------------------ multi-GPU tail */
+
+/* all-gather (nBlk, first word 0, last word 0, nRec, error) of every rank; the lowest rank's error, if
+   any, is thrown on every rank so that nobody is left waiting in a collective */
+static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_t mine[4], std::vector<uint32_t> &all)
+{ DistState *d = c->dist ; const int NR = d->nranks ;
+  DBuf<uint32_t> sb (5, s, &c->mt), rb ((size_t) 5 * NR, s, &c->mt) ;
+  uint32_t h[5] = { mine[0], mine[1], mine[2], mine[3], (uint32_t) localErr } ;
+  CK (cudaMemcpyAsync (sb.p, h, 20, cudaMemcpyHostToDevice, s)) ;
+  NCK (gNccl.AllGather (sb.p, rb.p, 5, ncclUint32, d->comm, s)) ;
+  std::vector<uint32_t> r ((size_t) 5 * NR) ;
+  CK (cudaMemcpyAsync (r.data (), rb.p, 20 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  all.resize ((size_t) 4 * NR) ;
+  for (int i = 0 ; i < NR ; ++i)
+    { for (int j = 0 ; j < 4 ; ++j) all[4*i + j] = r[5*i + j] ;
+      if (r[5*i + 4])
+	throw H10xError ((int) r[5*i + 4], std::string (h10x_strerror ((int) r[5*i + 4])) + " (rank " + std::to_string (i) + ")") ;
+    }
+}
+
+static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
+		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal)
+{
+  DistState *d = c->dist ; const int R = d->rank, NR = d->nranks ;
+  MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
+  StageTimer tm (c, s, ST_BINIDS) ;
+  d->nLocalBins = Dl ;
+
+  /* 1. rank-distinct hashes */
+  DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
+  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, dHash.p, dDepth.p, dFirst.p) ;
+
+  /* 2. owner = hash range: thresholds ceil (o * 2^(2k) / NR), monotone so the reference id order composes */
+  std::vector<uint64_t> thr ((size_t) NR + 1) ;
+  for (int o = 0 ; o <= NR ; ++o)
+    { unsigned __int128 t = ((unsigned __int128) o << (2 * P.k)) + (unsigned) (NR - 1) ; thr[o] = (uint64_t) (t / (unsigned) NR) ; }
+  DBuf<uint64_t> dThr ((size_t) NR + 1, s, mt), dSendOff ((size_t) NR + 1, s, mt) ;
+  CK (cudaMemcpyAsync (dThr.p, thr.data (), 8 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
+  LAUNCH (c, k_lower_bounds, 1, 64, 0, s, dHash.p, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
+  std::vector<uint64_t> sendOff ((size_t) NR + 1) ;
+  CK (cudaMemcpyAsync (sendOff.data (), dSendOff.p, 8 * ((size_t) NR + 1), cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  sendOff[0] = 0 ; sendOff[NR] = Dl ;
+
+  /* 3. counts */
+  std::vector<uint64_t> sendCnt (NR), cntMat ((size_t) NR * NR) ;
+  for (int o = 0 ; o < NR ; ++o) sendCnt[o] = sendOff[o+1] - sendOff[o] ;
+  DBuf<uint64_t> dCnt (NR, s, mt), dMat ((size_t) NR * NR, s, mt) ;
+  CK (cudaMemcpyAsync (dCnt.p, sendCnt.data (), 8 * (size_t) NR, cudaMemcpyHostToDevice, s)) ;
+  NCK (gNccl.AllGather (dCnt.p, dMat.p, NR, ncclUint64, d->comm, s)) ;
+  CK (cudaMemcpyAsync (cntMat.data (), dMat.p, 8 * (size_t) NR * NR, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  std::vector<uint64_t> recvCnt (NR), recvOff ((size_t) NR + 1, 0) ;
+  for (int r = 0 ; r < NR ; ++r) { recvCnt[r] = cntMat[(size_t) r * NR + R] ; recvOff[r+1] = recvOff[r] + recvCnt[r] ; }
+  const uint64_t Ro64 = recvOff[NR] ;
+  if (Ro64 >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 rank-distinct hashes for one owner") ;
+  const uint32_t Ro = (uint32_t) Ro64 ;
+
+  /* 4. all-to-all-v of (hash, depth, first block) to the hash-range owners */
+  DBuf<uint64_t> rHash (Ro, s, mt) ; DBuf<uint32_t> rDepth (Ro, s, mt), rFirst (Ro, s, mt) ;
+  NCK (gNccl.GroupStart ()) ;
+  for (int peer = 0 ; peer < NR ; ++peer)
+    { if (sendCnt[peer])
+	{ NCK (gNccl.Send (dHash.p + sendOff[peer], sendCnt[peer], ncclUint64, peer, d->comm, s)) ;
+	  NCK (gNccl.Send (dDepth.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	  NCK (gNccl.Send (dFirst.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	}
+      if (recvCnt[peer])
+	{ NCK (gNccl.Recv (rHash.p + recvOff[peer], recvCnt[peer], ncclUint64, peer, d->comm, s)) ;
+	  NCK (gNccl.Recv (rDepth.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	  NCK (gNccl.Recv (rFirst.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	}
+    }
+  NCK (gNccl.GroupEnd ()) ;
+  dHash.release () ; dDepth.release () ; dFirst.release () ;
+
+  /* 5. owner merge: depth = sum, first block = min over the (at most NR) copies of a hash */
+  const uint32_t nB2 = nBlkGlobal + 2 ;
+  uint32_t Do = 0 ;
+  DBuf<uint64_t> gHash ; DBuf<uint32_t> gDepth, gFirst, oi (Ro, s, mt), oSegIncl (Ro, s, mt) ;
+  DBuf<uint32_t> newCnt (nB2, s, mt) ;
+  CK (cudaMemsetAsync (newCnt.p, 0, 4 * (size_t) nB2, s)) ;
+  if (Ro)
+    { DBuf<uint64_t> oh (Ro, s, mt) ;
+      DBuf<uint32_t> iota (Ro, s, mt), head (Ro, s, mt), oSegStart, dummy (Ro, s, mt) ;
+      LAUNCH (c, k_iota, gridFor (Ro, 256), 256, 0, s, iota.p, (uint64_t) Ro) ;
+      cubCall (c, s, [&] (void *t, size_t &b)
+	{ return cub::DeviceRadixSort::SortPairs (t, b, rHash.p, oh.p, iota.p, oi.p, Ro, 0, 2 * P.k, s) ; }) ;
+      LAUNCH (c, k_head_flag, gridFor (Ro, 256), 256, 0, s, oh.p, (uint64_t) Ro, head.p) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, head.p, oSegIncl.p, Ro, s) ; }) ;
+      CK (cudaMemcpyAsync (&Do, oSegIncl.p + (Ro - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      oSegStart.alloc ((size_t) Do + 1, s, mt) ;
+      LAUNCH (c, k_seg_start, gridFor (Ro, 256), 256, 0, s, head.p, oSegIncl.p, (uint64_t) Ro, oi.p, oSegStart.p, dummy.p) ;
+      gHash.alloc (Do, s, mt) ; gDepth.alloc (Do, s, mt) ; gFirst.alloc (Do, s, mt) ;
+      LAUNCH (c, k_owner_merge, gridFor (Do, 256), 256, 0, s, Do, oSegStart.p, oh.p, oi.p, rDepth.p, rFirst.p,
+	      gHash.p, gDepth.p, gFirst.p, newCnt.p) ;
+    }
+  rHash.release () ; rDepth.release () ; rFirst.release () ;
+
+  /* 6. global id bases from every owner's per-block new-hash counts */
+  DBuf<uint32_t> newMat ((size_t) NR * nB2, s, mt), colSum (nB2, s, mt), below (nB2, s, mt), prefixAll (nB2, s, mt) ;
+  NCK (gNccl.AllGather (newCnt.p, newMat.p, nB2, ncclUint32, d->comm, s)) ;
+  LAUNCH (c, k_id_base, gridFor (nB2, 256), 256, 0, s, nB2, (uint32_t) NR, (uint32_t) R, newMat.p, colSum.p, below.p) ;
+  cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, colSum.p, prefixAll.p, nB2, s) ; }) ;
+  uint32_t tail[2] = { 0, 0 } ;
+  CK (cudaMemcpyAsync (&tail[0], prefixAll.p + (nB2 - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaMemcpyAsync (&tail[1], colSum.p + (nB2 - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  Dglobal = tail[0] + tail[1] ;
+  if ((uint64_t) Dglobal + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149, the same on every rank */
+    throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+  c->hashNumber = Dglobal + 1 ;
+
+  /* 7. ids of this owner's hashes: order by (first block, hash) = stable sort by first block of the
+	hash-sorted list; then the id of every received copy */
+  DBuf<uint32_t> gId (Do, s, mt), ans (Ro, s, mt) ;
+  if (Do)
+    { DBuf<uint32_t> iota (Do, s, mt), sf (Do, s, mt), sg (Do, s, mt), headPos (Do, s, mt), groupStart (Do, s, mt) ;
+      int bits = 1 ; while (((uint64_t) 1 << bits) < nB2) ++bits ;
+      LAUNCH (c, k_iota, gridFor (Do, 256), 256, 0, s, iota.p, (uint64_t) Do) ;
+      cubCall (c, s, [&] (void *t, size_t &b)
+	{ return cub::DeviceRadixSort::SortPairs (t, b, gFirst.p, sf.p, iota.p, sg.p, Do, 0, bits, s) ; }) ;
+      LAUNCH (c, k_group_head, gridFor (Do, 256), 256, 0, s, sf.p, Do, headPos.p) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveScan (t, b, headPos.p, groupStart.p, MaxOp (), Do, s) ; }) ;
+      LAUNCH (c, k_owner_ids, gridFor (Do, 256), 256, 0, s, Do, sf.p, sg.p, groupStart.p, prefixAll.p, below.p, gId.p) ;
+      LAUNCH (c, k_answer_ids, gridFor (Ro, 256), 256, 0, s, Ro, oSegIncl.p, oi.p, gId.p, ans.p) ;
+    }
+
+  /* 8. reverse all-to-all-v: the bin id of every rank-distinct hash, in the order it was sent */
+  c->localBinId.alloc (Dl, s, mt) ;
+  NCK (gNccl.GroupStart ()) ;
+  for (int peer = 0 ; peer < NR ; ++peer)
+    { if (recvCnt[peer]) NCK (gNccl.Send (ans.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+      if (sendCnt[peer]) NCK (gNccl.Recv (c->localBinId.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+    }
+  NCK (gNccl.GroupEnd ()) ;
+  if (H) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
+
+  /* 9. (id, hash, depth) of every bin to rank 0, which owns hashValue / hashDepth / hashIndex */
+  std::vector<uint64_t> mine2 = { Do, H }, all2 ((size_t) 2 * NR) ;
+  DBuf<uint64_t> d2 (2, s, mt), dAll2 ((size_t) 2 * NR, s, mt) ;
+  CK (cudaMemcpyAsync (d2.p, mine2.data (), 16, cudaMemcpyHostToDevice, s)) ;
+  NCK (gNccl.AllGather (d2.p, dAll2.p, 2, ncclUint64, d->comm, s)) ;
+  CK (cudaMemcpyAsync (all2.data (), dAll2.p, 16 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  d->nHashesGlobal = 0 ;
+  for (int r = 0 ; r < NR ; ++r) d->nHashesGlobal += all2[2*r + 1] ;
+  DBuf<uint32_t> tId, tDepth ; DBuf<uint64_t> tHash ;
+  if (R == 0)
+    { tId.alloc (Dglobal, s, mt) ; tDepth.alloc (Dglobal, s, mt) ; tHash.alloc (Dglobal, s, mt) ;
+      c->hashValue.alloc ((size_t) Dglobal + 1, s, mt) ; c->hashDepth.alloc ((size_t) Dglobal + 2, s, mt) ;
+      CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+      CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+      CK (cudaMemsetAsync (c->hashDepth.p + Dglobal + 1, 0, 4, s)) ;
+    }
+  NCK (gNccl.GroupStart ()) ;
+  if (Do)
+    { NCK (gNccl.Send (gId.p, Do, ncclUint32, 0, d->comm, s)) ;
+      NCK (gNccl.Send (gHash.p, Do, ncclUint64, 0, d->comm, s)) ;
+      NCK (gNccl.Send (gDepth.p, Do, ncclUint32, 0, d->comm, s)) ;
+    }
+  if (R == 0)
+    { uint64_t off = 0 ;
+      for (int r = 0 ; r < NR ; ++r)
+	{ uint64_t n = all2[2*r] ;
+	  if (n)
+	    { NCK (gNccl.Recv (tId.p + off, n, ncclUint32, r, d->comm, s)) ;
+	      NCK (gNccl.Recv (tHash.p + off, n, ncclUint64, r, d->comm, s)) ;
+	      NCK (gNccl.Recv (tDepth.p + off, n, ncclUint32, r, d->comm, s)) ;
+	    }
+	  off += n ;
+	}
+    }
+  NCK (gNccl.GroupEnd ()) ;
+  if (R == 0 && Dglobal)
+    LAUNCH (c, k_scatter_bins, gridFor (Dglobal, 256), 256, 0, s, Dglobal, tId.p, tHash.p, tDepth.p, c->hashValue.p, c->hashDepth.p) ;
+  CK (cudaStreamSynchronize (s)) ;	/* sends read gId/gHash/gDepth, freed on return */
 }
 
 /* ------------------------------------------------------------------ slab sizing / retry */
@@ -935,6 +1191,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
 { if (!c) return ;
   cudaSetDevice (c->P.device) ;
   if (c->own) cudaStreamSynchronize (c->own) ;
+  if (c->dist) { if (c->dist->comm) gNccl.CommDestroy (c->dist->comm) ; delete c->dist ; c->dist = nullptr ; }
   slab_free (c) ;
   for (auto e : c->evPool) cudaEventDestroy (e) ;
   for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
@@ -1079,6 +1336,66 @@ void *h10x_host_alloc (size_t bytes)
 { void *p = nullptr ; if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError () ; return nullptr ; } return p ; }
 
 void h10x_host_free (void *p) { if (p) cudaFreeHost (p) ; }
+
+int h10x_dist_unique_id (void *id128, char *err, size_t errlen)
+{ if (!id128) return H10X_ERR_BAD_PARAM ;
+  return guarded (err, errlen, [&] ()
+    { std::string why ;
+      if (!gNccl.load (why)) throw H10xError (H10X_ERR_UNSUPPORTED, why) ;
+      ncclUniqueId id ;
+      NCK (gNccl.GetUniqueId (&id)) ;
+      memcpy (id128, &id, sizeof (id)) ;
+    }) ;
+}
+
+int h10x_dist_init (h10x_ctx *c, int rank, int nranks, const void *id128, char *err, size_t errlen)
+{ if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_err (err, errlen, "bad rank / nranks") ; return H10X_ERR_BAD_PARAM ; }
+  return guarded (err, errlen, [&] ()
+    { std::string why ;
+      if (!gNccl.load (why)) throw H10xError (H10X_ERR_UNSUPPORTED, why) ;
+      CK (cudaSetDevice (c->P.device)) ;
+      if (!c->dist) c->dist = new DistState () ;
+      if (c->dist->comm) { gNccl.CommDestroy (c->dist->comm) ; c->dist->comm = nullptr ; }
+      ncclUniqueId id ; memcpy (&id, id128, sizeof (id)) ;
+      NCK (gNccl.CommInitRank (&c->dist->comm, nranks, id, rank)) ;
+      c->dist->rank = rank ; c->dist->nranks = nranks ;
+    }) ;
+}
+
+int h10x_gpu_build_device_dist (h10x_ctx *c, const void *d_fqb, uint64_t nRecords, void *stream, char *err, size_t errlen)
+{ if (!c || !c->dist || !c->dist->comm) { set_err (err, errlen, "h10x_dist_init has not been called") ; return H10X_ERR_BAD_PARAM ; }
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = stream ? (cudaStream_t) stream : c->own ;
+      /* the slab is sized generously up front: a retry after SlabFull would have to be collective */
+      size_t est = slab_estimate (c->P, nRecords, false) ;
+      est += est / 2 + ((size_t) 8 * c->dist->nranks << 22) ;
+      if (c->mt.cap < est) { reset_result (c) ; slab_resize (c, est) ; }
+      try { build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s, true, true) ; }
+      catch (const SlabFull &f)
+	{ throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ; }
+    }) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (stream ? (cudaStream_t) stream : c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
+  return st ;
+}
+
+int h10x_gpu_dist_info (h10x_ctx *c, h10x_dist_info *out)
+{ if (!c || !out || !c->dist) return H10X_ERR_BAD_PARAM ;
+  memset (out, 0, sizeof (*out)) ;
+  out->rank = c->dist->rank ; out->nranks = c->dist->nranks ;
+  out->blockBase = c->dist->blockBase ; out->nBlocksGlobal = c->dist->nBlocksGlobal ;
+  out->nReadsGlobal = c->dist->nReadsGlobal ; out->nHashesGlobal = c->dist->nHashesGlobal ;
+  out->nLocalBins = c->dist->nLocalBins ;
+  out->localBinId = c->localBinId.p ; out->localCodeOff = c->localCodeOff.p ; out->localCodes = c->localCodes.p ;
+  return H10X_OK ;
+}
+
+int h10x_gpu_memcpy_d2h (h10x_ctx *c, void *dst, const void *src, size_t bytes)
+{ if (!c || (!dst && bytes) || (!src && bytes)) return H10X_ERR_BAD_PARAM ;
+  if (cudaSetDevice (c->P.device) != cudaSuccess) return H10X_ERR_CUDA ;
+  if (bytes && cudaMemcpy (dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError () ; return H10X_ERR_CUDA ; }
+  return H10X_OK ;
+}
 
 int h10x_gpu_record_moshes (h10x_ctx *c, const void *fqb, uint64_t nRecords, uint64_t *outOff, uint64_t *outHash,
 			    uint64_t cap, char *err, size_t errlen)

@@ -144,6 +144,34 @@ void h10x_index_free (h10x_index *ix) ;
 void *h10x_host_alloc (size_t bytes) ;
 void h10x_host_free (void *p) ;
 
+/* ---- multi-GPU (new; the reference is single-process): one context per GPU, NCCL over NVLink ----
+   Ranks own consecutive barcode-run ranges of the data set, cut at run boundaries.  After
+   h10x_gpu_build_device_dist every rank holds its blocks' table and ClusterHash lists with GLOBAL bin
+   ids and its part of every bin's barcode list; rank 0 also holds hashValue / hashDepth / hashIndex.
+   -N must be 0 and no record may carry the all-A barcode word 0 (the chunk-boundary quirk of
+   hash10x.c:212 depends on global record positions). */
+#define H10X_DIST_ID_BYTES 128
+typedef struct h10x_dist_info {
+  int32_t rank, nranks ;
+  uint32_t blockBase ;		/* global number of this rank's local block b is blockBase + b */
+  uint32_t nBlocksGlobal ;	/* barcode runs over all ranks */
+  uint64_t nReadsGlobal, nHashesGlobal ;
+  uint32_t nLocalBins, reserved ;
+  const uint32_t *localBinId ;	/* device: bin id of each rank-distinct hash (ascending hash order) */
+  const uint32_t *localCodeOff ;	/* device: nLocalBins + 1 offsets into localCodes */
+  const uint32_t *localCodes ;	/* device: this rank's (global) block numbers of each bin, ascending */
+} h10x_dist_info ;
+
+/* rank 0 creates the NCCL unique id; the caller ships the 128 bytes to the other ranks (torch.distributed,
+   MPI, a file ...); every rank then joins with h10x_dist_init (collective) */
+int h10x_dist_unique_id (void *id128, char *err, size_t errlen) ;
+int h10x_dist_init (h10x_ctx *ctx, int rank, int nranks, const void *id128, char *err, size_t errlen) ;
+/* collective over all ranks; d_fqb holds this rank's records */
+int h10x_gpu_build_device_dist (h10x_ctx *ctx, const void *d_fqb, uint64_t nRecords, void *stream,
+				char *err, size_t errlen) ;
+int h10x_gpu_dist_info (h10x_ctx *ctx, h10x_dist_info *out) ;
+int h10x_gpu_memcpy_d2h (h10x_ctx *ctx, void *dst, const void *src, size_t bytes) ;
+
 /* moshes of each record without the index build (the K1 stage alone), for parity tests of
    seqhash.c:154-195: outCount[i] = number of moshes of record i in generation order, written to
    outHash[outOff[i]..]; arrays are HOST memory, outOff has nRecords+1 entries. */
