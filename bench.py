@@ -197,24 +197,37 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    # --- synthetic FQB generated in HBM (each rank its own barcode range of the data set) ---
+    # --- synthetic FQB generated in HBM: ONE data set (same genome), each rank a contiguous barcode range ---
+    from hash10x_b200 import shard
     synth = C.CDLL(os.path.join(ROOT, "hash10x_b200", "libh10xsynth.so"))
     synth.synth_layout_host.restype = C.c_uint64
     synth.synth_fqb_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
-    p = synth_params(orc, wl, seed=3 + rank)
+    p = synth_params(orc, wl, seed=3)
     if args.pairs:
         mean = (wl["pairs_min"] + wl["pairs_max"]) / 2
         p.nBarcodes = max(2, int(args.pairs / mean))
+    p.nBarcodes *= world                     # weak scaling: the per-GPU share stays fixed
     off = np.zeros(p.nBarcodes + 1, np.uint64)
-    n_rec = int(synth.synth_layout_host(C.byref(p), off.ctypes.data_as(C.c_void_p)))
+    synth.synth_layout_host(C.byref(p), off.ctypes.data_as(C.c_void_p))
+    cut = shard.plan_shards(off, world)
+    r0, r1 = shard.shard_records(off, cut, rank)
+    n_rec = r1 - r0
     fqb = torch.empty(n_rec * 30, dtype=torch.int32, device=dev)
-    st = synth.synth_fqb_device(C.byref(p), off.ctypes.data_as(C.c_void_p), 0, n_rec, fqb.data_ptr(), None)
+    st = synth.synth_fqb_device(C.byref(p), off.ctypes.data_as(C.c_void_p), r0, r1, fqb.data_ptr(), None)
     if st:
         raise RuntimeError("synthetic generator failed: cuda error %d" % st)
     torch.cuda.synchronize()
 
     g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local)
     stream = torch.cuda.current_stream()
+    if world > 1:
+        g.dist_init(rank, world, shard.share_unique_id(dist, rank, hash10x_b200.Hash10xGPU.dist_unique_id))
+
+    def build_resident():
+        if world > 1:
+            g.build_device_dist(fqb.data_ptr(), n_rec, stream.cuda_stream)
+        else:
+            g.build_device(fqb.data_ptr(), n_rec, stream.cuda_stream)
 
     def barrier():
         if dist is not None:
@@ -225,7 +238,7 @@ def run_ours(args, wl):
     sampler = ClockSampler(local, enabled=not args.no_clocks)
     sampler.start()
     for _ in range(args.warmup):
-        g.build_device(fqb.data_ptr(), n_rec, stream.cuda_stream)
+        build_resident()
     barrier()
     sampler.window()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -233,7 +246,7 @@ def run_ours(args, wl):
     launches = 0
     e0.record(stream)
     for _ in range(args.steps):
-        g.build_device(fqb.data_ptr(), n_rec, stream.cuda_stream)
+        build_resident()
         s = g.stats()
         launches += s["kernelLaunches"]
         for k_, v in s["msStage"].items():
@@ -243,15 +256,7 @@ def run_ours(args, wl):
     clocks = sampler.summary()
     ms = e0.elapsed_time(e1)
     stats = g.stats()
-    t = torch.tensor([ms, float(n_rec)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, total_pairs = float(tmax[0]), float(tsum[1])
-    else:
-        total_pairs = float(n_rec)
+    ms, total_pairs = shard.job_time_and_units(dist, torch, ms, n_rec, dev)
     ms_step = ms / args.steps
     value = total_pairs / (ms_step * 1e-3)
 
@@ -265,11 +270,16 @@ def run_ours(args, wl):
         del fqb
         torch.cuda.empty_cache()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        g.build_host_ptr(host, n_rec, want_index=False)          # warm-up (pinned arena allocation)
+        def build_e2e():
+            if world > 1:
+                g.build_host_dist_ptr(host, n_rec)
+            else:
+                g.build_host_ptr(host, n_rec, want_index=False)
+        build_e2e()                                               # warm-up (pinned arena allocation)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            g.build_host_ptr(host, n_rec, want_index=False)
+            build_e2e()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         td = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -278,10 +288,15 @@ def run_ours(args, wl):
         dt = float(td[0]) / e2e_steps
         s = g.stats()
         hn, H, nbm = s["nBins"] + 1, s["nHashes"], s["nBlocks"] + 1
-        d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H + 8 * (hn + 1) + 4 * H
+        if world == 1:
+            d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H + 8 * (hn + 1) + 4 * H
+        else:       # rank 0: table + values + depths + its blocks and ClusterHash lists (hash->code parts stay resident)
+            d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H
         e2e = {"value": total_pairs / dt, "unit": "read pairs/s", "h2d_bytes_per_step": n_rec * 120,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "h10x_gpu_build_host (include/h10x_gpu.h): pinned host FQB -> index arrays in pinned host memory"}
+               "bytes_are": "rank 0's, per step",
+               "api": ("h10x_gpu_build_host" if world == 1 else "h10x_gpu_build_host_dist") +
+                      " (include/h10x_gpu.h): pinned host FQB -> index arrays in pinned host memory"}
         del host_t
 
     if rank != 0:
@@ -326,7 +341,9 @@ def run_ours(args, wl):
             "config": {"workload": wl["desc"] + (" (cut to %d pairs per GPU by --pairs)" % n_rec if args.pairs else ""),
                        "pairs_per_gpu": n_rec, "barcodes_per_gpu": int(nB), "B": wl["B"], "k": 21, "w": 31,
                        "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % (n_rec * 120 / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else "barcode-range shards, one index per rank"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       "%d ranks: barcode-range shards, NCCL all-to-all-v of rank-distinct hashes to hash-range owners, "
+                       "global bin ids; hashValue/hashDepth/hashIndex on rank 0" % world},
             "roofline": roofline, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items() if v},

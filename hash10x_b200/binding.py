@@ -96,6 +96,7 @@ def load_library():
     L.h10x_dist_unique_id.argtypes = [vp, cp, sz]
     L.h10x_dist_init.argtypes = [vp, C.c_int, C.c_int, vp, cp, sz]
     L.h10x_gpu_build_device_dist.argtypes = [vp, vp, u64, vp, cp, sz]
+    L.h10x_gpu_build_host_dist.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_dist_info.argtypes = [vp, C.POINTER(CDistInfo)]
     L.h10x_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
@@ -249,6 +250,13 @@ class Hash10xGPU:
     def build_device_dist(self, dev_ptr, n_records, stream=0):
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_build_device_dist(self.ctx, dev_ptr, n_records, stream, err, len(err)), err)
+
+    def build_host_dist_ptr(self, ptr, n):
+        """collective; this rank's records in host memory -> (hashNumber, nHashes, nBlocksMax)"""
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_build_host_dist(self.ctx, ptr, n, C.byref(ci), err, len(err)), err)
+        return ci.hashNumber, ci.nHashes, ci.nBlocksMax
 
     def dist_info(self, download=True):
         di = CDistInfo()

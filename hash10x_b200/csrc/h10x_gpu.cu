@@ -1379,6 +1379,27 @@ int h10x_gpu_build_device_dist (h10x_ctx *c, const void *d_fqb, uint64_t nRecord
   return st ;
 }
 
+int h10x_gpu_build_host_dist (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_index *out, char *err, size_t errlen)
+{ if (!c || !out || (!fqb && nRecords) || !c->dist || !c->dist->comm) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      size_t est = slab_estimate (c->P, nRecords, true) ;
+      est += est / 2 + ((size_t) 8 * c->dist->nranks << 22) ;
+      if (c->mt.cap < est) { reset_result (c) ; slab_resize (c, est) ; }
+      reset_result (c) ;
+      try
+	{ DBuf<uint32_t> d ((size_t) nRecords * H10X_REC_WORDS, s, &c->mt) ;
+	  if (nRecords) CK (cudaMemcpyAsync (d.p, fqb, (size_t) nRecords * 120, cudaMemcpyHostToDevice, s)) ;
+	  build_device_impl (c, d.p, nRecords, s, false, true) ;
+	}
+      catch (const SlabFull &f)
+	{ throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ; }
+    }) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
+  return h10x_gpu_download (c, out, err, errlen) ;
+}
+
 int h10x_gpu_dist_info (h10x_ctx *c, h10x_dist_info *out)
 { if (!c || !out || !c->dist) return H10X_ERR_BAD_PARAM ;
   memset (out, 0, sizeof (*out)) ;

@@ -169,6 +169,9 @@ int h10x_dist_init (h10x_ctx *ctx, int rank, int nranks, const void *id128, char
 /* collective over all ranks; d_fqb holds this rank's records */
 int h10x_gpu_build_device_dist (h10x_ctx *ctx, const void *d_fqb, uint64_t nRecords, void *stream,
 				char *err, size_t errlen) ;
+/* the same with this rank's records in HOST memory: H2D, collective build, D2H of this rank's arrays */
+int h10x_gpu_build_host_dist (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x_index *out,
+			      char *err, size_t errlen) ;
 int h10x_gpu_dist_info (h10x_ctx *ctx, h10x_dist_info *out) ;
 int h10x_gpu_memcpy_d2h (h10x_ctx *ctx, void *dst, const void *src, size_t bytes) ;
 
