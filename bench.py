@@ -245,9 +245,14 @@ def run_ours(args, wl):
     stage_ms = {}
     launches = 0
     e0.record(stream)
+    lib_ms = 0.0
     for _ in range(args.steps):
+        t_py = time.perf_counter()
         build_resident()
+        if os.environ.get("H10X_TRACE"):
+            print("py-trace build call %.3f ms" % ((time.perf_counter() - t_py) * 1e3), file=sys.stderr)
         s = g.stats()
+        lib_ms += s["msTotal"]
         launches += s["kernelLaunches"]
         for k_, v in s["msStage"].items():
             stage_ms[k_] = stage_ms.get(k_, 0.0) + v
@@ -345,7 +350,7 @@ def run_ours(args, wl):
                        "%d ranks: barcode-range shards, NCCL all-to-all-v of rank-distinct hashes to hash-range owners, "
                        "global bin ids; hashValue/hashDepth/hashIndex on rank 0" % world},
             "roofline": roofline, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "lib_ms_per_step": lib_ms / args.steps,
             "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items() if v},
             "counts": {"pairs": R, "moshes": M, "block_unique_hashes": H, "bins": D, "blocks": nB,
                        "peak_device_bytes": stats["peakDeviceBytes"]}}

@@ -119,6 +119,7 @@ struct h10x_ctx {
   std::vector<Span> spans ;
   uint64_t launches = 0 ;
   /* multi-GPU (h10x_dist.cuh) */
+  bool slabClamped = false ;	/* the slab already takes all free device memory */
   struct DistState *dist = nullptr ;
   DBuf<uint32_t> localBinId, localCodeOff, localCodes ;	/* this rank's part of the hash->code lists */
   /* pinned host arena reused by h10x_gpu_download (one slot per index array) */
@@ -1093,15 +1094,16 @@ static void slab_resize (h10x_ctx *c, size_t want)
   size_t freeB = 0, totalB = 0 ;
   CK (cudaMemGetInfo (&freeB, &totalB)) ;
   size_t limit = freeB - std::min<size_t> (freeB / 50, (size_t) 512 << 20) ;	/* leave a little headroom */
-  if (want > limit) want = limit ;
-  want &= ~(size_t) 511 ;
+  want = (want + 511) & ~(size_t) 511 ;
+  if (want > limit) want = limit & ~(size_t) 511 ;
+  c->slabClamped = (want >= (limit & ~(size_t) 511)) ;
   CK (cudaMalloc ((void**) &c->mt.base, want)) ;
   c->mt.cap = want ; c->mt.reset () ;
 }
 
 /* run `body` (a complete build) inside the slab, growing the slab and re-running when it is too small */
 template <class F> static void with_slab (h10x_ctx *c, cudaStream_t s, size_t estimate, F body)
-{ if (c->mt.cap < estimate) { reset_result (c) ; slab_resize (c, estimate) ; }
+{ if (c->mt.cap < estimate && !c->slabClamped) { reset_result (c) ; slab_resize (c, estimate) ; }
   for (int attempt = 0 ; ; ++attempt)
     { try { body () ; return ; }
       catch (const SlabFull &f)
@@ -1116,7 +1118,9 @@ template <class F> static void with_slab (h10x_ctx *c, cudaStream_t s, size_t es
 }
 
 static size_t slab_estimate (const h10x_params &P, uint64_t nRec, bool withFqb)
-{ return (size_t) 420 * nRec + ((P.flags & H10X_FLAG_NO_TABLE) ? 0 : ((size_t) 4 << P.B)) + (withFqb ? 120 * nRec : 0)
+{ /* never more than the device can give: slab_resize clamps to free memory, and a clamped slab must
+     not look "too small" again on the next call */
+  return (size_t) 420 * nRec + ((P.flags & H10X_FLAG_NO_TABLE) ? 0 : ((size_t) 4 << P.B)) + (withFqb ? 120 * nRec : 0)
     + ((size_t) 64 << 20) ;
 }
 
@@ -1201,6 +1205,8 @@ void h10x_gpu_destroy (h10x_ctx *c)
 
 int h10x_gpu_build_device (h10x_ctx *c, const void *d_fqb, uint64_t nRecords, void *stream, char *err, size_t errlen)
 { if (!c) { set_err (err, errlen, "null context") ; return H10X_ERR_BAD_PARAM ; }
+  HostTrace apiTrace ;
+  struct Done { HostTrace &t ; ~Done () { t.mark ("api-total") ; } } done { apiTrace } ;
   int st = guarded (err, errlen, [&] ()
     { CK (cudaSetDevice (c->P.device)) ;
       cudaStream_t s = stream ? (cudaStream_t) stream : c->own ;
@@ -1370,7 +1376,7 @@ int h10x_gpu_build_device_dist (h10x_ctx *c, const void *d_fqb, uint64_t nRecord
       /* the slab is sized generously up front: a retry after SlabFull would have to be collective */
       size_t est = slab_estimate (c->P, nRecords, false) ;
       est += est / 2 + ((size_t) 8 * c->dist->nranks << 22) ;
-      if (c->mt.cap < est) { reset_result (c) ; slab_resize (c, est) ; }
+      if (c->mt.cap < est && !c->slabClamped) { reset_result (c) ; slab_resize (c, est) ; }
       try { build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s, true, true) ; }
       catch (const SlabFull &f)
 	{ throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ; }
@@ -1386,7 +1392,7 @@ int h10x_gpu_build_host_dist (h10x_ctx *c, const void *fqb, uint64_t nRecords, h
       cudaStream_t s = c->own ;
       size_t est = slab_estimate (c->P, nRecords, true) ;
       est += est / 2 + ((size_t) 8 * c->dist->nranks << 22) ;
-      if (c->mt.cap < est) { reset_result (c) ; slab_resize (c, est) ; }
+      if (c->mt.cap < est && !c->slabClamped) { reset_result (c) ; slab_resize (c, est) ; }
       reset_result (c) ;
       try
 	{ DBuf<uint32_t> d ((size_t) nRecords * H10X_REC_WORDS, s, &c->mt) ;
