@@ -65,12 +65,12 @@ struct DistState {
 
 /* rank-distinct hashes from the sorted entries: value, number of local blocks, first (global) block */
 __global__ void k_local_distinct (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sh,
-				  const uint32_t *__restrict__ se, const uint32_t *__restrict__ entryBlk,
+				  const uint32_t *__restrict__ se, const uint32_t *__restrict__ entryBlk, uint64_t wMul,
 				  uint64_t *__restrict__ dHash, uint32_t *__restrict__ dDepth, uint32_t *__restrict__ dFirst)
 { uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
   if (s >= nSeg) return ;
   uint32_t i = segStart[s] ;
-  dHash[s] = sh[i] ; dDepth[s] = segStart[s+1] - i ; dFirst[s] = entryBlk[se[i]] ;
+  dHash[s] = sh[i] * wMul ; dDepth[s] = segStart[s+1] - i ; dFirst[s] = entryBlk[se[i]] ;
 }
 
 /* off[o] = first index whose hash >= thr[o] (hashes ascending); one thread per threshold */

@@ -168,13 +168,15 @@ k_fused_block (FusedArgs a, HashParams hp)
 	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi = (Whi >> c) & HMASK ;
 	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi = (WRhi >> (2 * j)) & HMASK ;
 	      if (kk <= 16) { hhi = 0 ; rhi = 0 ; if (c >= 32) hlo = (Whi >> (c - 32)) & LMASK ; }
-	      uint64_t pf = h10x_mul64 (hlo, hhi, flo, fhi) & (((uint64_t) TOPHI << 32) | TOPLO) ;
-	      uint64_t pq = h10x_mul64 (rlo, rhi, flo, fhi) & (((uint64_t) TOPHI << 32) | TOPLO) ;
-	      uint64_t m = pf < pq ? pf : pq ;		/* canonical hash << SH */
+	      /* comparing the whole products orders them by their top 2k bits; when those are equal the
+		 two hashes are equal and either may be taken, so one mask after the min is enough */
+	      uint64_t pf = h10x_mul64 (hlo, hhi, flo, fhi) ;
+	      uint64_t pq = h10x_mul64 (rlo, rhi, flo, fhi) ;
+	      uint64_t m = (pf < pq ? pf : pq) & (((uint64_t) TOPHI << 32) | TOPLO) ;	/* canonical hash << SH */
 	      uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
 	      bool sel = q <= wLim ;
 	      if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
-	      if (sel) { col[(size_t) cnt * THREADS] = m | pr ; ++cnt ; }
+	      if (sel) { col[(size_t) cnt * THREADS] = m + pr ; ++cnt ; }	/* low SH bits of m are 0: + is | */
 	    }
 	}
       if (over) sBad = 1 ;
@@ -240,13 +242,14 @@ k_fused_block (FusedArgs a, HashParams hp)
 }
 
 /* Moves every block's unique list to its final place, in block order, and splits it into the
-   arrays the index stages use: eHash (hash value), eRead (read index, 16 bits: hash10x.c:37,180) and
+   arrays the index stages use: eHash (hash value DIVIDED BY w - every mosh is a multiple of w, so the
+   exact quotient hash * w^-1 mod 2^64 orders like the hash and needs log2(w) fewer radix bits), eRead (read index, 16 bits: hash10x.c:37,180) and
    entryBlk (1-based GLOBAL block number: blkBase is this rank's first block in a multi-GPU build).  One CTA per block.  Source kind by bit 63 of srcOff:
    0 = fused scratch (key = hash << sh | read, sh in bits 56..61); 1 = generic path arrays. */
 __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff, const uint32_t *__restrict__ blkCnt,
 			 const uint64_t *__restrict__ blkOff, const uint64_t *__restrict__ scratch,
 			 const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gRec,
-			 const uint32_t *__restrict__ blkStart, uint32_t blkBase,
+			 const uint32_t *__restrict__ blkStart, uint32_t blkBase, uint64_t wInvFull,
 			 uint64_t *__restrict__ eHash, uint16_t *__restrict__ eRead, uint32_t *__restrict__ entryBlk)
 { for (uint32_t blk = blockIdx.x ; blk < nProcBlk ; blk += gridDim.x)
     { uint64_t so = srcOff[blk] ;
@@ -256,7 +259,7 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	{ uint64_t off = so & 0x7fffffffffffffffull ;
 	  uint32_t r0 = blkStart[blk] ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
-	    { eHash[dst + i] = gHash[off + i] ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blkBase + blk + 1 ; }
+	    { eHash[dst + i] = gHash[off + i] * wInvFull ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blkBase + blk + 1 ; }
 	}
       else
 	{ uint32_t sh = (uint32_t) (so >> 56) ;
@@ -264,7 +267,7 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	  uint64_t rmask = ((uint64_t) 1 << sh) - 1 ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
 	    { uint64_t key = scratch[off + i] ;
-	      eHash[dst + i] = key >> sh ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blkBase + blk + 1 ;
+	      eHash[dst + i] = (key >> sh) * wInvFull ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blkBase + blk + 1 ;
 	    }
 	}
     }

@@ -15,6 +15,7 @@
 #include "../../include/h10x_gpu.h"
 #include "h10x_common.cuh"
 #include "h10x_fused.cuh"
+#include "h10x_cluster.cuh"
 
 #include <cub/cub.cuh>
 
@@ -283,14 +284,14 @@ __global__ void k_seg_start (const uint32_t *__restrict__ head, const uint32_t *
 }
 
 __global__ void k_bins (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ se,
-			const uint64_t *__restrict__ sh, const uint32_t *__restrict__ rank,
+			const uint64_t *__restrict__ sh, const uint32_t *__restrict__ rank, uint64_t wMul,
 			uint32_t *__restrict__ idOfSeg, uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
 { uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
   if (s >= nSeg) return ;
   uint32_t i = segStart[s] ;
   uint32_t id = 1u + rank[se[i]] ;
   idOfSeg[s] = id ;
-  hashValue[id] = sh[i] ;
+  hashValue[id] = sh[i] * wMul ;	/* the sort key is hash / w */
   hashDepth[id] = segStart[s+1] - i ;	/* one entry per (block, hash): hash10x.c:178 */
 }
 
@@ -434,10 +435,10 @@ static void reset_result (h10x_ctx *c)
 template <class K, class V>
 static void segmented_sort_blocks (h10x_ctx *c, cudaStream_t s, const K *kin, K *kout, const V *vin, V *vout,
 				   const std::vector<uint64_t> &hOff /* nSeg+1, host */, const uint64_t *dOff,
-				   bool stable)
+				   bool stable, size_t segFirst = 0, size_t segLast = (size_t) -1)
 {
   const uint64_t maxItems = (uint64_t) 1 << 30 ;
-  size_t nSeg = hOff.size () - 1, a = 0 ;
+  size_t nSeg = std::min (hOff.size () - 1, segLast), a = segFirst ;
   while (a < nSeg)
     { size_t b = a + 1 ;
       while (b < nSeg && hOff[b+1] - hOff[a] <= maxItems) ++b ;
@@ -472,7 +473,7 @@ struct HostTrace {
 
 static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
 		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
-		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal) ;
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul) ;
 static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_t mine[4], std::vector<uint32_t> &all) ;
 
 static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true,
@@ -740,6 +741,12 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
     }
 
   tr.mark ("generic") ;
+  /* the global sort runs on hash / w: exact division = multiplication by w^-1 mod 2^64 (w odd part) and a
+     shift (power-of-two part); quotients of multiples keep the order and need fewer radix passes */
+  const uint64_t wInvFull = c->hp.wTz ? 1 : c->hp.wInv ;
+  const uint64_t wDiv = c->hp.wTz ? 1 : (uint64_t) P.w ;
+  int sortBits = 2 * P.k ;
+  { uint64_t top = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ; sortBits = 1 ; while (sortBits < 64 && (top >> sortBits)) ++sortBits ; }
   /* -- final placement in block order: eHash / eRead / entryBlk -- */
   for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
   hBlkOff[nProcBlk] = H ;
@@ -750,7 +757,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
     if (nProcBlk)
       LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
-	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, eHash.p, eRead.p, entryBlk.p) ;
+	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, eHash.p, eRead.p, entryBlk.p) ;
     CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
   }
   scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
@@ -768,7 +775,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	LAUNCH (c, k_iota, gridFor (H, 256), 256, 0, s, iota.p, H) ;
 	/* stable LSD radix sort over the 2k hash bits: inside a bin, entries keep ascending index */
 	cubCall (c, s, [&] (void *t, size_t &b)
-	  { return cub::DeviceRadixSort::SortPairs (t, b, eHash.p, sh.p, iota.p, se.p, H, 0, 2 * P.k, s) ; }) ;
+	  { return cub::DeviceRadixSort::SortPairs (t, b, eHash.p, sh.p, iota.p, se.p, H, 0, sortBits, s) ; }) ;
       }
       { StageTimer tm (c, s, ST_BINIDS) ;
 	DBuf<uint32_t> head (H, s, mt) ;
@@ -792,7 +799,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
 	    CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
 	    CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-	    LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+	    LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, wDiv, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
 	  }
 	else
 	  { DBuf<uint32_t> isFirst (H, s, mt) ;	/* k_seg_start marks first entries; unused here */
@@ -806,7 +813,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	}
       else
 	{ uint32_t Dl = D ;
-	  dist_bins (c, s, H, sh.p, se.p, segIncl.p, Dl, segStart.p, entryBlk.p, nBlkGlobal, entryId.p, D) ;
+	  dist_bins (c, s, H, sh.p, se.p, segIncl.p, Dl, segStart.p, entryBlk.p, nBlkGlobal, entryId.p, D, wDiv) ;
 	}
     }
   else if (!dist)
@@ -816,7 +823,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
     }
   else
     { segStart.alloc (1, s, mt) ; CK (cudaMemsetAsync (segStart.p, 0, 4, s)) ;
-      dist_bins (c, s, 0, nullptr, nullptr, nullptr, 0, segStart.p, nullptr, nBlkGlobal, nullptr, D) ;
+      dist_bins (c, s, 0, nullptr, nullptr, nullptr, 0, segStart.p, nullptr, nBlkGlobal, nullptr, D, wDiv) ;
     }
 
   tr.mark ("bins-enq") ;
@@ -849,10 +856,55 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   c->clus.alloc (H, s, mt) ;
   if (H)
     { StageTimer tm (c, s, ST_CLUSTERS) ;
-      DBuf<uint16_t> rdS (H, s, mt) ;
-      DBuf<uint32_t> idS (H, s, mt) ;
-      segmented_sort_blocks<uint32_t, uint16_t> (c, s, entryId.p, idS.p, eRead.p, rdS.p, hBlkOff, blkOffProc.p, false) ;
-      LAUNCH (c, k_clus_pack, gridFor (H, 256), 256, 0, s, H, idS.p, rdS.p, c->clus.p) ;
+      struct ClusClass { uint32_t cap, threads ; } ;
+      static const ClusClass kCC[3] = { { 1024, 128 }, { 4096, 256 }, { 12288, 512 } } ;
+      int idBits = 1 ; while (((uint64_t) 1 << idBits) < (uint64_t) c->hashNumber) ++idBits ;
+      uint32_t digitBits = 8, passes = (idBits + 7) / 8 ;
+      for (uint32_t db = 9 ; db <= 10 ; ++db) if ((idBits + db - 1) / db < passes) { digitBits = db ; passes = (idBits + db - 1) / db ; }
+      std::vector<uint32_t> lists[3] ;
+      std::vector<std::pair<uint32_t, uint32_t>> bigRuns ;	/* blocks beyond the largest class */
+      for (uint32_t p = 0 ; p < nProcBlk ; ++p)
+	{ uint32_t n = hCnt[p] ; int ci = n <= kCC[0].cap ? 0 : n <= kCC[1].cap ? 1 : n <= kCC[2].cap ? 2 : -1 ;
+	  if (ci >= 0) lists[ci].push_back (p) ;
+	  else if (!bigRuns.empty () && bigRuns.back ().second == p) bigRuns.back ().second = p + 1 ;
+	  else bigRuns.push_back ({ p, p + 1 }) ;
+	}
+      int nSM = 148 ;
+      CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, P.device)) ;
+      DBuf<unsigned int> cwork (3, s, mt) ;
+      CK (cudaMemsetAsync (cwork.p, 0, 12, s)) ;
+      std::vector<DBuf<uint32_t>> dl (3) ;
+      for (int ci = 0 ; ci < 3 ; ++ci)
+	{ if (lists[ci].empty ()) continue ;
+	  const ClusClass &cc = kCC[ci] ;
+	  dl[ci].alloc (lists[ci].size (), s, mt) ;
+	  CK (cudaMemcpyAsync (dl[ci].p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
+	  const uint32_t nd = 1u << digitBits ;
+	  size_t smem = (size_t) cc.cap * 12 + 4 + (size_t) nd * 4 + (size_t) (cc.threads / 32) * nd * 2 + 16 ;
+	  const void *fn = cc.threads == 128 ? (const void*) k_cluster_sort<128> : cc.threads == 256 ? (const void*) k_cluster_sort<256>
+	    : (const void*) k_cluster_sort<512> ;
+	  CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+	  int occ = 1 ;
+	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) cc.threads, smem)) ;
+	  if (occ < 1) occ = 1 ;
+	  ClusterArgs ca ;
+	  ca.list = dl[ci].p ; ca.blkOff = blkOffProc.p ; ca.entryId = entryId.p ; ca.eRead = eRead.p ; ca.clus = c->clus.p ;
+	  ca.work = cwork.p + ci ; ca.nList = (uint32_t) lists[ci].size () ; ca.cap = cc.cap ; ca.digitBits = digitBits ; ca.passes = passes ;
+	  void *args[1] = { (void*) &ca } ;
+	  uint32_t grid = (uint32_t) std::min<size_t> (lists[ci].size (), (size_t) nSM * occ) ;
+	  CK (cudaLaunchKernel (fn, dim3 (grid), dim3 (cc.threads), args, smem, s)) ;
+	  ++c->launches ;
+	}
+      if (!bigRuns.empty ())
+	{ DBuf<uint16_t> rdS (H, s, mt) ;
+	  DBuf<uint32_t> idS (H, s, mt) ;
+	  for (auto &r : bigRuns)
+	    { segmented_sort_blocks<uint32_t, uint16_t> (c, s, entryId.p, idS.p, eRead.p, rdS.p, hBlkOff, blkOffProc.p, false, r.first, r.second) ;
+	      uint64_t a0 = hBlkOff[r.first], n = hBlkOff[r.second] - a0 ;
+	      if (n) LAUNCH (c, k_clus_pack, gridFor (n, 256), 256, 0, s, n, idS.p + a0, rdS.p + a0, c->clus.p + a0) ;
+	    }
+	}
+      CK (cudaStreamSynchronize (s)) ;	/* block lists are read by the async copies */
     }
   entryId.release () ; eRead.release () ; entryBlk.release () ;
 
@@ -922,7 +974,7 @@ static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_
 
 static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
 		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
-		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal)
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul)
 {
   DistState *d = c->dist ; const int R = d->rank, NR = d->nranks ;
   MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
@@ -931,7 +983,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 
   /* 1. rank-distinct hashes */
   DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
-  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, dHash.p, dDepth.p, dFirst.p) ;
+  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
 
   /* 2. owner = hash range: thresholds ceil (o * 2^(2k) / NR), monotone so the reference id order composes */
   std::vector<uint64_t> thr ((size_t) NR + 1) ;
