@@ -244,13 +244,15 @@ k_fused_block (FusedArgs a, HashParams hp)
 /* Moves every block's unique list to its final place, in block order, and splits it into the
    arrays the index stages use: eHash (hash value DIVIDED BY w - every mosh is a multiple of w, so the
    exact quotient hash * w^-1 mod 2^64 orders like the hash and needs log2(w) fewer radix bits), eRead (read index, 16 bits: hash10x.c:37,180) and
-   entryBlk (1-based GLOBAL block number: blkBase is this rank's first block in a multi-GPU build).  One CTA per block.  Source kind by bit 63 of srcOff:
+   entryBlk (1-based GLOBAL block number: blkBase is this rank's first block in a multi-GPU build); the
+   single-GPU tail takes the last two packed in one word, eBR = block | read << 32.  One CTA per block.  Source kind by bit 63 of srcOff:
    0 = fused scratch (key = hash << sh | read, sh in bits 56..61); 1 = generic path arrays. */
 __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff, const uint32_t *__restrict__ blkCnt,
 			 const uint64_t *__restrict__ blkOff, const uint64_t *__restrict__ scratch,
 			 const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gRec,
 			 const uint32_t *__restrict__ blkStart, uint32_t blkBase, uint64_t wInvFull,
-			 uint64_t *__restrict__ eHash, uint16_t *__restrict__ eRead, uint32_t *__restrict__ entryBlk)
+			 uint64_t *__restrict__ eHash, uint16_t *__restrict__ eRead, uint32_t *__restrict__ entryBlk,
+			 uint64_t *__restrict__ eBR)
 { for (uint32_t blk = blockIdx.x ; blk < nProcBlk ; blk += gridDim.x)
     { uint64_t so = srcOff[blk] ;
       uint32_t n = blkCnt[blk] ;
@@ -259,7 +261,11 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	{ uint64_t off = so & 0x7fffffffffffffffull ;
 	  uint32_t r0 = blkStart[blk] ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
-	    { eHash[dst + i] = gHash[off + i] * wInvFull ; eRead[dst + i] = (uint16_t) (gRec[off + i] - r0) ; entryBlk[dst + i] = blkBase + blk + 1 ; }
+	    { eHash[dst + i] = gHash[off + i] * wInvFull ;
+	      uint16_t rd = (uint16_t) (gRec[off + i] - r0) ;
+	      if (eBR) eBR[dst + i] = (uint64_t) (blkBase + blk + 1) | ((uint64_t) rd << 32) ;
+	      else { eRead[dst + i] = rd ; entryBlk[dst + i] = blkBase + blk + 1 ; }
+	    }
 	}
       else
 	{ uint32_t sh = (uint32_t) (so >> 56) ;
@@ -267,7 +273,10 @@ __global__ void k_place (uint32_t nProcBlk, const uint64_t *__restrict__ srcOff,
 	  uint64_t rmask = ((uint64_t) 1 << sh) - 1 ;
 	  for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
 	    { uint64_t key = scratch[off + i] ;
-	      eHash[dst + i] = (key >> sh) * wInvFull ; eRead[dst + i] = (uint16_t) (key & rmask) ; entryBlk[dst + i] = blkBase + blk + 1 ;
+	      eHash[dst + i] = (key >> sh) * wInvFull ;
+	      uint16_t rd = (uint16_t) (key & rmask) ;
+	      if (eBR) eBR[dst + i] = (uint64_t) (blkBase + blk + 1) | ((uint64_t) rd << 32) ;
+	      else { eRead[dst + i] = rd ; entryBlk[dst + i] = blkBase + blk + 1 ; }
 	    }
 	}
     }

@@ -279,7 +279,7 @@ __global__ void k_seg_start (const uint32_t *__restrict__ head, const uint32_t *
 			     uint32_t *__restrict__ isFirst)
 { uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
   if (i >= n) return ;
-  if (head[i]) { segStart[segIncl[i] - 1] = (uint32_t) i ; isFirst[se[i]] = 1u ; }
+  if (head[i]) { segStart[segIncl[i] - 1] = (uint32_t) i ; if (isFirst) isFirst[se[i]] = 1u ; }
   if (i == n - 1) segStart[segIncl[i]] = (uint32_t) n ;
 }
 
@@ -311,6 +311,43 @@ __global__ void k_codes (uint64_t n, const uint32_t *__restrict__ segIncl, const
   if (i >= n) return ;
   uint32_t s = segIncl[i] - 1 ;
   codes[codeOff[idOfSeg[s]] + (i - segStart[s])] = entryBlk[se[i]] ;
+}
+
+/* single-GPU tail.  Bin ids in insertion order (hash10x.c:147) = bins ordered by their first entry
+   (entries are stored in (block, hash) order): firstE[s] is sorted, the rank is the id. */
+__global__ void k_first_entry (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ se,
+			       uint32_t *__restrict__ firstE, uint32_t *__restrict__ segIdx)
+{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (s < nSeg) { firstE[s] = se[segStart[s]] ; segIdx[s] = s ; }
+}
+
+__global__ void k_bins_by_rank (uint32_t nSeg, const uint32_t *__restrict__ sortedSeg, const uint32_t *__restrict__ segStart,
+				const uint64_t *__restrict__ sh, uint64_t wMul, uint32_t *__restrict__ idOfSeg,
+				uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
+{ uint32_t r = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (r >= nSeg) return ;
+  uint32_t s = sortedSeg[r], id = r + 1u, i = segStart[s] ;
+  idOfSeg[s] = id ;
+  hashValue[id] = sh[i] * wMul ;		/* the sort key is hash / w */
+  hashDepth[id] = segStart[s+1] - i ;	/* one entry per (block, hash): hash10x.c:178 */
+}
+
+/* fillHashTable (hash10x.c:317-347) and, in the same pass, the transposed view: entry (bin id, read) laid
+   out bin-major next to its block number.  A stable sort of that by block number then yields every
+   block's ClusterHash list already ordered by bin id (hash10x.c:183) - no per-block sort, no scatter of
+   ids back to entry order. */
+__global__ void k_codes_tr (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ segStart,
+			    const uint32_t *__restrict__ idOfSeg, const uint32_t *__restrict__ se,
+			    const uint64_t *__restrict__ eBR, const uint64_t *__restrict__ codeOff,
+			    uint32_t *__restrict__ codes, uint64_t *__restrict__ idRead)
+{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= n) return ;
+  uint32_t s = segIncl[i] - 1 ;
+  uint32_t id = idOfSeg[s] ;
+  uint64_t pos = codeOff[id] + (i - segStart[s]) ;
+  uint64_t br = eBR[se[i]] ;
+  codes[pos] = (uint32_t) br ;
+  idRead[pos] = (uint64_t) id | (br & 0xffff00000000ull) ;
 }
 
 __global__ void k_clus_prep (uint64_t n, const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
@@ -752,12 +789,13 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   hBlkOff[nProcBlk] = H ;
   c->nHashes = H ;
   if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
-  DBuf<uint64_t> eHash (H, s, mt) ; DBuf<uint16_t> eRead (H, s, mt) ; DBuf<uint32_t> entryBlk (H, s, mt) ;
+  DBuf<uint64_t> eHash (H, s, mt), eBR ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk ;
+  if (dist) { eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; } else eBR.alloc (H, s, mt) ;
   { StageTimer tm (c, s, ST_DEDUP) ;
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
     if (nProcBlk)
       LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
-	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, eHash.p, eRead.p, entryBlk.p) ;
+	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, eHash.p, eRead.p, entryBlk.p, eBR.p) ;
     CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
   }
   scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
@@ -766,7 +804,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   tr.mark ("place") ;
   /* ---------------- bins: ids, values, depths ---------------- */
   uint32_t D = 0 ;
-  DBuf<uint32_t> entryId (H, s, mt) ;
+  DBuf<uint32_t> entryId ;
+  if (dist) entryId.alloc (H, s, mt) ;
   DBuf<uint32_t> se (H, s, mt), segIncl (H, s, mt), segStart, idOfSeg ;
   if (H)
     { DBuf<uint64_t> sh (H, s, mt) ;
@@ -789,29 +828,26 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)
 	      throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
 	    idOfSeg.alloc (D, s, mt) ;
-	    DBuf<uint32_t> isFirst (H, s, mt), rank (H, s, mt) ;
-	    CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
-	    LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
-	    cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, isFirst.p, rank.p, H, s) ; }) ;
+	    LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, (uint32_t*) nullptr) ;
+	    head.release () ;
+	    DBuf<uint32_t> firstE (D, s, mt), segIdx (D, s, mt), firstS (D, s, mt), sortedSeg (D, s, mt) ;
+	    LAUNCH (c, k_first_entry, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, firstE.p, segIdx.p) ;
+	    int eBits = 1 ; while (((uint64_t) 1 << eBits) < H) ++eBits ;
+	    cubCall (c, s, [&] (void *t, size_t &b)
+	      { return cub::DeviceRadixSort::SortPairs (t, b, firstE.p, firstS.p, segIdx.p, sortedSeg.p, D, 0, eBits, s) ; }) ;
 	    c->hashNumber = D + 1 ;
 	    c->hashValue.alloc ((size_t) D + 1, s, mt) ;
 	    c->hashDepth.alloc ((size_t) D + 2, s, mt) ;	/* one spare 0 so the scan yields codeOff[hashNumber] */
 	    CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
 	    CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
 	    CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-	    LAUNCH (c, k_bins, gridFor (D, 256), 256, 0, s, D, segStart.p, se.p, sh.p, rank.p, wDiv, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+	    LAUNCH (c, k_bins_by_rank, gridFor (D, 256), 256, 0, s, D, sortedSeg.p, segStart.p, sh.p, wDiv, idOfSeg.p,
+		    c->hashValue.p, c->hashDepth.p) ;
 	  }
 	else
-	  { DBuf<uint32_t> isFirst (H, s, mt) ;	/* k_seg_start marks first entries; unused here */
-	    CK (cudaMemsetAsync (isFirst.p, 0, 4 * H, s)) ;
-	    LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, isFirst.p) ;
-	  }
+	  LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, se.p, segStart.p, (uint32_t*) nullptr) ;
       }
-      if (!dist)
-	{ StageTimer tm (c, s, ST_ENTRYIDS) ;
-	  LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl.p, idOfSeg.p, se.p, entryId.p) ;
-	}
-      else
+      if (dist)
 	{ uint32_t Dl = D ;
 	  dist_bins (c, s, H, sh.p, se.p, segIncl.p, Dl, segStart.p, entryBlk.p, nBlkGlobal, entryId.p, D, wDiv) ;
 	}
@@ -839,22 +875,36 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       CK (cudaMemcpyAsync (c->localCodeOff.p, segStart.p, 4 * ((size_t) Dl + 1), cudaMemcpyDeviceToDevice, s)) ;
       if (H) LAUNCH (c, k_gather_u32, gridFor (H, 256), 256, 0, s, H, se.p, entryBlk.p, c->localCodes.p) ;
     }
-  else if (!(P.flags & H10X_FLAG_NO_CODES))
-    { StageTimer tm (c, s, ST_CODES) ;
+  else
+    { /* codes (bin-major block lists) are needed as the sort key even under H10X_FLAG_NO_CODES */
       size_t hn = c->hashNumber ;
-      c->codeOff.alloc (hn + 1, s, mt) ;
-      c->codes.alloc (H, s, mt) ;
-      cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
-      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+      DBuf<uint64_t> idRead (H, s, mt) ;
+      { StageTimer tm (c, s, ST_CODES) ;
+	c->codeOff.alloc (hn + 1, s, mt) ;
+	c->codes.alloc (H, s, mt) ;
+	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+	if (H)
+	  LAUNCH (c, k_codes_tr, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eBR.p,
+		  c->codeOff.p, c->codes.p, idRead.p) ;
+      }
+      se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; eBR.release () ;
+      c->clus.alloc (H, s, mt) ;
       if (H)
-	LAUNCH (c, k_codes, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, entryBlk.p,
-		c->codeOff.p, c->codes.p) ;
+	{ StageTimer tm (c, s, ST_CLUSTERS) ;
+	  DBuf<uint32_t> keysOut (H, s, mt) ;
+	  int bBits = 1 ; while (((uint64_t) 1 << bBits) < (uint64_t) nBlk + 2) ++bBits ;
+	  /* stable: inside a block the bin-major order, i.e. ascending bin id, is kept */
+	  cubCall (c, s, [&] (void *t, size_t &b)
+	    { return cub::DeviceRadixSort::SortPairs (t, b, c->codes.p, keysOut.p, idRead.p, c->clus.p, H, 0, bBits, s) ; }) ;
+	}
+      if (P.flags & H10X_FLAG_NO_CODES) { c->codes.release () ; c->codeOff.release () ; }
     }
   se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; entryBlk.release () ;
 
-  /* ---------------- code -> hash lists ---------------- */
-  c->clus.alloc (H, s, mt) ;
-  if (H)
+  /* ---------------- code -> hash lists (multi-GPU: ids came back per entry; sort inside each block) ---------------- */
+  if (dist) c->clus.alloc (H, s, mt) ;
+  if (dist && H)
     { StageTimer tm (c, s, ST_CLUSTERS) ;
       struct ClusClass { uint32_t cap, threads ; } ;
       static const ClusClass kCC[3] = { { 1024, 128 }, { 4096, 256 }, { 12288, 512 } } ;
@@ -1037,7 +1087,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   CK (cudaMemsetAsync (newCnt.p, 0, 4 * (size_t) nB2, s)) ;
   if (Ro)
     { DBuf<uint64_t> oh (Ro, s, mt) ;
-      DBuf<uint32_t> iota (Ro, s, mt), head (Ro, s, mt), oSegStart, dummy (Ro, s, mt) ;
+      DBuf<uint32_t> iota (Ro, s, mt), head (Ro, s, mt), oSegStart ;
       LAUNCH (c, k_iota, gridFor (Ro, 256), 256, 0, s, iota.p, (uint64_t) Ro) ;
       cubCall (c, s, [&] (void *t, size_t &b)
 	{ return cub::DeviceRadixSort::SortPairs (t, b, rHash.p, oh.p, iota.p, oi.p, Ro, 0, 2 * P.k, s) ; }) ;
@@ -1046,7 +1096,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       CK (cudaMemcpyAsync (&Do, oSegIncl.p + (Ro - 1), 4, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;
       oSegStart.alloc ((size_t) Do + 1, s, mt) ;
-      LAUNCH (c, k_seg_start, gridFor (Ro, 256), 256, 0, s, head.p, oSegIncl.p, (uint64_t) Ro, oi.p, oSegStart.p, dummy.p) ;
+      LAUNCH (c, k_seg_start, gridFor (Ro, 256), 256, 0, s, head.p, oSegIncl.p, (uint64_t) Ro, oi.p, oSegStart.p, (uint32_t*) nullptr) ;
       gHash.alloc (Do, s, mt) ; gDepth.alloc (Do, s, mt) ; gFirst.alloc (Do, s, mt) ;
       LAUNCH (c, k_owner_merge, gridFor (Do, 256), 256, 0, s, Do, oSegStart.p, oh.p, oi.p, rDepth.p, rFirst.p,
 	      gHash.p, gDepth.p, gFirst.p, newCnt.p) ;
