@@ -165,8 +165,17 @@ k_fused_block (FusedArgs a, HashParams hp)
 #pragma unroll
 	  for (int j = 0 ; j < 8 ; ++j)
 	    { const int c = SH - 2 * j ;		/* (W >> c) & mask: k-mer j, first base on top */
-	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi = (Whi >> c) & HMASK ;
-	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi = (WRhi >> (2 * j)) & HMASK ;
+	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi ;
+	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi ;
+	      if (K > 16)	/* the integer ALU pipe is the limiter: take the high fields with a multiply (FMA pipe) + one
+			   shift instead of shift + mask */
+		{ uint32_t tt, uu ;
+		  asm ("mul.lo.u32 %0, %1, %2;" : "=r" (tt) : "r" (WRhi), "r" (1u << (64 - 2 * K - 2 * j))) ;
+		  rhi = tt >> (64 - 2 * K) ;
+		  if (j == 0) hhi = Whi >> c ;	/* c = 64-2K: nothing above the field */
+		  else { asm ("mul.lo.u32 %0, %1, %2;" : "=r" (uu) : "r" (Whi), "r" (1u << (2 * j))) ; hhi = uu >> (64 - 2 * K) ; }
+		}
+	      else { hhi = (Whi >> c) & HMASK ; rhi = (WRhi >> (2 * j)) & HMASK ; }
 	      if (kk <= 16) { hhi = 0 ; rhi = 0 ; if (c >= 32) hlo = (Whi >> (c - 32)) & LMASK ; }
 	      /* comparing the whole products orders them by their top 2k bits; when those are equal the
 		 two hashes are equal and either may be taken, so one mask after the min is enough */
@@ -176,7 +185,12 @@ k_fused_block (FusedArgs a, HashParams hp)
 	      uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
 	      bool sel = q <= wLim ;
 	      if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
-	      if (sel) { col[(size_t) cnt * THREADS] = m + pr ; ++cnt ; }	/* low SH bits of m are 0: + is | */
+	      if (sel)	/* low SH bits of m are 0, so the read index simply drops in (an add, issued as IMAD: FMA pipe) */
+		{ uint32_t klo ;
+		  asm ("mad.lo.u32 %0, %1, 1, %2;" : "=r" (klo) : "r" (pr), "r" ((uint32_t) m)) ;
+		  col[(size_t) cnt * THREADS] = (m & 0xffffffff00000000ull) | klo ;
+		  asm ("mad.lo.u32 %0, %0, 1, 1;" : "+r" (cnt)) ;
+		}
 	    }
 	}
       if (over) sBad = 1 ;
