@@ -167,7 +167,7 @@ k_fused_block (FusedArgs a, HashParams hp)
 	    { const int c = SH - 2 * j ;		/* (W >> c) & mask: k-mer j, first base on top */
 	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi ;
 	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi ;
-	      if (K > 16)	/* the integer ALU pipe is the limiter: take the high fields with a multiply (FMA pipe) + one
+	      if constexpr (K > 16)	/* the integer ALU pipe is the limiter: take the high fields with a multiply (FMA pipe) + one
 			   shift instead of shift + mask */
 		{ uint32_t tt, uu ;
 		  asm ("mul.lo.u32 %0, %1, %2;" : "=r" (tt) : "r" (WRhi), "r" (1u << (64 - 2 * K - 2 * j))) ;

@@ -283,17 +283,6 @@ __global__ void k_seg_start (const uint32_t *__restrict__ head, const uint32_t *
   if (i == n - 1) segStart[segIncl[i]] = (uint32_t) n ;
 }
 
-__global__ void k_bins (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ se,
-			const uint64_t *__restrict__ sh, const uint32_t *__restrict__ rank, uint64_t wMul,
-			uint32_t *__restrict__ idOfSeg, uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
-{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
-  if (s >= nSeg) return ;
-  uint32_t i = segStart[s] ;
-  uint32_t id = 1u + rank[se[i]] ;
-  idOfSeg[s] = id ;
-  hashValue[id] = sh[i] * wMul ;	/* the sort key is hash / w */
-  hashDepth[id] = segStart[s+1] - i ;	/* one entry per (block, hash): hash10x.c:178 */
-}
 
 __global__ void k_entry_ids (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ idOfSeg,
 			     const uint32_t *__restrict__ se, uint32_t *__restrict__ entryId)
@@ -301,17 +290,6 @@ __global__ void k_entry_ids (uint64_t n, const uint32_t *__restrict__ segIncl, c
   if (i < n) entryId[se[i]] = idOfSeg[segIncl[i] - 1] ;
 }
 
-/* fillHashTable (hash10x.c:317-347): within a bin the sorted order is ascending entry index, i.e.
-   ascending block number */
-__global__ void k_codes (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ segStart,
-			 const uint32_t *__restrict__ idOfSeg, const uint32_t *__restrict__ se,
-			 const uint32_t *__restrict__ entryBlk,
-			 const uint64_t *__restrict__ codeOff, uint32_t *__restrict__ codes)
-{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
-  if (i >= n) return ;
-  uint32_t s = segIncl[i] - 1 ;
-  codes[codeOff[idOfSeg[s]] + (i - segStart[s])] = entryBlk[se[i]] ;
-}
 
 /* single-GPU tail.  Bin ids in insertion order (hash10x.c:147) = bins ordered by their first entry
    (entries are stored in (block, hash) order): firstE[s] is sorted, the rank is the id. */
@@ -350,13 +328,6 @@ __global__ void k_codes_tr (uint64_t n, const uint32_t *__restrict__ segIncl, co
   idRead[pos] = (uint64_t) id | (br & 0xffff00000000ull) ;
 }
 
-__global__ void k_clus_prep (uint64_t n, const uint32_t *__restrict__ eRec, const uint32_t *__restrict__ blkIncl,
-			     const uint32_t *__restrict__ blkStart, uint16_t *__restrict__ read16)
-{ uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
-  if (e >= n) return ;
-  uint32_t rec = eRec[e] ;
-  read16[e] = (uint16_t) (rec - blkStart[blkIncl[rec] - 1]) ;	/* U16 truncation: hash10x.c:37,180 */
-}
 
 __global__ void k_clus_pack (uint64_t n, const uint32_t *__restrict__ ids, const uint16_t *__restrict__ read16,
 			     uint64_t *__restrict__ clus)
@@ -429,11 +400,9 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 			    uint32_t nRuns, uint64_t nRec, int chunkSize, int64_t N, BlockTable &bt)
 {
   bt.start.clear () ;
-  uint64_t pos = 0, nReads = 0, curStart = 0, curN = 0 ;
+  uint64_t pos = 0, nReads = 0, curN = 0 ;
   uint32_t barcode = 0, r = 0 ;	/* r = run containing pos */
-  bool open = false ;		/* block 1 exists from the start with nRead 0 */
-  bt.start.push_back (0) ;
-  (void) open ;
+  bt.start.push_back (0) ;		/* block 1 exists from the start with nRead 0 */
   while (!N || nReads < (uint64_t) N)
     { int64_t thisChunk = (int64_t) chunkSize - (int64_t) curN ;
       if (thisChunk <= 0) return H10X_ERR_CHUNK_TOO_SMALL ;
@@ -446,13 +415,12 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 	{ uint64_t segEnd = std::min<uint64_t> (end, runStart[r+1]) ;
 	  uint64_t len = segEnd - pos ;
 	  if (runWord[r] == barcode) curN += len ;
-	  else { bt.start.push_back ((uint32_t) pos) ; curStart = pos ; curN = len ; barcode = runWord[r] ; }
+	  else { bt.start.push_back ((uint32_t) pos) ; curN = len ; barcode = runWord[r] ; }
 	  pos = segEnd ;
 	  if (pos == runStart[r+1] && r + 1 < nRuns) ++r ;
 	}
       nReads += n ;
     }
-  (void) curStart ;
   bt.nBlk = (uint32_t) bt.start.size () ;
   bt.start.push_back ((uint32_t) nRec) ;
   return H10X_OK ;
@@ -1030,6 +998,8 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
   StageTimer tm (c, s, ST_BINIDS) ;
   d->nLocalBins = Dl ;
+  HostTrace tr ;
+  auto mark = [&] (const char *w) { if (tr.on) { cudaStreamSynchronize (s) ; tr.mark (w) ; } } ;
 
   /* 1. rank-distinct hashes */
   DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
@@ -1047,6 +1017,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   CK (cudaStreamSynchronize (s)) ;
   sendOff[0] = 0 ; sendOff[NR] = Dl ;
 
+  mark ("d1-distinct") ;
   /* 3. counts */
   std::vector<uint64_t> sendCnt (NR), cntMat ((size_t) NR * NR) ;
   for (int o = 0 ; o < NR ; ++o) sendCnt[o] = sendOff[o+1] - sendOff[o] ;
@@ -1061,6 +1032,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   if (Ro64 >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 rank-distinct hashes for one owner") ;
   const uint32_t Ro = (uint32_t) Ro64 ;
 
+  mark ("d3-counts") ;
   /* 4. all-to-all-v of (hash, depth, first block) to the hash-range owners */
   DBuf<uint64_t> rHash (Ro, s, mt) ; DBuf<uint32_t> rDepth (Ro, s, mt), rFirst (Ro, s, mt) ;
   NCK (gNccl.GroupStart ()) ;
@@ -1078,6 +1050,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
     }
   NCK (gNccl.GroupEnd ()) ;
   dHash.release () ; dDepth.release () ; dFirst.release () ;
+  mark ("d4-alltoall") ;
 
   /* 5. owner merge: depth = sum, first block = min over the (at most NR) copies of a hash */
   const uint32_t nB2 = nBlkGlobal + 2 ;
@@ -1103,6 +1076,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
     }
   rHash.release () ; rDepth.release () ; rFirst.release () ;
 
+  mark ("d5-merge") ;
   /* 6. global id bases from every owner's per-block new-hash counts */
   DBuf<uint32_t> newMat ((size_t) NR * nB2, s, mt), colSum (nB2, s, mt), below (nB2, s, mt), prefixAll (nB2, s, mt) ;
   NCK (gNccl.AllGather (newCnt.p, newMat.p, nB2, ncclUint32, d->comm, s)) ;
@@ -1117,6 +1091,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
     throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
   c->hashNumber = Dglobal + 1 ;
 
+  mark ("d6-idbase") ;
   /* 7. ids of this owner's hashes: order by (first block, hash) = stable sort by first block of the
 	hash-sorted list; then the id of every received copy */
   DBuf<uint32_t> gId (Do, s, mt), ans (Ro, s, mt) ;
@@ -1132,6 +1107,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       LAUNCH (c, k_answer_ids, gridFor (Ro, 256), 256, 0, s, Ro, oSegIncl.p, oi.p, gId.p, ans.p) ;
     }
 
+  mark ("d7-ids") ;
   /* 8. reverse all-to-all-v: the bin id of every rank-distinct hash, in the order it was sent */
   c->localBinId.alloc (Dl, s, mt) ;
   NCK (gNccl.GroupStart ()) ;
@@ -1142,6 +1118,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   NCK (gNccl.GroupEnd ()) ;
   if (H) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
 
+  mark ("d8-reverse+entryids") ;
   /* 9. (id, hash, depth) of every bin to rank 0, which owns hashValue / hashDepth / hashIndex */
   std::vector<uint64_t> mine2 = { Do, H }, all2 ((size_t) 2 * NR) ;
   DBuf<uint64_t> d2 (2, s, mt), dAll2 ((size_t) 2 * NR, s, mt) ;
@@ -1181,6 +1158,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   if (R == 0 && Dglobal)
     LAUNCH (c, k_scatter_bins, gridFor (Dglobal, 256), 256, 0, s, Dglobal, tId.p, tHash.p, tDepth.p, c->hashValue.p, c->hashDepth.p) ;
   CK (cudaStreamSynchronize (s)) ;	/* sends read gId/gHash/gDepth, freed on return */
+  mark ("d9-gather0") ;
 }
 
 /* ------------------------------------------------------------------ slab sizing / retry */
