@@ -20,6 +20,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <iterator>
@@ -1206,6 +1208,7 @@ static size_t slab_estimate (const h10x_params &P, uint64_t nRec, bool withFqb)
 
 /* ------------------------------------------------------------------ C ABI */
 
+extern "C" { static void *pinned_alloc (size_t bytes) ; }
 static void set_err (char *err, size_t errlen, const char *msg)
 { if (err && errlen) { strncpy (err, msg, errlen - 1) ; err[errlen - 1] = 0 ; } }
 
@@ -1484,6 +1487,142 @@ int h10x_gpu_build_host_dist (h10x_ctx *c, const void *fqb, uint64_t nRecords, h
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
   return h10x_gpu_download (c, out, err, errlen) ;
+}
+
+/* ---- the whole seam on several GPUs of one node, from one process: one thread + one context per GPU ----
+   The file is cut into nGpus record ranges at barcode-run boundaries; every thread reads its range, joins
+   the NCCL communicator and runs the distributed build; the per-rank pieces are then stitched into one
+   host index (block table and ClusterHash slabs concatenate in rank order; rank 0 holds the bin table).
+   The hash->code lists stay distributed (codes / codeOff are NULL): --writeHash, --hashStats, --codeStats
+   and --hashDepthRange do not read them, and readHashFile rebuilds them anyway (hash10x.c:269-315). */
+int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path, h10x_index *out, char *err, size_t errlen)
+{ if (!p || !path || !out || nGpus < 1) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  int nDev = h10x_gpu_device_count () ;
+  if (nDev <= 0) { set_err (err, errlen, h10x_strerror (H10X_ERR_NO_DEVICE)) ; return H10X_ERR_NO_DEVICE ; }
+  if (nGpus > nDev) { set_err (err, errlen, "more GPUs requested than visible") ; return H10X_ERR_BAD_PARAM ; }
+  if (p->N != 0) { set_err (err, errlen, "-N is not supported with several GPUs") ; return H10X_ERR_UNSUPPORTED ; }
+  FILE *f = fopen (path, "rb") ;
+  if (!f) { set_err (err, errlen, "failed to open fqb file") ; return H10X_ERR_IO ; }
+  if (fseeko (f, 0, SEEK_END)) { fclose (f) ; set_err (err, errlen, "file read problem") ; return H10X_ERR_IO ; }
+  const uint64_t nRec = (uint64_t) ftello (f) / 120 ;
+  /* cuts: the first record at or after r*nRec/nGpus whose barcode differs from its predecessor's */
+  std::vector<uint64_t> cut ((size_t) nGpus + 1, 0) ;
+  cut[nGpus] = nRec ;
+  bool ioOk = true ;
+  for (int r = 1 ; r < nGpus && ioOk ; ++r)
+    { uint64_t pos = std::max<uint64_t> (nRec * (uint64_t) r / (uint64_t) nGpus, cut[r-1] + 1) ;
+      uint32_t prev = 0, cur = 0 ;
+      if (pos >= nRec) { cut[r] = nRec ; continue ; }
+      if (fseeko (f, (off_t) ((pos - 1) * 120), SEEK_SET) || fread (&prev, 4, 1, f) != 1) { ioOk = false ; break ; }
+      for ( ; pos < nRec ; ++pos)
+	{ if (fseeko (f, (off_t) (pos * 120), SEEK_SET) || fread (&cur, 4, 1, f) != 1) { ioOk = false ; break ; }
+	  if (cur != prev) break ;
+	}
+      cut[r] = pos ;
+    }
+  fclose (f) ;
+  if (!ioOk) { set_err (err, errlen, "file read problem") ; return H10X_ERR_IO ; }
+  int used = nGpus ;
+  while (used > 1 && cut[used-1] >= nRec) --used ;		/* fewer runs than GPUs: drop the empty tail ranks */
+  cut[used] = nRec ;
+
+  unsigned char id[H10X_DIST_ID_BYTES] ;
+  char e0[512] = "" ;
+  int st0 = (used > 1 || true) ? h10x_dist_unique_id (id, e0, sizeof (e0)) : H10X_OK ;
+  if (st0) { set_err (err, errlen, e0) ; return st0 ; }
+
+  std::vector<h10x_ctx*> ctxs (used, nullptr) ;
+  std::vector<int> status (used, H10X_OK) ;
+  std::vector<std::string> msgs (used) ;
+  std::vector<h10x_index> parts (used) ;
+  std::vector<uint32_t*> dFqb (used, nullptr) ;
+  std::atomic<int> arrived (0), failedEarly (0) ;
+  auto worker = [&] (int r)
+    { char e[512] = "" ;
+      h10x_params pr = *p ; pr.device = p->device + r ;
+      uint64_t n = cut[r+1] - cut[r] ;
+      void *stage[2] = { nullptr, nullptr } ;
+      int st = H10X_OK ;
+      ctxs[r] = h10x_gpu_create (&pr, e, sizeof (e)) ;
+      if (!ctxs[r]) st = H10X_ERR_BAD_PARAM ;
+      if (!st) st = h10x_dist_init (ctxs[r], r, used, id, e, sizeof (e)) ;
+      if (!st)
+	st = guarded (e, sizeof (e), [&] ()
+	  { h10x_ctx *c = ctxs[r] ;
+	    CK (cudaSetDevice (c->P.device)) ;
+	    FILE *fr = fopen (path, "rb") ;
+	    if (!fr) throw H10xError (H10X_ERR_IO, "failed to open fqb file") ;
+	    struct Closer { FILE *f ; ~Closer () { fclose (f) ; } } closer { fr } ;
+	    if (fseeko (fr, (off_t) (cut[r] * 120), SEEK_SET)) throw H10xError (H10X_ERR_IO, "file read problem") ;
+	    CK (cudaMalloc ((void**) &dFqb[r], std::max<uint64_t> (n * 120, 16))) ;
+	    const size_t chunkRecs = 1u << 19 ;
+	    stage[0] = pinned_alloc (chunkRecs * 120) ; stage[1] = pinned_alloc (chunkRecs * 120) ;
+	    cudaEvent_t done[2] ; CK (cudaEventCreate (&done[0])) ; CK (cudaEventCreate (&done[1])) ;
+	    uint64_t pos = 0 ; int cur = 0 ; bool usedBuf[2] = { false, false } ;
+	    while (pos < n)
+	      { size_t want = (size_t) std::min<uint64_t> (chunkRecs, n - pos) ;
+		if (usedBuf[cur]) CK (cudaEventSynchronize (done[cur])) ;
+		if (fread (stage[cur], 120, want, fr) != want) throw H10xError (H10X_ERR_IO, "file read problem") ;
+		CK (cudaMemcpyAsync ((char*) dFqb[r] + pos * 120, stage[cur], want * 120, cudaMemcpyHostToDevice, c->own)) ;
+		CK (cudaEventRecord (done[cur], c->own)) ; usedBuf[cur] = true ;
+		pos += want ; cur ^= 1 ;
+	      }
+	    CK (cudaStreamSynchronize (c->own)) ;
+	    cudaEventDestroy (done[0]) ; cudaEventDestroy (done[1]) ;
+	  }) ;
+      if (stage[0]) cudaFreeHost (stage[0]) ;
+      if (stage[1]) cudaFreeHost (stage[1]) ;
+      /* nobody enters the collective build unless every rank got this far */
+      if (st) failedEarly.fetch_add (1) ;
+      arrived.fetch_add (1) ;
+      while (arrived.load () < used) std::this_thread::yield () ;
+      if (!st && failedEarly.load () == 0)
+	{ st = h10x_gpu_build_device_dist (ctxs[r], dFqb[r], n, nullptr, e, sizeof (e)) ;
+	  if (!st) st = h10x_gpu_download (ctxs[r], &parts[r], e, sizeof (e)) ;
+	}
+      else if (!st) { st = H10X_ERR_IO ; snprintf (e, sizeof (e), "another rank failed before the build") ; }
+      status[r] = st ; msgs[r] = e ;
+    } ;
+  std::vector<std::thread> th ;
+  for (int r = 0 ; r < used ; ++r) th.emplace_back (worker, r) ;
+  for (auto &t : th) t.join () ;
+
+  int st = H10X_OK ;
+  for (int r = 0 ; r < used && !st ; ++r) if (status[r]) { st = status[r] ; set_err (err, errlen, msgs[r].c_str ()) ; }
+  if (!st)
+    st = guarded (err, errlen, [&] ()
+      { /* stitch: bin table from rank 0, block table + ClusterHash slabs in rank order */
+	uint64_t H = 0, reads = 0 ; uint32_t nb = 1 ;
+	for (int r = 0 ; r < used ; ++r) { H += parts[r].nHashes ; reads += parts[r].nReads ; nb += parts[r].nBlocksMax - 1 ; }
+	const h10x_index &z = parts[0] ;
+	out->B = z.B ; out->hashNumber = z.hashNumber ; out->nBlocksMax = nb ; out->nReads = reads ; out->nHashes = H ;
+	auto dup = [] (const void *src, size_t bytes) -> void*
+	  { void *d = malloc (bytes ? bytes : 1) ; if (!d) throw std::bad_alloc () ; if (bytes) memcpy (d, src, bytes) ; return d ; } ;
+	if (z.hashIndex) out->hashIndex = (uint32_t*) dup (z.hashIndex, (size_t) 4 << z.B) ;
+	out->hashValue = (uint64_t*) dup (z.hashValue, 8 * (size_t) z.hashNumber) ;
+	out->hashDepth = (uint32_t*) dup (z.hashDepth, 4 * (size_t) z.hashNumber) ;
+	out->blkNRead = (uint32_t*) calloc (nb, 4) ; out->blkNHash = (uint32_t*) calloc (nb, 4) ;
+	out->blkOff = (uint64_t*) calloc ((size_t) nb + 1, 8) ;
+	out->clusHash = (h10x_cluster_hash*) malloc ((H ? H : 1) * 8) ;
+	if (!out->blkNRead || !out->blkNHash || !out->blkOff || !out->clusHash) throw std::bad_alloc () ;
+	uint32_t b = 1 ; uint64_t e = 0 ;
+	for (int r = 0 ; r < used ; ++r)
+	  { const h10x_index &q = parts[r] ;
+	    for (uint32_t i = 1 ; i < q.nBlocksMax ; ++i, ++b)
+	      { out->blkNRead[b] = q.blkNRead[i] ; out->blkNHash[b] = q.blkNHash[i] ; out->blkOff[b] = e + q.blkOff[i] ; }
+	    if (q.nHashes) memcpy (out->clusHash + e, q.clusHash, 8 * q.nHashes) ;
+	    e += q.nHashes ;
+	  }
+	out->blkOff[nb] = H ;
+	out->pinned = 0 ; out->onDevice = 0 ;
+      }) ;
+  for (int r = 0 ; r < used ; ++r)
+    { if (dFqb[r]) { cudaSetDevice (p->device + r) ; cudaFree (dFqb[r]) ; }
+      if (ctxs[r]) h10x_gpu_destroy (ctxs[r]) ;
+    }
+  if (st) { h10x_index_free (out) ; memset (out, 0, sizeof (*out)) ; }
+  return st ;
 }
 
 int h10x_gpu_dist_info (h10x_ctx *c, h10x_dist_info *out)

@@ -20,7 +20,7 @@
 #include <string.h>
 #include <sys/resource.h>
 
-static struct { int k, w, r, B, N, chunkSize, clusterThreshold ; } params ;
+static struct { int k, w, r, B, N, chunkSize, clusterThreshold, gpus ; } params ;
 static FILE *outFile ;
 static h10x_index ix ;		/* the state --readFQB / --readHash leave behind */
 static int haveIndex = 0, indexFromGpu = 0 ;
@@ -67,6 +67,7 @@ static void usage (void)
   fprintf (stderr, "   -B <hash index table bitcount> [%d]\n", params.B) ;
   fprintf (stderr, "   -N <num records to read: 0 for all> [%d]\n", params.N) ;
   fprintf (stderr, "   -c <file chunkSize in readPairs> [%d]\n", params.chunkSize) ;
+  fprintf (stderr, "   --gpus <number of GPUs for --readFQB> [%d]\n", params.gpus) ;
   fprintf (stderr, "   -o | --output <output filename> : '-' for stdout\n") ;
   fprintf (stderr, "   --readFQB <sorted fqb input file name>: must have this or readHash (runs on the GPU)\n") ;
   fprintf (stderr, "   --readHash <hash input file name>\n") ;
@@ -100,13 +101,18 @@ static void readFQB (const char *path)
   printf ("\n") ;
   if (params.chunkSize <= 0) die ("chunkSize too small") ;
   if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
-  if (!(ctx = h10x_gpu_create (&p, err, sizeof (err)))) die ("%s", err) ;
-  int st = h10x_gpu_build_file (ctx, path, &ix, err, sizeof (err)) ;
+  int st ;
+  if (params.gpus > 1)		/* one thread and one context per GPU, NCCL inside the library */
+    st = h10x_gpu_build_file_multi (&p, params.gpus, path, &ix, err, sizeof (err)) ;
+  else
+    { if (!(ctx = h10x_gpu_create (&p, err, sizeof (err)))) die ("%s", err) ;
+      st = h10x_gpu_build_file (ctx, path, &ix, err, sizeof (err)) ;
+    }
   if (st == H10X_ERR_TABLE_TOO_SMALL) die ("hashTableSize is too small") ;
   else if (st == H10X_ERR_CHUNK_TOO_SMALL) die ("chunkSize too small") ;
   else if (st == H10X_ERR_IO) die ("file read problem") ;
   else if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
-  haveIndex = 1 ; indexFromGpu = 1 ;
+  haveIndex = 1 ; indexFromGpu = (params.gpus <= 1) ;
   totalAllocated += ((long) 4 << ix.B) + 12L * ix.hashNumber + 12L * (long) ix.nHashes ;
 
   int nBarcodes = (int) ix.nBlocksMax - 1, i ;
@@ -267,7 +273,7 @@ int main (int argc, char *argv[])
   outFile = stdout ;
   timeUpdate (stdout) ;
   params.k = 21 ; params.w = 31 ; params.r = 17 ; params.B = 28 ; params.N = 0 ;
-  params.chunkSize = 100000 ; params.clusterThreshold = 5 ;
+  params.chunkSize = 100000 ; params.clusterThreshold = 5 ; params.gpus = 1 ;
   if (!argc) usage () ;
 
   while (argc)
@@ -289,6 +295,7 @@ int main (int argc, char *argv[])
       else if (ARGMATCH ("-B", 2)) params.B = atoi (argv[-1]) ;
       else if (ARGMATCH ("-N", 2)) params.N = atoi (argv[-1]) ;
       else if (ARGMATCH ("-c", 2)) params.chunkSize = atoi (argv[-1]) ;
+      else if (ARGMATCH ("--gpus", 2)) params.gpus = atoi (argv[-1]) ;	/* new: GPUs used by --readFQB */
       else if (ARGMATCH ("-t", 2) || ARGMATCH ("--threads", 2))
 	fprintf (stderr, "  can't set thread number - not compiled with OMP\n") ;
       else if (ARGMATCH ("-o", 2) || ARGMATCH ("--output", 2))

@@ -173,6 +173,12 @@ int h10x_gpu_build_device_dist (h10x_ctx *ctx, const void *d_fqb, uint64_t nReco
 int h10x_gpu_build_host_dist (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x_index *out,
 			      char *err, size_t errlen) ;
 int h10x_gpu_dist_info (h10x_ctx *ctx, h10x_dist_info *out) ;
+/* the whole seam on nGpus GPUs of this node from ONE process (a thread and a context per GPU, devices
+   p->device .. p->device+nGpus-1): the file is cut at barcode-run boundaries, every GPU builds its range and
+   the pieces are stitched into one host index (malloc'ed; free with h10x_index_free).  codes / codeOff stay
+   NULL: the hash->code lists remain distributed and no command of the --readFQB ... --writeHash chain reads them. */
+int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path, h10x_index *out,
+			       char *err, size_t errlen) ;
 int h10x_gpu_memcpy_d2h (h10x_ctx *ctx, void *dst, const void *src, size_t bytes) ;
 
 /* moshes of each record without the index build (the K1 stage alone), for parity tests of

@@ -71,3 +71,26 @@ def test_cli_errors_match_reference(orc, gpu_lib, tmp_path):
         a, b = _run(ref, chain, str(tmp_path)), _run(CLI, chain, str(tmp_path))
         assert a.returncode != 0 and b.returncode == a.returncode, chain
         assert a.stderr.strip().splitlines()[-1] == b.stderr.strip().splitlines()[-1], chain
+
+
+def test_cli_multi_gpu_matches_reference(orc, gpu_lib, tmp_path):
+    """--gpus N (one process, a thread per GPU, NCCL inside the library) writes the reference's .hash"""
+    ref = orc.ref_binary("hash10x")
+    n = gpu_lib.h10x_gpu_device_count()
+    if ref is None or n < 2:
+        pytest.skip("needs oracle/_ref/hash10x and at least 2 GPUs")
+    p = orc.synth_params(seed=61, n_barcodes=90, pairs_min=5, pairs_max=250)
+    orc.synth_fqb(p).tofile(str(tmp_path / "in.fqb"))
+    chain = ["-B", "21", "--readFQB", "in.fqb", "--writeHash", "OUT.hash", "--hashStats", "--codeStats"]
+    a = _run(ref, [x.replace("OUT", "ref") for x in chain], str(tmp_path))
+    assert a.returncode == 0, a.stderr
+    for g in sorted({2, min(n, 8)}):
+        b = _run(CLI, ["--gpus", str(g)] + [x.replace("OUT", "gpu%d" % g) for x in chain], str(tmp_path))
+        assert b.returncode == 0, b.stderr
+        la = [x.replace("ref.hash", "X.hash") for x in _clean(a.stdout)]
+        lb = [x.replace("gpu%d.hash" % g, "X.hash") for x in _clean(b.stdout)
+              if not x.startswith("COMMAND --gpus") and not x.startswith("NCCL version")]   # NCCL_DEBUG banner
+        assert la == lb
+        ha, hb = hashfile.parse(str(tmp_path / "ref.hash")), hashfile.parse(str(tmp_path / ("gpu%d.hash" % g)))
+        assert ha.size == hb.size
+        hashfile.assert_strict_equal(ha, hb, table=True)
