@@ -16,6 +16,7 @@
 #include "h10x_common.cuh"
 #include "h10x_fused.cuh"
 #include "h10x_cluster.cuh"
+#include "h10x_bucket.cuh"
 
 #include <cub/cub.cuh>
 
@@ -759,14 +760,42 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   hBlkOff[nProcBlk] = H ;
   c->nHashes = H ;
   if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
-  DBuf<uint64_t> eHash (H, s, mt), eBR ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk ;
-  if (dist) { eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; } else eBR.alloc (H, s, mt) ;
+  /* single-GPU: bucket-major packed words (h10x_bucket.cuh); multi-GPU: block-major hash / read / block arrays */
+  int blkBits = 1 ; while (((uint64_t) 1 << blkBits) < (uint64_t) nBlk + 2) ++blkBits ;
+  const int nbBits = sortBits > 32 ? sortBits - 32 : 0 ;
+  const bool bucketed = !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
+  uint32_t nBuck = 1 ;
+  std::vector<uint64_t> hBucketBase ;
+  DBuf<uint64_t> eHash, eBR, words, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk ;
+  if (dist) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
+  else if (!bucketed) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
-    if (nProcBlk)
-      LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
-	      scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, eHash.p, eRead.p, entryBlk.p, eBR.p) ;
-    CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
+    if (bucketed)
+      { uint64_t top = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
+	nBuck = (uint32_t) (top >> 32) + 1 ;
+	const size_t nCnt = (size_t) nBuck * nProcBlk ;
+	DBuf<uint32_t> cnt (nCnt + 1, s, mt) ; DBuf<uint64_t> off (nCnt + 1, s, mt) ;
+	CK (cudaMemsetAsync (cnt.p + nCnt, 0, 4, s)) ;
+	LAUNCH (c, k_bucket_count, gridFor ((uint64_t) nProcBlk * 32, 256), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
+		scratch.p, gHash.p, wDiv, cnt.p) ;
+	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> cnt64 (cnt.p, CastU64 ()) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, cnt64, off.p, nCnt + 1, s) ; }) ;
+	bucketBase.alloc ((size_t) nBuck + 1, s, mt) ;
+	LAUNCH (c, k_bucket_base, gridFor (nBuck + 1, 256), 256, 0, s, nBuck, nProcBlk, off.p, H, bucketBase.p) ;
+	hBucketBase.resize ((size_t) nBuck + 1) ;
+	CK (cudaMemcpyAsync (hBucketBase.data (), bucketBase.p, 8 * ((size_t) nBuck + 1), cudaMemcpyDeviceToHost, s)) ;
+	words.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ;
+	LAUNCH (c, k_place_bucketed, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
+		cnt.p, off.p, bucketBase.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, words.p, eBR.p) ;
+	CK (cudaStreamSynchronize (s)) ;
+      }
+    else
+      { if (nProcBlk)
+	  LAUNCH (c, k_place, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, srcOff.p, blkCnt.p, blkOffProc.p,
+		  scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, eHash.p, eRead.p, entryBlk.p, eBR.p) ;
+	CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
+      }
   }
   scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
   if (!totalMoshes) totalMoshes = H ;
@@ -776,9 +805,48 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   uint32_t D = 0 ;
   DBuf<uint32_t> entryId ;
   if (dist) entryId.alloc (H, s, mt) ;
-  DBuf<uint32_t> se (H, s, mt), segIncl (H, s, mt), segStart, idOfSeg ;
-  if (H)
-    { DBuf<uint64_t> sh (H, s, mt) ;
+  DBuf<uint32_t> se, segIncl (H, s, mt), segStart, idOfSeg ;
+  DBuf<uint64_t> sw ;
+  if (bucketed)
+    { sw.alloc (H, s, mt) ;
+      { StageTimer tm (c, s, ST_HASHSORT) ;
+	const int endBit = 31 + std::min (32, sortBits) ;
+	for (uint32_t v = 0 ; v < nBuck ; ++v)
+	  { uint64_t b0 = hBucketBase[v], n = hBucketBase[v+1] - b0 ;
+	    if (!n) continue ;
+	    cubCall (c, s, [&] (void *t, size_t &b)
+	      { return cub::DeviceRadixSort::SortKeys (t, b, words.p + b0, sw.p + b0, n, 31, endBit, s) ; }) ;
+	  }
+      }
+      words.release () ;
+      { StageTimer tm (c, s, ST_BINIDS) ;
+	DBuf<uint32_t> head (H, s, mt) ;
+	LAUNCH (c, k_head_flag_sw, gridFor (H, 256), 256, 0, s, sw.p, H, bucketBase.p, nBuck, head.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, head.p, segIncl.p, H, s) ; }) ;
+	CK (cudaMemcpyAsync (&D, segIncl.p + (H - 1), 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
+	  throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+	segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
+	LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, (const uint32_t*) nullptr, segStart.p, (uint32_t*) nullptr) ;
+	head.release () ;
+	DBuf<uint64_t> fkey (D, s, mt), fkeyS (D, s, mt) ; DBuf<uint32_t> segIdx (D, s, mt), sortedSeg (D, s, mt) ;
+	LAUNCH (c, k_first_key_sw, gridFor (D, 256), 256, 0, s, D, segStart.p, sw.p, bucketBase.p, nBuck, eBR.p, sortBits, fkey.p, segIdx.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceRadixSort::SortPairs (t, b, fkey.p, fkeyS.p, segIdx.p, sortedSeg.p, D, 0, sortBits + blkBits, s) ; }) ;
+	c->hashNumber = D + 1 ;
+	c->hashValue.alloc ((size_t) D + 1, s, mt) ;
+	c->hashDepth.alloc ((size_t) D + 2, s, mt) ;
+	CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
+	LAUNCH (c, k_bins_by_rank_sw, gridFor (D, 256), 256, 0, s, D, sortedSeg.p, segStart.p, sw.p, bucketBase.p, nBuck, wDiv,
+		idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+      }
+    }
+  else if (H)
+    { se.alloc (H, s, mt) ;
+      DBuf<uint64_t> sh (H, s, mt) ;
       { StageTimer tm (c, s, ST_HASHSORT) ;
 	DBuf<uint32_t> iota (H, s, mt) ;
 	LAUNCH (c, k_iota, gridFor (H, 256), 256, 0, s, iota.p, H) ;
@@ -854,11 +922,14 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	c->codes.alloc (H, s, mt) ;
 	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
-	if (H)
+	if (H && bucketed)
+	  LAUNCH (c, k_codes_tr_sw, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, sw.p, bucketBase.p, nBuck,
+		  eBR.p, c->codeOff.p, c->codes.p, idRead.p) ;
+	else if (H)
 	  LAUNCH (c, k_codes_tr, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eBR.p,
 		  c->codeOff.p, c->codes.p, idRead.p) ;
       }
-      se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; eBR.release () ;
+      se.release () ; sw.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; eBR.release () ;
       c->clus.alloc (H, s, mt) ;
       if (H)
 	{ StageTimer tm (c, s, ST_CLUSTERS) ;
