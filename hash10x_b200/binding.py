@@ -53,6 +53,11 @@ class CDistInfo(C.Structure):
                 ("localCodeOff", C.c_void_p), ("localCodes", C.c_void_p)]
 
 
+class CGood(C.Structure):
+    _fields_ = [("nGood", C.c_uint64), ("hashNumber", C.c_uint32), ("nBlocksMax", C.c_uint32),
+                ("within", C.c_void_p), ("goodOff", C.c_void_p), ("good", C.c_void_p)]
+
+
 def lib_path():
     return os.path.join(_HERE, "libh10xgpu.so")
 
@@ -99,6 +104,7 @@ def load_library():
     L.h10x_gpu_build_host_dist.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_dist_info.argtypes = [vp, C.POINTER(CDistInfo)]
     L.h10x_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.h10x_gpu_depth_range.argtypes = [vp, C.c_int, C.c_int, C.POINTER(CGood), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -277,6 +283,14 @@ class Hash10xGPU:
             out["localCodeOff"] = off
             out["localCodes"] = pull(di.localCodes, int(off[-1]) if off.size else 0)
         return out
+
+    def depth_range(self, dmin, dmax):
+        """--hashDepthRange on the resident index -> (within u8, goodOff u64, good u16) host copies"""
+        cg = CGood()
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_depth_range(self.ctx, dmin, dmax, C.byref(cg), err, len(err)), err)
+        return (_arr(cg.within, cg.hashNumber, np.uint8), _arr(cg.goodOff, cg.nBlocksMax + 1, np.uint64),
+                _arr(cg.good, cg.nGood, np.uint16))
 
     def stats(self):
         cs = CStats()

@@ -124,6 +124,8 @@ struct h10x_ctx {
   uint64_t launches = 0 ;
   /* multi-GPU (h10x_dist.cuh) */
   bool slabClamped = false ;	/* the slab already takes all free device memory */
+  DBuf<uint8_t> within ;	/* --hashDepthRange flags per bin; only ever set (hash10x.c:535) until the next build */
+  void *goodSlot[3] = { nullptr, nullptr, nullptr } ; size_t goodCap[3] = { 0, 0, 0 } ;	/* pinned host: within, goodOff, good */
   struct DistState *dist = nullptr ;
   DBuf<uint32_t> localBinId, localCodeOff, localCodes ;	/* this rank's part of the hash->code lists */
   /* pinned host arena reused by h10x_gpu_download (one slot per index array) */
@@ -343,6 +345,43 @@ __global__ void k_shift_offsets (const uint64_t *__restrict__ in, uint64_t base,
   if (i < n) out[i] = (uint32_t) (in[i] - base) ;
 }
 
+/* ---- --hashDepthRange on the resident index ("next" row f1): hashWithinRangeBuild hash10x.c:528-539 ---- */
+__global__ void k_within (uint32_t hashNumber, const uint32_t *__restrict__ depth, int dmin, int dmax, uint8_t *__restrict__ within)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (i >= hashNumber) return ;
+  int n = (int) depth[i] ;
+  if (n >= dmin && n < dmax) within[i] = 1 ;	/* flags are only ever set */
+}
+
+/* goodHashesBuild hash10x.c:738-766, part 1: which entries of each block are good (bin within range);
+   blocks with more than 65535 hashes are skipped (:748).  One CTA per block. */
+__global__ void k_good_mark (uint32_t nBlocksMax, const uint64_t *__restrict__ blkOff, const uint32_t *__restrict__ blkNHash,
+			     const uint64_t *__restrict__ clus, const uint8_t *__restrict__ within, uint32_t *__restrict__ flag)
+{ for (uint32_t b = blockIdx.x ; b < nBlocksMax ; b += gridDim.x)
+    { const uint32_t n = b ? blkNHash[b] : 0 ;
+      const uint64_t off = blkOff[b] ;
+      const bool skip = n > 65535u ;
+      for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
+	flag[off + i] = (!skip && within[(uint32_t) clus[off + i]]) ? 1u : 0u ;
+    }
+}
+
+/* part 2: compact (depth of the bin, index inside the block) of the good entries, block after block */
+__global__ void k_good_compact (uint32_t nBlocksMax, const uint64_t *__restrict__ blkOff, const uint32_t *__restrict__ blkNHash,
+				const uint64_t *__restrict__ clus, const uint32_t *__restrict__ depth,
+				const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+				uint32_t *__restrict__ keyDepth, uint16_t *__restrict__ valIdx, uint64_t *__restrict__ goodOff,
+				uint64_t nEntries, uint32_t nGood)
+{ for (uint32_t b = blockIdx.x ; b <= nBlocksMax ; b += gridDim.x)
+    { if (b == nBlocksMax) { if (threadIdx.x == 0) goodOff[b] = nGood ; continue ; }
+      const uint32_t n = b ? blkNHash[b] : 0 ;
+      const uint64_t off = blkOff[b] ;
+      if (threadIdx.x == 0) goodOff[b] = off < nEntries ? pos[off] : nGood ;
+      for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
+	if (flag[off + i]) { uint32_t p = pos[off + i] ; keyDepth[p] = depth[(uint32_t) clus[off + i]] ; valIdx[p] = (uint16_t) i ; }
+    }
+}
+
 /* hashIndex[] (hash10x.c:139-152).  Sequential insertion puts bin n at the first slot of its probe
    sequence not held by a smaller id.  That fixed point is unique, so it can be reached in parallel:
    a bin claims a slot that is empty or holds a larger id (compare-and-swap); the displaced larger
@@ -431,7 +470,7 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 
 static void reset_result (h10x_ctx *c)
 { c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
-  c->localBinId.release () ; c->localCodeOff.release () ; c->localCodes.release () ;
+  c->localBinId.release () ; c->localCodeOff.release () ; c->localCodes.release () ; c->within.release () ;
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
   c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
@@ -1286,6 +1325,7 @@ static void set_err (char *err, size_t errlen, const char *msg)
 template <class F> static int guarded (char *err, size_t errlen, F f)
 { try { f () ; set_err (err, errlen, "") ; return H10X_OK ; }
   catch (const H10xError &e) { set_err (err, errlen, e.what ()) ; return e.code ; }
+  catch (const SlabFull &f) { set_err (err, errlen, ("device workspace too small: need " + std::to_string (f.need) + " bytes").c_str ()) ; return H10X_ERR_NOMEM ; }
   catch (const std::bad_alloc &) { set_err (err, errlen, "host out of memory") ; return H10X_ERR_NOMEM ; }
   catch (const std::exception &e) { set_err (err, errlen, e.what ()) ; return H10X_ERR_CUDA ; }
 }
@@ -1353,6 +1393,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
   slab_free (c) ;
   for (auto e : c->evPool) cudaEventDestroy (e) ;
   for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
+  for (int i = 0 ; i < 3 ; ++i) if (c->goodSlot[i]) cudaFreeHost (c->goodSlot[i]) ;
   if (c->own) { cudaStreamSynchronize (c->own) ; cudaStreamDestroy (c->own) ; }
   delete c ;
 }
@@ -1487,6 +1528,52 @@ int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *e
   if (d_fqb) cudaFree (d_fqb) ;
   if (st != H10X_OK) return st ;
   return h10x_gpu_download (c, out, err, errlen) ;
+}
+
+int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen)
+{ if (!c || !out || !c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      const uint32_t hn = c->hashNumber, nb = c->nBlocksMax ;
+      const uint64_t H = c->nHashes ;
+      if (!c->within.p) { c->within.alloc (hn, s, mt) ; CK (cudaMemsetAsync (c->within.p, 0, hn, s)) ; }
+      LAUNCH (c, k_within, gridFor (hn, 256), 256, 0, s, hn, c->hashDepth.p, dmin, dmax, c->within.p) ;
+      uint32_t nGood = 0 ;
+      DBuf<uint32_t> flag (H + 1, s, mt), pos (H + 1, s, mt) ;
+      DBuf<uint64_t> goodOff ((size_t) nb + 1, s, mt) ;
+      CK (cudaMemsetAsync (flag.p + H, 0, 4, s)) ;
+      LAUNCH (c, k_good_mark, std::min<uint32_t> (nb, 148 * 16), 256, 0, s, nb, c->blkOff.p, c->blkNHash.p, c->clus.p, c->within.p, flag.p) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, flag.p, pos.p, H + 1, s) ; }) ;
+      CK (cudaMemcpyAsync (&nGood, pos.p + H, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      DBuf<uint32_t> keyDepth (nGood, s, mt), keyS (nGood, s, mt) ;
+      DBuf<uint16_t> valIdx (nGood, s, mt), valS (nGood, s, mt) ;
+      LAUNCH (c, k_good_compact, std::min<uint32_t> (nb + 1, 148 * 16), 256, 0, s, nb, c->blkOff.p, c->blkNHash.p, c->clus.p,
+	      c->hashDepth.p, flag.p, pos.p, keyDepth.p, valIdx.p, goodOff.p, H, nGood) ;
+      flag.release () ; pos.release () ;
+      std::vector<uint64_t> hOff ((size_t) nb + 1) ;
+      CK (cudaMemcpyAsync (hOff.data (), goodOff.p, 8 * ((size_t) nb + 1), cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      /* sort by increasing depth inside every block; stable = ties keep list order, as glibc's qsort does */
+      if (nGood) segmented_sort_blocks<uint32_t, uint16_t> (c, s, keyDepth.p, keyS.p, valIdx.p, valS.p, hOff, goodOff.p, true) ;
+      auto pull = [&] (int slot, const void *src, size_t bytes) -> void*
+	{ if (c->goodCap[slot] < bytes || !c->goodSlot[slot])
+	    { if (c->goodSlot[slot]) cudaFreeHost (c->goodSlot[slot]) ;
+	      c->goodSlot[slot] = nullptr ; c->goodCap[slot] = 0 ;
+	      c->goodSlot[slot] = pinned_alloc (bytes) ; c->goodCap[slot] = bytes ? bytes : 1 ;
+	    }
+	  if (bytes) CK (cudaMemcpyAsync (c->goodSlot[slot], src, bytes, cudaMemcpyDeviceToHost, s)) ;
+	  return c->goodSlot[slot] ;
+	} ;
+      out->within = (uint8_t*) pull (0, c->within.p, hn) ;
+      out->goodOff = (uint64_t*) pull (1, goodOff.p, 8 * ((size_t) nb + 1)) ;
+      out->good = (uint16_t*) pull (2, valS.p, 2 * (size_t) nGood) ;
+      out->nGood = nGood ; out->hashNumber = hn ; out->nBlocksMax = nb ;
+      CK (cudaStreamSynchronize (s)) ;
+    }) ;
 }
 
 int h10x_gpu_stats (h10x_ctx *c, h10x_stats *out)

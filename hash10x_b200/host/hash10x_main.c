@@ -224,6 +224,25 @@ static int cmpGood (const void *a, const void *b)
 static void hashDepthRange (int min, int max)
 { if (!haveIndex) die ("cluster code called without setting hashDepthRange") ;
   uint32_t i, c ;
+  if (ctx && indexFromGpu)	/* the index is still resident on the GPU: build the lists there */
+    { char err[512] ; h10x_good_hashes g ;
+      int st = h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
+      if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+      if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
+      memcpy (hashWithinRange, g.within, ix.hashNumber) ;
+      hashRangeMin = min ; hashRangeMax = max ;
+      goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;
+      nGoodHashes = calloc (ix.nBlocksMax, sizeof (int)) ;
+      for (c = 0 ; c < ix.nBlocksMax ; ++c)
+	{ if (c && ix.blkNHash[c] > 65535)
+	    fprintf (stderr, "ignoring barcode %d - too many hashes %d > %d\n", (int) c, (int) ix.blkNHash[c], 65535) ;
+	  goodHashes[c] = g.good + g.goodOff[c] ;		/* slab owned by the context */
+	  nGoodHashes[c] = (int) (g.goodOff[c+1] - g.goodOff[c]) ;
+	}
+      printf ("  made goodHashes arrays for hash range %d to %d\n  ", hashRangeMin, hashRangeMax) ;
+      timeUpdate (outFile) ; fflush (outFile) ;
+      return ;
+    }
   if (!(hashWithinRange && min == hashRangeMin && max == hashRangeMax))
     { if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
       for (i = 0 ; i < ix.hashNumber ; ++i)	/* flags are only ever set, as in the reference */

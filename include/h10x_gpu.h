@@ -138,6 +138,21 @@ int h10x_gpu_build_host (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x
 int h10x_gpu_build_file (h10x_ctx *ctx, const char *path, h10x_index *out, char *err, size_t errlen) ;
 
 int h10x_gpu_stats (h10x_ctx *ctx, h10x_stats *out) ;
+
+/* "next" row: --hashDepthRange on the index resident after a single-GPU build.
+   hashWithinRangeBuild (hash10x.c:528-539): within[bin] is SET when min <= depth < max (flags accumulate over
+   calls until the next build); goodHashesBuild (hash10x.c:738-766): for every block the indices into its
+   ClusterHash list of the entries whose bin is within range, by increasing bin depth, ties in list order
+   (glibc's stable qsort); blocks with more than 65535 hashes get an empty list (:748).
+   The arrays are pinned host memory owned by the context, valid until the next call or build. */
+typedef struct h10x_good_hashes {
+  uint64_t nGood ;
+  uint32_t hashNumber, nBlocksMax ;
+  uint8_t *within ;		/* hashNumber */
+  uint64_t *goodOff ;		/* nBlocksMax + 1: block c's list is good[goodOff[c] .. goodOff[c+1]) */
+  uint16_t *good ;		/* nGood */
+} h10x_good_hashes ;
+int h10x_gpu_depth_range (h10x_ctx *ctx, int min, int max, h10x_good_hashes *out, char *err, size_t errlen) ;
 void h10x_index_free (h10x_index *ix) ;
 
 /* pinned host staging for callers that want the H2D copy to run at full PCIe rate */

@@ -337,3 +337,45 @@ int orc_write_hash (const orc_index *ix, const char *path)
   if (fclose (f)) ok = 0 ;
   return ok ? ORC_OK : ORC_IO ;
 }
+
+/* ---- hash10x.c:528-539 hashWithinRangeBuild + :738-766 goodHashesBuild ("next" row f1) ----
+   within[] (hashNumber bytes) is in/out: the reference only ever SETS flags (:535), so ranges accumulate
+   over successive --hashDepthRange commands.  good[] receives, block after block, the indices (into the
+   block's ClusterHash list) of the entries whose bin is within range, ordered by increasing bin depth;
+   glibc's qsort is a stable merge sort, so ties keep list order.  Blocks with more than 65535 hashes
+   get an empty list (:748).  PARITY UNPINNED: the reference never prints goodHashes (only --cluster
+   consumes them), so this restatement is checked by reading the code, not against reference output. */
+typedef struct { U32 depth ; U16 idx ; } GoodKey ;
+static int cmp_good (const void *a, const void *b)
+{ const GoodKey *x = a, *y = b ;
+  if (x->depth != y->depth) return x->depth < y->depth ? -1 : 1 ;
+  return (int) x->idx - (int) y->idx ;
+}
+
+int orc_good_hashes (U32 hashNumber, const U32 *hashDepth, U32 nBlocksMax, const U32 *blkNHash, const U64 *blkOff,
+		     const U64 *clus, int min, int max, U8 *within, U64 *goodOff, U16 *good)
+{ U32 i, c ;
+  struct { U32 hashNumber, nBlocksMax ; const U32 *hashDepth, *blkNHash ; const U64 *blkOff, *clus ; } x =
+    { hashNumber, nBlocksMax, hashDepth, blkNHash, blkOff, clus }, *ix = &x ;
+  for (i = 0 ; i < ix->hashNumber ; ++i)
+    { int n = (int) ix->hashDepth[i] ; if (n >= min && n < max) within[i] = 1 ; }
+  GoodKey *keys = malloc (65536 * sizeof (GoodKey)) ;
+  if (!keys) return ORC_NOMEM ;
+  U64 out = 0 ;
+  for (c = 0 ; c < ix->nBlocksMax ; ++c)
+    { goodOff[c] = out ;
+      U32 nh = c ? ix->blkNHash[c] : 0 ;
+      if (nh > 65535) continue ;
+      const U64 *ch = ix->clus + ix->blkOff[c] ;
+      int n = 0 ;
+      for (i = 0 ; i < nh ; ++i)
+	{ U32 id = (U32) ch[i] ;
+	  if (within[id]) { keys[n].depth = ix->hashDepth[id] ; keys[n].idx = (U16) i ; ++n ; }
+	}
+      qsort (keys, n, sizeof (GoodKey), cmp_good) ;
+      for (i = 0 ; i < (U32) n ; ++i) good[out++] = keys[i].idx ;
+    }
+  goodOff[ix->nBlocksMax] = out ;
+  free (keys) ;
+  return ORC_OK ;
+}

@@ -67,6 +67,8 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_int]
         L.orc_kmer_hashes.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_good_hashes.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.synth_layout.restype = C.c_uint64
         L.synth_layout.argtypes = [C.POINTER(SynthParams), C.c_void_p]
         L.synth_fill.argtypes = [C.POINTER(SynthParams), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -183,6 +185,24 @@ def kmer_hashes(h, hrc, k=21, factor1_=DEFAULT_FACTOR1):
     a, b = C.c_uint64(), C.c_uint64()
     lib().orc_kmer_hashes(h, hrc, factor1_, k, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def good_hashes(ix, dmin, dmax, within=None):
+    """hashWithinRangeBuild + goodHashesBuild (hash10x.c:528-539,738-766) on an Index:
+    returns (within flags, goodOff[nBlocksMax+1], good u16 indices)."""
+    hn, nb = int(ix.hashNumber), int(ix.nBlocksMax)
+    if within is None:
+        within = np.zeros(hn, np.uint8)
+    depth = np.ascontiguousarray(ix.hashDepth, np.uint32)
+    nh = np.ascontiguousarray(ix.blkNHash, np.uint32)
+    off = np.ascontiguousarray(ix.blkOff, np.uint64)
+    clus = np.ascontiguousarray(ix.clus, np.uint64)
+    good_off = np.zeros(nb + 1, np.uint64)
+    good = np.zeros(max(1, clus.size), np.uint16)
+    st = lib().orc_good_hashes(hn, depth.ctypes.data, nb, nh.ctypes.data, off.ctypes.data, clus.ctypes.data,
+                               dmin, dmax, within.ctypes.data, good_off.ctypes.data, good.ctypes.data)
+    assert st == 0
+    return within, good_off, good[:int(good_off[nb])]
 
 
 # ------------------------------------------------------------------ synthetic FQB (CPU)

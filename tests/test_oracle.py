@@ -152,3 +152,25 @@ def test_oracle_errors_equal_reference(orc, tmp_path):
     r = orc.run_reference(fqb, None, B=20)
     assert r.returncode != 0 and "hashTableSize is too small" in r.stderr
     assert orc.build(recs, B=20).status == 1
+
+
+def test_good_hashes_restatement_properties(orc):
+    """hashWithinRangeBuild + goodHashesBuild (hash10x.c:528-539,738-766) as restated by the oracle: flags only
+    ever set, lists hold exactly the in-range entries, ordered by depth with ties in list order."""
+    p = orc.synth_params(seed=81, n_barcodes=50, pairs_min=5, pairs_max=200, genome_len=80_000, mol_len=10_000)
+    ix = orc.build(orc.synth_fqb(p), B=20)
+    within, off, good = orc.good_hashes(ix, 3, 9)
+    depth = ix.hashDepth.astype(np.int64)
+    assert np.array_equal(within.astype(bool), (depth >= 3) & (depth < 9))
+    ids = (ix.clus & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    for c in range(1, ix.nBlocksMax):
+        lo, n = int(ix.blkOff[c]), int(ix.blkNHash[c])
+        lst = good[int(off[c]):int(off[c + 1])].astype(np.int64)
+        want = np.flatnonzero(within[ids[lo:lo + n]])
+        assert sorted(lst.tolist()) == want.tolist()
+        d = depth[ids[lo + lst]]
+        assert (np.diff(d) >= 0).all()
+        same = np.diff(d) == 0
+        assert (np.diff(lst)[same] > 0).all()
+    w2, _, good2 = orc.good_hashes(ix, 20, 30, within.copy())
+    assert (w2 >= within).all() and good2.size >= good.size       # ranges accumulate
