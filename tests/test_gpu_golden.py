@@ -91,3 +91,46 @@ def test_large_build_properties(orc, gpu_lib):
     want = orc.build(recs, B=24)
     hashfile.assert_strict_equal(hashfile.from_index(want), hashfile.from_index(got), table=True)
     assert np.array_equal(got.codes, want.codes)
+
+
+def test_scale_invariants_device_resident(orc, gpu_lib):
+    """5M read pairs generated on the GPU and built from device memory (the bench path): no oracle at this
+    size, so the checks are the size-independent ones - the reference's -DCHECK invariant (hash10x.c:341-345),
+    sortedness, id order, table reachability - plus agreement of the host-buffer entry point."""
+    import ctypes as C
+    import os
+    import torch
+    import hash10x_b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    synth = C.CDLL(os.path.join(root, "hash10x_b200", "libh10xsynth.so"))
+    synth.synth_fqb_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    p = orc.synth_params(seed=91, n_barcodes=12500, pairs_min=300, pairs_max=500, genome_len=100_000_000,
+                         mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, read_len=160)
+    n, off = orc.synth_layout(p)
+    fqb = torch.empty(n * 30, dtype=torch.int32, device="cuda")
+    assert synth.synth_fqb_device(C.byref(p), off.ctypes.data, 0, n, fqb.data_ptr(), None) == 0
+    with hash10x_b200.Hash10xGPU(B=26) as g:
+        g.build_device(fqb.data_ptr(), n)
+        ix = g.download()
+        st = g.stats()
+        host = fqb.cpu().numpy().view(np.uint32)
+        hn2, nh2, nb2 = g.build_host(host, want_index=False)
+    assert (hn2, nh2, nb2) == (ix.hashNumber, ix.nHashes, ix.nBlocksMax)
+    hn = ix.hashNumber
+    assert st["fusedBlocks"] == ix.nBlocksMax - 2 and ix.blkNHash[-1] == 0
+    assert np.array_equal(np.diff(ix.codeOff.astype(np.int64)), ix.hashDepth)
+    assert int(ix.hashDepth.sum()) == ix.nHashes == int(ix.blkNHash.sum())
+    ids = (ix.clus & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    assert (ix.clus >> np.uint64(48)).max() == 0
+    blk = np.repeat(np.arange(ix.nBlocksMax), ix.blkNHash)
+    sameb = blk[1:] == blk[:-1]
+    assert (np.diff(ids)[sameb] > 0).all() and ids.min() >= 1 and ids.max() == hn - 1
+    seg = np.repeat(np.arange(hn), ix.hashDepth)
+    assert (np.diff(ix.codes.astype(np.int64))[seg[1:] == seg[:-1]] > 0).all()
+    first = ix.codes[ix.codeOff[1:-1].astype(np.int64)].astype(np.int64)       # first block of every bin
+    assert (np.diff(first) >= 0).all()
+    hv = ix.hashValue[1:]
+    sameg = first[1:] == first[:-1]
+    assert (hv[1:][sameg] > hv[:-1][sameg]).all() and (hv % np.uint64(31) == 0).all()
+    assert np.unique(hv).size == hv.size
+    hashfile.check_table(hashfile.from_index(ix))
