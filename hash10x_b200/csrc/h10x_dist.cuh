@@ -20,6 +20,7 @@
  */
 #pragma once
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 struct NcclApi {
@@ -53,9 +54,30 @@ static NcclApi gNccl ;
 #define NCK(call) do { ncclResult_t r_ = (call) ; if (r_ != ncclSuccess) \
   throw H10xError (H10X_ERR_CUDA, std::string (#call) + ": " + gNccl.GetErrorString (r_)) ; } while (0)
 
+#define H10X_MAX_RANKS 16
+
+/* what a rank tells the others so that they can write straight into its receive buffers over NVLink */
+struct PeerInfo {
+  cudaIpcMemHandle_t handle ;	/* of the rank's workspace slab (one cudaMalloc) */
+  uint64_t pid ;		/* ranks living in the same process use the pointer itself */
+  uint64_t base ;		/* slab base address in the owning process */
+  uint64_t offHash, offDepth, offFirst ;	/* byte offsets of this build's receive arrays inside the slab */
+  int32_t device ;
+  int32_t ok ;
+} ;
+
+struct PeerMap {		/* a peer's slab as mapped into this process */
+  cudaIpcMemHandle_t handle ;
+  uint64_t pid = 0, base = 0 ;
+  char *mapped = nullptr ;
+  bool viaIpc = false ;
+} ;
+
 struct DistState {
   int rank = 0, nranks = 1 ;
   ncclComm_t comm = nullptr ;
+  int pushState = 0 ;		/* 0 untried, 1 peer stores work, -1 fall back to ncclSend/ncclRecv */
+  PeerMap peers[H10X_MAX_RANKS] ;
   /* results of the last distributed build */
   uint32_t blockBase = 0, nBlocksGlobal = 0, nLocalBins = 0 ;
   uint64_t nReadsGlobal = 0, nHashesGlobal = 0 ;
@@ -71,6 +93,43 @@ __global__ void k_local_distinct (uint32_t nSeg, const uint32_t *__restrict__ se
   if (s >= nSeg) return ;
   uint32_t i = segStart[s] ;
   dHash[s] = sh[i] * wMul ; dDepth[s] = segStart[s+1] - i ; dFirst[s] = entryBlk[se[i]] ;
+}
+
+/* The forward exchange as ONE kernel: every rank-distinct hash is computed from the sorted entries and
+   stored straight into the receive arrays of its hash-range owner - a peer GPU's memory mapped through
+   CUDA IPC (or plain peer access inside one process) - so the NVLink transfer overlaps the gathers that
+   produce the values and no send buffers or ncclSend/ncclRecv pairs exist.  Consecutive segments go to
+   consecutive remote slots, so the stores coalesce into full NVLink packets. */
+struct PushArgs {
+  uint64_t *hash[H10X_MAX_RANKS] ; uint32_t *depth[H10X_MAX_RANKS] ; uint32_t *first[H10X_MAX_RANKS] ;
+  uint64_t sendOff[H10X_MAX_RANKS + 1] ;	/* my segments [sendOff[o], sendOff[o+1]) belong to owner o */
+  uint64_t dstOff[H10X_MAX_RANKS] ;		/* where my share starts inside owner o's receive arrays */
+  int nranks ;
+} ;
+
+__global__ void k_push_distinct (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sh,
+				 const uint32_t *__restrict__ se, const uint32_t *__restrict__ entryBlk, uint64_t wMul,
+				 PushArgs a)
+{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (s >= nSeg) return ;
+  uint32_t i = segStart[s] ;
+  int o = 0 ;
+  while (o + 1 < a.nranks && (uint64_t) s >= a.sendOff[o + 1]) ++o ;
+  uint64_t dst = a.dstOff[o] + ((uint64_t) s - a.sendOff[o]) ;
+  a.hash[o][dst] = sh[i] * wMul ;
+  a.depth[o][dst] = segStart[s + 1] - i ;
+  a.first[o][dst] = entryBlk[se[i]] ;
+}
+
+/* off[o] = first segment whose hash reaches thr[o]; the segment hashes are sh[segStart[s]] * wMul, ascending */
+__global__ void k_lower_bounds_seg (const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sh, uint64_t wMul,
+				    uint32_t n, const uint64_t *__restrict__ thr, uint32_t nThr, uint64_t *__restrict__ off)
+{ uint32_t o = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (o >= nThr) return ;
+  uint64_t t = thr[o] ;
+  uint32_t lo = 0, hi = n ;
+  while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2 ; if (sh[segStart[mid]] * wMul < t) lo = mid + 1 ; else hi = mid ; }
+  off[o] = lo ;
 }
 
 /* off[o] = first index whose hash >= thr[o] (hashes ascending); one thread per threshold */

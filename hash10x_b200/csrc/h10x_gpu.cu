@@ -1113,23 +1113,20 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   HostTrace tr ;
   auto mark = [&] (const char *w) { if (tr.on) { cudaStreamSynchronize (s) ; tr.mark (w) ; } } ;
 
-  /* 1. rank-distinct hashes */
-  DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
-  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
-
   /* 2. owner = hash range: thresholds ceil (o * 2^(2k) / NR), monotone so the reference id order composes */
+  if (NR > H10X_MAX_RANKS) throw H10xError (H10X_ERR_UNSUPPORTED, "more ranks than H10X_MAX_RANKS") ;
   std::vector<uint64_t> thr ((size_t) NR + 1) ;
   for (int o = 0 ; o <= NR ; ++o)
     { unsigned __int128 t = ((unsigned __int128) o << (2 * P.k)) + (unsigned) (NR - 1) ; thr[o] = (uint64_t) (t / (unsigned) NR) ; }
   DBuf<uint64_t> dThr ((size_t) NR + 1, s, mt), dSendOff ((size_t) NR + 1, s, mt) ;
   CK (cudaMemcpyAsync (dThr.p, thr.data (), 8 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
-  LAUNCH (c, k_lower_bounds, 1, 64, 0, s, dHash.p, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
+  LAUNCH (c, k_lower_bounds_seg, 1, 64, 0, s, segStart, sh, wMul, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
   std::vector<uint64_t> sendOff ((size_t) NR + 1) ;
   CK (cudaMemcpyAsync (sendOff.data (), dSendOff.p, 8 * ((size_t) NR + 1), cudaMemcpyDeviceToHost, s)) ;
   CK (cudaStreamSynchronize (s)) ;
   sendOff[0] = 0 ; sendOff[NR] = Dl ;
 
-  mark ("d1-distinct") ;
+  mark ("d1-bounds") ;
   /* 3. counts */
   std::vector<uint64_t> sendCnt (NR), cntMat ((size_t) NR * NR) ;
   for (int o = 0 ; o < NR ; ++o) sendCnt[o] = sendOff[o+1] - sendOff[o] ;
@@ -1145,23 +1142,98 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   const uint32_t Ro = (uint32_t) Ro64 ;
 
   mark ("d3-counts") ;
-  /* 4. all-to-all-v of (hash, depth, first block) to the hash-range owners */
+  /* 4. all-to-all-v of (hash, depth, first block) to the hash-range owners.  Preferred: one kernel that
+	computes the rank-distinct values and stores them into the owners' receive arrays over NVLink (peer
+	memory through CUDA IPC); otherwise k_local_distinct + ncclSend/ncclRecv. */
   DBuf<uint64_t> rHash (Ro, s, mt) ; DBuf<uint32_t> rDepth (Ro, s, mt), rFirst (Ro, s, mt) ;
-  NCK (gNccl.GroupStart ()) ;
-  for (int peer = 0 ; peer < NR ; ++peer)
-    { if (sendCnt[peer])
-	{ NCK (gNccl.Send (dHash.p + sendOff[peer], sendCnt[peer], ncclUint64, peer, d->comm, s)) ;
-	  NCK (gNccl.Send (dDepth.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
-	  NCK (gNccl.Send (dFirst.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+  bool pushed = false ;
+  if (d->pushState >= 0 && !getenv ("H10X_NO_PEER_PUSH"))
+    { PeerInfo mine ; memset (&mine, 0, sizeof (mine)) ;
+      mine.ok = (cudaIpcGetMemHandle (&mine.handle, c->mt.base) == cudaSuccess) ? 1 : 0 ;
+      if (!mine.ok) cudaGetLastError () ;
+      mine.pid = (uint64_t) getpid () ; mine.base = (uint64_t) c->mt.base ; mine.device = P.device ;
+      mine.offHash = (uint64_t) ((char*) rHash.p - c->mt.base) ; mine.offDepth = (uint64_t) ((char*) rDepth.p - c->mt.base) ;
+      mine.offFirst = (uint64_t) ((char*) rFirst.p - c->mt.base) ;
+      DBuf<unsigned char> dInfo (sizeof (PeerInfo), s, mt), dInfos (sizeof (PeerInfo) * (size_t) NR, s, mt) ;
+      std::vector<PeerInfo> infos (NR) ;
+      CK (cudaMemcpyAsync (dInfo.p, &mine, sizeof (PeerInfo), cudaMemcpyHostToDevice, s)) ;
+      NCK (gNccl.AllGather (dInfo.p, dInfos.p, sizeof (PeerInfo), ncclUint8, d->comm, s)) ;
+      CK (cudaMemcpyAsync (infos.data (), dInfos.p, sizeof (PeerInfo) * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      /* map every peer's slab (cached while its handle stays the same) */
+      uint32_t ok = 1 ;
+      for (int r = 0 ; r < NR && ok ; ++r)
+	{ PeerMap &pm = d->peers[r] ;
+	  if (!infos[r].ok) { ok = 0 ; break ; }
+	  if (r == R) { pm.mapped = c->mt.base ; pm.viaIpc = false ; continue ; }
+	  bool same = pm.mapped && pm.pid == infos[r].pid && pm.base == infos[r].base
+	    && !memcmp (&pm.handle, &infos[r].handle, sizeof (cudaIpcMemHandle_t)) ;
+	  if (same) continue ;
+	  if (pm.mapped && pm.viaIpc) cudaIpcCloseMemHandle (pm.mapped) ;
+	  pm.mapped = nullptr ; pm.viaIpc = false ;
+	  if (infos[r].pid == mine.pid)		/* ranks are threads of one process: plain peer access */
+	    { int can = 0 ;
+	      cudaDeviceCanAccessPeer (&can, P.device, infos[r].device) ;
+	      cudaError_t e = can ? cudaDeviceEnablePeerAccess (infos[r].device, 0) : cudaErrorInvalidDevice ;
+	      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError () ; e = cudaSuccess ; }
+	      if (e != cudaSuccess) { cudaGetLastError () ; ok = 0 ; break ; }
+	      pm.mapped = (char*) infos[r].base ;
+	    }
+	  else
+	    { void *ptr = nullptr ;
+	      if (cudaIpcOpenMemHandle (&ptr, infos[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+		{ cudaGetLastError () ; ok = 0 ; break ; }
+	      pm.mapped = (char*) ptr ; pm.viaIpc = true ;
+	    }
+	  pm.handle = infos[r].handle ; pm.pid = infos[r].pid ; pm.base = infos[r].base ;
 	}
-      if (recvCnt[peer])
-	{ NCK (gNccl.Recv (rHash.p + recvOff[peer], recvCnt[peer], ncclUint64, peer, d->comm, s)) ;
-	  NCK (gNccl.Recv (rDepth.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
-	  NCK (gNccl.Recv (rFirst.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+      /* every rank must take the same path */
+      DBuf<uint32_t> dOk (1, s, mt), dOks (NR, s, mt) ;
+      std::vector<uint32_t> oks (NR) ;
+      CK (cudaMemcpyAsync (dOk.p, &ok, 4, cudaMemcpyHostToDevice, s)) ;
+      NCK (gNccl.AllGather (dOk.p, dOks.p, 1, ncclUint32, d->comm, s)) ;
+      CK (cudaMemcpyAsync (oks.data (), dOks.p, 4 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      bool all = true ; for (int r = 0 ; r < NR ; ++r) all = all && oks[r] ;
+      d->pushState = all ? 1 : -1 ;
+      if (all)
+	{ PushArgs pa ; memset (&pa, 0, sizeof (pa)) ;
+	  pa.nranks = NR ;
+	  for (int o = 0 ; o < NR ; ++o)
+	    { char *pb = d->peers[o].mapped ;
+	      pa.hash[o] = (uint64_t*) (pb + infos[o].offHash) ; pa.depth[o] = (uint32_t*) (pb + infos[o].offDepth) ;
+	      pa.first[o] = (uint32_t*) (pb + infos[o].offFirst) ;
+	      pa.sendOff[o] = sendOff[o] ;
+	      uint64_t before = 0 ; for (int src = 0 ; src < R ; ++src) before += cntMat[(size_t) src * NR + o] ;
+	      pa.dstOff[o] = before ;
+	    }
+	  pa.sendOff[NR] = Dl ;
+	  if (Dl) LAUNCH (c, k_push_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, pa) ;
+	  /* nobody reads its receive arrays before every rank's stores have landed: the collective is
+	     enqueued behind the kernel on each rank's stream */
+	  NCK (gNccl.AllGather (dOk.p, dOks.p, 1, ncclUint32, d->comm, s)) ;
+	  pushed = true ;
 	}
     }
-  NCK (gNccl.GroupEnd ()) ;
-  dHash.release () ; dDepth.release () ; dFirst.release () ;
+  if (!pushed)
+    { DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
+      if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+      NCK (gNccl.GroupStart ()) ;
+      for (int peer = 0 ; peer < NR ; ++peer)
+	{ if (sendCnt[peer])
+	    { NCK (gNccl.Send (dHash.p + sendOff[peer], sendCnt[peer], ncclUint64, peer, d->comm, s)) ;
+	      NCK (gNccl.Send (dDepth.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	      NCK (gNccl.Send (dFirst.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	    }
+	  if (recvCnt[peer])
+	    { NCK (gNccl.Recv (rHash.p + recvOff[peer], recvCnt[peer], ncclUint64, peer, d->comm, s)) ;
+	      NCK (gNccl.Recv (rDepth.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	      NCK (gNccl.Recv (rFirst.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	    }
+	}
+      NCK (gNccl.GroupEnd ()) ;
+      CK (cudaStreamSynchronize (s)) ;	/* the send buffers are freed on leaving this scope */
+    }
   mark ("d4-alltoall") ;
 
   /* 5. owner merge: depth = sum, first block = min over the (at most NR) copies of a hash */
@@ -1389,7 +1461,12 @@ void h10x_gpu_destroy (h10x_ctx *c)
 { if (!c) return ;
   cudaSetDevice (c->P.device) ;
   if (c->own) cudaStreamSynchronize (c->own) ;
-  if (c->dist) { if (c->dist->comm) gNccl.CommDestroy (c->dist->comm) ; delete c->dist ; c->dist = nullptr ; }
+  if (c->dist)
+    { for (int r = 0 ; r < H10X_MAX_RANKS ; ++r)
+	if (c->dist->peers[r].mapped && c->dist->peers[r].viaIpc) cudaIpcCloseMemHandle (c->dist->peers[r].mapped) ;
+      if (c->dist->comm) gNccl.CommDestroy (c->dist->comm) ;
+      delete c->dist ; c->dist = nullptr ;
+    }
   slab_free (c) ;
   for (auto e : c->evPool) cudaEventDestroy (e) ;
   for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
