@@ -62,6 +62,7 @@ struct PeerInfo {
   uint64_t pid ;		/* ranks living in the same process use the pointer itself */
   uint64_t base ;		/* slab base address in the owning process */
   uint64_t offHash, offDepth, offFirst ;	/* byte offsets of this build's receive arrays inside the slab */
+  uint64_t offBinId ;		/* ... and of the array that takes the bin ids coming back */
   int32_t device ;
   int32_t ok ;
 } ;
@@ -78,6 +79,7 @@ struct DistState {
   ncclComm_t comm = nullptr ;
   int pushState = 0 ;		/* 0 untried, 1 peer stores work, -1 fall back to ncclSend/ncclRecv */
   PeerMap peers[H10X_MAX_RANKS] ;
+  std::vector<cudaStream_t> copyStreams ;
   /* results of the last distributed build */
   uint32_t blockBase = 0, nBlocksGlobal = 0, nLocalBins = 0 ;
   uint64_t nReadsGlobal = 0, nHashesGlobal = 0 ;

@@ -1146,7 +1146,20 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	computes the rank-distinct values and stores them into the owners' receive arrays over NVLink (peer
 	memory through CUDA IPC); otherwise k_local_distinct + ncclSend/ncclRecv. */
   DBuf<uint64_t> rHash (Ro, s, mt) ; DBuf<uint32_t> rDepth (Ro, s, mt), rFirst (Ro, s, mt) ;
+  c->localBinId.alloc (Dl, s, mt) ;
   bool pushed = false ;
+  std::vector<PeerInfo> infos (NR) ;
+  /* peer copies run on side streams (copy engines) and are joined back into s */
+  auto peerCopy = [&] (int peer, void *dst, const void *src, size_t bytes)
+    { if (!bytes) return ;
+      if (d->copyStreams.empty ())
+	for (int i = 0 ; i < NR ; ++i) { cudaStream_t cs ; CK (cudaStreamCreateWithFlags (&cs, cudaStreamNonBlocking)) ; d->copyStreams.push_back (cs) ; }
+      cudaStream_t cs = d->copyStreams[peer] ;
+      cudaEvent_t ready = ctx_event (c), done = ctx_event (c) ;
+      CK (cudaEventRecord (ready, s)) ; CK (cudaStreamWaitEvent (cs, ready, 0)) ;
+      CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToDevice, cs)) ;
+      CK (cudaEventRecord (done, cs)) ; CK (cudaStreamWaitEvent (s, done, 0)) ;
+    } ;
   if (d->pushState >= 0 && !getenv ("H10X_NO_PEER_PUSH"))
     { PeerInfo mine ; memset (&mine, 0, sizeof (mine)) ;
       mine.ok = (cudaIpcGetMemHandle (&mine.handle, c->mt.base) == cudaSuccess) ? 1 : 0 ;
@@ -1154,8 +1167,8 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       mine.pid = (uint64_t) getpid () ; mine.base = (uint64_t) c->mt.base ; mine.device = P.device ;
       mine.offHash = (uint64_t) ((char*) rHash.p - c->mt.base) ; mine.offDepth = (uint64_t) ((char*) rDepth.p - c->mt.base) ;
       mine.offFirst = (uint64_t) ((char*) rFirst.p - c->mt.base) ;
+      mine.offBinId = (uint64_t) ((char*) c->localBinId.p - c->mt.base) ;
       DBuf<unsigned char> dInfo (sizeof (PeerInfo), s, mt), dInfos (sizeof (PeerInfo) * (size_t) NR, s, mt) ;
-      std::vector<PeerInfo> infos (NR) ;
       CK (cudaMemcpyAsync (dInfo.p, &mine, sizeof (PeerInfo), cudaMemcpyHostToDevice, s)) ;
       NCK (gNccl.AllGather (dInfo.p, dInfos.p, sizeof (PeerInfo), ncclUint8, d->comm, s)) ;
       CK (cudaMemcpyAsync (infos.data (), dInfos.p, sizeof (PeerInfo) * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
@@ -1181,8 +1194,11 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	    }
 	  else
 	    { void *ptr = nullptr ;
-	      if (cudaIpcOpenMemHandle (&ptr, infos[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
-		{ cudaGetLastError () ; ok = 0 ; break ; }
+	      cudaError_t e = cudaIpcOpenMemHandle (&ptr, infos[r].handle, cudaIpcMemLazyEnablePeerAccess) ;
+	      if (e != cudaSuccess)
+		{ if (tr.on) fprintf (stderr, "h10x-trace rank %d: cudaIpcOpenMemHandle(rank %d) failed: %s\n", R, r, cudaGetErrorString (e)) ;
+		  cudaGetLastError () ; ok = 0 ; break ;
+		}
 	      pm.mapped = (char*) ptr ; pm.viaIpc = true ;
 	    }
 	  pm.handle = infos[r].handle ; pm.pid = infos[r].pid ; pm.base = infos[r].base ;
@@ -1196,6 +1212,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       CK (cudaStreamSynchronize (s)) ;
       bool all = true ; for (int r = 0 ; r < NR ; ++r) all = all && oks[r] ;
       d->pushState = all ? 1 : -1 ;
+      if (tr.on && R == 0) fprintf (stderr, "h10x-trace peer push %s\n", all ? "active" : "unavailable, using ncclSend/ncclRecv") ;
       if (all)
 	{ PushArgs pa ; memset (&pa, 0, sizeof (pa)) ;
 	  pa.nranks = NR ;
@@ -1208,7 +1225,24 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	      pa.dstOff[o] = before ;
 	    }
 	  pa.sendOff[NR] = Dl ;
-	  if (Dl) LAUNCH (c, k_push_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, pa) ;
+	  /* two ways to move the data: SM stores from the producing kernel (k_push_distinct), or local
+	     materialisation + copy engines.  Measured on 8 B200s (1.3 GB leaving each rank): SM stores 14.4 ms
+	     (~110 GB/s per GPU, no better than ncclSend/ncclRecv), copy engines 6.3 ms; at 2 ranks the kernel
+	     wins (3.3 ms).  H10X_PEER_KERNEL / H10X_PEER_COPY force one. */
+	  const bool useCopy = getenv ("H10X_PEER_COPY") || (NR > 2 && !getenv ("H10X_PEER_KERNEL")) ;
+	  if (useCopy)
+	    { DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
+	      if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+	      for (int k = 1 ; k <= NR ; ++k)
+		{ int o = (R + k) % NR ;		/* start with the next rank: spread the load over the links */
+		  uint64_t n = sendCnt[o] ;
+		  peerCopy (o, pa.hash[o] + pa.dstOff[o], dHash.p + sendOff[o], 8 * n) ;
+		  peerCopy (o, pa.depth[o] + pa.dstOff[o], dDepth.p + sendOff[o], 4 * n) ;
+		  peerCopy (o, pa.first[o] + pa.dstOff[o], dFirst.p + sendOff[o], 4 * n) ;
+		}
+	      CK (cudaStreamSynchronize (s)) ;	/* the staging arrays go out of scope */
+	    }
+	  else if (Dl) LAUNCH (c, k_push_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, pa) ;
 	  /* nobody reads its receive arrays before every rank's stores have landed: the collective is
 	     enqueued behind the kernel on each rank's stream */
 	  NCK (gNccl.AllGather (dOk.p, dOks.p, 1, ncclUint32, d->comm, s)) ;
@@ -1293,25 +1327,25 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 
   mark ("d7-ids") ;
   /* 8. reverse all-to-all-v: the bin id of every rank-distinct hash, in the order it was sent */
-  c->localBinId.alloc (Dl, s, mt) ;
-  NCK (gNccl.GroupStart ()) ;
-  for (int peer = 0 ; peer < NR ; ++peer)
-    { if (recvCnt[peer]) NCK (gNccl.Send (ans.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
-      if (sendCnt[peer]) NCK (gNccl.Recv (c->localBinId.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+  if (pushed)
+    { for (int k = 1 ; k <= NR ; ++k)
+	{ int src = (R + k) % NR ;
+	  uint64_t before = 0 ; for (int o = 0 ; o < R ; ++o) before += cntMat[(size_t) src * NR + o] ;	/* src's sendOff[R] */
+	  uint32_t *dst = (uint32_t*) (d->peers[src].mapped + infos[src].offBinId) + before ;
+	  peerCopy (src, dst, ans.p + recvOff[src], 4 * recvCnt[src]) ;
+	}
     }
-  NCK (gNccl.GroupEnd ()) ;
-  if (H) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
+  else
+    { NCK (gNccl.GroupStart ()) ;
+      for (int peer = 0 ; peer < NR ; ++peer)
+	{ if (recvCnt[peer]) NCK (gNccl.Send (ans.p + recvOff[peer], recvCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	  if (sendCnt[peer]) NCK (gNccl.Recv (c->localBinId.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	}
+      NCK (gNccl.GroupEnd ()) ;
+    }
 
-  mark ("d8-reverse+entryids") ;
+  mark ("d8-reverse") ;
   /* 9. (id, hash, depth) of every bin to rank 0, which owns hashValue / hashDepth / hashIndex */
-  std::vector<uint64_t> mine2 = { Do, H }, all2 ((size_t) 2 * NR) ;
-  DBuf<uint64_t> d2 (2, s, mt), dAll2 ((size_t) 2 * NR, s, mt) ;
-  CK (cudaMemcpyAsync (d2.p, mine2.data (), 16, cudaMemcpyHostToDevice, s)) ;
-  NCK (gNccl.AllGather (d2.p, dAll2.p, 2, ncclUint64, d->comm, s)) ;
-  CK (cudaMemcpyAsync (all2.data (), dAll2.p, 16 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
-  CK (cudaStreamSynchronize (s)) ;
-  d->nHashesGlobal = 0 ;
-  for (int r = 0 ; r < NR ; ++r) d->nHashesGlobal += all2[2*r + 1] ;
   DBuf<uint32_t> tId, tDepth ; DBuf<uint64_t> tHash ;
   if (R == 0)
     { tId.alloc (Dglobal, s, mt) ; tDepth.alloc (Dglobal, s, mt) ; tHash.alloc (Dglobal, s, mt) ;
@@ -1320,25 +1354,52 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
       CK (cudaMemsetAsync (c->hashDepth.p + Dglobal + 1, 0, 4, s)) ;
     }
-  NCK (gNccl.GroupStart ()) ;
-  if (Do)
-    { NCK (gNccl.Send (gId.p, Do, ncclUint32, 0, d->comm, s)) ;
-      NCK (gNccl.Send (gHash.p, Do, ncclUint64, 0, d->comm, s)) ;
-      NCK (gNccl.Send (gDepth.p, Do, ncclUint32, 0, d->comm, s)) ;
-    }
+  std::vector<uint64_t> mine2 = { Do, H, 0, 0, 0 }, all2 ((size_t) 5 * NR) ;
   if (R == 0)
-    { uint64_t off = 0 ;
-      for (int r = 0 ; r < NR ; ++r)
-	{ uint64_t n = all2[2*r] ;
-	  if (n)
-	    { NCK (gNccl.Recv (tId.p + off, n, ncclUint32, r, d->comm, s)) ;
-	      NCK (gNccl.Recv (tHash.p + off, n, ncclUint64, r, d->comm, s)) ;
-	      NCK (gNccl.Recv (tDepth.p + off, n, ncclUint32, r, d->comm, s)) ;
-	    }
-	  off += n ;
-	}
+    { mine2[2] = (uint64_t) ((char*) tId.p - c->mt.base) ; mine2[3] = (uint64_t) ((char*) tHash.p - c->mt.base) ;
+      mine2[4] = (uint64_t) ((char*) tDepth.p - c->mt.base) ;
     }
-  NCK (gNccl.GroupEnd ()) ;
+  DBuf<uint64_t> d2 (5, s, mt), dAll2 ((size_t) 5 * NR, s, mt) ;
+  CK (cudaMemcpyAsync (d2.p, mine2.data (), 40, cudaMemcpyHostToDevice, s)) ;
+  /* this collective is also the barrier behind the reverse copies: after it every rank's localBinId is complete */
+  NCK (gNccl.AllGather (d2.p, dAll2.p, 5, ncclUint64, d->comm, s)) ;
+  CK (cudaMemcpyAsync (all2.data (), dAll2.p, 40 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  if (H) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
+  d->nHashesGlobal = 0 ;
+  for (int r = 0 ; r < NR ; ++r) d->nHashesGlobal += all2[5*r + 1] ;
+  if (pushed)
+    { uint64_t before = 0 ; for (int r = 0 ; r < R ; ++r) before += all2[5*r] ;
+      char *z = d->peers[0].mapped ;
+      peerCopy (0, (uint32_t*) (z + all2[2]) + before, gId.p, 4 * (size_t) Do) ;
+      peerCopy (0, (uint64_t*) (z + all2[3]) + before, gHash.p, 8 * (size_t) Do) ;
+      peerCopy (0, (uint32_t*) (z + all2[4]) + before, gDepth.p, 4 * (size_t) Do) ;
+      DBuf<uint32_t> b1 (1, s, mt), bN (NR, s, mt) ;
+      CK (cudaMemsetAsync (b1.p, 0, 4, s)) ;
+      NCK (gNccl.AllGather (b1.p, bN.p, 1, ncclUint32, d->comm, s)) ;	/* barrier: rank 0 scatters only complete data */
+      CK (cudaStreamSynchronize (s)) ;
+    }
+  else
+    { NCK (gNccl.GroupStart ()) ;
+      if (Do)
+	{ NCK (gNccl.Send (gId.p, Do, ncclUint32, 0, d->comm, s)) ;
+	  NCK (gNccl.Send (gHash.p, Do, ncclUint64, 0, d->comm, s)) ;
+	  NCK (gNccl.Send (gDepth.p, Do, ncclUint32, 0, d->comm, s)) ;
+	}
+      if (R == 0)
+	{ uint64_t off = 0 ;
+	  for (int r = 0 ; r < NR ; ++r)
+	    { uint64_t n = all2[5*r] ;
+	      if (n)
+		{ NCK (gNccl.Recv (tId.p + off, n, ncclUint32, r, d->comm, s)) ;
+		  NCK (gNccl.Recv (tHash.p + off, n, ncclUint64, r, d->comm, s)) ;
+		  NCK (gNccl.Recv (tDepth.p + off, n, ncclUint32, r, d->comm, s)) ;
+		}
+	      off += n ;
+	    }
+	}
+      NCK (gNccl.GroupEnd ()) ;
+    }
   if (R == 0 && Dglobal)
     LAUNCH (c, k_scatter_bins, gridFor (Dglobal, 256), 256, 0, s, Dglobal, tId.p, tHash.p, tDepth.p, c->hashValue.p, c->hashDepth.p) ;
   CK (cudaStreamSynchronize (s)) ;	/* sends read gId/gHash/gDepth, freed on return */
@@ -1464,6 +1525,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
   if (c->dist)
     { for (int r = 0 ; r < H10X_MAX_RANKS ; ++r)
 	if (c->dist->peers[r].mapped && c->dist->peers[r].viaIpc) cudaIpcCloseMemHandle (c->dist->peers[r].mapped) ;
+      for (auto cs : c->dist->copyStreams) cudaStreamDestroy (cs) ;
       if (c->dist->comm) gNccl.CommDestroy (c->dist->comm) ;
       delete c->dist ; c->dist = nullptr ;
     }
