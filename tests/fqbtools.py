@@ -49,3 +49,21 @@ def const_records(barcode_word, n, base1, base2):
     poly-C none: SURVEY.md Appendix E)."""
     rec = make_record(barcode_word, np.full(135, base1), np.full(151, base2))
     return np.tile(rec, (n, 1))
+
+
+def mixed_records(words, counts, kinds, seed):
+    """runs of random / poly-A / poly-C / dinucleotide-repeat reads (used by the property tests)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for w, n, kind in zip(words, counts, kinds):
+        if kind == "rand":
+            out.append(random_records(rng, [w], [n]))
+        elif kind == "polyA":
+            out.append(const_records(w, n, 0, 0))
+        elif kind == "polyC":
+            out.append(const_records(w, n, 1, 1))
+        else:
+            r1 = np.tile([0, 1], 68)[:135]
+            r2 = np.tile([2, 3], 76)[:151]
+            out.append(np.tile(make_record(w, r1, r2), (n, 1)))
+    return np.concatenate(out).astype(np.uint32)

@@ -215,3 +215,34 @@ def test_bad_parameters(gpu_lib):
             _gpu(**kw)
     with _gpu(B=31, flags=1) as g:        # H10X_FLAG_WIDE_B models the "B bound relaxed" oracle
         assert g.ctx
+
+
+def test_random_small_inputs_match_oracle(orc, gpu_lib):
+    """seeded twin of tests/test_oracle_property.py on the GPU: barcode word 0 runs, low-complexity reads,
+    random -c / -N; same index or the same error as the oracle (which that test pins to the reference)"""
+    import hash10x_b200
+    rng = np.random.default_rng(12345)
+    pool = [0, 0, 5, 9, 77, 0x3FFFFFFF, 0xFFFFFFFF]
+    kinds_pool = ["rand", "rand", "polyA", "polyC", "repeat"]
+    n_ok = n_err = 0
+    for _case in range(60):
+        n_runs = int(rng.integers(1, 8))
+        words = [pool[int(rng.integers(0, len(pool)))] for _ in range(n_runs)]
+        counts = [int(rng.integers(1, 10)) for _ in range(n_runs)]
+        kinds = [kinds_pool[int(rng.integers(0, len(kinds_pool)))] for _ in range(n_runs)]
+        chunk = int(rng.integers(1, 15))
+        N = [0, 0, 1, 3, 7, 11, 19, 40][int(rng.integers(0, 8))]
+        recs = fqbtools.mixed_records(words, counts, kinds, int(rng.integers(0, 2 ** 31)))
+        want = orc.build(recs, B=20, chunk=chunk, N=N)
+        with _gpu(B=20, chunkSize=chunk, N=N) as g:
+            if want.status != 0:
+                with pytest.raises(hash10x_b200.H10xError) as e:
+                    g.build_host(recs)
+                assert e.value.code == want.status
+                n_err += 1
+                continue
+            got = g.build_host(recs)
+        hashfile.assert_strict_equal(hashfile.from_index(want), hashfile.from_index(got), table=True)
+        assert np.array_equal(got.codes, want.codes) and np.array_equal(got.clus, want.clus)
+        n_ok += 1
+    assert n_ok >= 20 and n_err >= 5
