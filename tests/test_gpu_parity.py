@@ -56,7 +56,8 @@ def test_synthetic_strict(orc, gpu_lib, seed, nb, pmin, pmax):
     assert st["nBins"] == want.hashNumber - 1
 
 
-@pytest.mark.parametrize("k,w,r", [(21, 31, 17), (16, 32, 17), (31, 7, 3), (11, 1, 9), (25, 12, 17), (5, 3, 1)])
+@pytest.mark.parametrize("k,w,r", [(21, 31, 17), (16, 32, 17), (31, 7, 3), (11, 1, 9), (25, 12, 17), (5, 3, 1),
+                                   (21, 1, 17), (23, 31, 17), (13, 3, 2), (22, 64, 5), (15, 30, 17), (21, 62, 17)])
 def test_parameters(orc, gpu_lib, k, w, r):
     p = orc.synth_params(seed=11, n_barcodes=25, pairs_min=3, pairs_max=60, genome_len=50_000, mol_len=5_000)
     recs = orc.synth_fqb(p)
