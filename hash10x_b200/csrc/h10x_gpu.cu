@@ -124,6 +124,8 @@ struct h10x_ctx {
   uint64_t launches = 0 ;
   /* multi-GPU (h10x_dist.cuh) */
   bool slabClamped = false ;	/* the slab already takes all free device memory */
+  /* host-buffer builds start the D2H of an index array as soon as it is final, on a second stream */
+  bool earlyDl = false ; cudaStream_t dlStream = 0 ; bool slotDone[9] = { false, false, false, false, false, false, false, false, false } ;
   DBuf<uint8_t> within ;	/* --hashDepthRange flags per bin; only ever set (hash10x.c:535) until the next build */
   void *goodSlot[3] = { nullptr, nullptr, nullptr } ; size_t goodCap[3] = { 0, 0, 0 } ;	/* pinned host: within, goodOff, good */
   struct DistState *dist = nullptr ;
@@ -136,6 +138,31 @@ struct h10x_ctx {
 static cudaEvent_t ctx_event (h10x_ctx *c)
 { if (c->evUsed == c->evPool.size ()) { cudaEvent_t e ; CK (cudaEventCreate (&e)) ; c->evPool.push_back (e) ; }
   return c->evPool[c->evUsed++] ;
+}
+
+enum { SLOT_INDEX = 0, SLOT_VALUE, SLOT_DEPTH, SLOT_NREAD, SLOT_NHASH, SLOT_BLKOFF, SLOT_CLUS, SLOT_CODEOFF, SLOT_CODES } ;
+
+static void *host_slot (h10x_ctx *c, int i, size_t bytes)
+{ if (c->hostCap[i] < bytes || !c->hostSlot[i])
+    { if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
+      c->hostSlot[i] = nullptr ; c->hostCap[i] = 0 ;
+      void *p = nullptr ;
+      CK (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault)) ;
+      c->hostSlot[i] = p ; c->hostCap[i] = bytes ? bytes : 1 ;
+    }
+  return c->hostSlot[i] ;
+}
+
+/* during a host-buffer build: copy a finished index array to its pinned host slot behind an event,
+   while later stages keep the SMs busy */
+static void early_pull (h10x_ctx *c, cudaStream_t s, int slot, const void *src, size_t bytes)
+{ if (!c->earlyDl || !src) return ;
+  void *dst = host_slot (c, slot, bytes) ;
+  cudaEvent_t ready = ctx_event (c) ;
+  CK (cudaEventRecord (ready, s)) ;
+  CK (cudaStreamWaitEvent (c->dlStream, ready, 0)) ;
+  if (bytes) CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, c->dlStream)) ;
+  c->slotDone[slot] = true ;
 }
 
 struct StageTimer {
@@ -474,6 +501,7 @@ static void reset_result (h10x_ctx *c)
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
   c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
+  for (int i = 0 ; i < 9 ; ++i) c->slotDone[i] = false ;
   memset (&c->stats, 0, sizeof (c->stats)) ;
 }
 
@@ -939,6 +967,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       dist_bins (c, s, 0, nullptr, nullptr, nullptr, 0, segStart.p, nullptr, nBlkGlobal, nullptr, D, wDiv) ;
     }
 
+  if (!dist) { early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ; early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ; }
   tr.mark ("bins-enq") ;
   /* ---------------- hash -> code CSR ---------------- */
   if (dist)
@@ -979,6 +1008,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    { return cub::DeviceRadixSort::SortPairs (t, b, c->codes.p, keysOut.p, idRead.p, c->clus.p, H, 0, bBits, s) ; }) ;
 	}
       if (P.flags & H10X_FLAG_NO_CODES) { c->codes.release () ; c->codeOff.release () ; }
+      else { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
+      early_pull (c, s, SLOT_CLUS, c->clus.p, 8 * H) ;
     }
   se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; entryBlk.release () ;
 
@@ -1409,7 +1440,8 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 /* ------------------------------------------------------------------ slab sizing / retry */
 
 static void slab_free (h10x_ctx *c)
-{ reset_result (c) ;
+{ if (c->dlStream) cudaStreamSynchronize (c->dlStream) ;	/* early downloads read the slab */
+  reset_result (c) ;
   if (c->mt.base) { cudaFree (c->mt.base) ; c->mt.base = nullptr ; }
   c->mt.cap = 0 ; c->mt.reset () ;
 }
@@ -1522,6 +1554,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
 { if (!c) return ;
   cudaSetDevice (c->P.device) ;
   if (c->own) cudaStreamSynchronize (c->own) ;
+  if (c->dlStream) { cudaStreamSynchronize (c->dlStream) ; cudaStreamDestroy (c->dlStream) ; c->dlStream = 0 ; }
   if (c->dist)
     { for (int r = 0 ; r < H10X_MAX_RANKS ; ++r)
 	if (c->dist->peers[r].mapped && c->dist->peers[r].viaIpc) cudaIpcCloseMemHandle (c->dist->peers[r].mapped) ;
@@ -1588,12 +1621,8 @@ int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
       auto pull = [&] (void **dst, const void *src, size_t bytes)
 	{ int i = slot++ ;
 	  if (!src) { *dst = nullptr ; return ; }
-	  if (c->hostCap[i] < bytes || !c->hostSlot[i])
-	    { if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
-	      c->hostSlot[i] = nullptr ; c->hostCap[i] = 0 ;
-	      c->hostSlot[i] = pinned_alloc (bytes) ; c->hostCap[i] = bytes ? bytes : 1 ;
-	    }
-	  *dst = c->hostSlot[i] ;
+	  if (c->slotDone[i]) { *dst = c->hostSlot[i] ; return ; }	/* already on its way (early_pull) */
+	  *dst = host_slot (c, i, bytes) ;
 	  if (bytes) CK (cudaMemcpyAsync (*dst, src, bytes, cudaMemcpyDeviceToHost, s)) ;
 	} ;
       pull ((void**) &out->hashIndex, c->hashIndex.p, c->hashIndex.p ? ((size_t) 4 << c->P.B) : 0) ;
@@ -1606,6 +1635,8 @@ int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
       pull ((void**) &out->codeOff, c->codeOff.p, c->codeOff.p ? 8 * (hn + 1) : 0) ;
       pull ((void**) &out->codes, c->codes.p, c->codes.p ? 4 * H : 0) ;
       CK (cudaStreamSynchronize (s)) ;
+      if (c->dlStream) CK (cudaStreamSynchronize (c->dlStream)) ;
+      for (int i = 0 ; i < 9 ; ++i) c->slotDone[i] = false ;
     }) ;
   if (st != H10X_OK) memset (out, 0, sizeof (*out)) ;
   return st ;
@@ -1622,7 +1653,11 @@ int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_i
 	{ reset_result (c) ;
 	  DBuf<uint32_t> d ((size_t) n * H10X_REC_WORDS, s, &c->mt) ;
 	  if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
-	  build_device_impl (c, d.p, n, s, false) ;
+	  if (!c->dlStream) CK (cudaStreamCreateWithFlags (&c->dlStream, cudaStreamNonBlocking)) ;
+	  c->earlyDl = true ;
+	  try { build_device_impl (c, d.p, n, s, false) ; }
+	  catch (...) { c->earlyDl = false ; cudaStreamSynchronize (c->dlStream) ; throw ; }
+	  c->earlyDl = false ;
 	}) ;
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
