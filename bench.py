@@ -42,8 +42,10 @@ WORKLOADS = {
 }
 
 
-def synth_params(orc, wl, seed=3):
-    return orc.synth_params(seed=seed, genome_len=wl["genome_len"], n_barcodes=wl["n_barcodes"],
+def synth_params(mod, wl, seed=3):
+    """mod: hash10x_b200.synth (GPU arm) or oracle.orc (CPU legs) - the same parameter struct"""
+    make = getattr(mod, "make_params", None) or mod.synth_params
+    return make(seed=seed, genome_len=wl["genome_len"], n_barcodes=wl["n_barcodes"],
                             pairs_min=wl["pairs_min"], pairs_max=wl["pairs_max"],
                             mol_per_barcode=wl["mol_per_barcode"], mol_len=wl["mol_len"],
                             snp_period=wl["snp_period"], err_rate=wl["err_rate"], read_len=wl.get("read_len", 151))
@@ -184,8 +186,7 @@ def run_ours(args, wl):
     import numpy as np
     import torch
     import hash10x_b200
-    from hash10x_b200 import binding
-    from oracle import orc  # generator layout + cpu_baseline leg only
+    from hash10x_b200 import synth as gsynth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,23 +200,17 @@ def run_ours(args, wl):
 
     # --- synthetic FQB generated in HBM: ONE data set (same genome), each rank a contiguous barcode range ---
     from hash10x_b200 import shard
-    synth = C.CDLL(os.path.join(ROOT, "hash10x_b200", "libh10xsynth.so"))
-    synth.synth_layout_host.restype = C.c_uint64
-    synth.synth_fqb_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
-    p = synth_params(orc, wl, seed=3)
+    p = synth_params(gsynth, wl, seed=3)
     if args.pairs:
         mean = (wl["pairs_min"] + wl["pairs_max"]) / 2
         p.nBarcodes = max(2, int(args.pairs / mean))
     p.nBarcodes *= world                     # weak scaling: the per-GPU share stays fixed
-    off = np.zeros(p.nBarcodes + 1, np.uint64)
-    synth.synth_layout_host(C.byref(p), off.ctypes.data_as(C.c_void_p))
+    _n_total, off = gsynth.layout(p)
     cut = shard.plan_shards(off, world)
     r0, r1 = shard.shard_records(off, cut, rank)
     n_rec = r1 - r0
     fqb = torch.empty(n_rec * 30, dtype=torch.int32, device=dev)
-    st = synth.synth_fqb_device(C.byref(p), off.ctypes.data_as(C.c_void_p), r0, r1, fqb.data_ptr(), None)
-    if st:
-        raise RuntimeError("synthetic generator failed: cuda error %d" % st)
+    gsynth.fill_device(p, off, r0, r1, fqb.data_ptr())
     torch.cuda.synchronize()
 
     g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local)
@@ -343,6 +338,7 @@ def run_ours(args, wl):
     # --- cpu baseline: the reference's own CPU path on a bounded sample, rank 0, N=1 only ---
     cpu = None
     if world == 1 and not args.no_cpu:
+        from oracle import orc          # the only use of oracle/ in this arm: the timed CPU baseline
         recs, nb = cpu_sample(orc, wl, args.cpu_pairs)
         dt, kind, how = time_reference(orc, recs, wl["B"])
         cpu = {"value": recs.shape[0] / dt, "unit": "read pairs/s", "cores": 1, "kind": kind,

@@ -7,9 +7,13 @@ import ctypes as C
 import os
 import subprocess
 
+import sys
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+if os.path.dirname(_HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "liborc.so")
 REF_DIR = os.path.join(_HERE, "_ref")
 
@@ -37,11 +41,7 @@ class OrcIndex(C.Structure):
                 ("codes", C.POINTER(C.c_uint32))]
 
 
-class SynthParams(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("genomeLen", C.c_uint64), ("nBarcodes", C.c_uint32),
-                ("pairsMin", C.c_uint32), ("pairsMax", C.c_uint32), ("molPerBarcode", C.c_uint32),
-                ("molLen", C.c_uint32), ("snpPeriod", C.c_uint32), ("errThresh", C.c_uint32),
-                ("readLen", C.c_uint32)]
+from hash10x_b200.synth import SynthParams, make_params as _make_synth_params  # shared parameter struct
 
 
 _lib = None
@@ -207,10 +207,9 @@ def good_hashes(ix, dmin, dmax, within=None):
 
 # ------------------------------------------------------------------ synthetic FQB (CPU)
 
-def synth_params(seed=1, genome_len=200_000, n_barcodes=40, pairs_min=20, pairs_max=120,
-                 mol_per_barcode=4, mol_len=20_000, snp_period=500, err_rate=0.002, read_len=151):
-    return SynthParams(seed, genome_len, n_barcodes, pairs_min, pairs_max, mol_per_barcode,
-                       mol_len, snp_period, int(err_rate * 2 ** 32), read_len)
+def synth_params(**kw):
+    """parameters of the synthetic data set (see hash10x_b200/synth.py::make_params)"""
+    return _make_synth_params(**kw)
 
 
 def synth_layout(p):

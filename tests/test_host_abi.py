@@ -68,8 +68,6 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h")) and f != "synth_fqb.h":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle" not in text.replace("the oracle", "").replace("oracle/", "ORACLEDIR/") or \
-                    "import" not in text or "from oracle" not in text, f
                 assert "from oracle" not in text and "import oracle" not in text and "liborc" not in text, f
 
 
