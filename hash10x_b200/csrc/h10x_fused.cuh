@@ -33,10 +33,15 @@
 #include "h10x_common.cuh"
 
 #define H10X_BLK_FALLBACK 0xffffffffu
-#define H10X_BUCKET_LIMIT 48u		/* longest bucket the insertion sort will take */
+#define H10X_BUCKET_LIMIT 48u		/* longest bucket the in-bucket ordering will take (its cost is quadratic) */
 
-__device__ __forceinline__ uint32_t h10x_swap_pairs (uint32_t x)
-{ return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1) ; }
+/* complement of x with the two bits of every base swapped, ~(((x >> 1) & 0x5555..) | ((x << 1) & 0xaaaa..)): the bit
+   select and the inversion are one LOP3 (lut = ~((a & c) | (b & ~c)) = 0x1b) */
+__device__ __forceinline__ uint32_t h10x_swap_pairs_not (uint32_t x)
+{ uint32_t r ;
+  asm ("lop3.b32 %0, %1, %2, %3, 0x1b;" : "=r" (r) : "r" (x >> 1), "r" (x << 1), "r" (0x55555555u)) ;
+  return r ;
+}
 
 /* low 64 bits of (xhi:xlo) * (fhi:flo) in three multiply instructions */
 __device__ __forceinline__ uint64_t h10x_mul64 (uint32_t xlo, uint32_t xhi, uint32_t flo, uint32_t fhi)
@@ -105,8 +110,8 @@ k_fused_block (FusedArgs a, HashParams hp)
 {
   extern __shared__ __align__ (16) unsigned char smemRaw[] ;
   uint64_t *S = (uint64_t*) smemRaw ;			/* cap keys, bucketed */
-  uint32_t *start = (uint32_t*) (S + a.cap) ;		/* nbuck + 1 */
-  uint32_t *cur = start + a.nbuck + 1 ;			/* nbuck */
+  uint32_t *start = (uint32_t*) (S + a.cap) ;		/* nbuck + 1: bucket counts, then starts, then ends */
+  uint32_t *cur = start ;				/* the dedup scan reuses it */
   __shared__ uint32_t sCount, sBad, sTicket, warpTmp[33] ;
   __shared__ unsigned long long sBase ;
 
@@ -134,7 +139,8 @@ k_fused_block (FusedArgs a, HashParams hp)
   const uint32_t base = isR2 ? 15u : 0u ;
   const uint32_t src0 = base + wi, src1 = base + min (wi + 1, 9u), src2 = base + min (wi + 2, 9u) ;
   const bool has1 = wi + 1 <= 9, has2 = wi + 2 <= 9 ;
-  uint64_t *const col = a.stage + ((size_t) blockIdx.x * THREADS) * a.rowCap + t ;	/* slot i at col[i*THREADS] */
+  uint64_t *const G = a.stage + ((size_t) blockIdx.x * THREADS) * a.rowCap ;	/* this CTA's staging area */
+  uint64_t *const col = G + t ;							/* the lane's column: slot i at col[i*THREADS] */
 
   for (;;)
     { if (t == 0) { sTicket = atomicAdd (a.work, 1u) ; sCount = 0 ; sBad = 0 ; }
@@ -160,7 +166,7 @@ k_fused_block (FusedArgs a, HashParams hp)
 	  if (!has2) w2 = 0 ;
 	  if (!laneActive) continue ;
 	  const uint32_t Whi = __funnelshift_l (w1, w0, sh), Wlo = __funnelshift_l (w2, w1, sh) ;	/* bases p0..p0+31 */
-	  const uint32_t WRhi = h10x_swap_pairs (__brev (~Wlo)), WRlo = h10x_swap_pairs (__brev (~Whi)) ;
+	  const uint32_t WRhi = h10x_swap_pairs_not (__brev (Wlo)), WRlo = h10x_swap_pairs_not (__brev (Whi)) ;
 	  if (cnt + 8 > a.rowCap) { over = true ; cnt = 0 ; }
 #pragma unroll
 	  for (int j = 0 ; j < 8 ; ++j)
@@ -202,7 +208,6 @@ k_fused_block (FusedArgs a, HashParams hp)
       if (!bad)
 	{ /* ---- bucket histogram on the top hash bits ---- */
 	  for (uint32_t i = 0 ; i < cnt ; ++i) atomicAdd (&start[(uint32_t) (col[(size_t) i * THREADS] >> buckShift)], 1u) ;
-	  if (n == 0 && t == 0) start[0] = 1 ;	/* hash10x.c:167-168: the phantom entry of an empty block */
 	  __syncthreads () ;
 	  for (uint32_t i = t ; i < a.nbuck ; i += THREADS) if (start[i] > H10X_BUCKET_LIMIT) sBad = 1 ;
 	  __syncthreads () ;
@@ -211,31 +216,38 @@ k_fused_block (FusedArgs a, HashParams hp)
       uint32_t U = 0 ;
       if (!bad)
 	{ cta_exclusive_scan<THREADS> (start, a.nbuck + 1, warpTmp) ;
-	  for (uint32_t i = t ; i < a.nbuck ; i += THREADS) cur[i] = start[i] ;
-	  __syncthreads () ;
-	  /* ---- scatter to buckets ---- */
+	  /* ---- scatter to buckets; start[b] is the cursor, so afterwards it is the END of bucket b ---- */
 	  for (uint32_t i = 0 ; i < cnt ; ++i)
 	    { uint64_t key = col[(size_t) i * THREADS] ;
-	      S[atomicAdd (&cur[(uint32_t) (key >> buckShift)], 1u)] = key ;
+	      S[atomicAdd (&start[(uint32_t) (key >> buckShift)], 1u)] = key ;
 	    }
-	  if (n == 0) { if (t == 0) S[0] = 0 ; n = 1 ; }
 	  __syncthreads () ;
-	  /* ---- insertion sort inside each bucket: buckets are in hash order, so S ends up sorted ---- */
-	  for (uint32_t b = t ; b < a.nbuck ; b += THREADS)
-	    { uint32_t lo = start[b], hi = start[b + 1] ;
-	      for (uint32_t i = lo + 1 ; i < hi ; ++i)
-		{ uint64_t key = S[i] ; uint32_t j = i ;
-		  while (j > lo && S[j - 1] > key) { S[j] = S[j - 1] ; --j ; }
-		  S[j] = key ;
-		}
+	  /* ---- order inside the buckets by counting, one thread per key: its place is the bucket's start plus the
+		 number of smaller keys in the bucket (equal keys - the same k-mer twice in one read pair - keep their
+		 order).  Buckets are in hash order, so the places are the sorted order of the whole block.  The sorted
+		 keys go to the CTA's staging area (every column has been read by now) and come back to S in order:
+		 balanced work for all 32 lanes, where a per-bucket insertion sort kept 4-10 of them busy. ---- */
+	  for (uint32_t i = t ; i < n ; i += THREADS)
+	    { const uint64_t key = S[i] ;
+	      const uint32_t b = (uint32_t) (key >> buckShift) ;
+	      const uint32_t lo = b ? start[b - 1] : 0u, hi = start[b] ;
+	      uint32_t r = lo ;
+#pragma unroll 1		/* a bucket holds 1.5 keys on average: unrolled remainders only add branches */
+	      for (uint32_t j = lo ; j < i ; ++j) r += (S[j] <= key) ? 1u : 0u ;
+#pragma unroll 1
+	      for (uint32_t j = i + 1 ; j < hi ; ++j) r += (S[j] < key) ? 1u : 0u ;
+	      G[r] = key ;
 	    }
+	  if (n == 0) { if (t == 0) G[0] = 0 ; n = 1 ; }	/* hash10x.c:167-168: the phantom entry of an empty block */
+	  __syncthreads () ;
+	  for (uint32_t i = t ; i < n ; i += THREADS) S[i] = __ldcg (G + i) ;
 	  __syncthreads () ;
 	  /* ---- dedup: keep the first key of every run of equal hashes (lowest read index) ---- */
 	  const uint32_t per = (n + THREADS - 1) / THREADS ;
 	  const uint32_t lo = min (t * per, n), hi = min (lo + per, n) ;
 	  uint32_t ucnt = 0 ;
 	  for (uint32_t i = lo ; i < hi ; ++i) ucnt += (i == 0 || (S[i] >> SH) != (S[i - 1] >> SH)) ? 1u : 0u ;
-	  cur[t] = ucnt ;			/* nbuck >= THREADS */
+	  cur[t] = ucnt ;			/* the bucket array is free again; nbuck >= THREADS */
 	  __syncthreads () ;
 	  U = cta_exclusive_scan<THREADS> (cur, THREADS, warpTmp) ;
 	  if (t == 0) sBase = atomicAdd (a.cursor, (unsigned long long) U) ;

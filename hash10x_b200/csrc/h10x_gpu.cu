@@ -670,8 +670,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   const int c1 = (n1 + 7) / 8, c2 = (n2 + 7) / 8 ;
   const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && n1 >= 8 && nProcBlk > 0 ;
   struct FusedClass { uint32_t cap, nbuck, lb, threads, rowCap ; } ;
-  static const FusedClass kClasses[4] = { { 1024, 256, 8, 128, 32 }, { 4096, 1024, 10, 256, 48 },
-					  { 12288, 2048, 11, 512, 64 }, { 24576, 4096, 12, 1024, 64 } } ;
+  static const FusedClass kClasses[4] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 },
+					  { 12288, 4096, 12, 512, 64 }, { 24576, 8192, 13, 1024, 64 } } ;
   const int nClasses = 4 ;
   DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
   uint64_t nFused = 0 ;
@@ -701,7 +701,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       const void *fn[4] ;
       for (int ci = 0 ; ci < nClasses ; ++ci)
 	{ const FusedClass &fc = kClasses[ci] ;
-	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) 2 * fc.nbuck + 1) + 16 ;
+	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) fc.nbuck + 1) + 16 ;
 #define FUSED_FN(T) (k21 ? (const void*) k_fused_block<T, true, 21> : wodd ? (const void*) k_fused_block<T, true, 0> \
 		     : (const void*) k_fused_block<T, false, 0>)
 	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
@@ -833,7 +833,11 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   const bool bucketed = !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
   uint32_t nBuck = 1 ;
   std::vector<uint64_t> hBucketBase ;
-  DBuf<uint64_t> eHash, eBR, words, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk ;
+  DBuf<uint64_t> eHash, eBR, words, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk, key32 ;
+  /* key/value tail (h10x_bucket.cuh): the payload travels through the hash sort; H10X_TAIL_WORDS=1 keeps the
+     packed-word variant for comparison */
+  static const bool kvTailEnv = !(getenv ("H10X_TAIL_WORDS") && atoi (getenv ("H10X_TAIL_WORDS"))) ;
+  const bool kvTail = bucketed && kvTailEnv ;
   if (dist) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
   else if (!bucketed) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
@@ -852,9 +856,17 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	LAUNCH (c, k_bucket_base, gridFor (nBuck + 1, 256), 256, 0, s, nBuck, nProcBlk, off.p, H, bucketBase.p) ;
 	hBucketBase.resize ((size_t) nBuck + 1) ;
 	CK (cudaMemcpyAsync (hBucketBase.data (), bucketBase.p, 8 * ((size_t) nBuck + 1), cudaMemcpyDeviceToHost, s)) ;
-	words.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ;
-	LAUNCH (c, k_place_bucketed, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
-		cnt.p, off.p, bucketBase.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, words.p, eBR.p) ;
+	eBR.alloc (H, s, mt) ;
+	if (kvTail)
+	  { key32.alloc (H, s, mt) ;
+	    LAUNCH (c, k_place_bucketed_kv, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
+		    cnt.p, off.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, key32.p, eBR.p) ;
+	  }
+	else
+	  { words.alloc (H, s, mt) ;
+	    LAUNCH (c, k_place_bucketed, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
+		    cnt.p, off.p, bucketBase.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, words.p, eBR.p) ;
+	  }
 	CK (cudaStreamSynchronize (s)) ;
       }
     else
@@ -872,9 +884,53 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   uint32_t D = 0 ;
   DBuf<uint32_t> entryId ;
   if (dist) entryId.alloc (H, s, mt) ;
-  DBuf<uint32_t> se, segIncl (H, s, mt), segStart, idOfSeg ;
-  DBuf<uint64_t> sw ;
-  if (bucketed)
+  DBuf<uint32_t> se, segIncl, segStart, idOfSeg, sk ;
+  DBuf<uint64_t> sw, sv ;
+  if (!kvTail) segIncl.alloc (H, s, mt) ;
+  if (kvTail)
+    { sk.alloc (H, s, mt) ; sv.alloc (H, s, mt) ;
+      { StageTimer tm (c, s, ST_HASHSORT) ;
+	const int endBit = std::min (32, sortBits) ;
+	for (uint32_t v = 0 ; v < nBuck ; ++v)
+	  { uint64_t b0 = hBucketBase[v], n = hBucketBase[v+1] - b0 ;
+	    if (!n) continue ;
+	    /* stable: inside a bin the placement order = ascending block is kept */
+	    cubCall (c, s, [&] (void *t, size_t &b)
+	      { return cub::DeviceRadixSort::SortPairs (t, b, key32.p + b0, sk.p + b0, eBR.p + b0, sv.p + b0, n, 0, endBit, s) ; }) ;
+	  }
+      }
+      key32.release () ; eBR.release () ;
+      { StageTimer tm (c, s, ST_BINIDS) ;
+	/* first position of every bin, in one selection pass over the sorted keys (the bound on D is only known
+	   afterwards, so the output is sized for the worst case and released with the stage) */
+	segStart.alloc ((size_t) H + 1, s, mt) ;
+	DBuf<uint32_t> dD (1, s, mt) ;
+	HeadPredKV pred = { sk.p, bucketBase.p, nBuck } ;
+	cub::CountingInputIterator<uint32_t> iota (0u) ;
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceSelect::If (t, b, iota, segStart.p, dD.p, (::cuda::std::int64_t) H, pred, s) ; }) ;
+	CK (cudaMemcpyAsync (&D, dD.p, 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
+	  throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+	const uint32_t H32 = (uint32_t) H ;
+	CK (cudaMemcpyAsync (segStart.p + D, &H32, 4, cudaMemcpyHostToDevice, s)) ;	/* pageable source: copied before the call returns */
+	idOfSeg.alloc (D, s, mt) ;
+	DBuf<uint64_t> fkey (D, s, mt), fkeyS (D, s, mt) ; DBuf<uint32_t> segIdx (D, s, mt), sortedSeg (D, s, mt) ;
+	LAUNCH (c, k_first_key_kv, gridFor (D, 256), 256, 0, s, D, segStart.p, sk.p, sv.p, bucketBase.p, nBuck, sortBits, fkey.p, segIdx.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceRadixSort::SortPairs (t, b, fkey.p, fkeyS.p, segIdx.p, sortedSeg.p, D, 0, sortBits + blkBits, s) ; }) ;
+	c->hashNumber = D + 1 ;
+	c->hashValue.alloc ((size_t) D + 1, s, mt) ;
+	c->hashDepth.alloc ((size_t) D + 2, s, mt) ;
+	CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
+	LAUNCH (c, k_bins_by_rank_kv, gridFor (D, 256), 256, 0, s, D, sortedSeg.p, fkeyS.p, segStart.p, sortBits, wDiv,
+		idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+      }
+    }
+  else if (bucketed)
     { sw.alloc (H, s, mt) ;
       { StageTimer tm (c, s, ST_HASHSORT) ;
 	const int endBit = 31 + std::min (32, sortBits) ;
@@ -990,14 +1046,18 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	c->codes.alloc (H, s, mt) ;
 	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
-	if (H && bucketed)
+	if (H && kvTail)
+	  LAUNCH (c, k_codes_seg_kv, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, idOfSeg.p, sv.p,
+		  c->codeOff.p, c->codes.p, idRead.p) ;
+	else if (H && bucketed)
 	  LAUNCH (c, k_codes_tr_sw, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, sw.p, bucketBase.p, nBuck,
 		  eBR.p, c->codeOff.p, c->codes.p, idRead.p) ;
 	else if (H)
 	  LAUNCH (c, k_codes_tr, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eBR.p,
 		  c->codeOff.p, c->codes.p, idRead.p) ;
       }
-      se.release () ; sw.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; eBR.release () ;
+      se.release () ; sw.release () ; sk.release () ; sv.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ;
+      eHash.release () ; eBR.release () ;
       c->clus.alloc (H, s, mt) ;
       if (H)
 	{ StageTimer tm (c, s, ST_CLUSTERS) ;

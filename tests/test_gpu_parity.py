@@ -99,9 +99,14 @@ def test_generic_only_flag_and_fallbacks(orc, gpu_lib):
     ])
     _, _, st = _compare(orc, mixed, B=21)
     assert st["genericBlocks"] >= 1 and st["fusedBlocks"] >= 25
+    # blocks of the largest shared-memory class (many duplicate hashes: a 2 Mb genome) stay on the fused path ...
     big = orc.synth_params(seed=14, n_barcodes=4, pairs_min=1500, pairs_max=2600, genome_len=2_000_000)
     _, _, st = _compare(orc, orc.synth_fqb(big), B=21)
-    assert st["genericBlocks"] >= 1
+    assert st["fusedBlocks"] + st["genericBlocks"] == 3
+    # ... and blocks beyond it (> ~2800 read pairs) are handed to the generic path by the host
+    huge = orc.synth_params(seed=15, n_barcodes=3, pairs_min=3000, pairs_max=3400, genome_len=2_000_000)
+    _, _, st = _compare(orc, orc.synth_fqb(huge), B=21)
+    assert st["genericBlocks"] == 2 and st["fusedBlocks"] == 0
 
 
 def test_edge_sizes(orc, gpu_lib):
