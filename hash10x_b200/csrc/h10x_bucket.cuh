@@ -1,12 +1,17 @@
-/* h10x_bucket.cuh - single-GPU hash grouping on packed words.
+/* h10x_bucket.cuh - single-GPU hash grouping: bucket-major (key, value) pairs.
  *
  * Every block's unique list leaves the fused kernel sorted by hash, so splitting the entries by the top
  * bits of q = hash / w costs nothing: a bucket is a contiguous piece of every list.  The entries are
- * placed BUCKET-MAJOR (block-ascending inside a bucket) as one 64-bit word each,
- *        word = (q mod 2^32) << 31 | index inside the bucket,
- * and each bucket is radix-sorted on bits [31, 63) - keys only, 4 passes of 16 B per entry instead of
- * 5 passes of 24 B for (64-bit key, 32-bit value) pairs.  Ties keep the index order, i.e. ascending block.
- * After the sort, position i of bucket v decodes to q = v << 32 | word >> 31 and entry e = base[v] + (word & 2^31-1).
+ * placed BUCKET-MAJOR (block-ascending inside a bucket) as
+ *        key   = q mod 2^32                 (32 bits; the bucket number carries the bits above)
+ *        value = block | read << 32         (64 bits)
+ * and each bucket is radix-sorted, stable, on the key: 4 passes of 24 B per entry.  Ties keep the placement
+ * order, i.e. ascending block, which is the order fillHashTable (hash10x.c:317-347) produces.  Because the
+ * payload travels with the key, no later stage has to chase an entry index back into block-major arrays:
+ * position i of bucket v holds q = v << 32 | sk[i] and (block, read) = sv[i].
+ * (Round 1 sorted packed words `key << 31 | index in bucket`, keys only, and gathered (block, read) by index
+ * afterwards: 244.9 ms per 200M-pair build against 213.2 ms for this layout - hash sort 58 -> 49 ms, codes
+ * 26 -> 10 ms, bin ids 24 -> 19 ms.)
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -52,107 +57,6 @@ __global__ void k_bucket_base (uint32_t nb, uint32_t nProcBlk, const uint64_t *_
   if (v < nb) base[v] = off[(size_t) v * nProcBlk] ;
   if (v == nb) base[v] = total ;
 }
-
-/* bucket-major placement: packed sort word and eBR = (global block number | read << 32).  One CTA per block. */
-__global__ void k_place_bucketed (uint32_t nProcBlk, uint32_t nb, const uint64_t *__restrict__ srcOff,
-				  const uint32_t *__restrict__ blkCnt, const uint32_t *__restrict__ cnt,
-				  const uint64_t *__restrict__ off, const uint64_t *__restrict__ bucketBase,
-				  const uint64_t *__restrict__ scratch, const uint64_t *__restrict__ gHash,
-				  const uint32_t *__restrict__ gRec, const uint32_t *__restrict__ blkStart,
-				  uint32_t blkBase, uint64_t wInvFull, uint64_t *__restrict__ words, uint64_t *__restrict__ eBR)
-{ __shared__ uint64_t sOff[H10X_MAX_BUCKETS] ;	/* where bucket v of this block starts, minus its first list index */
-  __shared__ uint32_t sBnd[H10X_MAX_BUCKETS + 1] ;
-  for (uint32_t blk = blockIdx.x ; blk < nProcBlk ; blk += gridDim.x)
-    { const uint64_t so = srcOff[blk] ;
-      const uint32_t n = blkCnt[blk] ;
-      __syncthreads () ;
-      if (threadIdx.x == 0)
-	{ uint32_t run = 0 ;
-	  for (uint32_t v = 0 ; v < nb ; ++v) { sBnd[v] = run ; run += cnt[(size_t) v * nProcBlk + blk] ; }
-	  sBnd[nb] = run ;
-	}
-      __syncthreads () ;
-      for (uint32_t v = threadIdx.x ; v < nb ; v += blockDim.x) sOff[v] = off[(size_t) v * nProcBlk + blk] - bucketBase[v] - sBnd[v] ;
-      __syncthreads () ;
-      const bool generic = (so >> 63) != 0 ;
-      const uint32_t sh = generic ? 0 : (uint32_t) (so >> 56) ;
-      const uint64_t o = generic ? (so & 0x7fffffffffffffffull) : (so & 0x00ffffffffffffffull) ;
-      const uint64_t rmask = ((uint64_t) 1 << sh) - 1 ;
-      const uint32_t r0 = blkStart[blk] ;
-      for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
-	{ uint64_t hash ; uint16_t rd ;
-	  if (generic) { hash = gHash[o + i] ; rd = (uint16_t) (gRec[o + i] - r0) ; }
-	  else { uint64_t key = scratch[o + i] ; hash = key >> sh ; rd = (uint16_t) (key & rmask) ; }
-	  const uint64_t q = hash * wInvFull ;
-	  const uint32_t v = (uint32_t) (q >> 32) ;
-	  const uint64_t idx = sOff[v] + i ;			/* index inside bucket v */
-	  const uint64_t pos = bucketBase[v] + idx ;
-	  words[pos] = ((q & 0xffffffffull) << 31) | idx ;
-	  eBR[pos] = (uint64_t) (blkBase + blk + 1) | ((uint64_t) rd << 32) ;
-	}
-    }
-}
-
-__global__ void k_head_flag_sw (const uint64_t *__restrict__ sw, uint64_t n, const uint64_t *__restrict__ base, uint32_t nb,
-				uint32_t *__restrict__ head)
-{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
-  if (i >= n) return ;
-  uint32_t v = h10x_bucket_of (i, base, nb) ;
-  head[i] = (i == base[v] || (sw[i] >> 31) != (sw[i-1] >> 31)) ? 1u : 0u ;
-}
-
-/* key of a bin for the id order (hash10x.c:147): first block holding it, then hash */
-__global__ void k_first_key_sw (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sw,
-				const uint64_t *__restrict__ base, uint32_t nb, const uint64_t *__restrict__ eBR, int qBits,
-				uint64_t *__restrict__ key, uint32_t *__restrict__ segIdx)
-{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
-  if (s >= nSeg) return ;
-  uint64_t i = segStart[s] ;
-  uint32_t v = h10x_bucket_of (i, base, nb) ;
-  uint64_t w = sw[i] ;
-  uint64_t q = ((uint64_t) v << 32) | (w >> 31) ;
-  uint64_t e = base[v] + (w & 0x7fffffffull) ;
-  key[s] = ((uint64_t) (uint32_t) eBR[e] << qBits) | q ;
-  segIdx[s] = s ;
-}
-
-__global__ void k_bins_by_rank_sw (uint32_t nSeg, const uint32_t *__restrict__ sortedSeg, const uint32_t *__restrict__ segStart,
-				   const uint64_t *__restrict__ sw, const uint64_t *__restrict__ base, uint32_t nb, uint64_t wMul,
-				   uint32_t *__restrict__ idOfSeg, uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
-{ uint32_t r = blockIdx.x * blockDim.x + threadIdx.x ;
-  if (r >= nSeg) return ;
-  uint32_t s = sortedSeg[r], id = r + 1u ;
-  uint64_t i = segStart[s] ;
-  uint32_t v = h10x_bucket_of (i, base, nb) ;
-  idOfSeg[s] = id ;
-  hashValue[id] = (((uint64_t) v << 32) | (sw[i] >> 31)) * wMul ;
-  hashDepth[id] = segStart[s+1] - (uint32_t) i ;
-}
-
-__global__ void k_codes_tr_sw (uint64_t n, const uint32_t *__restrict__ segIncl, const uint32_t *__restrict__ segStart,
-			       const uint32_t *__restrict__ idOfSeg, const uint64_t *__restrict__ sw,
-			       const uint64_t *__restrict__ base, uint32_t nb, const uint64_t *__restrict__ eBR,
-			       const uint64_t *__restrict__ codeOff, uint32_t *__restrict__ codes, uint64_t *__restrict__ idRead)
-{ uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
-  if (i >= n) return ;
-  uint32_t s = segIncl[i] - 1 ;
-  uint32_t id = idOfSeg[s] ;
-  uint64_t pos = codeOff[id] + (i - segStart[s]) ;
-  uint32_t v = h10x_bucket_of (i, base, nb) ;
-  uint64_t br = eBR[base[v] + (sw[i] & 0x7fffffffull)] ;
-  codes[pos] = (uint32_t) br ;
-  idRead[pos] = (uint64_t) id | (br & 0xffff00000000ull) ;
-}
-
-/* ------------------------------------------------------------------ key/value variant
- *
- * The packed words above make every later stage chase `index inside the bucket` back into eBR: one random
- * 8-byte gather per entry (the `codes` stage) and per bin (the id order).  Carrying the payload through the
- * sort removes those gathers: a bucket is sorted as (32-bit key = q mod 2^32, 64-bit value = block | read << 32)
- * pairs, stable, so ties keep the placement order = ascending block.  The library's pair passes on 32-bit keys
- * also rank faster than its 64-bit key-only passes (measured 1.2e11 vs 0.95e11 entries/s per pass).
- * After the sort, position i of bucket v holds q = v << 32 | sk[i] and (block, read) = sv[i].
- */
 
 /* bucket-major placement of (key, value).  One CTA per block. */
 __global__ void k_place_bucketed_kv (uint32_t nProcBlk, uint32_t nb, const uint64_t *__restrict__ srcOff,
@@ -201,13 +105,18 @@ __global__ void k_place_bucketed_kv (uint32_t nProcBlk, uint32_t nb, const uint6
 }
 
 /* selects the first position of every bin in the sorted order (for cub::DeviceSelect::If over a counting
-   iterator): the key changes, or a new bucket starts */
+   iterator): the key changes, or a new bucket starts.  Most positions repeat the key of their predecessor, so the
+   bucket test runs for nearly every entry: hashes are uniform, the bucket holding i is almost always
+   floor (i * nb / H) (scale = 2^64 * nb / H), and only a wrong guess pays for the binary search. */
 struct HeadPredKV {
-  const uint32_t *sk ; const uint64_t *base ; uint32_t nb ;
+  const uint32_t *sk ; const uint64_t *base ; uint32_t nb ; uint64_t scale ;
   __device__ __forceinline__ bool operator() (uint32_t i) const
   { if (i == 0) return true ;
     if (sk[i] != sk[i-1]) return true ;
     if (nb == 1) return false ;
+    uint32_t v = min ((uint32_t) __umul64hi ((uint64_t) i, scale), nb - 1) ;
+    const uint64_t b0 = base[v] ;
+    if (b0 <= i && i < base[v+1]) return b0 == i ;
     return base[h10x_bucket_of (i, base, nb)] == i ;
   }
 } ;

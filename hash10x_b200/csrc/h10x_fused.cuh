@@ -103,9 +103,13 @@ struct FusedArgs {
   uint32_t n1, n2 ;		/* k-mers of read 1 / read 2 */
 } ;
 
+/* CTAs per SM that the shared memory of a size class allows (h10x_gpu.cu, kClasses): the register budget follows it */
+__host__ __device__ constexpr int h10x_fused_ctas_per_sm (int threads)
+{ return threads <= 256 ? 5 : threads <= 384 ? 4 : threads <= 512 ? 2 : 1 ; }
+
 /* K > 0: k fixed at compile time (shifts and masks become immediates); K == 0: k from hp */
 template <int THREADS, bool WODD, int K>
-__global__ void __launch_bounds__ (THREADS)
+__global__ void __launch_bounds__ (THREADS, h10x_fused_ctas_per_sm (THREADS))
 k_fused_block (FusedArgs a, HashParams hp)
 {
   extern __shared__ __align__ (16) unsigned char smemRaw[] ;

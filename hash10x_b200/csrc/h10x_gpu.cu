@@ -670,14 +670,15 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   const int c1 = (n1 + 7) / 8, c2 = (n2 + 7) / 8 ;
   const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && n1 >= 8 && nProcBlk > 0 ;
   struct FusedClass { uint32_t cap, nbuck, lb, threads, rowCap ; } ;
-  static const FusedClass kClasses[4] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 },
+  /* shared memory per CTA = 8 * cap + 4 * nbuck (+ 1 KB the driver reserves): 5, 5, 4, 2 and 1 CTAs per SM */
+  static const FusedClass kClasses[5] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 }, { 5632, 2048, 11, 384, 48 },
 					  { 12288, 4096, 12, 512, 64 }, { 24576, 8192, 13, 1024, 64 } } ;
-  const int nClasses = 4 ;
+  const int nClasses = 5 ;
   DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
   uint64_t nFused = 0 ;
   if (fusedOK)
     { StageTimer tm (c, s, ST_FUSED) ;
-      std::vector<uint32_t> lists[4] ;
+      std::vector<uint32_t> lists[5] ;
       const double perPair = (double) (n1 + n2) / (double) P.w ;	/* expected moshes per read pair */
       for (uint32_t p = 0 ; p < nProcBlk ; ++p)
 	{ uint32_t nRead = bt.start[p+1] - bt.start[p] ;
@@ -697,14 +698,15 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       const bool wodd = (c->hp.wTz == 0) ;
       const bool k21 = (P.k == 21 && wodd) ;
       /* pass 1: grids and the staging area they need (launches run one after another and share it) */
-      uint32_t grid[4] = { 0, 0, 0, 0 } ; size_t smemB[4] ; size_t stageKeys = 0 ;
-      const void *fn[4] ;
+      uint32_t grid[5] = { 0, 0, 0, 0, 0 } ; size_t smemB[5] ; size_t stageKeys = 0 ;
+      const void *fn[5] ;
       for (int ci = 0 ; ci < nClasses ; ++ci)
 	{ const FusedClass &fc = kClasses[ci] ;
 	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) fc.nbuck + 1) + 16 ;
 #define FUSED_FN(T) (k21 ? (const void*) k_fused_block<T, true, 21> : wodd ? (const void*) k_fused_block<T, true, 0> \
 		     : (const void*) k_fused_block<T, false, 0>)
-	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
+	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 384 ? FUSED_FN (384)
+	    : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
 #undef FUSED_FN
 	  if (lists[ci].empty ()) continue ;
 	  CK (cudaFuncSetAttribute (fn[ci], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemB[ci])) ;
@@ -827,17 +829,13 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   hBlkOff[nProcBlk] = H ;
   c->nHashes = H ;
   if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
-  /* single-GPU: bucket-major packed words (h10x_bucket.cuh); multi-GPU: block-major hash / read / block arrays */
+  /* single-GPU: bucket-major (key, value) pairs (h10x_bucket.cuh); multi-GPU: block-major hash / read / block arrays */
   int blkBits = 1 ; while (((uint64_t) 1 << blkBits) < (uint64_t) nBlk + 2) ++blkBits ;
   const int nbBits = sortBits > 32 ? sortBits - 32 : 0 ;
   const bool bucketed = !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
   uint32_t nBuck = 1 ;
   std::vector<uint64_t> hBucketBase ;
-  DBuf<uint64_t> eHash, eBR, words, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk, key32 ;
-  /* key/value tail (h10x_bucket.cuh): the payload travels through the hash sort; H10X_TAIL_WORDS=1 keeps the
-     packed-word variant for comparison */
-  static const bool kvTailEnv = !(getenv ("H10X_TAIL_WORDS") && atoi (getenv ("H10X_TAIL_WORDS"))) ;
-  const bool kvTail = bucketed && kvTailEnv ;
+  DBuf<uint64_t> eHash, eBR, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk, key32 ;
   if (dist) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
   else if (!bucketed) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
@@ -856,17 +854,9 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	LAUNCH (c, k_bucket_base, gridFor (nBuck + 1, 256), 256, 0, s, nBuck, nProcBlk, off.p, H, bucketBase.p) ;
 	hBucketBase.resize ((size_t) nBuck + 1) ;
 	CK (cudaMemcpyAsync (hBucketBase.data (), bucketBase.p, 8 * ((size_t) nBuck + 1), cudaMemcpyDeviceToHost, s)) ;
-	eBR.alloc (H, s, mt) ;
-	if (kvTail)
-	  { key32.alloc (H, s, mt) ;
-	    LAUNCH (c, k_place_bucketed_kv, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
-		    cnt.p, off.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, key32.p, eBR.p) ;
-	  }
-	else
-	  { words.alloc (H, s, mt) ;
-	    LAUNCH (c, k_place_bucketed, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
-		    cnt.p, off.p, bucketBase.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, words.p, eBR.p) ;
-	  }
+	key32.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ;
+	LAUNCH (c, k_place_bucketed_kv, std::min<uint32_t> (nProcBlk, 148 * 16), 256, 0, s, nProcBlk, nBuck, srcOff.p, blkCnt.p,
+		cnt.p, off.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, blkBase, wInvFull, key32.p, eBR.p) ;
 	CK (cudaStreamSynchronize (s)) ;
       }
     else
@@ -885,9 +875,9 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   DBuf<uint32_t> entryId ;
   if (dist) entryId.alloc (H, s, mt) ;
   DBuf<uint32_t> se, segIncl, segStart, idOfSeg, sk ;
-  DBuf<uint64_t> sw, sv ;
-  if (!kvTail) segIncl.alloc (H, s, mt) ;
-  if (kvTail)
+  DBuf<uint64_t> sv ;
+  if (!bucketed) segIncl.alloc (H, s, mt) ;
+  if (bucketed)
     { sk.alloc (H, s, mt) ; sv.alloc (H, s, mt) ;
       { StageTimer tm (c, s, ST_HASHSORT) ;
 	const int endBit = std::min (32, sortBits) ;
@@ -905,7 +895,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	   afterwards, so the output is sized for the worst case and released with the stage) */
 	segStart.alloc ((size_t) H + 1, s, mt) ;
 	DBuf<uint32_t> dD (1, s, mt) ;
-	HeadPredKV pred = { sk.p, bucketBase.p, nBuck } ;
+	HeadPredKV pred = { sk.p, bucketBase.p, nBuck, (uint64_t) ((((unsigned __int128) nBuck) << 64) / H) } ;
 	cub::CountingInputIterator<uint32_t> iota (0u) ;
 	cubCall (c, s, [&] (void *t, size_t &b)
 	  { return cub::DeviceSelect::If (t, b, iota, segStart.p, dD.p, (::cuda::std::int64_t) H, pred, s) ; }) ;
@@ -927,43 +917,6 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
 	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
 	LAUNCH (c, k_bins_by_rank_kv, gridFor (D, 256), 256, 0, s, D, sortedSeg.p, fkeyS.p, segStart.p, sortBits, wDiv,
-		idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
-      }
-    }
-  else if (bucketed)
-    { sw.alloc (H, s, mt) ;
-      { StageTimer tm (c, s, ST_HASHSORT) ;
-	const int endBit = 31 + std::min (32, sortBits) ;
-	for (uint32_t v = 0 ; v < nBuck ; ++v)
-	  { uint64_t b0 = hBucketBase[v], n = hBucketBase[v+1] - b0 ;
-	    if (!n) continue ;
-	    cubCall (c, s, [&] (void *t, size_t &b)
-	      { return cub::DeviceRadixSort::SortKeys (t, b, words.p + b0, sw.p + b0, n, 31, endBit, s) ; }) ;
-	  }
-      }
-      words.release () ;
-      { StageTimer tm (c, s, ST_BINIDS) ;
-	DBuf<uint32_t> head (H, s, mt) ;
-	LAUNCH (c, k_head_flag_sw, gridFor (H, 256), 256, 0, s, sw.p, H, bucketBase.p, nBuck, head.p) ;
-	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, head.p, segIncl.p, H, s) ; }) ;
-	CK (cudaMemcpyAsync (&D, segIncl.p + (H - 1), 4, cudaMemcpyDeviceToHost, s)) ;
-	CK (cudaStreamSynchronize (s)) ;
-	if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
-	  throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
-	segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
-	LAUNCH (c, k_seg_start, gridFor (H, 256), 256, 0, s, head.p, segIncl.p, H, (const uint32_t*) nullptr, segStart.p, (uint32_t*) nullptr) ;
-	head.release () ;
-	DBuf<uint64_t> fkey (D, s, mt), fkeyS (D, s, mt) ; DBuf<uint32_t> segIdx (D, s, mt), sortedSeg (D, s, mt) ;
-	LAUNCH (c, k_first_key_sw, gridFor (D, 256), 256, 0, s, D, segStart.p, sw.p, bucketBase.p, nBuck, eBR.p, sortBits, fkey.p, segIdx.p) ;
-	cubCall (c, s, [&] (void *t, size_t &b)
-	  { return cub::DeviceRadixSort::SortPairs (t, b, fkey.p, fkeyS.p, segIdx.p, sortedSeg.p, D, 0, sortBits + blkBits, s) ; }) ;
-	c->hashNumber = D + 1 ;
-	c->hashValue.alloc ((size_t) D + 1, s, mt) ;
-	c->hashDepth.alloc ((size_t) D + 2, s, mt) ;
-	CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
-	CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
-	CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-	LAUNCH (c, k_bins_by_rank_sw, gridFor (D, 256), 256, 0, s, D, sortedSeg.p, segStart.p, sw.p, bucketBase.p, nBuck, wDiv,
 		idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
       }
     }
@@ -1046,18 +999,18 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	c->codes.alloc (H, s, mt) ;
 	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
-	if (H && kvTail)
+	if (H && bucketed)
 	  LAUNCH (c, k_codes_seg_kv, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, idOfSeg.p, sv.p,
 		  c->codeOff.p, c->codes.p, idRead.p) ;
-	else if (H && bucketed)
-	  LAUNCH (c, k_codes_tr_sw, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, sw.p, bucketBase.p, nBuck,
-		  eBR.p, c->codeOff.p, c->codes.p, idRead.p) ;
 	else if (H)
 	  LAUNCH (c, k_codes_tr, gridFor (H, 256), 256, 0, s, H, segIncl.p, segStart.p, idOfSeg.p, se.p, eBR.p,
 		  c->codeOff.p, c->codes.p, idRead.p) ;
       }
-      se.release () ; sw.release () ; sk.release () ; sv.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ;
+      se.release () ; sk.release () ; sv.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ;
       eHash.release () ; eBR.release () ;
+      /* the block sort below only reads codes[]: its copy to the host runs beside the sort */
+      if (!(P.flags & H10X_FLAG_NO_CODES))
+	{ early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
       c->clus.alloc (H, s, mt) ;
       if (H)
 	{ StageTimer tm (c, s, ST_CLUSTERS) ;
@@ -1068,7 +1021,6 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    { return cub::DeviceRadixSort::SortPairs (t, b, c->codes.p, keysOut.p, idRead.p, c->clus.p, H, 0, bBits, s) ; }) ;
 	}
       if (P.flags & H10X_FLAG_NO_CODES) { c->codes.release () ; c->codeOff.release () ; }
-      else { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
       early_pull (c, s, SLOT_CLUS, c->clus.p, 8 * H) ;
     }
   se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; entryBlk.release () ;
