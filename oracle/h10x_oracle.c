@@ -314,7 +314,7 @@ static int write_array (FILE *f, const void *data, int size, int max, int dim0)
 
 /* ---- hash10x.c:244-267 writeHashFile, SURVEY.md Appendix B.  Raw pointers are written as 0;
    Array dims follow the reference's growth so that the file has the reference's size. ---- */
-int orc_write_hash (const orc_index *ix, const char *path)
+int orc_write_hash_clustered (const orc_index *ix, const U32 *nSub, const double *pointToMin, const char *path)
 {
   FILE *f = fopen (path, "wb") ; if (!f) return ORC_IO ;
   U32 version = 2 ; U16 chSize = 8, cbSize = 32 ; int32_t B = ix->B ;
@@ -330,13 +330,20 @@ int orc_write_hash (const orc_index *ix, const char *path)
   U32 nb = ix->nBlocksMax, b ;
   U32 *cb = calloc ((size_t) nb * 8, sizeof (U32)) ;
   if (!cb) { fclose (f) ; return ORC_NOMEM ; }
-  for (b = 0 ; b < nb ; ++b) { cb[8*b] = ix->blkNRead[b] ; cb[8*b+1] = ix->blkNHash[b] ; }
+  for (b = 0 ; b < nb ; ++b)
+    { cb[8*b] = ix->blkNRead[b] ; cb[8*b+1] = ix->blkNHash[b] ;
+      if (nSub) cb[8*b+2] = nSub[b] ;
+      if (pointToMin) memcpy (&cb[8*b+6], &pointToMin[b], 8) ;
+    }
   ok = ok && write_array (f, cb, 32, (int) nb, 1200) ;
   free (cb) ;
   ok = ok && (!ix->nHashes || fwrite (ix->clus, 8, ix->nHashes, f) == ix->nHashes) ;
   if (fclose (f)) ok = 0 ;
   return ok ? ORC_OK : ORC_IO ;
 }
+
+int orc_write_hash (const orc_index *ix, const char *path)
+{ return orc_write_hash_clustered (ix, NULL, NULL, path) ; }
 
 /* ---- hash10x.c:528-539 hashWithinRangeBuild + :738-766 goodHashesBuild ("next" row f1) ----
    within[] (hashNumber bytes) is in/out: the reference only ever SETS flags (:535), so ranges accumulate
@@ -377,5 +384,109 @@ int orc_good_hashes (U32 hashNumber, const U32 *hashDepth, U32 nBlocksMax, const
     }
   goodOff[ix->nBlocksMax] = out ;
   free (keys) ;
+  return ORC_OK ;
+}
+
+/* ---- hash10x.c:770-835 codeClusterFind + :837-868 codeClusterReadMerge ("next" row f2), as run by the
+   `--cluster codeMin codeMax` branch of the command loop (hash10x.c:1241-1256) ----
+   In/out: clus (byte 6 of every ClusterHash = subCluster), nSub and pointToMin (ClusterBlock.nSubCluster /
+   .pointToMin, hash10x.c:62-70).  goodOff/good are the goodHashes lists of orc_good_hashes.  Written as the
+   reference runs it: good hash 0 is never scanned (the loop starts at i = 1, :789), codes first seen at step i
+   are counted at index i and therefore never enter that step's maximum (:793-806), a 256th sub-cluster abandons
+   the block without resetting pointToMin (:810-817), and the read merge relabels by connected components with
+   the smallest label winning (:848-858).  PARITY: pinned against the reference binary by
+   tests/test_oracle.py::test_cluster_equals_reference_binary (`--readHash --hashDepthRange --cluster --writeHash`
+   on a file whose subCluster bytes are zero, so the reference's uninitialised malloc bytes, hash10x.c:175, do
+   not enter). */
+/* ClusterHash entries outside the current good lists keep the labels of an earlier --cluster command; when such a
+   label exceeds the block's new nSubCluster the reference indexes past trueCluster[] (hash10x.c:843,846: undefined
+   behaviour).  Here, and in the CUDA path, such a label counts as 0 = unclustered; this counter lets the tests
+   check that a pinned case never depends on it. */
+static U64 orcStaleLabels = 0 ;
+U64 orc_cluster_stale_labels (void) { return orcStaleLabels ; }
+
+int orc_cluster (const U32 *hashDepth, const U64 *codeOff, const U32 *codes, U32 nBlocksMax,
+		 const U32 *blkNRead, const U32 *blkNHash, const U64 *blkOff, U64 *clus,
+		 const U64 *goodOff, const U16 *good, int codeMin, int codeMax, int clusterThreshold,
+		 U32 *nSub, double *pointToMin)
+{ if (!codeMin) codeMin = 1 ;
+  if (!codeMax) codeMax = (int) nBlocksMax ;
+  if (codeMax > (int) nBlocksMax) return ORC_BAD_PARAM ;	/* the reference would index past clusterBlocks */
+  int *minShare = calloc (nBlocksMax ? nBlocksMax : 1, sizeof (int)) ;
+  int *minShareCount = malloc (65536 * sizeof (int)) ;
+  int clusterMin[257] ;
+  if (!minShare || !minShareCount) { free (minShare) ; free (minShareCount) ; return ORC_NOMEM ; }
+  int code ;
+  for (code = codeMin ; code < codeMax ; ++code)
+    { U8 *cb = (U8*) (clus + blkOff[code]) ;		/* ClusterHash i is bytes 8i..8i+7; subCluster is byte 6 */
+      const U64 *ch = clus + blkOff[code] ;
+      const U16 *g = good + goodOff[code] ;
+      int n = (int) (goodOff[code+1] - goodOff[code]) ;
+      int i, j ;
+      /* ---- codeClusterFind ---- */
+      if (n)
+	{ for (i = 0 ; i < n ; ++i) cb[8 * (size_t) g[i] + 6] = 0 ;
+	  nSub[code] = 0 ; pointToMin[code] = 0.0 ;
+	  memset (minShare, 0, (size_t) nBlocksMax * sizeof (int)) ;
+	  for (i = 1 ; i < n ; ++i)
+	    { U32 x = (U32) ch[g[i]] ;
+	      U32 nc = hashDepth[x] ;
+	      memset (minShareCount, 0, (size_t) n * sizeof (int)) ;
+	      for (j = 0 ; j < (int) nc ; ++j)
+		{ int cj = (int) codes[codeOff[x] + j] ;
+		  if (cj == code) continue ;
+		  if (!minShare[cj]) minShare[cj] = i + 1 ;
+		  ++minShareCount[minShare[cj] - 1] ;
+		}
+	      int msMax = 0, msTot = 0, msBest = 0 ;
+	      for (j = 0 ; j < i ; ++j)
+		{ if (minShareCount[j] > msMax) { msBest = j ; msMax = minShareCount[j] ; }
+		  msTot += minShareCount[j] ;
+		}
+	      if (msMax >= clusterThreshold)
+		{ U8 *sub = &cb[8 * (size_t) g[msBest] + 6] ;
+		  if (!*sub)
+		    { if (++nSub[code] > 255)
+			{ nSub[code] = 0 ;
+			  for (j = 0 ; j < i ; ++j) cb[8 * (size_t) g[j] + 6] = 0 ;
+			  break ;
+			}
+		      *sub = (U8) nSub[code] ;
+		      clusterMin[nSub[code]] = msBest ;
+		    }
+		  cb[8 * (size_t) g[i] + 6] = *sub ;
+		  pointToMin[code] += minShareCount[clusterMin[*sub]] / (double) msTot ;
+		}
+	    }
+	}
+      /* ---- codeClusterReadMerge ---- */
+      if (!nSub[code]) continue ;
+      { int ns = (int) nSub[code] ;
+	U32 nRead = blkNRead[code], nHash = blkNHash[code] ;
+	int *readMap = calloc (nRead ? nRead : 1, sizeof (int)) ;
+	int trueCluster[257], deadCluster[257] ;
+	if (!readMap) { free (minShare) ; free (minShareCount) ; return ORC_NOMEM ; }
+	for (i = 0 ; i <= 256 ; ++i) { trueCluster[i] = i <= ns ? i : 0 ; deadCluster[i] = 0 ; }
+	for (i = 0 ; i < (int) nHash ; ++i)
+	  { if (cb[8 * (size_t) i + 6] > ns) ++orcStaleLabels ;
+	    int hashCluster = trueCluster[cb[8 * (size_t) i + 6]] ; if (!hashCluster) continue ;
+	    U16 rd = (U16) (ch[i] >> 32) ;
+	    int readCluster = trueCluster[readMap[rd]] ;
+	    if (hashCluster == readCluster) continue ;
+	    else if (!readCluster) readMap[rd] = hashCluster ;
+	    else
+	      { if (hashCluster > readCluster) { int t = hashCluster ; hashCluster = readCluster ; readCluster = t ; }
+		for (j = 1 ; j <= ns ; ++j) if (trueCluster[j] == readCluster) trueCluster[j] = hashCluster ;
+		deadCluster[readCluster] = 1 ;
+	      }
+	  }
+	for (j = 1 ; j <= ns ; ++j) deadCluster[j] = deadCluster[j-1] + 1 - deadCluster[j] ;
+	for (j = 1 ; j <= ns ; ++j) trueCluster[j] = deadCluster[trueCluster[j]] ;
+	nSub[code] = (U32) deadCluster[ns] ;
+	for (i = 0 ; i < (int) nHash ; ++i) cb[8 * (size_t) i + 6] = (U8) trueCluster[cb[8 * (size_t) i + 6]] ;
+	free (readMap) ;
+      }
+    }
+  free (minShare) ; free (minShareCount) ;
   return ORC_OK ;
 }

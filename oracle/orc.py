@@ -69,6 +69,9 @@ def lib():
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_good_hashes.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_cluster_stale_labels.restype = C.c_uint64
         L.synth_layout.restype = C.c_uint64
         L.synth_layout.argtypes = [C.POINTER(SynthParams), C.c_void_p]
         L.synth_fill.argtypes = [C.POINTER(SynthParams), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -203,6 +206,38 @@ def good_hashes(ix, dmin, dmax, within=None):
                                dmin, dmax, within.ctypes.data, good_off.ctypes.data, good.ctypes.data)
     assert st == 0
     return within, good_off, good[:int(good_off[nb])]
+
+
+def cluster(ix, good_off, good, code_min=0, code_max=0, threshold=5, clus=None, n_sub=None, point_to_min=None):
+    """`--cluster codeMin codeMax` (codeClusterFind + codeClusterReadMerge, hash10x.c:770-868) on an Index and its
+    goodHashes lists: returns (clus with the subCluster bytes set, nSubCluster[nBlocksMax], pointToMin[nBlocksMax]).
+    clus / n_sub / point_to_min carry the state of an earlier --cluster command."""
+    nb = int(ix.nBlocksMax)
+    clus = np.array(ix.clus if clus is None else clus, np.uint64, copy=True)
+    if clus.size == 0:
+        clus = np.zeros(1, np.uint64)
+    n_sub = np.zeros(nb, np.uint32) if n_sub is None else np.array(n_sub, np.uint32, copy=True)
+    ptm = np.zeros(nb, np.float64) if point_to_min is None else np.array(point_to_min, np.float64, copy=True)
+    depth = np.ascontiguousarray(ix.hashDepth, np.uint32)
+    code_off = np.ascontiguousarray(ix.codeOff, np.uint64)
+    codes = np.ascontiguousarray(ix.codes, np.uint32)
+    nr = np.ascontiguousarray(ix.blkNRead, np.uint32)
+    nh = np.ascontiguousarray(ix.blkNHash, np.uint32)
+    off = np.ascontiguousarray(ix.blkOff, np.uint64)
+    good_off = np.ascontiguousarray(good_off, np.uint64)
+    good = np.ascontiguousarray(good, np.uint16)
+    st = lib().orc_cluster(depth.ctypes.data, code_off.ctypes.data, codes.ctypes.data, nb, nr.ctypes.data,
+                           nh.ctypes.data, off.ctypes.data, clus.ctypes.data, good_off.ctypes.data,
+                           good.ctypes.data if good.size else None, code_min, code_max, threshold,
+                           n_sub.ctypes.data, ptm.ctypes.data)
+    assert st == 0, st
+    return clus[:int(ix.nHashes)], n_sub, ptm
+
+
+def cluster_stale_labels():
+    """entries whose label from an earlier --cluster exceeded the block's new nSubCluster (undefined behaviour in
+    the reference, treated as unclustered here), summed over all cluster() calls of this process"""
+    return int(lib().orc_cluster_stale_labels())
 
 
 # ------------------------------------------------------------------ synthetic FQB (CPU)

@@ -40,6 +40,7 @@ def parse(path, keep_table=True):
     hf.blkNHash = cb[:, 1].copy()
     hf.blkNSub = cb[:, 2].copy()
     hf.blkParent = cb[:, 3].copy()
+    hf.blkPointToMin = np.frombuffer(d, np.float64).reshape(-1, 4)[:hf.nBlocksMax, 3].copy()
     hf.nHashes = int(hf.blkNHash[1:].sum()) if hf.nBlocksMax > 1 else 0
     raw = np.frombuffer(buf, np.uint64, hf.nHashes, off).copy()
     off += 8 * hf.nHashes
@@ -47,6 +48,7 @@ def parse(path, keep_table=True):
     hf.clusRaw = raw
     hf.clusIdx = (raw & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     hf.clusRead = ((raw >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.uint16)
+    hf.clusSub = ((raw >> np.uint64(48)) & np.uint64(0xFF)).astype(np.uint8)
     hf.blkOff = np.zeros(hf.nBlocksMax + 1, np.uint64)
     if hf.nBlocksMax > 1:
         hf.blkOff[2:] = np.cumsum(hf.blkNHash[1:].astype(np.uint64))

@@ -174,3 +174,72 @@ def test_good_hashes_restatement_properties(orc):
         assert (np.diff(lst)[same] > 0).all()
     w2, _, good2 = orc.good_hashes(ix, 20, 30, within.copy())
     assert (w2 >= within).all() and good2.size >= good.size       # ranges accumulate
+
+
+CLUSTER_CASES = [
+    # seed, barcodes, pairs min/max, genome, molecule length, molecules per barcode, depth range, threshold, code range
+    (31, 200, 40, 160, 60_000, 20_000, 2, 3, 200, 3, 0, 0),
+    (34, 300, 100, 250, 200_000, 20_000, 4, 4, 400, 3, 0, 0),
+    (35, 500, 60, 160, 300_000, 15_000, 5, 3, 100, 2, 7, 450),
+    (36, 250, 150, 300, 100_000, 10_000, 6, 6, 60, 4, 0, 0),
+    (37, 120, 20, 80, 40_000, 8_000, 3, 2, 13, 1, 0, 0),
+]
+
+
+def _cluster_case(orc, seed, nb, pmin, pmax, genome, mol, mpb):
+    p = orc.synth_params(seed=seed, n_barcodes=nb, pairs_min=pmin, pairs_max=pmax, genome_len=genome, mol_len=mol,
+                         mol_per_barcode=mpb)
+    return orc.synth_fqb(p)
+
+
+@pytest.mark.parametrize("seed,nb,pmin,pmax,genome,mol,mpb,dmin,dmax,thr,cmin,cmax", CLUSTER_CASES)
+def test_cluster_equals_reference_binary(orc, tmp_path, seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr, cmin, cmax):
+    """--hashDepthRange + --cluster (hash10x.c:528-539,738-868): the oracle's restatements against the reference
+    binary.  The reference reads a .hash whose subCluster bytes are zero (written by the oracle), so its own
+    uninitialised ClusterHash bytes (hash10x.c:175) never enter; its --writeHash then exposes nSubCluster,
+    pointToMin and every subCluster byte, which also pins goodHashesBuild (the clustering walks the good lists
+    in order)."""
+    _need_ref(orc)
+    import subprocess
+    recs = _cluster_case(orc, seed, nb, pmin, pmax, genome, mol, mpb)
+    B = 20
+    src, dst = str(tmp_path / "o.hash"), str(tmp_path / "r.hash")
+    assert orc.build_and_write(recs, src, B=B) == 0
+    cmd = [orc.ref_binary(), "-B", str(B), "-ct", str(thr), "--readHash", src, "--hashDepthRange", str(dmin), str(dmax),
+           "--cluster", str(cmin), str(cmax), "--writeHash", dst]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref = hashfile.parse(dst)
+    ix = orc.build(recs, B=B)
+    _within, goff, good = orc.good_hashes(ix, dmin, dmax)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, cmin, cmax, thr)
+    assert np.array_equal(ref.blkNSub, nsub)
+    assert np.array_equal(ref.blkPointToMin.view(np.uint64), ptm.view(np.uint64))      # bit-exact doubles
+    assert np.array_equal(ref.clusRaw, clus)
+    assert int(nsub.sum()) > 0 and int(ref.clusSub.max()) > 0          # the case does cluster something
+
+
+def test_cluster_twice_carries_state_like_the_reference(orc, tmp_path):
+    """A second --hashDepthRange / --cluster pair works on what the first left behind: within[] flags accumulate
+    (hash10x.c:535), only the good entries are wiped (:783) and a block without good hashes is merged again with
+    its old labels (:780,840)."""
+    _need_ref(orc)
+    import subprocess
+    recs = _cluster_case(orc, 36, 250, 150, 300, 100_000, 10_000, 6)
+    src, dst = str(tmp_path / "o.hash"), str(tmp_path / "r.hash")
+    assert orc.build_and_write(recs, src, B=20) == 0
+    cmd = [orc.ref_binary(), "-B", "20", "-ct", "4", "--readHash", src, "--hashDepthRange", "6", "60", "--cluster", "0", "0",
+           "--hashDepthRange", "2", "5", "-ct", "2", "--cluster", "10", "200", "--writeHash", dst]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref = hashfile.parse(dst)
+    ix = orc.build(recs, B=20)
+    within, goff, good = orc.good_hashes(ix, 6, 60)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 4)
+    within, goff, good = orc.good_hashes(ix, 2, 5, within)
+    stale = orc.cluster_stale_labels()
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 10, 200, 2, clus=clus, n_sub=nsub, point_to_min=ptm)
+    assert orc.cluster_stale_labels() == stale      # the case stays clear of the reference's out-of-bounds read
+    assert np.array_equal(ref.blkNSub, nsub)
+    assert np.array_equal(ref.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    assert np.array_equal(ref.clusRaw, clus)
