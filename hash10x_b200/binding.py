@@ -35,7 +35,8 @@ class CIndex(C.Structure):
                 ("hashIndex", C.c_void_p), ("hashValue", C.c_void_p), ("hashDepth", C.c_void_p),
                 ("blkNRead", C.c_void_p), ("blkNHash", C.c_void_p), ("blkOff", C.c_void_p),
                 ("clusHash", C.c_void_p), ("codeOff", C.c_void_p), ("codes", C.c_void_p),
-                ("onDevice", C.c_int32), ("pinned", C.c_int32)]
+                ("onDevice", C.c_int32), ("pinned", C.c_int32),
+                ("blkNSubCluster", C.c_void_p), ("blkPointToMin", C.c_void_p)]
 
 
 class CStats(C.Structure):
@@ -56,6 +57,12 @@ class CDistInfo(C.Structure):
 class CGood(C.Structure):
     _fields_ = [("nGood", C.c_uint64), ("hashNumber", C.c_uint32), ("nBlocksMax", C.c_uint32),
                 ("within", C.c_void_p), ("goodOff", C.c_void_p), ("good", C.c_void_p)]
+
+
+class CClusters(C.Structure):
+    _fields_ = [("nBlocksMax", C.c_uint32), ("reserved", C.c_uint32), ("nHashes", C.c_uint64),
+                ("nSubCluster", C.c_void_p), ("pointToMin", C.c_void_p), ("clusHash", C.c_void_p),
+                ("msKernel", C.c_double)]
 
 
 def lib_path():
@@ -105,6 +112,7 @@ def load_library():
     L.h10x_gpu_dist_info.argtypes = [vp, C.POINTER(CDistInfo)]
     L.h10x_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.h10x_gpu_depth_range.argtypes = [vp, C.c_int, C.c_int, C.POINTER(CGood), cp, sz]
+    L.h10x_gpu_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(CClusters), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -292,6 +300,15 @@ class Hash10xGPU:
         return (_arr(cg.within, cg.hashNumber, np.uint8), _arr(cg.goodOff, cg.nBlocksMax + 1, np.uint64),
                 _arr(cg.good, cg.nGood, np.uint16))
 
+    def cluster(self, code_min=0, code_max=0, threshold=5):
+        """--cluster codeMin codeMax (-ct threshold) on the resident index and goodHashes ->
+        (clus u64 with the subCluster bytes set, nSubCluster u32, pointToMin f64, kernel ms) host copies"""
+        cc = CClusters()
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_cluster(self.ctx, code_min, code_max, threshold, C.byref(cc), err, len(err)), err)
+        return (_arr(cc.clusHash, cc.nHashes, np.uint64), _arr(cc.nSubCluster, cc.nBlocksMax, np.uint32),
+                _arr(cc.pointToMin, cc.nBlocksMax, np.float64), cc.msKernel)
+
     def stats(self):
         cs = CStats()
         self.lib.h10x_gpu_stats(self.ctx, C.byref(cs))
@@ -321,7 +338,11 @@ def write_hash(index_arrays, path):
                                               ix.blkNHash, ix.blkOff, ix.clus)]
     ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
                 keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
-                keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0)
+                keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0, None, None)
+    nsub, ptm = getattr(ix, "blkNSub", None), getattr(ix, "blkPointToMin", None)
+    if nsub is not None and ptm is not None:
+        keep += [np.ascontiguousarray(nsub, np.uint32), np.ascontiguousarray(ptm, np.float64)]
+        ci.blkNSubCluster, ci.blkPointToMin = keep[-2].ctypes.data, keep[-1].ctypes.data
     st = L.h10x_write_hash(C.byref(ci), path.encode())
     if st:
         raise H10xError(st, "write fail")

@@ -17,6 +17,7 @@
 #include "h10x_fused.cuh"
 #include "h10x_cluster.cuh"
 #include "h10x_bucket.cuh"
+#include "h10x_subcluster.cuh"
 
 #include <cub/cub.cuh>
 
@@ -127,6 +128,11 @@ struct h10x_ctx {
   /* host-buffer builds start the D2H of an index array as soon as it is final, on a second stream */
   bool earlyDl = false ; cudaStream_t dlStream = 0 ; bool slotDone[9] = { false, false, false, false, false, false, false, false, false } ;
   DBuf<uint8_t> within ;	/* --hashDepthRange flags per bin; only ever set (hash10x.c:535) until the next build */
+  /* goodHashes of the last --hashDepthRange (hash10x.c:722-766), resident for --cluster; ClusterBlock.nSubCluster /
+     .pointToMin (hash10x.c:62-70) once a --cluster command ran */
+  DBuf<uint64_t> goodOffD ; DBuf<uint16_t> goodD ; bool haveGood = false ;
+  DBuf<uint32_t> blkNSub ; DBuf<double> blkPtm ;
+  void *clusSlot[2] = { nullptr, nullptr } ; size_t clusCap[2] = { 0, 0 } ;	/* pinned host: nSubCluster, pointToMin */
   void *goodSlot[3] = { nullptr, nullptr, nullptr } ; size_t goodCap[3] = { 0, 0, 0 } ;	/* pinned host: within, goodOff, good */
   struct DistState *dist = nullptr ;
   DBuf<uint32_t> localBinId, localCodeOff, localCodes ;	/* this rank's part of the hash->code lists */
@@ -498,6 +504,7 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 static void reset_result (h10x_ctx *c)
 { c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
   c->localBinId.release () ; c->localCodeOff.release () ; c->localCodes.release () ; c->within.release () ;
+  c->goodOffD.release () ; c->goodD.release () ; c->haveGood = false ; c->blkNSub.release () ; c->blkPtm.release () ;
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
   c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
@@ -1578,6 +1585,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
   for (auto e : c->evPool) cudaEventDestroy (e) ;
   for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
   for (int i = 0 ; i < 3 ; ++i) if (c->goodSlot[i]) cudaFreeHost (c->goodSlot[i]) ;
+  for (int i = 0 ; i < 2 ; ++i) if (c->clusSlot[i]) cudaFreeHost (c->clusSlot[i]) ;
   if (c->own) { cudaStreamSynchronize (c->own) ; cudaStreamDestroy (c->own) ; }
   delete c ;
 }
@@ -1616,6 +1624,8 @@ void h10x_index_free (h10x_index *ix)
   void *ps[] = { ix->hashIndex, ix->hashValue, ix->hashDepth, ix->blkNRead, ix->blkNHash, ix->blkOff,
 		 ix->clusHash, ix->codeOff, ix->codes } ;
   for (void *p : ps) if (p) { if (ix->pinned) cudaFreeHost (p) ; else free (p) ; }
+  if (!ix->pinned) { free (ix->blkNSubCluster) ; free (ix->blkPointToMin) ; }	/* h10x_read_hash's; otherwise borrowed */
+  ix->blkNSubCluster = nullptr ; ix->blkPointToMin = nullptr ;
   ix->hashIndex = nullptr ; ix->hashValue = nullptr ; ix->hashDepth = nullptr ; ix->blkNRead = nullptr ;
   ix->blkNHash = nullptr ; ix->blkOff = nullptr ; ix->clusHash = nullptr ; ix->codeOff = nullptr ; ix->codes = nullptr ;
 }
@@ -1729,14 +1739,18 @@ int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out
       LAUNCH (c, k_within, gridFor (hn, 256), 256, 0, s, hn, c->hashDepth.p, dmin, dmax, c->within.p) ;
       uint32_t nGood = 0 ;
       DBuf<uint32_t> flag (H + 1, s, mt), pos (H + 1, s, mt) ;
-      DBuf<uint64_t> goodOff ((size_t) nb + 1, s, mt) ;
+      c->haveGood = false ;
+      c->goodD.release () ; c->goodOffD.alloc ((size_t) nb + 1, s, mt) ;
+      DBuf<uint64_t> &goodOff = c->goodOffD ;
       CK (cudaMemsetAsync (flag.p + H, 0, 4, s)) ;
       LAUNCH (c, k_good_mark, std::min<uint32_t> (nb, 148 * 16), 256, 0, s, nb, c->blkOff.p, c->blkNHash.p, c->clus.p, c->within.p, flag.p) ;
       cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, flag.p, pos.p, H + 1, s) ; }) ;
       CK (cudaMemcpyAsync (&nGood, pos.p + H, 4, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;
       DBuf<uint32_t> keyDepth (nGood, s, mt), keyS (nGood, s, mt) ;
-      DBuf<uint16_t> valIdx (nGood, s, mt), valS (nGood, s, mt) ;
+      DBuf<uint16_t> valIdx (nGood, s, mt) ;
+      c->goodD.alloc (nGood, s, mt) ;
+      DBuf<uint16_t> &valS = c->goodD ;
       LAUNCH (c, k_good_compact, std::min<uint32_t> (nb + 1, 148 * 16), 256, 0, s, nb, c->blkOff.p, c->blkNHash.p, c->clus.p,
 	      c->hashDepth.p, flag.p, pos.p, keyDepth.p, valIdx.p, goodOff.p, H, nGood) ;
       flag.release () ; pos.release () ;
@@ -1759,7 +1773,92 @@ int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out
       out->good = (uint16_t*) pull (2, valS.p, 2 * (size_t) nGood) ;
       out->nGood = nGood ; out->hashNumber = hn ; out->nBlocksMax = nb ;
       CK (cudaStreamSynchronize (s)) ;
+      c->haveGood = true ;
     }) ;
+}
+
+/* --cluster codeMin codeMax (hash10x.c:1241-1256) on the resident index and goodHashes: h10x_subcluster.cuh */
+int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out, char *err, size_t errlen)
+{ if (!c || !out) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  if (!c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->haveGood) { set_err (err, errlen, "you must set hashDepthRange before cluster") ; return H10X_ERR_BAD_PARAM ; }	/* hash10x.c:1258 */
+  if (!c->codes.p || !c->codeOff.p) { set_err (err, errlen, "the hash->code lists were not built (H10X_FLAG_NO_CODES)") ; return H10X_ERR_BAD_PARAM ; }
+  if (clusterThreshold < 1) { set_err (err, errlen, "clusterThreshold must be at least 1") ; return H10X_ERR_BAD_PARAM ; }
+  if (!codeMin) codeMin = 1 ;
+  if (!codeMax) codeMax = (int) c->nBlocksMax ;
+  if (codeMin < 1 || codeMax > (int) c->nBlocksMax)
+    { set_err (err, errlen, "code range outside the barcode blocks") ; return H10X_ERR_BAD_PARAM ; }
+  void *scratch = nullptr ;
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      const uint32_t nb = c->nBlocksMax ;
+      const uint64_t H = c->nHashes ;
+      if (!c->blkNSub.p)
+	{ c->blkNSub.alloc (nb, s, mt) ; c->blkPtm.alloc (nb, s, mt) ;
+	  CK (cudaMemsetAsync (c->blkNSub.p, 0, 4 * (size_t) nb, s)) ;
+	  CK (cudaMemsetAsync (c->blkPtm.p, 0, 8 * (size_t) nb, s)) ;
+	}
+      cudaEvent_t evA = ctx_event (c), evB = ctx_event (c) ;
+      if (codeMax > codeMin)
+	{ int nSM = 148 ;
+	  CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, c->P.device)) ;
+	  int occ = 1 ;
+	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, 0)) ;
+	  occ = std::max (1, std::min (occ, 4)) ;
+	  uint32_t cap = 1024 ; int lg = 10 ;
+	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
+	  /* per CTA: the table, 8 warps of counters, the triples, the two label fallbacks */
+	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_WARPS * 65536 * 4 + (size_t) 3 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
+	  size_t freeB = 0, totalB = 0 ;
+	  CK (cudaMemGetInfo (&freeB, &totalB)) ;
+	  size_t budget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
+	  uint32_t grid = (uint32_t) std::min<size_t> ((size_t) nSM * occ, (size_t) (codeMax - codeMin)) ;
+	  grid = (uint32_t) std::min<size_t> (grid, budget / perCta) ;
+	  if (grid < 1) throw H10xError (H10X_ERR_NOMEM, "not enough device memory for the cluster workspace") ;
+	  const size_t bytes = perCta * grid + 256 ;
+	  CK (cudaMalloc (&scratch, bytes)) ;
+	  CK (cudaMemsetAsync (scratch, 0, bytes, s)) ;
+	  char *p = (char*) scratch ;
+	  SubClusterArgs a ;
+	  a.work = (unsigned int*) p ; p += 256 ;
+	  a.table = (unsigned long long*) p ; p += (size_t) cap * 8 * grid ;
+	  a.cnt = (uint32_t*) p ; p += (size_t) H10X_SC_WARPS * 65536 * 4 * grid ;
+	  a.res = (uint32_t*) p ; p += (size_t) 3 * 65536 * 4 * grid ;
+	  a.readLabG = (int*) p ; p += (size_t) 65536 * 4 * grid ;
+	  a.gsubG = (uint8_t*) p ;
+	  a.tableCap = cap ; a.tableShift = (uint32_t) (32 - lg) ;
+	  a.clus = (unsigned long long*) c->clus.p ; a.blkOff = c->blkOff.p ; a.blkNHash = c->blkNHash.p ; a.blkNRead = c->blkNRead.p ;
+	  a.hashDepth = c->hashDepth.p ; a.codeOff = c->codeOff.p ; a.codes = c->codes.p ;
+	  a.goodOff = c->goodOffD.p ; a.good = c->goodD.p ;
+	  a.nSub = c->blkNSub.p ; a.pointToMin = c->blkPtm.p ;
+	  a.codeMin = (uint32_t) codeMin ; a.codeMax = (uint32_t) codeMax ; a.threshold = clusterThreshold ;
+	  CK (cudaEventRecord (evA, s)) ;
+	  LAUNCH (c, k_subcluster, grid, H10X_SC_THREADS, 0, s, a) ;
+	  CK (cudaEventRecord (evB, s)) ;
+	}
+      auto pull = [&] (int slot, const void *src, size_t bytes) -> void*
+	{ if (c->clusCap[slot] < bytes || !c->clusSlot[slot])
+	    { if (c->clusSlot[slot]) cudaFreeHost (c->clusSlot[slot]) ;
+	      c->clusSlot[slot] = nullptr ; c->clusCap[slot] = 0 ;
+	      c->clusSlot[slot] = pinned_alloc (bytes) ; c->clusCap[slot] = bytes ? bytes : 1 ;
+	    }
+	  if (bytes) CK (cudaMemcpyAsync (c->clusSlot[slot], src, bytes, cudaMemcpyDeviceToHost, s)) ;
+	  return c->clusSlot[slot] ;
+	} ;
+      out->nSubCluster = (uint32_t*) pull (0, c->blkNSub.p, 4 * (size_t) nb) ;
+      out->pointToMin = (double*) pull (1, c->blkPtm.p, 8 * (size_t) nb) ;
+      out->clusHash = (h10x_cluster_hash*) host_slot (c, SLOT_CLUS, 8 * H) ;
+      if (H) CK (cudaMemcpyAsync (out->clusHash, c->clus.p, 8 * H, cudaMemcpyDeviceToHost, s)) ;
+      out->nBlocksMax = nb ; out->nHashes = H ;
+      CK (cudaStreamSynchronize (s)) ;
+      if (codeMax > codeMin) { float ms = 0 ; CK (cudaEventElapsedTime (&ms, evA, evB)) ; out->msKernel = ms ; }
+    }) ;
+  if (scratch) { cudaStreamSynchronize (c->own) ; cudaFree (scratch) ; }
+  if (st != H10X_OK) { cudaGetLastError () ; memset (out, 0, sizeof (*out)) ; }
+  return st ;
 }
 
 int h10x_gpu_stats (h10x_ctx *c, h10x_stats *out)

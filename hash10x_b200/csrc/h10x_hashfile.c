@@ -4,8 +4,8 @@
  * Arrays serialised as array.c:213-238 does (raw 32-byte ArrayStruct, then `dim` elements).
  * SURVEY.md Appendix B lists every field.  What differs from a reference-written file, and why it
  * does not matter to its reader: the raw pointers inside ArrayStruct / ClusterBlock are written as
- * 0 (readHashFile overwrites them, hash10x.c:305, array.c:223) and ClusterHash bytes 6-7 are 0 (the
- * reference leaves malloc garbage there, hash10x.c:175).  `dim` follows the reference's growth rule
+ * 0 (readHashFile overwrites them, hash10x.c:305, array.c:223) and ClusterHash bytes 6-7 are 0 until --cluster
+ * sets byte 6 (the reference leaves malloc garbage there, hash10x.c:175).  `dim` follows the reference's growth rule
  * (array.c:144-170) so the file has exactly the size the reference would write.
  */
 #include "../../include/h10x_gpu.h"
@@ -66,7 +66,11 @@ int h10x_write_hash (const h10x_index *ix, const char *path)
       uint32_t nb = ix->nBlocksMax, b ;
       uint32_t *cb = calloc ((size_t) nb * 8, sizeof (uint32_t)) ;
       if (!cb) { fclose (f) ; return H10X_ERR_NOMEM ; }
-      for (b = 0 ; b < nb ; ++b) { cb[8*b] = ix->blkNRead[b] ; cb[8*b + 1] = ix->blkNHash[b] ; }
+      for (b = 0 ; b < nb ; ++b)
+	{ cb[8*b] = ix->blkNRead[b] ; cb[8*b + 1] = ix->blkNHash[b] ;
+	  if (ix->blkNSubCluster) cb[8*b + 2] = ix->blkNSubCluster[b] ;
+	  if (ix->blkPointToMin) memcpy (&cb[8*b + 6], &ix->blkPointToMin[b], 8) ;
+	}
       ok = put_array (f, cb, 32, (int) nb, 1200) ;	/* dim0 = 1200: hash10x.c:1151 */
       free (cb) ;
     }
@@ -125,9 +129,11 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   if (fread (cb, 32, a.dim, f) != (size_t) a.dim) { seterr (err, errlen, "failed to read clusterBlocks array") ; goto fail ; }
   { uint32_t nb = out->nBlocksMax, b ;
     out->blkNRead = calloc (nb, 4) ; out->blkNHash = calloc (nb, 4) ; out->blkOff = calloc ((size_t) nb + 1, 8) ;
-    if (!out->blkNRead || !out->blkNHash || !out->blkOff) { st = H10X_ERR_NOMEM ; goto fail ; }
+    out->blkNSubCluster = calloc (nb, 4) ; out->blkPointToMin = calloc (nb, 8) ;
+    if (!out->blkNRead || !out->blkNHash || !out->blkOff || !out->blkNSubCluster || !out->blkPointToMin) { st = H10X_ERR_NOMEM ; goto fail ; }
     for (b = 0 ; b < nb ; ++b)
       { out->blkNRead[b] = cb[8*b] ; out->blkNHash[b] = b ? cb[8*b + 1] : 0 ;
+	out->blkNSubCluster[b] = cb[8*b + 2] ; memcpy (&out->blkPointToMin[b], &cb[8*b + 6], 8) ;
 	out->blkOff[b] = out->nHashes ;
 	if (b) { out->nReads += out->blkNRead[b] ; out->nHashes += out->blkNHash[b] ; }
       }
@@ -142,7 +148,7 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   free (cb) ;
   fclose (f) ;
   free (out->hashIndex) ; free (out->hashValue) ; free (out->hashDepth) ; free (out->blkNRead) ;
-  free (out->blkNHash) ; free (out->blkOff) ; free (out->clusHash) ;
+  free (out->blkNHash) ; free (out->blkOff) ; free (out->clusHash) ; free (out->blkNSubCluster) ; free (out->blkPointToMin) ;
   memset (out, 0, sizeof (*out)) ;
   return st ;
 }

@@ -1,0 +1,287 @@
+/* h10x_subcluster.cuh - `--cluster codeMin codeMax` on the resident index ("next" row f2 of SURVEY.md section 8):
+ * codeClusterFind (hash10x.c:770-835) + codeClusterReadMerge (hash10x.c:837-868), one persistent CTA per barcode block.
+ *
+ * The reference walks a block's good hashes i = 1 .. n-1 in order and keeps, per other barcode cj, the first step
+ * at which cj shared a hash with this block (minShare[cj] = i + 1).  That is a minimum, so it does not depend on the
+ * order of the walk:
+ *
+ *   A  every (good hash i, barcode cj holding it) pair does an atomic min into a per-CTA open-addressing table
+ *      cj -> min (i + 1), all warps of the CTA in parallel;
+ *   B  a warp per good hash i counts, over the barcodes of hash i, how many have minShare - 1 == j for every j < i
+ *      (barcodes first seen at step i sit at index i and never enter, hash10x.c:793-806), and keeps the largest
+ *      count (first j wins ties, :803), the total, and nothing else: (msBest, msMax, msTot) of step i;
+ *   C  one warp replays the cheap sequential part (:807-824) over those triples: sub-cluster creation and joining,
+ *      the 255-cluster limit, and the pointToMin sum in the reference's order of double additions;
+ *   E  codeClusterReadMerge is a connected-components problem (sub-clusters joined through shared reads, the
+ *      smallest label wins, :848-858): min-label propagation over (sub-cluster, read) edges with pointer jumping,
+ *      then the reference's compaction of the surviving labels (:862-865).
+ *
+ * The table entries carry a 16-bit stamp (one per block handled by the CTA), so the table is never cleared between
+ * blocks: an entry with another stamp is empty.  Table, per-warp counters and the triples live in global memory
+ * (L2 for the counters and triples); the labels of good entries and of reads sit in shared memory when they fit.
+ * Labels left by an earlier --cluster on entries outside the current good lists that exceed the block's new
+ * nSubCluster count as 0 (the reference reads past trueCluster[] there: undefined behaviour; same rule as the oracle).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define H10X_SC_THREADS 256
+#define H10X_SC_WARPS (H10X_SC_THREADS / 32)
+#define H10X_SC_GSUB_SMEM 16384		/* good-entry labels kept in shared memory up to this many good hashes */
+#define H10X_SC_READ_SMEM 4096		/* read labels kept in shared memory up to this many read pairs */
+#define H10X_SC_VBUF 128		/* per-warp buffer of a hash's barcodes' minShare values */
+
+struct SubClusterArgs {
+  unsigned long long *clus ;		/* ClusterHash as one word: bin id | read << 32 | subCluster << 48 */
+  const uint64_t *blkOff ; const uint32_t *blkNHash, *blkNRead ;
+  const uint32_t *hashDepth ; const uint64_t *codeOff ; const uint32_t *codes ;
+  const uint64_t *goodOff ; const uint16_t *good ;
+  uint32_t *nSub ; double *pointToMin ;
+  uint32_t codeMin, codeMax ; int threshold ;
+  unsigned int *work ;			/* ticket counter */
+  unsigned long long *table ;		/* per CTA: tableCap entries (barcode << 32 | stamp << 16 | minShare), zeroed once */
+  uint32_t tableCap, tableShift ;	/* power of two >= 2 * blocks; shift = 32 - log2 (tableCap) */
+  uint32_t *cnt ;			/* per warp: 65536 counters, all zero between uses */
+  uint32_t *res ;			/* per CTA: 3 * 65536 words: msBest, msMax, msTot of every step */
+  uint8_t *gsubG ;			/* per CTA: 65536 bytes, labels of the good entries when they do not fit in smem */
+  int *readLabG ;			/* per CTA: 65536 ints, read labels when they do not fit in smem */
+} ;
+
+__device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t mask, uint32_t shift, uint32_t stamp,
+					      uint32_t cj, uint32_t val)
+{ const unsigned long long tag = ((unsigned long long) cj << 32) | ((unsigned long long) stamp << 16) ;
+  const unsigned long long cand = tag | val ;
+  uint32_t h = (cj * 0x9E3779B1u) >> shift ;
+  for (;;)
+    { unsigned long long old = __ldcg (tab + h) ;
+      if ((old & ~0xffffull) == tag)			/* this barcode, this block */
+	{ if (val < (uint32_t) (old & 0xffffull)) atomicMin (tab + h, cand) ;
+	  return ;
+	}
+      if ((uint32_t) ((old >> 16) & 0xffffull) != stamp)	/* left by an earlier block, or never used: claim it */
+	{ if (atomicCAS (tab + h, old, cand) == old) return ;
+	  continue ;					/* someone else took the slot: look at it again */
+	}
+      h = (h + 1) & mask ;
+    }
+}
+
+/* minShare of a barcode that step A has entered (0 if it is not there, which cannot happen for a barcode of a
+   scanned hash) */
+__device__ __forceinline__ uint32_t sc_table_get (const unsigned long long *tab, uint32_t mask, uint32_t shift, uint32_t stamp,
+						  uint32_t cj)
+{ const unsigned long long tag = ((unsigned long long) cj << 32) | ((unsigned long long) stamp << 16) ;
+  uint32_t h = (cj * 0x9E3779B1u) >> shift ;
+  for (uint32_t probes = 0 ; probes <= mask ; ++probes)
+    { unsigned long long old = __ldcg (tab + h) ;
+      if ((old & ~0xffffull) == tag) return (uint32_t) (old & 0xffffull) ;
+      if ((uint32_t) ((old >> 16) & 0xffffull) != stamp) return 0 ;
+      h = (h + 1) & mask ;
+    }
+  return 0 ;
+}
+
+__global__ void __launch_bounds__ (H10X_SC_THREADS)
+k_subcluster (SubClusterArgs a)
+{
+  __shared__ uint8_t gsubS[H10X_SC_GSUB_SMEM] ;
+  __shared__ int readLabS[H10X_SC_READ_SMEM] ;
+  __shared__ uint16_t vbuf[H10X_SC_WARPS][H10X_SC_VBUF] ;
+  __shared__ uint16_t clusterMin[256] ;
+  __shared__ int label[257], newLab[257] ;
+  __shared__ uint32_t sTicket, sNs, sChanged ;
+
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5 ;
+  unsigned long long *tab = a.table + (size_t) blockIdx.x * a.tableCap ;
+  const uint32_t mask = a.tableCap - 1, shift = a.tableShift ;
+  uint32_t *cnt = a.cnt + ((size_t) blockIdx.x * H10X_SC_WARPS + w) * 65536 ;
+  uint32_t *resBest = a.res + (size_t) blockIdx.x * 3 * 65536, *resMax = resBest + 65536, *resTot = resMax + 65536 ;
+  uint32_t stamp = 0 ;
+
+  for (;;)
+    { if (t == 0) sTicket = atomicAdd (a.work, 1u) ;
+      __syncthreads () ;
+      const uint32_t code = a.codeMin + sTicket ;
+      __syncthreads () ;
+      if (code >= a.codeMax) break ;
+
+      unsigned long long *ch = a.clus + a.blkOff[code] ;
+      const uint16_t *g = a.good + a.goodOff[code] ;
+      const uint32_t n = (uint32_t) (a.goodOff[code + 1] - a.goodOff[code]) ;
+      const uint32_t nHash = a.blkNHash[code] ;
+
+      if (n)	/* ---------------- codeClusterFind ---------------- */
+	{ if (++stamp == 0x10000u)		/* 16-bit stamps used up: start over with a clean table */
+	    { for (size_t i = t ; i < a.tableCap ; i += H10X_SC_THREADS) tab[i] = 0 ;
+	      stamp = 1 ;
+	      __syncthreads () ;
+	    }
+	  uint8_t *gsub = (n <= H10X_SC_GSUB_SMEM) ? gsubS : a.gsubG + (size_t) blockIdx.x * 65536 ;
+	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS) gsub[i] = 0 ;		/* :783 wipe */
+
+	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block */
+	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
+	    { const uint32_t x = (uint32_t) ch[g[i]] ;
+	      const uint32_t nc = a.hashDepth[x] ;
+	      const uint32_t *cl = a.codes + a.codeOff[x] ;
+	      for (uint32_t j = lane ; j < nc ; j += 32)
+		{ const uint32_t cj = cl[j] ;
+		  if (cj != code) sc_table_min (tab, mask, shift, stamp, cj, i + 1) ;
+		}
+	    }
+	  __syncthreads () ;
+
+	  /* B: per step i the best earlier step, its count and the total (hash10x.c:793-806) */
+	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
+	    { const uint32_t x = (uint32_t) ch[g[i]] ;
+	      const uint32_t nc = a.hashDepth[x] ;
+	      const uint32_t *cl = a.codes + a.codeOff[x] ;
+	      uint32_t tot = 0 ;
+	      for (uint32_t j = lane ; j < nc ; j += 32)
+		{ const uint32_t cj = cl[j] ;
+		  uint32_t v = 0xffffu ;
+		  if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+		  if (j < H10X_SC_VBUF) vbuf[w][j] = (uint16_t) v ;
+		  if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
+		}
+	      __syncwarp () ;
+	      uint32_t bMax = 0, bBest = 0xffffffffu ;
+	      for (uint32_t j = lane ; j < nc ; j += 32)
+		{ uint32_t v ;
+		  if (j < H10X_SC_VBUF) v = vbuf[w][j] ;
+		  else { const uint32_t cj = cl[j] ; v = 0xffffu ;
+			 if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; } }
+		  if (v != 0xffffu)
+		    { const uint32_t c = __ldcg (cnt + v) ;
+		      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+		    }
+		}
+#pragma unroll
+	      for (int d = 16 ; d ; d >>= 1)
+		{ const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
+		  if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
+		  tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
+		}
+	      __syncwarp () ;
+	      for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
+		{ uint32_t v ;
+		  if (j < H10X_SC_VBUF) v = vbuf[w][j] ;
+		  else { const uint32_t cj = cl[j] ; v = 0xffffu ;
+			 if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; } }
+		  if (v != 0xffffu) cnt[v] = 0 ;
+		}
+	      __syncwarp () ;
+	      if (lane == 0) { resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ; }
+	    }
+	  __syncthreads () ;
+
+	  /* C: the sequential part, by one warp in lock step (hash10x.c:807-824) */
+	  if (w == 0)
+	    { uint32_t nsub = 0 ; double ptm = 0.0 ; bool abandoned = false ;
+	      for (uint32_t i0 = 1 ; i0 < n && !abandoned ; i0 += 32)
+		{ const uint32_t mine = i0 + lane ;
+		  const uint32_t mb = mine < n ? __ldcg (resBest + mine) : 0u, mm = mine < n ? __ldcg (resMax + mine) : 0u,
+		    mt = mine < n ? __ldcg (resTot + mine) : 0u ;
+		  const uint32_t steps = min (32u, n - i0) ;
+		  for (uint32_t k = 0 ; k < steps ; ++k)
+		    { const uint32_t i = i0 + k ;
+		      const uint32_t b = __shfl_sync (0xffffffffu, mb, k), m = __shfl_sync (0xffffffffu, mm, k),
+			tt = __shfl_sync (0xffffffffu, mt, k) ;
+		      if ((long long) m < (long long) a.threshold) continue ;
+		      uint32_t sb = gsub[b] ;
+		      if (!sb)				/* create a new cluster */
+			{ if (++nsub > 255u)		/* abandon this clustering (:810-817) */
+			    { nsub = 0 ;
+			      __syncwarp () ;
+			      for (uint32_t j = lane ; j < i ; j += 32) gsub[j] = 0 ;
+			      abandoned = true ;
+			      break ;
+			    }
+			  sb = nsub ;
+			  __syncwarp () ;
+			  if (lane == 0) { gsub[b] = (uint8_t) sb ; clusterMin[sb] = (uint16_t) b ; }
+			}
+		      __syncwarp () ;
+		      if (lane == 0) gsub[i] = (uint8_t) sb ;
+		      __syncwarp () ;
+		      const uint32_t cm = clusterMin[sb] ;
+		      uint32_t cAt = m ;
+		      if (cm != b)			/* count of the cluster's own minimum at this step */
+			{ const uint32_t x = (uint32_t) ch[g[i]] ;
+			  const uint32_t nc = a.hashDepth[x] ;
+			  const uint32_t *cl = a.codes + a.codeOff[x] ;
+			  cAt = 0 ;
+			  for (uint32_t j = lane ; j < nc ; j += 32)
+			    { const uint32_t cj = cl[j] ;
+			      if (cj != code && sc_table_get (tab, mask, shift, stamp, cj) - 1u == cm) ++cAt ;
+			    }
+#pragma unroll
+			  for (int d = 16 ; d ; d >>= 1) cAt += __shfl_xor_sync (0xffffffffu, cAt, d) ;
+			}
+		      ptm += (double) (int) cAt / (double) (int) tt ;
+		    }
+		}
+	      if (lane == 0) { a.nSub[code] = nsub ; a.pointToMin[code] = ptm ; }
+	    }
+	  __syncthreads () ;
+	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS) ((uint8_t*) (ch + g[i]))[6] = gsub[i] ;
+	  __syncthreads () ;
+	}
+
+      /* ---------------- codeClusterReadMerge ---------------- */
+      if (t == 0) sNs = a.nSub[code] ;
+      __syncthreads () ;
+      const uint32_t ns = sNs ;
+      if (ns)
+	{ const uint32_t nRead = a.blkNRead[code] ;
+	  const uint32_t nR = min (nRead, 65536u) ;
+	  int *readLab = (nR <= H10X_SC_READ_SMEM) ? readLabS : a.readLabG + (size_t) blockIdx.x * 65536 ;
+	  for (uint32_t s = t ; s <= 256 ; s += H10X_SC_THREADS) label[s] = s <= ns ? (int) s : 0 ;
+	  __syncthreads () ;
+	  for (;;)
+	    { if (t == 0) sChanged = 0 ;
+	      for (uint32_t r = t ; r < nR ; r += H10X_SC_THREADS) readLab[r] = 0x7fffffff ;
+	      __syncthreads () ;
+	      for (uint32_t e = t ; e < nHash ; e += H10X_SC_THREADS)
+		{ const unsigned long long wd = __ldcg (ch + e) ;	/* byte 6 was just rewritten: read past L1 */
+		  const uint32_t s = (uint32_t) (wd >> 48) & 0xffu ;
+		  if (s && s <= ns) atomicMin (readLab + ((uint32_t) (wd >> 32) & 0xffffu), label[s]) ;
+		}
+	      __syncthreads () ;
+	      for (uint32_t e = t ; e < nHash ; e += H10X_SC_THREADS)
+		{ const unsigned long long wd = __ldcg (ch + e) ;	/* byte 6 was just rewritten: read past L1 */
+		  const uint32_t s = (uint32_t) (wd >> 48) & 0xffu ;
+		  if (s && s <= ns)
+		    { const int m = readLab[(uint32_t) (wd >> 32) & 0xffffu] ;
+		      if (m < label[s]) { atomicMin (label + s, m) ; sChanged = 1 ; }
+		    }
+		}
+	      __syncthreads () ;
+	      for (uint32_t s = 1 + t ; s <= ns ; s += H10X_SC_THREADS)	/* pointer jumping: labels only ever decrease */
+		{ const int l = label[s], ll = label[l] ;
+		  if (ll < l) { atomicMin (label + s, ll) ; sChanged = 1 ; }
+		}
+	      __syncthreads () ;
+	      const bool again = sChanged != 0 ;
+	      __syncthreads () ;
+	      if (!again) break ;
+	    }
+	  /* surviving labels are the component minima; renumber them 1.. in order (hash10x.c:862-865) */
+	  if (t == 0)
+	    { int live = 0 ;
+	      newLab[0] = 0 ;
+	      for (uint32_t s = 1 ; s <= ns ; ++s) { if (label[s] == (int) s) ++live ; newLab[s] = live ; }	/* = deadCluster[] */
+	      for (uint32_t s = 1 ; s <= ns ; ++s) label[s] = newLab[label[s]] ;
+	      label[0] = 0 ;
+	      a.nSub[code] = (uint32_t) live ;
+	    }
+	  __syncthreads () ;
+	  for (uint32_t e = t ; e < nHash ; e += H10X_SC_THREADS)
+	    { const uint32_t s = (uint32_t) (__ldcg (ch + e) >> 48) & 0xffu ;
+	      ((uint8_t*) (ch + e))[6] = (uint8_t) (s <= ns ? label[s] : 0) ;
+	    }
+	  __syncthreads () ;
+	}
+    }
+}

@@ -8,8 +8,9 @@
  * leaves the same state behind (hash table, values, depths, block table, ClusterHash lists,
  * hash->code lists) for --writeHash, --hashStats, --codeStats and --hashDepthRange, which are O(bins)
  * / O(hashes) host passes exactly as in the reference.  --readHash loads a .hash file written by
- * either program.  The research probes (--cluster, --cribBuild, --hashExplore, ...) are out of scope
- *  and die with a message saying so.
+ * either program.  --cluster (with -ct) runs on the GPU too, on the index --readFQB left there.  The research
+ * probes (--clusterReport, --cribBuild, --hashExplore, ...) are out of scope and die with a
+ * message saying so.
  */
 #define _GNU_SOURCE
 #include "h10x_gpu.h"
@@ -73,6 +74,8 @@ static void usage (void)
   fprintf (stderr, "   --readHash <hash input file name>\n") ;
   fprintf (stderr, "   --writeHash <hash output file name>\n") ;
   fprintf (stderr, "   --hashDepthRange <min> <max>: set limits for hash counts\n") ;
+  fprintf (stderr, "   -ct | --clusterThreshold <clusterThreshold> [%d]\n", params.clusterThreshold) ;
+  fprintf (stderr, "   --cluster <codeMin> <codeMax> : cluster this range of barcodes; 0 for codeMax means to end (runs on the GPU)\n") ;
   fprintf (stderr, "   --hashStats : distribution of hash counts and summary info\n") ;
   fprintf (stderr, "   --codeStats : distribution of barcode/cluster sizes and summary info\n") ;
   fprintf (stderr, "   --gpuStats : per-stage device times and roofline bytes of the last --readFQB\n") ;
@@ -273,6 +276,26 @@ static void hashDepthRange (int min, int max)
   timeUpdate (outFile) ; fflush (outFile) ;
 }
 
+/* ---- --cluster codeMin codeMax: hash10x.c:1241-1261, on the GPU (h10x_gpu_cluster) ---- */
+static void clusterCodes (int codeMin, int codeMax)
+{ if (!goodHashes)
+    { fprintf (outFile, "!! you must set hashDepthRange before cluster\n") ;
+      if (outFile != stdout) fprintf (stderr, "!! you must set hashDepthRange before cluster\n") ;
+      return ;
+    }
+  if (!(ctx && indexFromGpu))
+    die ("--cluster runs on the index that --readFQB left on the GPU: after --readHash or a multi-GPU build, write the index with --writeHash and run it in hash10x --readHash") ;
+  if (!codeMin) codeMin = 1 ;
+  if (!codeMax) codeMax = (int) ix.nBlocksMax ;
+  char err[512] ; h10x_clusters cl ;
+  int st = h10x_gpu_cluster (ctx, codeMin, codeMax, params.clusterThreshold, &cl, err, sizeof (err)) ;
+  if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+  ix.clusHash = cl.clusHash ;			/* the context's pinned copy, subCluster bytes set */
+  ix.blkNSubCluster = cl.nSubCluster ; ix.blkPointToMin = cl.pointToMin ;
+  fprintf (outFile, "  clustered codes %d to %d\n", codeMin, codeMax) ;
+  if (outFile != stdout) printf ("  clustered codes %d to %d\n", codeMin, codeMax) ;
+}
+
 static void gpuStats (void)
 { h10x_stats s ; int i ;
   if (!ctx || !indexFromGpu || h10x_gpu_stats (ctx, &s)) { fprintf (stderr, "  no GPU build to report\n") ; return ; }
@@ -338,12 +361,14 @@ int main (int argc, char *argv[])
 	}
       else if (ARGMATCH ("--writeHash", 2)) writeHash (argv[-1]) ;
       else if (ARGMATCH ("--hashDepthRange", 3)) hashDepthRange (atoi (argv[-2]), atoi (argv[-1])) ;
+      else if (ARGMATCH ("-ct", 2) || ARGMATCH ("--clusterThreshold", 2)) params.clusterThreshold = atoi (argv[-1]) ;
+      else if (ARGMATCH ("--cluster", 3)) clusterCodes (atoi (argv[-2]), atoi (argv[-1])) ;
       else if (ARGMATCH ("--hashStats", 1)) hashStats () ;
       else if (ARGMATCH ("--codeStats", 1)) codeStats () ;
       else if (ARGMATCH ("--gpuStats", 1)) gpuStats () ;
       else if (ARGMATCH ("--help", 1)) usage () ;
       else if (ARGMATCH ("--quit", 1) || ARGMATCH ("--exit", 1)) break ;
-      else if (!strcmp (*argv, "--cluster") || !strcmp (*argv, "--clusterReport") || !strcmp (*argv, "--clusterSplit")
+      else if (!strcmp (*argv, "--clusterReport") || !strcmp (*argv, "--clusterSplit")
 	       || !strcmp (*argv, "--cribBuild") || !strcmp (*argv, "--cribSummary") || !strcmp (*argv, "--hashInfo")
 	       || !strcmp (*argv, "--hashExplore") || !strcmp (*argv, "--doubleShared") || !strcmp (*argv, "--codeExplore")
 	       || !strcmp (*argv, "--errorFix") || !strcmp (*argv, "--shareScan") || !strcmp (*argv, "--interactive"))

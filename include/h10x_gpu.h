@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define H10X_ABI_VERSION 1
+#define H10X_ABI_VERSION 2
 
 /* return codes; the host turns 1 and 2 into the reference's die() texts
    ("hashTableSize is too small" hash10x.c:149, "chunkSize too small" hash10x.c:206) */
@@ -87,6 +87,11 @@ typedef struct h10x_index {
   int32_t onDevice ;		/* 1: the pointers above are device pointers owned by the context */
   int32_t pinned ;		/* 0 malloc, 1 cudaHostAlloc (both freed by h10x_index_free), 2 = the
 				   context's reusable pinned arena: valid until its next download */
+  /* ClusterBlock.nSubCluster / .pointToMin (hash10x.c:62-70), nBlocksMax each; NULL = all zero (never clustered).
+     Not owned by the index: h10x_read_hash allocates them with the block table and h10x_index_free releases
+     them only then (pinned == 0); after h10x_gpu_cluster the host points them at h10x_clusters' arrays. */
+  uint32_t *blkNSubCluster ;
+  double *blkPointToMin ;
 } h10x_index ;
 
 /* per-build measurements for the roofline report */
@@ -154,6 +159,26 @@ typedef struct h10x_good_hashes {
 } h10x_good_hashes ;
 int h10x_gpu_depth_range (h10x_ctx *ctx, int min, int max, h10x_good_hashes *out, char *err, size_t errlen) ;
 void h10x_index_free (h10x_index *ix) ;
+
+/* "next" row: `--cluster codeMin codeMax` (hash10x.c:1241-1256) on the index and the goodHashes
+   lists resident after h10x_gpu_depth_range: codeClusterFind (hash10x.c:770-835) assigns the good entries of
+   every block codeMin <= code < codeMax (0 0 = all blocks, as in the reference) to sub-clusters of hashes that
+   are first shared with the same other barcodes, clusterThreshold = -ct (hash10x.c:32,1137, default 5, >= 1);
+   codeClusterReadMerge (hash10x.c:837-868) merges sub-clusters joined by a read pair and renumbers them.
+   Results are the reference's, bit for bit: ClusterHash.subCluster of every entry (the resident ClusterHash array
+   is updated in place and copied out), ClusterBlock.nSubCluster and .pointToMin per block.  State accumulates over
+   calls like the reference's globals, until the next build.  Arrays are pinned host memory owned by the context,
+   valid until the next call, download or build; clusHash is the same buffer h10x_gpu_download hands out. */
+typedef struct h10x_clusters {
+  uint32_t nBlocksMax, reserved ;
+  uint64_t nHashes ;
+  uint32_t *nSubCluster ;	/* nBlocksMax */
+  double *pointToMin ;		/* nBlocksMax */
+  h10x_cluster_hash *clusHash ;	/* nHashes, subCluster set */
+  double msKernel ;		/* CUDA-event time of the clustering kernel */
+} h10x_clusters ;
+int h10x_gpu_cluster (h10x_ctx *ctx, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out,
+		      char *err, size_t errlen) ;
 
 /* pinned host staging for callers that want the H2D copy to run at full PCIe rate */
 void *h10x_host_alloc (size_t bytes) ;

@@ -1,0 +1,120 @@
+"""GPU parity for the "next" row f2: `--hashDepthRange` + `--cluster` through the C ABI
+(h10x_gpu_depth_range, h10x_gpu_cluster) against the oracle's restatement of codeClusterFind + codeClusterReadMerge
+(hash10x.c:770-868), which tests/test_oracle.py pins against the reference binary.  Bit-exact: every subCluster byte,
+nSubCluster, and pointToMin as IEEE doubles."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hashfile
+from test_oracle import CLUSTER_CASES, _cluster_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(**kw):
+    import hash10x_b200
+    return hash10x_b200.Hash10xGPU(**kw)
+
+
+def _same(got, want):
+    clus, nsub, ptm = got[:3]
+    wclus, wnsub, wptm = want
+    assert np.array_equal(nsub, wnsub)
+    assert np.array_equal(ptm.view(np.uint64), wptm.view(np.uint64))
+    assert np.array_equal(clus, wclus)
+
+
+@pytest.mark.parametrize("seed,nb,pmin,pmax,genome,mol,mpb,dmin,dmax,thr,cmin,cmax", CLUSTER_CASES)
+def test_cluster_matches_oracle(orc, gpu_lib, seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr, cmin, cmax):
+    recs = _cluster_case(orc, seed, nb, pmin, pmax, genome, mol, mpb)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, dmin, dmax)
+    want = orc.cluster(ix, goff, good, cmin, cmax, thr)
+    assert int(want[1].sum()) > 0
+    with _gpu(B=20) as g:
+        g.build_host(recs)
+        _gw, ggoff, ggood = g.depth_range(dmin, dmax)
+        assert np.array_equal(ggoff, goff) and np.array_equal(ggood, good)
+        got = g.cluster(cmin, cmax, thr)
+        _same(got, want)
+        assert got[3] > 0.0
+        # the resident ClusterHash array was updated in place: a fresh download carries the labels
+        assert np.array_equal(g.download().clus, want[0])
+
+
+def test_cluster_twice_carries_state(orc, gpu_lib):
+    recs = _cluster_case(orc, 36, 250, 150, 300, 100_000, 10_000, 6)
+    ix = orc.build(recs, B=20)
+    within, goff, good = orc.good_hashes(ix, 6, 60)
+    c1 = orc.cluster(ix, goff, good, 0, 0, 4)
+    within, goff2, good2 = orc.good_hashes(ix, 2, 5, within)
+    c2 = orc.cluster(ix, goff2, good2, 10, 200, 2, clus=c1[0], n_sub=c1[1], point_to_min=c1[2])
+    with _gpu(B=20) as g:
+        g.build_host(recs)
+        g.depth_range(6, 60)
+        _same(g.cluster(0, 0, 4), c1)
+        g.depth_range(2, 5)
+        _same(g.cluster(10, 200, 2), c2)
+
+
+def test_cluster_large_blocks_use_the_global_memory_label_arrays(orc, gpu_lib):
+    # > 16384 good hashes and > 4096 read pairs in a block: both shared-memory label arrays fall back to global memory
+    p = orc.synth_params(seed=44, n_barcodes=24, pairs_min=4300, pairs_max=4800, genome_len=1_200_000, mol_len=80_000,
+                         mol_per_barcode=8)
+    recs = orc.synth_fqb(p)
+    ix = orc.build(recs, B=22)
+    _w, goff, good = orc.good_hashes(ix, 1, 25)
+    assert int(np.diff(goff.astype(np.int64)).max()) > 16384 and int(ix.blkNRead.max()) > 4096
+    want = orc.cluster(ix, goff, good, 0, 0, 1)
+    assert int(want[1].sum()) > 0
+    with _gpu(B=22) as g:
+        g.build_host(recs)
+        g.depth_range(1, 25)
+        _same(g.cluster(0, 0, 1), want)
+
+
+def test_cluster_argument_checks(orc, gpu_lib):
+    import hash10x_b200
+    recs = _cluster_case(orc, 37, 120, 20, 80, 40_000, 8_000, 3)
+    with _gpu(B=20) as g:
+        g.build_host(recs)
+        with pytest.raises(hash10x_b200.H10xError, match="you must set hashDepthRange before cluster"):
+            g.cluster(0, 0, 5)                       # hash10x.c:1258
+        g.depth_range(2, 13)
+        with pytest.raises(hash10x_b200.H10xError, match="clusterThreshold"):
+            g.cluster(0, 0, 0)
+        with pytest.raises(hash10x_b200.H10xError, match="code range"):
+            g.cluster(0, 10_000, 1)
+        clus, nsub, ptm, _ms = g.cluster(5, 5, 1)    # empty range: nothing changes
+        assert not nsub.any() and not ptm.any()
+        g.build_host(recs)                            # a new build drops the good lists
+        with pytest.raises(hash10x_b200.H10xError, match="you must set hashDepthRange before cluster"):
+            g.cluster(0, 0, 5)
+
+
+def test_cli_cluster_writes_the_reference_fields(orc, gpu_lib, tmp_path):
+    """hash10x-b200 --readFQB --hashDepthRange -ct --cluster --writeHash: nSubCluster, pointToMin and the subCluster
+    bytes land in the .hash exactly where the reference's --writeHash puts them (hash10x.c:62-70,256-261)."""
+    import hash10x_b200
+    exe = os.path.join(os.path.dirname(hash10x_b200.__file__), "bin", "hash10x-b200")
+    recs = _cluster_case(orc, 34, 300, 100, 250, 200_000, 20_000, 4)
+    fqb, out = str(tmp_path / "a.fqb"), str(tmp_path / "g.hash")
+    recs.tofile(fqb)
+    r = subprocess.run([exe, "-B", "20", "--readFQB", fqb, "--hashDepthRange", "4", "400", "-ct", "3", "--cluster", "0", "0",
+                        "--writeHash", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "  clustered codes 1 to %d" % (301 + 0) in r.stdout
+    hf = hashfile.parse(out)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, 4, 400)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 3)
+    assert np.array_equal(hf.blkNSub, nsub)
+    assert np.array_equal(hf.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    assert np.array_equal(hf.clusRaw, clus)
+    hashfile.assert_strict_equal(hashfile.from_index(ix), hf, table=True)
+    # --cluster before --hashDepthRange: the reference's warning, not an error (hash10x.c:1258)
+    r = subprocess.run([exe, "-B", "20", "--readFQB", fqb, "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "!! you must set hashDepthRange before cluster" in r.stdout
