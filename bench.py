@@ -310,8 +310,8 @@ def run_ours(args, wl):
     dom = max(stage_ms.items(), key=lambda kv: kv[1])
     R, M, H, D, nB = stats["nRecords"], stats["nMoshes"], stats["nHashes"], stats["nBins"], stats["nBlocks"]
     stage_bytes = {   # algorithmic bytes of each stage per build (DESIGN.md "kernels")
-        "moshes": 120 * R + 12 * M, "fused": 120 * R + 8 * H, "blocksort": 24 * M, "dedup": 8 * H + 16 * H,
-        "hashsort": 24 * H, "binids": 12 * H + 12 * D, "entryids": 8 * H, "codes": 16 * H + 12 * H + 12 * D,
+        "moshes": 120 * R + 12 * M, "fused": 120 * R + 8 * H, "blocksort": 24 * M, "dedup": 8 * H + 12 * H,
+        "hashsort": 24 * H, "binids": 4 * H + 40 * D, "entryids": 8 * H, "codes": 20 * H + 12 * D,
         "clusters": 12 * H + 8 * H, "table": (4 << wl["B"]) + 12 * D, "runs": 4 * R * 3, "other": 0}
     dom_ms = dom[1] / args.steps
     dom_bytes = stage_bytes.get(dom[0], 0)
@@ -327,7 +327,7 @@ def run_ours(args, wl):
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": "profiles/r01_fused_traffic.json (ncu dram__bytes_read+write at 50M pairs) x pairs" if traffic else None,
-                "note": "the fused kernel is bound by the integer ALU pipe (ncu: ALU 61 %, DRAM 7 %), see profiles/README.md",
+                "note": "the fused kernel is bound by the integer pipes (ncu: ALU 59 %, FMA/IMAD 42 %, issue 74 %, DRAM 7 %), see profiles/README.md",
                 "ms_per_launch_group": dom_ms, "share_of_step": dom_ms / ms_step}
     pipe_ach = stats["algorithmicBytes"] / (ms_step * 1e-3) / 1e9
     pipeline = {"bound": "hbm", "algorithmic_bytes": stats["algorithmicBytes"],

@@ -1807,11 +1807,12 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, c->P.device)) ;
 	  int occ = 1 ;
 	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, 0)) ;
-	  occ = std::max (1, std::min (occ, 4)) ;
+	  occ = std::max (1, std::min (occ, 5)) ;
 	  uint32_t cap = 1024 ; int lg = 10 ;
 	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
 	  /* per CTA: the table, 8 warps of counters, the triples, the two label fallbacks */
-	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_WARPS * 65536 * 4 + (size_t) 3 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
+	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_SMALL_CAP * 8 + (size_t) H10X_SC_WARPS * 65536 * 4
+	    + (size_t) 3 * 65536 * 4 + (size_t) 2 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
 	  size_t freeB = 0, totalB = 0 ;
 	  CK (cudaMemGetInfo (&freeB, &totalB)) ;
 	  size_t budget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
@@ -1825,6 +1826,8 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  SubClusterArgs a ;
 	  a.work = (unsigned int*) p ; p += 256 ;
 	  a.table = (unsigned long long*) p ; p += (size_t) cap * 8 * grid ;
+	  a.tableSmall = (unsigned long long*) p ; p += (size_t) H10X_SC_SMALL_CAP * 8 * grid ;
+	  a.pre = (uint32_t*) p ; p += (size_t) 2 * 65536 * 4 * grid ;
 	  a.cnt = (uint32_t*) p ; p += (size_t) H10X_SC_WARPS * 65536 * 4 * grid ;
 	  a.res = (uint32_t*) p ; p += (size_t) 3 * 65536 * 4 * grid ;
 	  a.readLabG = (int*) p ; p += (size_t) 65536 * 4 * grid ;

@@ -31,6 +31,9 @@
 #define H10X_SC_GSUB_SMEM 16384		/* good-entry labels kept in shared memory up to this many good hashes */
 #define H10X_SC_READ_SMEM 4096		/* read labels kept in shared memory up to this many read pairs */
 #define H10X_SC_VBUF 128		/* per-warp buffer of a hash's barcodes' minShare values */
+#define H10X_SC_SMALL_CAP 16384u	/* entries of the L2-resident table (128 KB per CTA) */
+#define H10X_SC_SMALL_SHIFT 18u		/* 32 - log2 (H10X_SC_SMALL_CAP) */
+#define H10X_SC_SMALL_LIMIT 9800u	/* barcodes it takes before the block is redone with the big table */
 
 struct SubClusterArgs {
   unsigned long long *clus ;		/* ClusterHash as one word: bin id | read << 32 | subCluster << 48 */
@@ -42,14 +45,19 @@ struct SubClusterArgs {
   unsigned int *work ;			/* ticket counter */
   unsigned long long *table ;		/* per CTA: tableCap entries (barcode << 32 | stamp << 16 | minShare), zeroed once */
   uint32_t tableCap, tableShift ;	/* power of two >= 2 * blocks; shift = 32 - log2 (tableCap) */
+  unsigned long long *tableSmall ;	/* per CTA: H10X_SC_SMALL_CAP entries that stay in L2; the big table takes over when
+					   a block shares hashes with more barcodes than fit */
+  uint32_t *pre ;			/* per CTA: 2 * 65536 words: depth and codes offset of every good hash's bin */
   uint32_t *cnt ;			/* per warp: 65536 counters, all zero between uses */
   uint32_t *res ;			/* per CTA: 3 * 65536 words: msBest, msMax, msTot of every step */
   uint8_t *gsubG ;			/* per CTA: 65536 bytes, labels of the good entries when they do not fit in smem */
   int *readLabG ;			/* per CTA: 65536 ints, read labels when they do not fit in smem */
 } ;
 
+/* claims, overflow: shared-memory words of the CTA.  Every new barcode counts; past `limit` the overflow flag goes
+   up and everybody leaves (the caller redoes the block with the big table, whose limit is never reached). */
 __device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t mask, uint32_t shift, uint32_t stamp,
-					      uint32_t cj, uint32_t val)
+					      uint32_t cj, uint32_t val, uint32_t *claims, volatile uint32_t *overflow, uint32_t limit)
 { const unsigned long long tag = ((unsigned long long) cj << 32) | ((unsigned long long) stamp << 16) ;
   const unsigned long long cand = tag | val ;
   uint32_t h = (cj * 0x9E3779B1u) >> shift ;
@@ -60,7 +68,11 @@ __device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t 
 	  return ;
 	}
       if ((uint32_t) ((old >> 16) & 0xffffull) != stamp)	/* left by an earlier block, or never used: claim it */
-	{ if (atomicCAS (tab + h, old, cand) == old) return ;
+	{ if (*overflow) return ;
+	  if (atomicCAS (tab + h, old, cand) == old)
+	    { if (atomicAdd (claims, 1u) >= limit) *overflow = 1u ;
+	      return ;
+	    }
 	  continue ;					/* someone else took the slot: look at it again */
 	}
       h = (h + 1) & mask ;
@@ -90,11 +102,12 @@ k_subcluster (SubClusterArgs a)
   __shared__ uint16_t vbuf[H10X_SC_WARPS][H10X_SC_VBUF] ;
   __shared__ uint16_t clusterMin[256] ;
   __shared__ int label[257], newLab[257] ;
-  __shared__ uint32_t sTicket, sNs, sChanged ;
+  __shared__ uint32_t sTicket, sNs, sChanged, sClaims, sOverflow ;
 
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5 ;
-  unsigned long long *tab = a.table + (size_t) blockIdx.x * a.tableCap ;
-  const uint32_t mask = a.tableCap - 1, shift = a.tableShift ;
+  unsigned long long *const tabBig = a.table + (size_t) blockIdx.x * a.tableCap ;
+  unsigned long long *const tabSmall = a.tableSmall + (size_t) blockIdx.x * H10X_SC_SMALL_CAP ;
+  uint32_t *preNc = a.pre + (size_t) blockIdx.x * 2 * 65536, *preOff = preNc + 65536 ;
   uint32_t *cnt = a.cnt + ((size_t) blockIdx.x * H10X_SC_WARPS + w) * 65536 ;
   uint32_t *resBest = a.res + (size_t) blockIdx.x * 3 * 65536, *resMax = resBest + 65536, *resTot = resMax + 65536 ;
   uint32_t stamp = 0 ;
@@ -112,49 +125,99 @@ k_subcluster (SubClusterArgs a)
       const uint32_t nHash = a.blkNHash[code] ;
 
       if (n)	/* ---------------- codeClusterFind ---------------- */
-	{ if (++stamp == 0x10000u)		/* 16-bit stamps used up: start over with a clean table */
-	    { for (size_t i = t ; i < a.tableCap ; i += H10X_SC_THREADS) tab[i] = 0 ;
-	      stamp = 1 ;
-	      __syncthreads () ;
+	{ uint8_t *gsub = (n <= H10X_SC_GSUB_SMEM) ? gsubS : a.gsubG + (size_t) blockIdx.x * 65536 ;
+	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS)
+	    { gsub[i] = 0 ;								/* :783 wipe */
+	      const uint32_t x = (uint32_t) ch[g[i]] ;				/* bin of good hash i: its depth and barcode list */
+	      preNc[i] = a.hashDepth[x] ; preOff[i] = (uint32_t) a.codeOff[x] ;	/* fewer than 2^32 entries on a device */
 	    }
-	  uint8_t *gsub = (n <= H10X_SC_GSUB_SMEM) ? gsubS : a.gsubG + (size_t) blockIdx.x * 65536 ;
-	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS) gsub[i] = 0 ;		/* :783 wipe */
 
-	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block */
-	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
-	    { const uint32_t x = (uint32_t) ch[g[i]] ;
-	      const uint32_t nc = a.hashDepth[x] ;
-	      const uint32_t *cl = a.codes + a.codeOff[x] ;
-	      for (uint32_t j = lane ; j < nc ; j += 32)
-		{ const uint32_t cj = cl[j] ;
-		  if (cj != code) sc_table_min (tab, mask, shift, stamp, cj, i + 1) ;
+	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block; first in the small table */
+	  unsigned long long *tab = tabSmall ;
+	  uint32_t mask = H10X_SC_SMALL_CAP - 1, shift = H10X_SC_SMALL_SHIFT, limit = H10X_SC_SMALL_LIMIT ;
+	  for (int attempt = 0 ; attempt < 2 ; ++attempt)
+	    { if (++stamp == 0x10000u)		/* 16-bit stamps used up: start over with clean tables */
+		{ for (size_t i = t ; i < a.tableCap ; i += H10X_SC_THREADS) tabBig[i] = 0 ;
+		  for (uint32_t i = t ; i < H10X_SC_SMALL_CAP ; i += H10X_SC_THREADS) tabSmall[i] = 0 ;
+		  stamp = 1 ;
 		}
+	      if (t == 0) { sClaims = 0 ; sOverflow = 0 ; }
+	      __syncthreads () ;
+	      { /* the first 32 barcodes of the warp's next hash are loaded while the current one is worked on */
+		uint32_t ncN = 0, offN = 0, cjN = 0 ;
+		if (1 + w < n)
+		  { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
+		for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
+		  { const uint32_t nc = ncN, cj0 = cjN ;
+		    const uint32_t *cl = a.codes + offN ;
+		    if (i + H10X_SC_WARPS < n)
+		      { ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
+			if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
+		      }
+		    for (uint32_t j = lane ; j < nc ; j += 32)
+		      { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
+			if (cj != code) sc_table_min (tab, mask, shift, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
+		      }
+		  }
+	      }
+	      __syncthreads () ;
+	      if (!sOverflow) break ;
+	      __syncthreads () ;
+	      tab = tabBig ; mask = a.tableCap - 1 ; shift = a.tableShift ; limit = 0xffffffffu ;
 	    }
-	  __syncthreads () ;
 
 	  /* B: per step i the best earlier step, its count and the total (hash10x.c:793-806) */
+	  uint32_t ncN = 0, offN = 0, cjN = 0 ;
+	  if (1 + w < n)
+	    { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
 	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
-	    { const uint32_t x = (uint32_t) ch[g[i]] ;
-	      const uint32_t nc = a.hashDepth[x] ;
-	      const uint32_t *cl = a.codes + a.codeOff[x] ;
-	      uint32_t tot = 0 ;
-	      for (uint32_t j = lane ; j < nc ; j += 32)
-		{ const uint32_t cj = cl[j] ;
-		  uint32_t v = 0xffffu ;
-		  if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-		  if (j < H10X_SC_VBUF) vbuf[w][j] = (uint16_t) v ;
-		  if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
+	    { const uint32_t nc = ncN, cj0 = cjN ;
+	      const uint32_t *cl = a.codes + offN ;
+	      if (i + H10X_SC_WARPS < n)
+		{ ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
+		  if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
 		}
-	      __syncwarp () ;
-	      uint32_t bMax = 0, bBest = 0xffffffffu ;
-	      for (uint32_t j = lane ; j < nc ; j += 32)
-		{ uint32_t v ;
-		  if (j < H10X_SC_VBUF) v = vbuf[w][j] ;
-		  else { const uint32_t cj = cl[j] ; v = 0xffffu ;
-			 if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; } }
-		  if (v != 0xffffu)
-		    { const uint32_t c = __ldcg (cnt + v) ;
+	      uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
+	      if (nc <= H10X_SC_VBUF)		/* the usual case: count equal values among the hash's barcodes in shared memory */
+		{ for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
+		      uint32_t v = 0xffffu ;
+		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+		      vbuf[w][j] = (uint16_t) v ;
+		    }
+		  __syncwarp () ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t v = vbuf[w][j] ;
+		      if (v == 0xffffu) continue ;
+		      ++tot ;
+		      uint32_t c = 0 ;
+		      for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
 		      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+		    }
+		}
+	      else				/* a deep bin: per-warp counters in global memory */
+		{ for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t cj = cl[j] ;
+		      uint32_t v = 0xffffu ;
+		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+		      if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
+		    }
+		  __syncwarp () ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t cj = cl[j] ;
+		      uint32_t v = 0xffffu ;
+		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+		      if (v != 0xffffu)
+			{ const uint32_t c = __ldcg (cnt + v) ;
+			  if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+			}
+		    }
+		  __syncwarp () ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
+		    { const uint32_t cj = cl[j] ;
+		      uint32_t v = 0xffffu ;
+		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+		      if (v != 0xffffu) cnt[v] = 0 ;
 		    }
 		}
 #pragma unroll
@@ -162,14 +225,6 @@ k_subcluster (SubClusterArgs a)
 		{ const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
 		  if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
 		  tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
-		}
-	      __syncwarp () ;
-	      for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
-		{ uint32_t v ;
-		  if (j < H10X_SC_VBUF) v = vbuf[w][j] ;
-		  else { const uint32_t cj = cl[j] ; v = 0xffffu ;
-			 if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; } }
-		  if (v != 0xffffu) cnt[v] = 0 ;
 		}
 	      __syncwarp () ;
 	      if (lane == 0) { resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ; }
@@ -208,9 +263,8 @@ k_subcluster (SubClusterArgs a)
 		      const uint32_t cm = clusterMin[sb] ;
 		      uint32_t cAt = m ;
 		      if (cm != b)			/* count of the cluster's own minimum at this step */
-			{ const uint32_t x = (uint32_t) ch[g[i]] ;
-			  const uint32_t nc = a.hashDepth[x] ;
-			  const uint32_t *cl = a.codes + a.codeOff[x] ;
+			{ const uint32_t nc = __ldcg (preNc + i) ;
+			  const uint32_t *cl = a.codes + __ldcg (preOff + i) ;
 			  cAt = 0 ;
 			  for (uint32_t j = lane ; j < nc ; j += 32)
 			    { const uint32_t cj = cl[j] ;

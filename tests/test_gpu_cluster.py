@@ -76,6 +76,24 @@ def test_cluster_large_blocks_use_the_global_memory_label_arrays(orc, gpu_lib):
         _same(g.cluster(0, 0, 1), want)
 
 
+def test_cluster_many_sharing_barcodes_use_the_big_table_and_deep_bins(orc, gpu_lib):
+    # 10500 barcodes on a 3 kb genome: every block shares hashes with > 9800 others (the L2-resident table overflows and
+    # the block is redone with the full-size one) and bins are thousands deep (per-warp counters instead of the
+    # 128-entry shared-memory buffer)
+    p = orc.synth_params(seed=61, n_barcodes=10500, pairs_min=6, pairs_max=8, genome_len=3000, mol_len=1500,
+                         mol_per_barcode=2)
+    recs = orc.synth_fqb(p)
+    ix = orc.build(recs, B=20)
+    assert int(ix.hashDepth.max()) > 128
+    _w, goff, good = orc.good_hashes(ix, 2, 20000)
+    want = orc.cluster(ix, goff, good, 0, 0, 5)
+    assert int(want[1].sum()) > 0
+    with _gpu(B=20) as g:
+        g.build_host(recs)
+        g.depth_range(2, 20000)
+        _same(g.cluster(0, 0, 5), want)
+
+
 def test_cluster_argument_checks(orc, gpu_lib):
     import hash10x_b200
     recs = _cluster_case(orc, 37, 120, 20, 80, 40_000, 8_000, 3)
