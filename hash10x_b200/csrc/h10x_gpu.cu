@@ -1812,7 +1812,7 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
 	  /* per CTA: the table, 8 warps of counters, the triples, the two label fallbacks */
 	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_SMALL_CAP * 8 + (size_t) H10X_SC_WARPS * 65536 * 4
-	    + (size_t) 3 * 65536 * 4 + (size_t) 2 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
+	    + (size_t) 6 * 65536 * 4 + (size_t) 2 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
 	  size_t freeB = 0, totalB = 0 ;
 	  CK (cudaMemGetInfo (&freeB, &totalB)) ;
 	  size_t budget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
@@ -1829,7 +1829,7 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  a.tableSmall = (unsigned long long*) p ; p += (size_t) H10X_SC_SMALL_CAP * 8 * grid ;
 	  a.pre = (uint32_t*) p ; p += (size_t) 2 * 65536 * 4 * grid ;
 	  a.cnt = (uint32_t*) p ; p += (size_t) H10X_SC_WARPS * 65536 * 4 * grid ;
-	  a.res = (uint32_t*) p ; p += (size_t) 3 * 65536 * 4 * grid ;
+	  a.res = (uint32_t*) p ; p += (size_t) 6 * 65536 * 4 * grid ;
 	  a.readLabG = (int*) p ; p += (size_t) 65536 * 4 * grid ;
 	  a.gsubG = (uint8_t*) p ;
 	  a.tableCap = cap ; a.tableShift = (uint32_t) (32 - lg) ;

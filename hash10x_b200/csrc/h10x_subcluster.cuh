@@ -10,8 +10,10 @@
  *   B  a warp per good hash i counts, over the barcodes of hash i, how many have minShare - 1 == j for every j < i
  *      (barcodes first seen at step i sit at index i and never enter, hash10x.c:793-806), and keeps the largest
  *      count (first j wins ties, :803), the total, and nothing else: (msBest, msMax, msTot) of step i;
- *   C  one warp replays the cheap sequential part (:807-824) over those triples: sub-cluster creation and joining,
- *      the 255-cluster limit, and the pointToMin sum in the reference's order of double additions;
+ *   C  one warp replays the cheap sequential part (:807-824) over those triples - sub-cluster creation and joining,
+ *      the 255-cluster limit - and records per step which earlier hash founded the joined cluster; all warps then
+ *      compute the steps' pointToMin terms in parallel (a recount only where the founder is not msBest) and one warp
+ *      adds them in the reference's order of double additions;
  *   E  codeClusterReadMerge is a connected-components problem (sub-clusters joined through shared reads, the
  *      smallest label wins, :848-858): min-label propagation over (sub-cluster, read) edges with pointer jumping,
  *      then the reference's compaction of the surviving labels (:862-865).
@@ -49,7 +51,7 @@ struct SubClusterArgs {
 					   a block shares hashes with more barcodes than fit */
   uint32_t *pre ;			/* per CTA: 2 * 65536 words: depth and codes offset of every good hash's bin */
   uint32_t *cnt ;			/* per warp: 65536 counters, all zero between uses */
-  uint32_t *res ;			/* per CTA: 3 * 65536 words: msBest, msMax, msTot of every step */
+  uint32_t *res ;			/* per CTA: 6 * 65536 words: msBest, msMax, msTot, clusterMin index and (double) term of every step */
   uint8_t *gsubG ;			/* per CTA: 65536 bytes, labels of the good entries when they do not fit in smem */
   int *readLabG ;			/* per CTA: 65536 ints, read labels when they do not fit in smem */
 } ;
@@ -109,7 +111,9 @@ k_subcluster (SubClusterArgs a)
   unsigned long long *const tabSmall = a.tableSmall + (size_t) blockIdx.x * H10X_SC_SMALL_CAP ;
   uint32_t *preNc = a.pre + (size_t) blockIdx.x * 2 * 65536, *preOff = preNc + 65536 ;
   uint32_t *cnt = a.cnt + ((size_t) blockIdx.x * H10X_SC_WARPS + w) * 65536 ;
-  uint32_t *resBest = a.res + (size_t) blockIdx.x * 3 * 65536, *resMax = resBest + 65536, *resTot = resMax + 65536 ;
+  uint32_t *resBest = a.res + (size_t) blockIdx.x * 6 * 65536, *resMax = resBest + 65536, *resTot = resMax + 65536,
+    *resCm = resTot + 65536 ;
+  double *resTerm = (double*) (resCm + 65536) ;
   uint32_t stamp = 0 ;
 
   for (;;)
@@ -231,52 +235,75 @@ k_subcluster (SubClusterArgs a)
 	    }
 	  __syncthreads () ;
 
-	  /* C: the sequential part, by one warp in lock step (hash10x.c:807-824) */
+	  /* C1: the sequential part, by one warp in lock step (hash10x.c:807-824).  Which cluster a step joins or founds
+	     depends only on (msBest, msMax >= threshold) and on the labels so far; the pointToMin term of the step needs
+	     the count at the cluster's founding hash clusterMin[], so C1 only records that index per step ... */
 	  if (w == 0)
-	    { uint32_t nsub = 0 ; double ptm = 0.0 ; bool abandoned = false ;
-	      for (uint32_t i0 = 1 ; i0 < n && !abandoned ; i0 += 32)
+	    { uint32_t nsub = 0 ; bool abandoned = false ;
+	      for (uint32_t i0 = 1 ; i0 < n ; i0 += 32)
 		{ const uint32_t mine = i0 + lane ;
-		  const uint32_t mb = mine < n ? __ldcg (resBest + mine) : 0u, mm = mine < n ? __ldcg (resMax + mine) : 0u,
-		    mt = mine < n ? __ldcg (resTot + mine) : 0u ;
-		  const uint32_t steps = min (32u, n - i0) ;
-		  for (uint32_t k = 0 ; k < steps ; ++k)
-		    { const uint32_t i = i0 + k ;
-		      const uint32_t b = __shfl_sync (0xffffffffu, mb, k), m = __shfl_sync (0xffffffffu, mm, k),
-			tt = __shfl_sync (0xffffffffu, mt, k) ;
-		      if ((long long) m < (long long) a.threshold) continue ;
-		      uint32_t sb = gsub[b] ;
-		      if (!sb)				/* create a new cluster */
-			{ if (++nsub > 255u)		/* abandon this clustering (:810-817) */
-			    { nsub = 0 ;
+		  uint32_t myCm = 0xffffffffu ;
+		  if (!abandoned)
+		    { const uint32_t mb = mine < n ? __ldcg (resBest + mine) : 0u, mm = mine < n ? __ldcg (resMax + mine) : 0u ;
+		      const uint32_t steps = min (32u, n - i0) ;
+		      for (uint32_t k = 0 ; k < steps ; ++k)
+			{ const uint32_t i = i0 + k ;
+			  const uint32_t b = __shfl_sync (0xffffffffu, mb, k), m = __shfl_sync (0xffffffffu, mm, k) ;
+			  if ((long long) m < (long long) a.threshold) continue ;
+			  uint32_t sb = gsub[b] ;
+			  if (!sb)				/* create a new cluster */
+			    { if (++nsub > 255u)		/* abandon this clustering (:810-817); pointToMin keeps its terms */
+				{ nsub = 0 ;
+				  __syncwarp () ;
+				  for (uint32_t j = lane ; j < i ; j += 32) gsub[j] = 0 ;
+				  abandoned = true ;
+				  break ;
+				}
+			      sb = nsub ;
 			      __syncwarp () ;
-			      for (uint32_t j = lane ; j < i ; j += 32) gsub[j] = 0 ;
-			      abandoned = true ;
-			      break ;
+			      if (lane == 0) { gsub[b] = (uint8_t) sb ; clusterMin[sb] = (uint16_t) b ; }
 			    }
-			  sb = nsub ;
 			  __syncwarp () ;
-			  if (lane == 0) { gsub[b] = (uint8_t) sb ; clusterMin[sb] = (uint16_t) b ; }
+			  if (lane == 0) gsub[i] = (uint8_t) sb ;
+			  __syncwarp () ;
+			  if (lane == k) myCm = clusterMin[sb] ;
 			}
-		      __syncwarp () ;
-		      if (lane == 0) gsub[i] = (uint8_t) sb ;
-		      __syncwarp () ;
-		      const uint32_t cm = clusterMin[sb] ;
-		      uint32_t cAt = m ;
-		      if (cm != b)			/* count of the cluster's own minimum at this step */
-			{ const uint32_t nc = __ldcg (preNc + i) ;
-			  const uint32_t *cl = a.codes + __ldcg (preOff + i) ;
-			  cAt = 0 ;
-			  for (uint32_t j = lane ; j < nc ; j += 32)
-			    { const uint32_t cj = cl[j] ;
-			      if (cj != code && sc_table_get (tab, mask, shift, stamp, cj) - 1u == cm) ++cAt ;
-			    }
-#pragma unroll
-			  for (int d = 16 ; d ; d >>= 1) cAt += __shfl_xor_sync (0xffffffffu, cAt, d) ;
-			}
-		      ptm += (double) (int) cAt / (double) (int) tt ;
 		    }
+		  if (mine < n) resCm[mine] = myCm ;
 		}
-	      if (lane == 0) { a.nSub[code] = nsub ; a.pointToMin[code] = ptm ; }
+	      if (lane == 0) a.nSub[code] = nsub ;
+	    }
+	  __syncthreads () ;
+	  /* C2: ... all warps then compute the terms minShareCount[clusterMin] / msTot (:823) in parallel ... */
+	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
+	    { const uint32_t cm = __ldcg (resCm + i) ;
+	      if (cm == 0xffffffffu) { if (lane == 0) resTerm[i] = 0.0 ; continue ; }
+	      uint32_t cAt = __ldcg (resMax + i) ;
+	      if (cm != __ldcg (resBest + i))		/* the cluster was founded by another hash: count that one at this step */
+		{ const uint32_t nc = __ldcg (preNc + i) ;
+		  const uint32_t *cl = a.codes + __ldcg (preOff + i) ;
+		  cAt = 0 ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t cj = cl[j] ;
+		      if (cj != code && sc_table_get (tab, mask, shift, stamp, cj) - 1u == cm) ++cAt ;
+		    }
+#pragma unroll
+		  for (int d = 16 ; d ; d >>= 1) cAt += __shfl_xor_sync (0xffffffffu, cAt, d) ;
+		}
+	      if (lane == 0) resTerm[i] = (double) (int) cAt / (double) (int) __ldcg (resTot + i) ;
+	    }
+	  __syncthreads () ;
+	  /* C3: ... and one warp adds them in step order, as the reference's double accumulation does (x + 0.0 == x for
+	     the steps that joined nothing) */
+	  if (w == 0)
+	    { double ptm = 0.0 ;
+	      for (uint32_t i0 = 1 ; i0 < n ; i0 += 32)
+		{ const uint32_t mine = i0 + lane ;
+		  const double v = mine < n ? __ldcg (resTerm + mine) : 0.0 ;
+		  const uint32_t steps = min (32u, n - i0) ;
+		  for (uint32_t k = 0 ; k < steps ; ++k) ptm += __shfl_sync (0xffffffffu, v, k) ;
+		}
+	      if (lane == 0) a.pointToMin[code] = ptm ;
 	    }
 	  __syncthreads () ;
 	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS) ((uint8_t*) (ch + g[i]))[6] = gsub[i] ;
