@@ -1806,7 +1806,8 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	{ int nSM = 148 ;
 	  CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, c->P.device)) ;
 	  int occ = 1 ;
-	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, 0)) ;
+	  CK (cudaFuncSetAttribute (k_subcluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) H10X_SC_DYN_SMEM)) ;
+	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, H10X_SC_DYN_SMEM)) ;
 	  occ = std::max (1, std::min (occ, 5)) ;
 	  uint32_t cap = 1024 ; int lg = 10 ;
 	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
@@ -1839,7 +1840,7 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  a.nSub = c->blkNSub.p ; a.pointToMin = c->blkPtm.p ;
 	  a.codeMin = (uint32_t) codeMin ; a.codeMax = (uint32_t) codeMax ; a.threshold = clusterThreshold ;
 	  CK (cudaEventRecord (evA, s)) ;
-	  LAUNCH (c, k_subcluster, grid, H10X_SC_THREADS, 0, s, a) ;
+	  LAUNCH (c, k_subcluster, grid, H10X_SC_THREADS, H10X_SC_DYN_SMEM, s, a) ;
 	  CK (cudaEventRecord (evB, s)) ;
 	}
       auto pull = [&] (int slot, const void *src, size_t bytes) -> void*

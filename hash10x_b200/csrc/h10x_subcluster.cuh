@@ -19,8 +19,10 @@
  *      then the reference's compaction of the surviving labels (:862-865).
  *
  * The table entries carry a 16-bit stamp (one per block handled by the CTA), so the table is never cleared between
- * blocks: an entry with another stamp is empty.  Table, per-warp counters and the triples live in global memory
- * (L2 for the counters and triples); the labels of good entries and of reads sit in shared memory when they fit.
+ * blocks: an entry with another stamp is empty.  A 16K-entry table per CTA stays in L2; a block that shares hashes
+ * with more barcodes than that is redone with a table sized for all blocks.  Step counters are 8-bit, packed in the
+ * warp's shared memory (bins up to 128 deep, blocks up to 4096 good hashes), otherwise 32-bit in global memory; the
+ * labels of good entries and of reads sit in shared memory when they fit.
  * Labels left by an earlier --cluster on entries outside the current good lists that exceed the block's new
  * nSubCluster count as 0 (the reference reads past trueCluster[] there: undefined behaviour; same rule as the oracle).
  */
@@ -33,6 +35,8 @@
 #define H10X_SC_GSUB_SMEM 16384		/* good-entry labels kept in shared memory up to this many good hashes */
 #define H10X_SC_READ_SMEM 4096		/* read labels kept in shared memory up to this many read pairs */
 #define H10X_SC_VBUF 128		/* per-warp buffer of a hash's barcodes' minShare values */
+#define H10X_SC_CNT_STEPS 4096		/* steps whose counters fit in a warp's 4 KB of packed 8-bit counters */
+#define H10X_SC_DYN_SMEM (H10X_SC_GSUB_SMEM + H10X_SC_WARPS * H10X_SC_CNT_STEPS)
 #define H10X_SC_SMALL_CAP 16384u	/* entries of the L2-resident table (128 KB per CTA) */
 #define H10X_SC_SMALL_SHIFT 18u		/* 32 - log2 (H10X_SC_SMALL_CAP) */
 #define H10X_SC_SMALL_LIMIT 9800u	/* barcodes it takes before the block is redone with the big table */
@@ -99,8 +103,12 @@ __device__ __forceinline__ uint32_t sc_table_get (const unsigned long long *tab,
 __global__ void __launch_bounds__ (H10X_SC_THREADS)
 k_subcluster (SubClusterArgs a)
 {
-  __shared__ uint8_t gsubS[H10X_SC_GSUB_SMEM] ;
-  __shared__ int readLabS[H10X_SC_READ_SMEM] ;
+  /* dynamic shared memory: labels of the good entries (16 KB), then 32 KB that are the warps' packed 8-bit step counters
+     during codeClusterFind and the read labels during codeClusterReadMerge */
+  extern __shared__ __align__ (16) unsigned char scSmem[] ;
+  uint8_t *const gsubS = scSmem ;
+  uint32_t *const cntS = (uint32_t*) (scSmem + H10X_SC_GSUB_SMEM) ;
+  int *const readLabS = (int*) (scSmem + H10X_SC_GSUB_SMEM) ;
   __shared__ uint16_t vbuf[H10X_SC_WARPS][H10X_SC_VBUF] ;
   __shared__ uint16_t clusterMin[256] ;
   __shared__ int label[257], newLab[257] ;
@@ -135,6 +143,9 @@ k_subcluster (SubClusterArgs a)
 	      const uint32_t x = (uint32_t) ch[g[i]] ;				/* bin of good hash i: its depth and barcode list */
 	      preNc[i] = a.hashDepth[x] ; preOff[i] = (uint32_t) a.codeOff[x] ;	/* fewer than 2^32 entries on a device */
 	    }
+
+	  const bool smemCnt = n <= H10X_SC_CNT_STEPS ;
+	  if (smemCnt) for (uint32_t i = t ; i < H10X_SC_WARPS * H10X_SC_CNT_STEPS / 4 ; i += H10X_SC_THREADS) cntS[i] = 0 ;
 
 	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block; first in the small table */
 	  unsigned long long *tab = tabSmall ;
@@ -182,21 +193,26 @@ k_subcluster (SubClusterArgs a)
 		  if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
 		}
 	      uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
-	      if (nc <= H10X_SC_VBUF)		/* the usual case: count equal values among the hash's barcodes in shared memory */
-		{ for (uint32_t j = lane ; j < nc ; j += 32)
+	      if (nc <= H10X_SC_VBUF && smemCnt)	/* the usual case: 8-bit counters of the warp, four to a shared-memory word */
+		{ uint32_t *cw = cntS + w * (H10X_SC_CNT_STEPS / 4) ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)
 		    { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
 		      uint32_t v = 0xffffu ;
 		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
 		      vbuf[w][j] = (uint16_t) v ;
+		      if (v != 0xffffu) { atomicAdd (cw + (v >> 2), 1u << (8 * (v & 3))) ; ++tot ; }	/* at most 128 per counter */
 		    }
 		  __syncwarp () ;
 		  for (uint32_t j = lane ; j < nc ; j += 32)
 		    { const uint32_t v = vbuf[w][j] ;
 		      if (v == 0xffffu) continue ;
-		      ++tot ;
-		      uint32_t c = 0 ;
-		      for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
+		      const uint32_t c = (cw[v >> 2] >> (8 * (v & 3))) & 0xffu ;
 		      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+		    }
+		  __syncwarp () ;
+		  for (uint32_t j = lane ; j < nc ; j += 32)
+		    { const uint32_t v = vbuf[w][j] ;
+		      if (v != 0xffffu) cw[v >> 2] = 0 ;
 		    }
 		}
 	      else				/* a deep bin: per-warp counters in global memory */
