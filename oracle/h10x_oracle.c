@@ -350,8 +350,9 @@ int orc_write_hash (const orc_index *ix, const char *path)
    over successive --hashDepthRange commands.  good[] receives, block after block, the indices (into the
    block's ClusterHash list) of the entries whose bin is within range, ordered by increasing bin depth;
    glibc's qsort is a stable merge sort, so ties keep list order.  Blocks with more than 65535 hashes
-   get an empty list (:748).  PARITY UNPINNED: the reference never prints goodHashes (only --cluster
-   consumes them), so this restatement is checked by reading the code, not against reference output. */
+   get an empty list (:748).  PARITY: the reference never prints goodHashes, but its --cluster walks them in
+   order, so this restatement is pinned together with orc_cluster below (tests/test_oracle.py::
+   test_cluster_equals_reference_binary). */
 typedef struct { U32 depth ; U16 idx ; } GoodKey ;
 static int cmp_good (const void *a, const void *b)
 { const GoodKey *x = a, *y = b ;
