@@ -1808,12 +1808,13 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  int occ = 1 ;
 	  CK (cudaFuncSetAttribute (k_subcluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) H10X_SC_DYN_SMEM)) ;
 	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, H10X_SC_DYN_SMEM)) ;
-	  occ = std::max (1, std::min (occ, 5)) ;
+	  if (occ < 1) throw H10xError (H10X_ERR_CUDA, "k_subcluster does not fit on this device") ;
 	  uint32_t cap = 1024 ; int lg = 10 ;
 	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
-	  /* per CTA: the table, 8 warps of counters, the triples, the two label fallbacks */
-	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_SMALL_CAP * 8 + (size_t) H10X_SC_WARPS * 65536 * 4
-	    + (size_t) 6 * 65536 * 4 + (size_t) 2 * 65536 * 4 + 65536 + (size_t) 65536 * 4 ;
+	  /* per CTA: the global table, 32 warps of deep-bin counters, bin depth / offset, the per-step results, and the
+	     global-memory versions of the per-step arrays and read labels for blocks that do not fit in shared memory */
+	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_WARPS * 65536 * 4 + (size_t) 2 * 65536 * 4 + (size_t) 6 * 65536 * 4
+	    + (size_t) 65536 * (2 + 4 + 2 + 1) + (size_t) 65536 * 4 ;
 	  size_t freeB = 0, totalB = 0 ;
 	  CK (cudaMemGetInfo (&freeB, &totalB)) ;
 	  size_t budget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
@@ -1827,11 +1828,13 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  SubClusterArgs a ;
 	  a.work = (unsigned int*) p ; p += 256 ;
 	  a.table = (unsigned long long*) p ; p += (size_t) cap * 8 * grid ;
-	  a.tableSmall = (unsigned long long*) p ; p += (size_t) H10X_SC_SMALL_CAP * 8 * grid ;
-	  a.pre = (uint32_t*) p ; p += (size_t) 2 * 65536 * 4 * grid ;
 	  a.cnt = (uint32_t*) p ; p += (size_t) H10X_SC_WARPS * 65536 * 4 * grid ;
+	  a.pre = (uint32_t*) p ; p += (size_t) 2 * 65536 * 4 * grid ;
 	  a.res = (uint32_t*) p ; p += (size_t) 6 * 65536 * 4 * grid ;
+	  a.firstG = (uint32_t*) p ; p += (size_t) 65536 * 4 * grid ;
 	  a.readLabG = (int*) p ; p += (size_t) 65536 * 4 * grid ;
+	  a.parG = (uint16_t*) p ; p += (size_t) 65536 * 2 * grid ;
+	  a.fscanG = (uint16_t*) p ; p += (size_t) 65536 * 2 * grid ;
 	  a.gsubG = (uint8_t*) p ;
 	  a.tableCap = cap ; a.tableShift = (uint32_t) (32 - lg) ;
 	  a.clus = (unsigned long long*) c->clus.p ; a.blkOff = c->blkOff.p ; a.blkNHash = c->blkNHash.p ; a.blkNRead = c->blkNRead.p ;

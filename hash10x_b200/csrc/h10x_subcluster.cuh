@@ -1,28 +1,33 @@
 /* h10x_subcluster.cuh - `--cluster codeMin codeMax` on the resident index ("next" row f2 of SURVEY.md section 8):
- * codeClusterFind (hash10x.c:770-835) + codeClusterReadMerge (hash10x.c:837-868), one persistent CTA per barcode block.
+ * codeClusterFind (hash10x.c:770-835) + codeClusterReadMerge (hash10x.c:837-868), one persistent 1024-thread CTA per
+ * SM taking whole barcode blocks.
  *
  * The reference walks a block's good hashes i = 1 .. n-1 in order and keeps, per other barcode cj, the first step
- * at which cj shared a hash with this block (minShare[cj] = i + 1).  That is a minimum, so it does not depend on the
- * order of the walk:
+ * at which cj shared a hash with this block (minShare[cj] = i + 1).  Nothing in that walk is really sequential:
  *
- *   A  every (good hash i, barcode cj holding it) pair does an atomic min into a per-CTA open-addressing table
- *      cj -> min (i + 1), all warps of the CTA in parallel;
- *   B  a warp per good hash i counts, over the barcodes of hash i, how many have minShare - 1 == j for every j < i
+ *   A  minShare is a minimum, so every (good hash i, barcode cj holding it) pair does an atomic min into an
+ *      open-addressing table cj -> min (i + 1), all 32 warps in parallel.  The table lives in SHARED memory (16K
+ *      entries); a block that shares hashes with more barcodes than fit is redone with a global-memory table sized
+ *      for all blocks.  Entries carry a 16-bit stamp (one per block handled by the CTA), so neither table is ever
+ *      cleared between blocks: an entry with another stamp is empty.
+ *   B  a warp per step i counts, over the barcodes of hash i, how many have minShare - 1 == j for every j < i
  *      (barcodes first seen at step i sit at index i and never enter, hash10x.c:793-806), and keeps the largest
- *      count (first j wins ties, :803), the total, and nothing else: (msBest, msMax, msTot) of step i;
- *   C  one warp replays the cheap sequential part (:807-824) over those triples - sub-cluster creation and joining,
- *      the 255-cluster limit - and records per step which earlier hash founded the joined cluster; all warps then
- *      compute the steps' pointToMin terms in parallel (a recount only where the founder is not msBest) and one warp
- *      adds them in the reference's order of double additions;
- *   E  codeClusterReadMerge is a connected-components problem (sub-clusters joined through shared reads, the
- *      smallest label wins, :848-858): min-label propagation over (sub-cluster, read) edges with pointer jumping,
- *      then the reference's compaction of the surviving labels (:862-865).
+ *      count (first j wins ties, :803) and the total: (msBest, msMax, msTot) of step i.
+ *   C  the label logic (:807-824) is a forest: a step with msMax >= clusterThreshold points at the earlier hash
+ *      msBest and takes its cluster; a hash that is pointed at without having a cluster of its own founds one.  So a
+ *      step's cluster is the ROOT of its chain of msBest pointers, roots are exactly the hashes that are not such
+ *      steps themselves, cluster numbers are handed out in the order in which roots are first pointed at, and the
+ *      hash whose count enters pointToMin (clusterMin[], :820-823) is that root.  Pointer jumping finds the roots, an
+ *      atomic min per root its first direct child, a scan over the steps the numbering; the 256th founding step
+ *      abandons the block (:810-817: every label 0, pointToMin keeps the terms of the earlier steps).  All warps then
+ *      compute the steps' terms count / msTot (a recount only where the root is not msBest) and one warp adds them
+ *      in step order, i.e. in the reference's order of double additions.
+ *   E  codeClusterReadMerge is connected components (sub-clusters joined through shared reads, the smallest label
+ *      wins, :848-858): min-label propagation over (sub-cluster, read) edges with pointer jumping, then the
+ *      reference's renumbering of the surviving labels (:862-865).
  *
- * The table entries carry a 16-bit stamp (one per block handled by the CTA), so the table is never cleared between
- * blocks: an entry with another stamp is empty.  A 16K-entry table per CTA stays in L2; a block that shares hashes
- * with more barcodes than that is redone with a table sized for all blocks.  Step counters are 8-bit, packed in the
- * warp's shared memory (bins up to 128 deep, blocks up to 4096 good hashes), otherwise 32-bit in global memory; the
- * labels of good entries and of reads sit in shared memory when they fit.
+ * Per-step arrays sit in shared memory for blocks of up to 8192 good hashes and in global memory above that; bins
+ * deeper than 128 barcodes count through per-warp global counters instead of the warp's shared-memory buffer.
  * Labels left by an earlier --cluster on entries outside the current good lists that exceed the block's new
  * nSubCluster count as 0 (the reference reads past trueCluster[] there: undefined behaviour; same rule as the oracle).
  */
@@ -30,16 +35,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define H10X_SC_THREADS 256
+#define H10X_SC_THREADS 1024
 #define H10X_SC_WARPS (H10X_SC_THREADS / 32)
-#define H10X_SC_GSUB_SMEM 16384		/* good-entry labels kept in shared memory up to this many good hashes */
-#define H10X_SC_READ_SMEM 4096		/* read labels kept in shared memory up to this many read pairs */
+#define H10X_SC_STEPS_SMEM 8192u	/* good hashes of a block whose per-step arrays fit in shared memory */
+#define H10X_SC_READ_SMEM 4096u		/* read labels kept in shared memory up to this many read pairs */
 #define H10X_SC_VBUF 128		/* per-warp buffer of a hash's barcodes' minShare values */
-#define H10X_SC_CNT_STEPS 4096		/* steps whose counters fit in a warp's 4 KB of packed 8-bit counters */
-#define H10X_SC_DYN_SMEM (H10X_SC_GSUB_SMEM + H10X_SC_WARPS * H10X_SC_CNT_STEPS)
-#define H10X_SC_SMALL_CAP 16384u	/* entries of the L2-resident table (128 KB per CTA) */
+#define H10X_SC_SMALL_CAP 16384u	/* entries of the shared-memory table (128 KB) */
 #define H10X_SC_SMALL_SHIFT 18u		/* 32 - log2 (H10X_SC_SMALL_CAP) */
-#define H10X_SC_SMALL_LIMIT 9800u	/* barcodes it takes before the block is redone with the big table */
+#define H10X_SC_SMALL_LIMIT 9800u	/* barcodes it takes before the block is redone with the global table */
+/* dynamic shared memory: table | root pointers u16 (read labels later) | first child u32 | founder scan u16 | labels u8 */
+#define H10X_SC_DYN_SMEM (H10X_SC_SMALL_CAP * 8 + H10X_SC_STEPS_SMEM * (2 + 4 + 2 + 1))
 
 struct SubClusterArgs {
   unsigned long long *clus ;		/* ClusterHash as one word: bin id | read << 32 | subCluster << 48 */
@@ -51,24 +56,28 @@ struct SubClusterArgs {
   unsigned int *work ;			/* ticket counter */
   unsigned long long *table ;		/* per CTA: tableCap entries (barcode << 32 | stamp << 16 | minShare), zeroed once */
   uint32_t tableCap, tableShift ;	/* power of two >= 2 * blocks; shift = 32 - log2 (tableCap) */
-  unsigned long long *tableSmall ;	/* per CTA: H10X_SC_SMALL_CAP entries that stay in L2; the big table takes over when
-					   a block shares hashes with more barcodes than fit */
   uint32_t *pre ;			/* per CTA: 2 * 65536 words: depth and codes offset of every good hash's bin */
-  uint32_t *cnt ;			/* per warp: 65536 counters, all zero between uses */
-  uint32_t *res ;			/* per CTA: 6 * 65536 words: msBest, msMax, msTot, clusterMin index and (double) term of every step */
-  uint8_t *gsubG ;			/* per CTA: 65536 bytes, labels of the good entries when they do not fit in smem */
+  uint32_t *cnt ;			/* per warp: 65536 counters, all zero between uses (bins deeper than H10X_SC_VBUF) */
+  uint32_t *res ;			/* per CTA: 6 * 65536 words: msBest, msMax, msTot, root and (double) term of every step */
+  /* per CTA, for blocks whose per-step arrays do not fit in shared memory: 65536 entries each */
+  uint16_t *parG ; uint32_t *firstG ; uint16_t *fscanG ; uint8_t *gsubG ;
   int *readLabG ;			/* per CTA: 65536 ints, read labels when they do not fit in smem */
 } ;
 
+/* table words are read past L1 when the table is in global memory (they change under atomics of other warps) and
+   as volatile shared loads otherwise */
+__device__ __forceinline__ unsigned long long sc_table_load (const unsigned long long *tab, uint32_t h, bool inSmem)
+{ return inSmem ? ((const volatile unsigned long long*) tab)[h] : __ldcg (tab + h) ; }
+
 /* claims, overflow: shared-memory words of the CTA.  Every new barcode counts; past `limit` the overflow flag goes
-   up and everybody leaves (the caller redoes the block with the big table, whose limit is never reached). */
-__device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t mask, uint32_t shift, uint32_t stamp,
+   up and everybody leaves (the caller redoes the block with the global table, whose limit is never reached). */
+__device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t mask, uint32_t shift, bool inSmem, uint32_t stamp,
 					      uint32_t cj, uint32_t val, uint32_t *claims, volatile uint32_t *overflow, uint32_t limit)
 { const unsigned long long tag = ((unsigned long long) cj << 32) | ((unsigned long long) stamp << 16) ;
   const unsigned long long cand = tag | val ;
   uint32_t h = (cj * 0x9E3779B1u) >> shift ;
   for (;;)
-    { unsigned long long old = __ldcg (tab + h) ;
+    { unsigned long long old = sc_table_load (tab, h, inSmem) ;
       if ((old & ~0xffffull) == tag)			/* this barcode, this block */
 	{ if (val < (uint32_t) (old & 0xffffull)) atomicMin (tab + h, cand) ;
 	  return ;
@@ -87,12 +96,12 @@ __device__ __forceinline__ void sc_table_min (unsigned long long *tab, uint32_t 
 
 /* minShare of a barcode that step A has entered (0 if it is not there, which cannot happen for a barcode of a
    scanned hash) */
-__device__ __forceinline__ uint32_t sc_table_get (const unsigned long long *tab, uint32_t mask, uint32_t shift, uint32_t stamp,
-						  uint32_t cj)
+__device__ __forceinline__ uint32_t sc_table_get (const unsigned long long *tab, uint32_t mask, uint32_t shift, bool inSmem,
+						  uint32_t stamp, uint32_t cj)
 { const unsigned long long tag = ((unsigned long long) cj << 32) | ((unsigned long long) stamp << 16) ;
   uint32_t h = (cj * 0x9E3779B1u) >> shift ;
   for (uint32_t probes = 0 ; probes <= mask ; ++probes)
-    { unsigned long long old = __ldcg (tab + h) ;
+    { unsigned long long old = sc_table_load (tab, h, inSmem) ;
       if ((old & ~0xffffull) == tag) return (uint32_t) (old & 0xffffull) ;
       if ((uint32_t) ((old >> 16) & 0xffffull) != stamp) return 0 ;
       h = (h + 1) & mask ;
@@ -100,29 +109,28 @@ __device__ __forceinline__ uint32_t sc_table_get (const unsigned long long *tab,
   return 0 ;
 }
 
-__global__ void __launch_bounds__ (H10X_SC_THREADS)
+__global__ void __launch_bounds__ (H10X_SC_THREADS, 1)
 k_subcluster (SubClusterArgs a)
 {
-  /* dynamic shared memory: labels of the good entries (16 KB), then 32 KB that are the warps' packed 8-bit step counters
-     during codeClusterFind and the read labels during codeClusterReadMerge */
   extern __shared__ __align__ (16) unsigned char scSmem[] ;
-  uint8_t *const gsubS = scSmem ;
-  uint32_t *const cntS = (uint32_t*) (scSmem + H10X_SC_GSUB_SMEM) ;
-  int *const readLabS = (int*) (scSmem + H10X_SC_GSUB_SMEM) ;
+  unsigned long long *const tabSmall = (unsigned long long*) scSmem ;
+  unsigned char *const stepSmem = scSmem + (size_t) H10X_SC_SMALL_CAP * 8 ;
   __shared__ uint16_t vbuf[H10X_SC_WARPS][H10X_SC_VBUF] ;
-  __shared__ uint16_t clusterMin[256] ;
   __shared__ int label[257], newLab[257] ;
-  __shared__ uint32_t sTicket, sNs, sChanged, sClaims, sOverflow ;
+  __shared__ uint32_t warpSum[H10X_SC_WARPS] ;
+  __shared__ uint32_t sTicket, sNs, sChanged, sClaims, sOverflow, sTotal, sAbandonAt ;
 
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5 ;
   unsigned long long *const tabBig = a.table + (size_t) blockIdx.x * a.tableCap ;
-  unsigned long long *const tabSmall = a.tableSmall + (size_t) blockIdx.x * H10X_SC_SMALL_CAP ;
   uint32_t *preNc = a.pre + (size_t) blockIdx.x * 2 * 65536, *preOff = preNc + 65536 ;
   uint32_t *cnt = a.cnt + ((size_t) blockIdx.x * H10X_SC_WARPS + w) * 65536 ;
   uint32_t *resBest = a.res + (size_t) blockIdx.x * 6 * 65536, *resMax = resBest + 65536, *resTot = resMax + 65536,
     *resCm = resTot + 65536 ;
   double *resTerm = (double*) (resCm + 65536) ;
   uint32_t stamp = 0 ;
+
+  for (uint32_t i = t ; i < H10X_SC_SMALL_CAP ; i += H10X_SC_THREADS) tabSmall[i] = 0 ;	/* stamp 0 = never used */
+  __syncthreads () ;
 
   for (;;)
     { if (t == 0) sTicket = atomicAdd (a.work, 1u) ;
@@ -137,19 +145,23 @@ k_subcluster (SubClusterArgs a)
       const uint32_t nHash = a.blkNHash[code] ;
 
       if (n)	/* ---------------- codeClusterFind ---------------- */
-	{ uint8_t *gsub = (n <= H10X_SC_GSUB_SMEM) ? gsubS : a.gsubG + (size_t) blockIdx.x * 65536 ;
+	{ /* per-step arrays: par = msBest pointer, later the root; first = first direct child of a root; fscan = number of
+	     founding steps up to here; gsub = the labels (ClusterHash.subCluster of the good entries) */
+	  const bool stepsInSmem = n <= H10X_SC_STEPS_SMEM ;
+	  volatile uint16_t *par = stepsInSmem ? (uint16_t*) stepSmem : a.parG + (size_t) blockIdx.x * 65536 ;
+	  volatile uint32_t *first = stepsInSmem ? (uint32_t*) (stepSmem + H10X_SC_STEPS_SMEM * 2) : a.firstG + (size_t) blockIdx.x * 65536 ;
+	  volatile uint16_t *fscan = stepsInSmem ? (uint16_t*) (stepSmem + H10X_SC_STEPS_SMEM * 6) : a.fscanG + (size_t) blockIdx.x * 65536 ;
+	  volatile uint8_t *gsub = stepsInSmem ? (uint8_t*) (stepSmem + H10X_SC_STEPS_SMEM * 8) : a.gsubG + (size_t) blockIdx.x * 65536 ;
 	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS)
-	    { gsub[i] = 0 ;								/* :783 wipe */
+	    { par[i] = (uint16_t) i ; first[i] = 0xffffffffu ;
 	      const uint32_t x = (uint32_t) ch[g[i]] ;				/* bin of good hash i: its depth and barcode list */
 	      preNc[i] = a.hashDepth[x] ; preOff[i] = (uint32_t) a.codeOff[x] ;	/* fewer than 2^32 entries on a device */
 	    }
 
-	  const bool smemCnt = n <= H10X_SC_CNT_STEPS ;
-	  if (smemCnt) for (uint32_t i = t ; i < H10X_SC_WARPS * H10X_SC_CNT_STEPS / 4 ; i += H10X_SC_THREADS) cntS[i] = 0 ;
-
-	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block; first in the small table */
+	  /* A: minShare of every barcode that shares a good hash i >= 1 with this block; first in the shared-memory table */
 	  unsigned long long *tab = tabSmall ;
 	  uint32_t mask = H10X_SC_SMALL_CAP - 1, shift = H10X_SC_SMALL_SHIFT, limit = H10X_SC_SMALL_LIMIT ;
+	  bool inSmem = true ;
 	  for (int attempt = 0 ; attempt < 2 ; ++attempt)
 	    { if (++stamp == 0x10000u)		/* 16-bit stamps used up: start over with clean tables */
 		{ for (size_t i = t ; i < a.tableCap ; i += H10X_SC_THREADS) tabBig[i] = 0 ;
@@ -171,126 +183,149 @@ k_subcluster (SubClusterArgs a)
 		      }
 		    for (uint32_t j = lane ; j < nc ; j += 32)
 		      { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
-			if (cj != code) sc_table_min (tab, mask, shift, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
+			if (cj != code) sc_table_min (tab, mask, shift, inSmem, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
 		      }
 		  }
 	      }
 	      __syncthreads () ;
 	      if (!sOverflow) break ;
 	      __syncthreads () ;
-	      tab = tabBig ; mask = a.tableCap - 1 ; shift = a.tableShift ; limit = 0xffffffffu ;
+	      tab = tabBig ; mask = a.tableCap - 1 ; shift = a.tableShift ; limit = 0xffffffffu ; inSmem = false ;
 	    }
 
-	  /* B: per step i the best earlier step, its count and the total (hash10x.c:793-806) */
-	  uint32_t ncN = 0, offN = 0, cjN = 0 ;
-	  if (1 + w < n)
-	    { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
-	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
-	    { const uint32_t nc = ncN, cj0 = cjN ;
-	      const uint32_t *cl = a.codes + offN ;
-	      if (i + H10X_SC_WARPS < n)
-		{ ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
-		  if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
-		}
-	      uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
-	      if (nc <= H10X_SC_VBUF && smemCnt)	/* the usual case: 8-bit counters of the warp, four to a shared-memory word */
-		{ uint32_t *cw = cntS + w * (H10X_SC_CNT_STEPS / 4) ;
-		  for (uint32_t j = lane ; j < nc ; j += 32)
-		    { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
-		      uint32_t v = 0xffffu ;
-		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-		      vbuf[w][j] = (uint16_t) v ;
-		      if (v != 0xffffu) { atomicAdd (cw + (v >> 2), 1u << (8 * (v & 3))) ; ++tot ; }	/* at most 128 per counter */
-		    }
-		  __syncwarp () ;
-		  for (uint32_t j = lane ; j < nc ; j += 32)
-		    { const uint32_t v = vbuf[w][j] ;
-		      if (v == 0xffffu) continue ;
-		      const uint32_t c = (cw[v >> 2] >> (8 * (v & 3))) & 0xffu ;
-		      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
-		    }
-		  __syncwarp () ;
-		  for (uint32_t j = lane ; j < nc ; j += 32)
-		    { const uint32_t v = vbuf[w][j] ;
-		      if (v != 0xffffu) cw[v >> 2] = 0 ;
-		    }
-		}
-	      else				/* a deep bin: per-warp counters in global memory */
-		{ for (uint32_t j = lane ; j < nc ; j += 32)
-		    { const uint32_t cj = cl[j] ;
-		      uint32_t v = 0xffffu ;
-		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-		      if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
-		    }
-		  __syncwarp () ;
-		  for (uint32_t j = lane ; j < nc ; j += 32)
-		    { const uint32_t cj = cl[j] ;
-		      uint32_t v = 0xffffu ;
-		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-		      if (v != 0xffffu)
-			{ const uint32_t c = __ldcg (cnt + v) ;
-			  if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
-			}
-		    }
-		  __syncwarp () ;
-		  for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
-		    { const uint32_t cj = cl[j] ;
-		      uint32_t v = 0xffffu ;
-		      if (cj != code) { v = sc_table_get (tab, mask, shift, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-		      if (v != 0xffffu) cnt[v] = 0 ;
-		    }
-		}
+	  /* B: per step i the best earlier step, its count and the total (hash10x.c:793-806); the step points at it when
+	     the count reaches the threshold (:807) */
+	  { uint32_t ncN = 0, offN = 0, cjN = 0 ;
+	    if (1 + w < n)
+	      { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
+	    for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
+	      { const uint32_t nc = ncN, cj0 = cjN ;
+		const uint32_t *cl = a.codes + offN ;
+		if (i + H10X_SC_WARPS < n)
+		  { ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
+		    if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
+		  }
+		uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
+		if (nc <= H10X_SC_VBUF)		/* the usual case: count equal values among the hash's barcodes in shared memory */
+		  { for (uint32_t j = lane ; j < nc ; j += 32)
+		      { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
+			uint32_t v = 0xffffu ;
+			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			vbuf[w][j] = (uint16_t) v ;
+		      }
+		    __syncwarp () ;
+		    for (uint32_t j = lane ; j < nc ; j += 32)
+		      { const uint32_t v = vbuf[w][j] ;
+			if (v == 0xffffu) continue ;
+			++tot ;
+			uint32_t c = 0 ;
+			for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
+			if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+		      }
+		  }
+		else				/* a deep bin: per-warp counters in global memory */
+		  { for (uint32_t j = lane ; j < nc ; j += 32)
+		      { const uint32_t cj = cl[j] ;
+			uint32_t v = 0xffffu ;
+			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
+		      }
+		    __syncwarp () ;
+		    for (uint32_t j = lane ; j < nc ; j += 32)
+		      { const uint32_t cj = cl[j] ;
+			uint32_t v = 0xffffu ;
+			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			if (v != 0xffffu)
+			  { const uint32_t c = __ldcg (cnt + v) ;
+			    if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+			  }
+		      }
+		    __syncwarp () ;
+		    for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
+		      { const uint32_t cj = cl[j] ;
+			uint32_t v = 0xffffu ;
+			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			if (v != 0xffffu) cnt[v] = 0 ;
+		      }
+		  }
 #pragma unroll
-	      for (int d = 16 ; d ; d >>= 1)
-		{ const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
-		  if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
-		  tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
-		}
-	      __syncwarp () ;
-	      if (lane == 0) { resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ; }
-	    }
+		for (int d = 16 ; d ; d >>= 1)
+		  { const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
+		    if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
+		    tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
+		  }
+		__syncwarp () ;
+		if (lane == 0)
+		  { resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ;
+		    if ((long long) bMax >= (long long) a.threshold) par[i] = (uint16_t) bBest ;
+		  }
+	      }
+	  }
 	  __syncthreads () ;
 
-	  /* C1: the sequential part, by one warp in lock step (hash10x.c:807-824).  Which cluster a step joins or founds
-	     depends only on (msBest, msMax >= threshold) and on the labels so far; the pointToMin term of the step needs
-	     the count at the cluster's founding hash clusterMin[], so C1 only records that index per step ... */
-	  if (w == 0)
-	    { uint32_t nsub = 0 ; bool abandoned = false ;
-	      for (uint32_t i0 = 1 ; i0 < n ; i0 += 32)
-		{ const uint32_t mine = i0 + lane ;
-		  uint32_t myCm = 0xffffffffu ;
-		  if (!abandoned)
-		    { const uint32_t mb = mine < n ? __ldcg (resBest + mine) : 0u, mm = mine < n ? __ldcg (resMax + mine) : 0u ;
-		      const uint32_t steps = min (32u, n - i0) ;
-		      for (uint32_t k = 0 ; k < steps ; ++k)
-			{ const uint32_t i = i0 + k ;
-			  const uint32_t b = __shfl_sync (0xffffffffu, mb, k), m = __shfl_sync (0xffffffffu, mm, k) ;
-			  if ((long long) m < (long long) a.threshold) continue ;
-			  uint32_t sb = gsub[b] ;
-			  if (!sb)				/* create a new cluster */
-			    { if (++nsub > 255u)		/* abandon this clustering (:810-817); pointToMin keeps its terms */
-				{ nsub = 0 ;
-				  __syncwarp () ;
-				  for (uint32_t j = lane ; j < i ; j += 32) gsub[j] = 0 ;
-				  abandoned = true ;
-				  break ;
-				}
-			      sb = nsub ;
-			      __syncwarp () ;
-			      if (lane == 0) { gsub[b] = (uint8_t) sb ; clusterMin[sb] = (uint16_t) b ; }
-			    }
-			  __syncwarp () ;
-			  if (lane == 0) gsub[i] = (uint8_t) sb ;
-			  __syncwarp () ;
-			  if (lane == k) myCm = clusterMin[sb] ;
-			}
-		    }
-		  if (mine < n) resCm[mine] = myCm ;
-		}
-	      if (lane == 0) a.nSub[code] = nsub ;
+	  /* C: the labels (hash10x.c:807-824) as a forest - see the head of this file.
+	     first[r] = the first step that points straight at root r */
+	  for (uint32_t i = 1 + t ; i < n ; i += H10X_SC_THREADS)
+	    { const uint32_t b = par[i] ;
+	      if (b != i && par[b] == b) atomicMin ((uint32_t*) first + b, i) ;
 	    }
+	  if (t == 0) sAbandonAt = n ;
 	  __syncthreads () ;
-	  /* C2: ... all warps then compute the terms minShareCount[clusterMin] / msTot (:823) in parallel ... */
+	  /* founding steps, counted in step order */
+	  { const uint32_t per = (n + H10X_SC_THREADS - 1) / H10X_SC_THREADS ;
+	    const uint32_t lo = min (t * per, n), hi = min (lo + per, n) ;
+	    uint32_t sum = 0 ;
+	    for (uint32_t i = lo ; i < hi ; ++i)
+	      { const uint32_t b = par[i] ; sum += (b != i && par[b] == b && first[b] == i) ? 1u : 0u ; }
+	    uint32_t inc = sum ;
+#pragma unroll
+	    for (int d = 1 ; d < 32 ; d <<= 1) { const uint32_t u = __shfl_up_sync (0xffffffffu, inc, d) ; if (lane >= d) inc += u ; }
+	    if (lane == 31) warpSum[w] = inc ;
+	    __syncthreads () ;
+	    if (w == 0)
+	      { const uint32_t v = warpSum[lane] ; uint32_t iv = v ;
+#pragma unroll
+		for (int d = 1 ; d < 32 ; d <<= 1) { const uint32_t u = __shfl_up_sync (0xffffffffu, iv, d) ; if (lane >= d) iv += u ; }
+		warpSum[lane] = iv - v ;
+		if (lane == 31) sTotal = iv ;
+	      }
+	    __syncthreads () ;
+	    uint32_t run = warpSum[w] + inc - sum ;
+	    for (uint32_t i = lo ; i < hi ; ++i)
+	      { const uint32_t b = par[i] ;
+		const uint32_t f = (b != i && par[b] == b && first[b] == i) ? 1u : 0u ;
+		run += f ;
+		fscan[i] = (uint16_t) run ;
+		if (f && run == 256u) sAbandonAt = i ;		/* the step that would found cluster 256 (:810) */
+	      }
+	  }
+	  __syncthreads () ;
+	  /* roots by pointer jumping: pointers only ever move to an ancestor, so reading a half-updated one is fine */
+	  for (int round = 0 ; round < 17 ; ++round)
+	    { if (t == 0) sChanged = 0 ;
+	      __syncthreads () ;
+	      for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS)
+		{ const uint32_t p0 = par[i], pp = par[p0] ;
+		  if (pp != p0) { par[i] = (uint16_t) pp ; sChanged = 1 ; }
+		}
+	      __syncthreads () ;
+	      const bool again = sChanged != 0 ;
+	      __syncthreads () ;
+	      if (!again) break ;
+	    }
+	  { const uint32_t total = sTotal, abandonAt = sAbandonAt ;
+	    const bool abandoned = total > 255u ;
+	    for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS)
+	      { const uint32_t r = par[i] ;
+		uint32_t lab = 0 ;
+		if (!abandoned) { const uint32_t f = first[r] ; if (f != 0xffffffffu) lab = fscan[f] ; }
+		gsub[i] = (uint8_t) lab ;
+		resCm[i] = (r != i && i < abandonAt) ? r : 0xffffffffu ;	/* the step's clusterMin[], if it joined anything */
+	      }
+	    if (t == 0) a.nSub[code] = abandoned ? 0u : total ;
+	  }
+	  __syncthreads () ;
+	  /* the terms minShareCount[clusterMin] / msTot (:823) in parallel ... */
 	  for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
 	    { const uint32_t cm = __ldcg (resCm + i) ;
 	      if (cm == 0xffffffffu) { if (lane == 0) resTerm[i] = 0.0 ; continue ; }
@@ -301,7 +336,7 @@ k_subcluster (SubClusterArgs a)
 		  cAt = 0 ;
 		  for (uint32_t j = lane ; j < nc ; j += 32)
 		    { const uint32_t cj = cl[j] ;
-		      if (cj != code && sc_table_get (tab, mask, shift, stamp, cj) - 1u == cm) ++cAt ;
+		      if (cj != code && sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u == cm) ++cAt ;
 		    }
 #pragma unroll
 		  for (int d = 16 ; d ; d >>= 1) cAt += __shfl_xor_sync (0xffffffffu, cAt, d) ;
@@ -309,7 +344,7 @@ k_subcluster (SubClusterArgs a)
 	      if (lane == 0) resTerm[i] = (double) (int) cAt / (double) (int) __ldcg (resTot + i) ;
 	    }
 	  __syncthreads () ;
-	  /* C3: ... and one warp adds them in step order, as the reference's double accumulation does (x + 0.0 == x for
+	  /* ... and one warp adds them in step order, as the reference's double accumulation does (x + 0.0 == x for
 	     the steps that joined nothing) */
 	  if (w == 0)
 	    { double ptm = 0.0 ;
@@ -321,7 +356,6 @@ k_subcluster (SubClusterArgs a)
 		}
 	      if (lane == 0) a.pointToMin[code] = ptm ;
 	    }
-	  __syncthreads () ;
 	  for (uint32_t i = t ; i < n ; i += H10X_SC_THREADS) ((uint8_t*) (ch + g[i]))[6] = gsub[i] ;
 	  __syncthreads () ;
 	}
@@ -333,7 +367,7 @@ k_subcluster (SubClusterArgs a)
       if (ns)
 	{ const uint32_t nRead = a.blkNRead[code] ;
 	  const uint32_t nR = min (nRead, 65536u) ;
-	  int *readLab = (nR <= H10X_SC_READ_SMEM) ? readLabS : a.readLabG + (size_t) blockIdx.x * 65536 ;
+	  int *readLab = (nR <= H10X_SC_READ_SMEM) ? (int*) stepSmem : a.readLabG + (size_t) blockIdx.x * 65536 ;
 	  for (uint32_t s = t ; s <= 256 ; s += H10X_SC_THREADS) label[s] = s <= ns ? (int) s : 0 ;
 	  __syncthreads () ;
 	  for (;;)
