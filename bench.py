@@ -36,6 +36,10 @@ WORKLOADS = {
     "yeast": dict(genome_len=12_000_000, n_barcodes=10_000, pairs_min=150, pairs_max=350,
                   mol_per_barcode=10, mol_len=50_000, snp_period=500, err_rate=0.004, B=24, read_len=151,
                   desc="BASELINE configs[1]: synthetic yeast-scale diploid (12 Mb, ~2.5M read pairs, 10k barcodes, 60x), -B 24"),
+    "gb10th": dict(genome_len=100_000_000, n_barcodes=50_000, pairs_min=300, pairs_max=500,
+                   mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=26, read_len=160,
+                   desc="one tenth of BASELINE configs[2] at the same barcode density (100 Mb genome, 50k barcodes, ~20M read "
+                        "pairs, -B 26): the profiling-sized stand-in for the 1 Gb sharing structure"),
     "human8": dict(genome_len=3_100_000_000, n_barcodes=187_500, pairs_min=300, pairs_max=500,
                    mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=30, read_len=160,
                    desc="one eighth of BASELINE configs[3]: 3.1 Gb human-scale genome, 75M read pairs per GPU, -B 30, 160+160 bp reads"),

@@ -40,6 +40,7 @@
 #define H10X_SC_STEPS_SMEM 8192u	/* good hashes of a block whose per-step arrays fit in shared memory */
 #define H10X_SC_READ_SMEM 4096u		/* read labels kept in shared memory up to this many read pairs */
 #define H10X_SC_VBUF 128		/* per-warp buffer of a hash's barcodes' minShare values */
+#define H10X_SC_GROUP 4			/* steps whose barcode lists a warp loads together */
 #define H10X_SC_SMALL_CAP 16384u	/* entries of the shared-memory table (128 KB) */
 #define H10X_SC_SMALL_SHIFT 18u		/* 32 - log2 (H10X_SC_SMALL_CAP) */
 #define H10X_SC_SMALL_LIMIT 9800u	/* barcodes it takes before the block is redone with the global table */
@@ -170,23 +171,34 @@ k_subcluster (SubClusterArgs a)
 		}
 	      if (t == 0) { sClaims = 0 ; sOverflow = 0 ; }
 	      __syncthreads () ;
-	      { /* the first 32 barcodes of the warp's next hash are loaded while the current one is worked on */
-		uint32_t ncN = 0, offN = 0, cjN = 0 ;
-		if (1 + w < n)
-		  { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
-		for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
-		  { const uint32_t nc = ncN, cj0 = cjN ;
-		    const uint32_t *cl = a.codes + offN ;
-		    if (i + H10X_SC_WARPS < n)
-		      { ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
-			if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
-		      }
-		    for (uint32_t j = lane ; j < nc ; j += 32)
-		      { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
-			if (cj != code) sc_table_min (tab, mask, shift, inSmem, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
-		      }
-		  }
-	      }
+	      /* a warp takes 8 consecutive steps at a time: lanes 0-7 fetch their bin depth / list offset (one L2 round trip),
+		 then the first 64 barcodes of 4 steps are loaded together (8 independent DRAM loads in flight per lane) before
+		 any of them is worked on - the kernel is bound by the latency of these loads, not by their bytes */
+	      for (uint32_t c0 = 1 + 8 * w ; c0 < n ; c0 += 8 * H10X_SC_WARPS)
+		{ uint32_t myNc = 0, myOff = 0 ;
+		  if (lane < 8 && c0 + lane < n) { myNc = __ldcg (preNc + c0 + lane) ; myOff = __ldcg (preOff + c0 + lane) ; }
+		  for (uint32_t q0 = 0 ; q0 < 8 ; q0 += H10X_SC_GROUP)
+		    { uint32_t nc[H10X_SC_GROUP], off[H10X_SC_GROUP], cja[H10X_SC_GROUP], cjb[H10X_SC_GROUP] ;
+#pragma unroll
+		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
+			{ nc[q] = __shfl_sync (0xffffffffu, myNc, q0 + q) ; off[q] = __shfl_sync (0xffffffffu, myOff, q0 + q) ; }
+#pragma unroll
+		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)	/* `code` stands for "no barcode here": it is skipped anyway */
+			{ cja[q] = lane < nc[q] ? a.codes[(size_t) off[q] + lane] : code ;
+			  cjb[q] = lane + 32 < nc[q] ? a.codes[(size_t) off[q] + 32 + lane] : code ;
+			}
+#pragma unroll
+		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
+			{ const uint32_t i = c0 + q0 + q ;
+			  if (cja[q] != code) sc_table_min (tab, mask, shift, inSmem, stamp, cja[q], i + 1, &sClaims, &sOverflow, limit) ;
+			  if (cjb[q] != code) sc_table_min (tab, mask, shift, inSmem, stamp, cjb[q], i + 1, &sClaims, &sOverflow, limit) ;
+			  for (uint32_t j = lane + 64 ; j < nc[q] ; j += 32)
+			    { const uint32_t cj = a.codes[(size_t) off[q] + j] ;
+			      if (cj != code) sc_table_min (tab, mask, shift, inSmem, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
+			    }
+			}
+		    }
+		}
 	      __syncthreads () ;
 	      if (!sOverflow) break ;
 	      __syncthreads () ;
@@ -195,72 +207,82 @@ k_subcluster (SubClusterArgs a)
 
 	  /* B: per step i the best earlier step, its count and the total (hash10x.c:793-806); the step points at it when
 	     the count reaches the threshold (:807) */
-	  { uint32_t ncN = 0, offN = 0, cjN = 0 ;
-	    if (1 + w < n)
-	      { ncN = __ldcg (preNc + 1 + w) ; offN = __ldcg (preOff + 1 + w) ; if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ; }
-	    for (uint32_t i = 1 + w ; i < n ; i += H10X_SC_WARPS)
-	      { const uint32_t nc = ncN, cj0 = cjN ;
-		const uint32_t *cl = a.codes + offN ;
-		if (i + H10X_SC_WARPS < n)
-		  { ncN = __ldcg (preNc + i + H10X_SC_WARPS) ; offN = __ldcg (preOff + i + H10X_SC_WARPS) ;
-		    if (lane < ncN) cjN = a.codes[(size_t) offN + lane] ;
-		  }
-		uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
-		if (nc <= H10X_SC_VBUF)		/* the usual case: count equal values among the hash's barcodes in shared memory */
-		  { for (uint32_t j = lane ; j < nc ; j += 32)
-		      { const uint32_t cj = j < 32 ? cj0 : cl[j] ;
-			uint32_t v = 0xffffu ;
-			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-			vbuf[w][j] = (uint16_t) v ;
-		      }
-		    __syncwarp () ;
-		    for (uint32_t j = lane ; j < nc ; j += 32)
-		      { const uint32_t v = vbuf[w][j] ;
-			if (v == 0xffffu) continue ;
-			++tot ;
-			uint32_t c = 0 ;
-			for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
-			if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
-		      }
-		  }
-		else				/* a deep bin: per-warp counters in global memory */
-		  { for (uint32_t j = lane ; j < nc ; j += 32)
-		      { const uint32_t cj = cl[j] ;
-			uint32_t v = 0xffffu ;
-			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-			if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
-		      }
-		    __syncwarp () ;
-		    for (uint32_t j = lane ; j < nc ; j += 32)
-		      { const uint32_t cj = cl[j] ;
-			uint32_t v = 0xffffu ;
-			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-			if (v != 0xffffu)
-			  { const uint32_t c = __ldcg (cnt + v) ;
-			    if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
-			  }
-		      }
-		    __syncwarp () ;
-		    for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
-		      { const uint32_t cj = cl[j] ;
-			uint32_t v = 0xffffu ;
-			if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
-			if (v != 0xffffu) cnt[v] = 0 ;
-		      }
-		  }
+	  for (uint32_t c0 = 1 + 8 * w ; c0 < n ; c0 += 8 * H10X_SC_WARPS)
+	    { uint32_t myNc = 0, myOff = 0 ;
+	      if (lane < 8 && c0 + lane < n) { myNc = __ldcg (preNc + c0 + lane) ; myOff = __ldcg (preOff + c0 + lane) ; }
+	      for (uint32_t q0 = 0 ; q0 < 8 ; q0 += H10X_SC_GROUP)
+		{ uint32_t ncs[H10X_SC_GROUP], off[H10X_SC_GROUP], cja[H10X_SC_GROUP], cjb[H10X_SC_GROUP] ;
 #pragma unroll
-		for (int d = 16 ; d ; d >>= 1)
-		  { const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
-		    if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
-		    tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
-		  }
-		__syncwarp () ;
-		if (lane == 0)
-		  { resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ;
-		    if ((long long) bMax >= (long long) a.threshold) par[i] = (uint16_t) bBest ;
-		  }
-	      }
-	  }
+		  for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
+		    { ncs[q] = __shfl_sync (0xffffffffu, myNc, q0 + q) ; off[q] = __shfl_sync (0xffffffffu, myOff, q0 + q) ; }
+#pragma unroll
+		  for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
+		    { cja[q] = lane < ncs[q] ? a.codes[(size_t) off[q] + lane] : code ;
+		      cjb[q] = lane + 32 < ncs[q] ? a.codes[(size_t) off[q] + 32 + lane] : code ;
+		    }
+#pragma unroll
+		  for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
+		    { const uint32_t i = c0 + q0 + q ;
+		      if (i >= n) continue ;			/* warp-uniform */
+		      const uint32_t nc = ncs[q] ;
+		      const uint32_t *cl = a.codes + off[q] ;
+		      uint32_t tot = 0, bMax = 0, bBest = 0xffffffffu ;
+		      if (nc <= H10X_SC_VBUF)		/* the usual case: count equal values among the hash's barcodes in shared memory */
+			{ for (uint32_t j = lane ; j < nc ; j += 32)
+			    { const uint32_t cj = j < 32 ? cja[q] : j < 64 ? cjb[q] : cl[j] ;
+			      uint32_t v = 0xffffu ;
+			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      vbuf[w][j] = (uint16_t) v ;
+			    }
+			  __syncwarp () ;
+			  for (uint32_t j = lane ; j < nc ; j += 32)
+			    { const uint32_t v = vbuf[w][j] ;
+			      if (v == 0xffffu) continue ;
+			      ++tot ;
+			      uint32_t c = 0 ;
+			      for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
+			      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+			    }
+			}
+		      else				/* a deep bin: per-warp counters in global memory */
+			{ for (uint32_t j = lane ; j < nc ; j += 32)
+			    { const uint32_t cj = cl[j] ;
+			      uint32_t v = 0xffffu ;
+			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
+			    }
+			  __syncwarp () ;
+			  for (uint32_t j = lane ; j < nc ; j += 32)
+			    { const uint32_t cj = cl[j] ;
+			      uint32_t v = 0xffffu ;
+			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (v != 0xffffu)
+				{ const uint32_t c = __ldcg (cnt + v) ;
+				  if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
+				}
+			    }
+			  __syncwarp () ;
+			  for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
+			    { const uint32_t cj = cl[j] ;
+			      uint32_t v = 0xffffu ;
+			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (v != 0xffffu) cnt[v] = 0 ;
+			    }
+			}
+#pragma unroll
+		      for (int d = 16 ; d ; d >>= 1)
+			{ const uint32_t oMax = __shfl_xor_sync (0xffffffffu, bMax, d), oBest = __shfl_xor_sync (0xffffffffu, bBest, d) ;
+			  if (oMax > bMax || (oMax == bMax && oBest < bBest)) { bMax = oMax ; bBest = oBest ; }
+			  tot += __shfl_xor_sync (0xffffffffu, tot, d) ;
+			}
+		      __syncwarp () ;
+		      if (lane == 0)
+			{ resBest[i] = bMax ? bBest : 0u ; resMax[i] = bMax ; resTot[i] = tot ;
+			  if ((long long) bMax >= (long long) a.threshold) par[i] = (uint16_t) bBest ;
+			}
+		    }
+		}
+	    }
 	  __syncthreads () ;
 
 	  /* C: the labels (hash10x.c:807-824) as a forest - see the head of this file.
