@@ -237,10 +237,13 @@ k_subcluster (SubClusterArgs a)
 			  __syncwarp () ;
 			  for (uint32_t j = lane ; j < nc ; j += 32)
 			    { const uint32_t v = vbuf[w][j] ;
+			      const uint32_t r0 = j & ~31u ;				/* this round of 32 barcodes: equal values by one match ... */
+			      const uint32_t live = nc - r0 >= 32u ? 0xffffffffu : (1u << (nc - r0)) - 1u ;
+			      uint32_t c = __popc (__match_any_sync (live, v)) ;
 			      if (v == 0xffffu) continue ;
 			      ++tot ;
-			      uint32_t c = 0 ;
-			      for (uint32_t k = 0 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
+			      for (uint32_t k = 0 ; k < r0 ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;	/* ... the other rounds one by one */
+			      for (uint32_t k = r0 + 32 ; k < nc ; ++k) c += (vbuf[w][k] == v) ? 1u : 0u ;
 			      if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
 			    }
 			}
