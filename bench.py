@@ -15,6 +15,7 @@ the unmodified reference; the oracle port if that binary is missing) on a bounde
 workload on this box's host cores.  --readFQB is single-threaded in the reference even with -DOMP.
 """
 import argparse
+import io
 import json
 import os
 import subprocess
@@ -387,10 +388,25 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     name = args.workload or ("1gb" if world == 1 else "human8")
     wl = WORKLOADS[name]
-    if args.impl == "reference":
-        run_reference_arm(args, wl)
-    else:
-        run_ours(args, wl)
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 themselves
+    # (NCCL prints "NCCL version ..." there when NCCL_DEBUG is set) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    captured = io.StringIO()
+    py_out, sys.stdout = sys.stdout, captured
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args, wl)
+        else:
+            run_ours(args, wl)
+    finally:
+        sys.stdout = py_out
+        sys.stdout.flush()
+        os.dup2(real_out, 1)
+        os.close(real_out)
+    sys.stdout.write(captured.getvalue())
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
