@@ -146,6 +146,8 @@ class Index:
         self.clus = _arr(ci.clusHash, H, np.uint64)
         self.codeOff = _arr(ci.codeOff, hn + 1, np.uint64) if ci.codeOff else None
         self.codes = _arr(ci.codes, H, np.uint32) if ci.codes else None
+        self.blkNSub = _arr(ci.blkNSubCluster, nb, np.uint32) if ci.blkNSubCluster else None
+        self.blkPointToMin = _arr(ci.blkPointToMin, nb, np.float64) if ci.blkPointToMin else None
         self.status = 0
 
 

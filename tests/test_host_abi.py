@@ -111,3 +111,57 @@ def test_synth_generator_is_deterministic_and_well_formed(orc):
     assert (a[:, 14] == 0x7FFFFF).all() and (a[:, 10:14] == 0xFFFFFFFF).all()
     part = orc.synth_fqb(p, 5, 17)
     assert np.array_equal(part, a[5:17])
+
+
+def test_hash_writer_reader_carry_the_cluster_fields(orc, tmp_path):
+    """ClusterBlock.nSubCluster / .pointToMin and ClusterHash.subCluster (what --cluster leaves behind) go through
+    h10x_write_hash / h10x_read_hash at the reference's offsets (hash10x.c:62-70,256-261): the file parses to the
+    oracle's values and, where the reference binary is available, has the reference's bytes outside the raw
+    pointers its reader overwrites."""
+    import subprocess
+    import hash10x_b200
+    from hash10x_b200 import binding
+    import hashfile
+    p = orc.synth_params(seed=37, n_barcodes=120, pairs_min=20, pairs_max=80, genome_len=40_000, mol_len=8_000,
+                         mol_per_barcode=3)
+    recs = orc.synth_fqb(p)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, 2, 13)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 1)
+    assert int(nsub.sum()) > 0
+    ix.clus, ix.blkNSub, ix.blkPointToMin = clus, nsub, ptm
+    ours = str(tmp_path / "ours.hash")
+    binding.write_hash(ix, ours)
+    hf = hashfile.parse(ours)
+    assert np.array_equal(hf.blkNSub, nsub) and np.array_equal(hf.clusRaw, clus)
+    assert np.array_equal(hf.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    L = hash10x_b200.load_library()
+    ci = binding.CIndex()
+    err = C.create_string_buffer(256)
+    assert L.h10x_read_hash(ours.encode(), 20, C.byref(ci), err, 256) == 0
+    got = binding.Index(ci, L)
+    L.h10x_index_free(C.byref(ci))
+    assert np.array_equal(got.blkNSub, nsub) and np.array_equal(got.clus, clus)
+    assert np.array_equal(got.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    if orc.ref_binary() is None:
+        return
+    src, ref = str(tmp_path / "src.hash"), str(tmp_path / "ref.hash")
+    assert orc.build_and_write(recs, src, B=20) == 0
+    r = subprocess.run([orc.ref_binary(), "-B", "20", "-ct", "1", "--readHash", src, "--hashDepthRange", "2", "13",
+                        "--cluster", "0", "0", "--writeHash", ref], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    a, b = bytearray(open(ours, "rb").read()), bytearray(open(ref, "rb").read())
+    assert len(a) == len(b)
+    # blank the raw pointers: ArrayStruct.base of both Arrays and ClusterBlock.clusHash of every block
+    hn, nb = int(ix.hashNumber), int(ix.nBlocksMax)
+    off = 16 + (4 << 20) + 4 + 8 * hn
+    for buf in (a, b):
+        buf[off + 8:off + 16] = bytes(8)
+    depth_dim = hf.depthDim
+    off2 = off + 32 + 4 * depth_dim
+    for buf in (a, b):
+        buf[off2 + 8:off2 + 16] = bytes(8)
+        for blk in range(hf.blkDim):
+            o = off2 + 32 + 32 * blk + 16
+            buf[o:o + 8] = bytes(8)
+    assert a == b
