@@ -46,3 +46,50 @@ def test_oracle_equals_reference_on_random_small_inputs(orc, tmp_path_factory, c
     a, b = hashfile.parse(str(d / "r.hash")), hashfile.parse(str(d / "o.hash"))
     assert a.size == b.size
     hashfile.assert_strict_equal(a, b, table=True)
+
+
+@st.composite
+def cluster_case(draw):
+    seed = draw(st.integers(1, 10 ** 6))
+    nb = draw(st.integers(20, 160))
+    pmin = draw(st.integers(5, 60))
+    pmax = pmin + draw(st.integers(0, 80))
+    genome = draw(st.sampled_from([20_000, 40_000, 90_000]))
+    mol = draw(st.sampled_from([4_000, 9_000, 15_000]))
+    mpb = draw(st.integers(1, 6))
+    dmin = draw(st.integers(1, 6))
+    dmax = dmin + draw(st.integers(2, 120))
+    thr = draw(st.integers(1, 6))
+    cmin = draw(st.sampled_from([0, 0, 1, 3, 10]))
+    cmax = draw(st.sampled_from([0, 0, nb // 2 + 5, nb + 1]))
+    return seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr, cmin, cmax
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(case=cluster_case())
+def test_cluster_oracle_equals_reference_on_random_cases(orc, tmp_path_factory, case):
+    """--hashDepthRange + --cluster (hash10x.c:528-539,738-868): random synthetic data sets, depth ranges, thresholds
+    and code ranges through the reference binary (from a .hash with zeroed subCluster bytes) and the oracle."""
+    if orc.ref_binary() is None:
+        pytest.skip("oracle/_ref/hash10x not built (no /root/reference on this machine)")
+    import subprocess
+    seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr, cmin, cmax = case
+    p = orc.synth_params(seed=seed, n_barcodes=nb, pairs_min=pmin, pairs_max=pmax, genome_len=genome, mol_len=mol,
+                         mol_per_barcode=mpb)
+    recs = orc.synth_fqb(p)
+    d = tmp_path_factory.mktemp("cprop")
+    src, dst = str(d / "o.hash"), str(d / "r.hash")
+    assert orc.build_and_write(recs, src, B=20) == 0
+    ix = orc.build(recs, B=20)
+    if cmax > int(ix.nBlocksMax) or (cmax and cmin >= cmax):
+        cmax = 0
+    r = subprocess.run([orc.ref_binary(), "-B", "20", "-ct", str(thr), "--readHash", src, "--hashDepthRange", str(dmin),
+                        str(dmax), "--cluster", str(cmin), str(cmax), "--writeHash", dst],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref = hashfile.parse(dst)
+    _w, goff, good = orc.good_hashes(ix, dmin, dmax)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, cmin, cmax, thr)
+    assert np.array_equal(ref.blkNSub, nsub)
+    assert np.array_equal(ref.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    assert np.array_equal(ref.clusRaw, clus)
