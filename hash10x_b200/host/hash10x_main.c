@@ -209,6 +209,11 @@ static void codeStats (void)
   int max ; int *a = countHist (ix.blkNHash, ix.nBlocksMax, &max) ;
   histogramReport ("CODE_SIZE", a, max) ;
   free (a) ;
+  if (ix.blkNSubCluster)	/* only once some block has sub-clusters: arrayMax(clusterHist) > 1, hash10x.c:401 */
+    { a = countHist (ix.blkNSubCluster, ix.nBlocksMax, &max) ;
+      if (max > 1) histogramReport ("CODE_CLUSTER", a, max) ;
+      free (a) ;
+    }
 }
 
 /* ---- --hashDepthRange: hashWithinRangeBuild + goodHashesBuild, hash10x.c:528-539,738-766 ---- */

@@ -133,6 +133,14 @@ def test_cli_cluster_writes_the_reference_fields(orc, gpu_lib, tmp_path):
     assert np.array_equal(hf.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
     assert np.array_equal(hf.clusRaw, clus)
     hashfile.assert_strict_equal(hashfile.from_index(ix), hf, table=True)
+    # --codeStats after --cluster adds the CODE_CLUSTER histogram of nSubCluster (hash10x.c:388-402)
+    r = subprocess.run([exe, "-B", "20", "--readFQB", fqb, "--hashDepthRange", "4", "400", "-ct", "3", "--cluster", "0", "0",
+                        "--codeStats"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    hist = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("CODE_CLUSTER_HIST")]
+    want = np.bincount(nsub)
+    assert [int(h[2]) for h in hist] == want.tolist() and [int(h[1]) for h in hist] == list(range(want.size))
+    assert any(ln.startswith("CODE_CLUSTER_STATS MEAN") for ln in r.stdout.splitlines())
     # --cluster before --hashDepthRange: the reference's warning, not an error (hash10x.c:1258)
     r = subprocess.run([exe, "-B", "20", "--readFQB", fqb, "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "!! you must set hashDepthRange before cluster" in r.stdout
