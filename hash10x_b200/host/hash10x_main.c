@@ -28,6 +28,8 @@ static int haveIndex = 0, indexFromGpu = 0 ;
 static h10x_ctx *ctx = 0 ;
 static long totalAllocated = 0 ;
 
+static void resetDerived (void) ;	/* drops what --hashDepthRange built on the previous index */
+
 static void die (const char *format, ...)
 { va_list args ;
   va_start (args, format) ;
@@ -103,6 +105,7 @@ static void readFQB (const char *path)
   if (params.N) printf (", first %d records", params.N) ;
   printf ("\n") ;
   if (params.chunkSize <= 0) die ("chunkSize too small") ;
+  resetDerived () ;		/* the good lists may point into the context's memory */
   if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
   int st ;
   if (params.gpus > 1)		/* one thread and one context per GPU, NCCL inside the library */
@@ -134,6 +137,7 @@ static void readFQB (const char *path)
 /* ---- --readHash: readHashFile() hash10x.c:269-315; hash->code lists rebuilt as in fillHashTable ---- */
 static void readHash (const char *path)
 { char err[512] ;
+  resetDerived () ;
   int st = h10x_read_hash (path, params.B, &ix, err, sizeof (err)) ;
   if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
   haveIndex = 1 ; indexFromGpu = 0 ;
@@ -223,6 +227,11 @@ static uint16_t **goodHashes = 0 ;
 static int *nGoodHashes = 0 ;
 
 typedef struct { uint32_t depth ; uint16_t idx ; } GoodKey ;
+static void resetDerived (void)	/* a new index: the reference's initialise() starts over too (and leaks, hash10x.c:1099-1118) */
+{ free (hashWithinRange) ; hashWithinRange = 0 ; hashRangeMin = hashRangeMax = 0 ;
+  free (goodHashes) ; goodHashes = 0 ; free (nGoodHashes) ; nGoodHashes = 0 ;	/* the lists themselves: context slab or small leaks */
+}
+
 static int cmpGood (const void *a, const void *b)
 { const GoodKey *x = a, *y = b ;
   if (x->depth != y->depth) return x->depth < y->depth ? -1 : 1 ;
