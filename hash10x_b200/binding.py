@@ -112,6 +112,7 @@ def load_library():
     L.h10x_gpu_dist_info.argtypes = [vp, C.POINTER(CDistInfo)]
     L.h10x_gpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.h10x_gpu_depth_range.argtypes = [vp, C.c_int, C.c_int, C.POINTER(CGood), cp, sz]
+    L.h10x_gpu_load_index.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(CClusters), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
@@ -301,6 +302,22 @@ class Hash10xGPU:
         self._check(self.lib.h10x_gpu_depth_range(self.ctx, dmin, dmax, C.byref(cg), err, len(err)), err)
         return (_arr(cg.within, cg.hashNumber, np.uint8), _arr(cg.goodOff, cg.nBlocksMax + 1, np.uint64),
                 _arr(cg.good, cg.nGood, np.uint16))
+
+    def load_index(self, ix):
+        """make a host index (numpy arrays as in Index, with codeOff / codes) the resident one: --readHash's counterpart"""
+        keep = [np.ascontiguousarray(a) for a in (ix.hashValue, ix.hashDepth, ix.blkNRead, ix.blkNHash, ix.blkOff, ix.clus,
+                                                  ix.codeOff, ix.codes)]
+        tab = np.ascontiguousarray(ix.hashIndex) if getattr(ix, "hashIndex", None) is not None else None
+        ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
+                    tab.ctypes.data if tab is not None else None, keep[0].ctypes.data, keep[1].ctypes.data,
+                    keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data, keep[5].ctypes.data,
+                    keep[6].ctypes.data, keep[7].ctypes.data, 0, 0, None, None)
+        nsub, ptm = getattr(ix, "blkNSub", None), getattr(ix, "blkPointToMin", None)
+        if nsub is not None and ptm is not None:
+            keep += [np.ascontiguousarray(nsub, np.uint32), np.ascontiguousarray(ptm, np.float64)]
+            ci.blkNSubCluster, ci.blkPointToMin = keep[-2].ctypes.data, keep[-1].ctypes.data
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_load_index(self.ctx, C.byref(ci), err, len(err)), err)
 
     def cluster(self, code_min=0, code_max=0, threshold=5):
         """--cluster codeMin codeMax (-ct threshold) on the resident index and goodHashes ->

@@ -1686,6 +1686,47 @@ int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_i
   return h10x_gpu_download (c, out, err, errlen) ;
 }
 
+/* readHashFile()'s counterpart for the device (hash10x.c:269-315 + fillHashTable :317-347 done by the caller): a host
+   index - from h10x_read_hash, with the hash->code lists rebuilt - becomes the resident index, so that
+   --hashDepthRange and --cluster run on the GPU in a session that starts with --readHash as the README pipelines do */
+int h10x_gpu_load_index (h10x_ctx *c, const h10x_index *h, char *err, size_t errlen)
+{ if (!c || !h || h->onDevice) { set_err (err, errlen, "null or device index") ; return H10X_ERR_BAD_PARAM ; }
+  if (c->dist) { set_err (err, errlen, "not on a distributed context") ; return H10X_ERR_BAD_PARAM ; }
+  if (h->B != c->P.B) { set_err (err, errlen, "incompatible hash table size") ; return H10X_ERR_BAD_PARAM ; }
+  if (!h->hashValue || !h->hashDepth || !h->blkNRead || !h->blkNHash || !h->blkOff || (h->nHashes && !h->clusHash)
+      || h->hashNumber < 1 || h->nBlocksMax < 1)
+    { set_err (err, errlen, "incomplete index") ; return H10X_ERR_BAD_PARAM ; }
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      const size_t hn = h->hashNumber, nb = h->nBlocksMax, H = h->nHashes ;
+      /* the arrays themselves plus what --hashDepthRange needs beside them */
+      const size_t estimate = 64 * H + 32 * hn + 64 * nb + (h->hashIndex ? ((size_t) 4 << h->B) : 0) + ((size_t) 64 << 20) ;
+      with_slab (c, s, estimate, [&] ()
+	{ reset_result (c) ;
+	  MemTrack *mt = &c->mt ;
+	  auto up = [&] (auto &buf, const void *src, size_t n, size_t elem)
+	    { buf.alloc (n, s, mt) ; if (n) CK (cudaMemcpyAsync (buf.p, src, n * elem, cudaMemcpyHostToDevice, s)) ; } ;
+	  if (h->hashIndex) up (c->hashIndex, h->hashIndex, (size_t) 1 << h->B, 4) ;
+	  up (c->hashValue, h->hashValue, hn, 8) ;
+	  c->hashDepth.alloc (hn + 1, s, mt) ;		/* one spare 0 as after a build */
+	  CK (cudaMemcpyAsync (c->hashDepth.p, h->hashDepth, 4 * hn, cudaMemcpyHostToDevice, s)) ;
+	  CK (cudaMemsetAsync (c->hashDepth.p + hn, 0, 4, s)) ;
+	  up (c->blkNRead, h->blkNRead, nb, 4) ; up (c->blkNHash, h->blkNHash, nb, 4) ;
+	  up (c->blkOff, h->blkOff, nb + 1, 8) ;
+	  up (c->clus, h->clusHash, H, 8) ;
+	  if (h->codeOff && h->codes) { up (c->codeOff, h->codeOff, hn + 1, 8) ; up (c->codes, h->codes, H, 4) ; }
+	  if (h->blkNSubCluster && h->blkPointToMin)	/* what an earlier --cluster left in the file */
+	    { up (c->blkNSub, h->blkNSubCluster, nb, 4) ; up (c->blkPtm, h->blkPointToMin, nb, 8) ; }
+	  c->hashNumber = (uint32_t) hn ; c->nBlocksMax = (uint32_t) nb ; c->nReads = h->nReads ; c->nHashes = H ;
+	  CK (cudaStreamSynchronize (s)) ;
+	  c->haveIndex = true ;
+	}) ;
+    }) ;
+  if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
+  return st ;
+}
+
 int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *err, size_t errlen)
 { if (!c || !path || !out) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
   FILE *f = fopen (path, "rb") ;

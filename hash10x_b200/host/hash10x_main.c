@@ -157,6 +157,19 @@ static void readHash (const char *path)
       { uint32_t x = ix.clusHash[e].hash ; ix.codes[ix.codeOff[x] + fill[x]++] = b ; }
   free (fill) ;
   fprintf (outFile, "  filled hash table: %ld hashes from %d barcodes in %d bins\n", nHashes, (int) ix.nBlocksMax, (int) ix.hashNumber) ;
+  /* with a GPU the index moves there as well, so that --hashDepthRange and --cluster run on it as after --readFQB */
+  if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
+  if (h10x_gpu_device_count () > 0)
+    { h10x_params p ;
+      memset (&p, 0, sizeof (p)) ;
+      p.k = params.k ; p.w = params.w ; p.B = params.B ; p.N = params.N ; p.chunkSize = params.chunkSize > 0 ? params.chunkSize : 1 ;
+      p.factor1 = h10x_factor1_from_seed (params.r) ;
+      p.device = getenv ("H10X_DEVICE") ? atoi (getenv ("H10X_DEVICE")) : 0 ;
+      if (!(ctx = h10x_gpu_create (&p, err, sizeof (err)))) die ("%s", err) ;
+      st = h10x_gpu_load_index (ctx, &ix, err, sizeof (err)) ;
+      if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+      indexFromGpu = 1 ;
+    }
 }
 
 static void writeHash (const char *path)
@@ -298,14 +311,24 @@ static void clusterCodes (int codeMin, int codeMax)
       return ;
     }
   if (!(ctx && indexFromGpu))
-    die ("--cluster runs on the index that --readFQB left on the GPU: after --readHash or a multi-GPU build, write the index with --writeHash and run it in hash10x --readHash") ;
+    die ("--cluster runs on the GPU-resident index (--readFQB on one GPU, or --readHash with a GPU present): there is no CPU clustering in this program") ;
   if (!codeMin) codeMin = 1 ;
   if (!codeMax) codeMax = (int) ix.nBlocksMax ;
   char err[512] ; h10x_clusters cl ;
   int st = h10x_gpu_cluster (ctx, codeMin, codeMax, params.clusterThreshold, &cl, err, sizeof (err)) ;
   if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
-  ix.clusHash = cl.clusHash ;			/* the context's pinned copy, subCluster bytes set */
-  ix.blkNSubCluster = cl.nSubCluster ; ix.blkPointToMin = cl.pointToMin ;
+  if (ix.pinned == 0)		/* an index h10x_read_hash malloc'ed: keep its own arrays (h10x_index_free frees them) */
+    { size_t nb = ix.nBlocksMax ;
+      memcpy (ix.clusHash, cl.clusHash, 8 * (size_t) ix.nHashes) ;
+      if (!ix.blkNSubCluster) ix.blkNSubCluster = malloc (4 * nb) ;
+      if (!ix.blkPointToMin) ix.blkPointToMin = malloc (8 * nb) ;
+      if (!ix.blkNSubCluster || !ix.blkPointToMin) die ("myalloc failure") ;
+      memcpy (ix.blkNSubCluster, cl.nSubCluster, 4 * nb) ; memcpy (ix.blkPointToMin, cl.pointToMin, 8 * nb) ;
+    }
+  else
+    { ix.clusHash = cl.clusHash ;		/* the context's pinned copy, subCluster bytes set */
+      ix.blkNSubCluster = cl.nSubCluster ; ix.blkPointToMin = cl.pointToMin ;
+    }
   fprintf (outFile, "  clustered codes %d to %d\n", codeMin, codeMax) ;
   if (outFile != stdout) printf ("  clustered codes %d to %d\n", codeMin, codeMax) ;
 }

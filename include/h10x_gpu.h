@@ -142,6 +142,12 @@ int h10x_gpu_build_host (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x
 /* same, reading `path` as readFQB's fread loop does (whole 120-byte records only) */
 int h10x_gpu_build_file (h10x_ctx *ctx, const char *path, h10x_index *out, char *err, size_t errlen) ;
 
+/* readHashFile()'s counterpart for the device (hash10x.c:269-315): a HOST index (h10x_read_hash + the hash->code lists
+   the caller rebuilt as fillHashTable does, hash10x.c:317-347) becomes the context's resident index, so that
+   h10x_gpu_depth_range / h10x_gpu_cluster serve a session that starts with --readHash (README.md:29,50-51).
+   ctx must have been created with the file's B; nSubCluster / pointToMin of an earlier --cluster travel too. */
+int h10x_gpu_load_index (h10x_ctx *ctx, const h10x_index *host, char *err, size_t errlen) ;
+
 int h10x_gpu_stats (h10x_ctx *ctx, h10x_stats *out) ;
 
 /* "next" row: --hashDepthRange on the index resident after a single-GPU build.

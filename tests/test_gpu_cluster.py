@@ -144,3 +144,34 @@ def test_cli_cluster_writes_the_reference_fields(orc, gpu_lib, tmp_path):
     # --cluster before --hashDepthRange: the reference's warning, not an error (hash10x.c:1258)
     r = subprocess.run([exe, "-B", "20", "--readFQB", fqb, "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "!! you must set hashDepthRange before cluster" in r.stdout
+
+
+def test_loaded_index_clusters_like_a_built_one(orc, gpu_lib, tmp_path):
+    """--readHash's counterpart on the device (h10x_gpu_load_index): a host index, here the oracle's with the labels of an
+    earlier --cluster, becomes the resident one; --hashDepthRange / --cluster then continue from that state.  The CLI
+    does the same after --readHash when a GPU is present (the README's read-then-cluster sessions)."""
+    import hash10x_b200
+    from hash10x_b200 import binding
+    recs = _cluster_case(orc, 36, 250, 150, 300, 100_000, 10_000, 6)
+    ix = orc.build(recs, B=20)
+    within, goff, good = orc.good_hashes(ix, 6, 60)
+    c1 = orc.cluster(ix, goff, good, 0, 0, 4)
+    within2, goff2, good2 = orc.good_hashes(ix, 2, 5)         # a fresh session: the within[] flags start empty again
+    c2 = orc.cluster(ix, goff2, good2, 10, 200, 2, clus=c1[0], n_sub=c1[1], point_to_min=c1[2])
+    ix.clus, ix.blkNSub, ix.blkPointToMin = c1
+    with _gpu(B=20) as g:
+        g.load_index(ix)
+        _gw, ggoff, ggood = g.depth_range(2, 5)
+        assert np.array_equal(ggoff, goff2) and np.array_equal(ggood, good2)
+        _same(g.cluster(10, 200, 2), c2)
+    # the same through the host program: session 1 writes the clustered index, session 2 reads it and goes on
+    exe = os.path.join(os.path.dirname(hash10x_b200.__file__), "bin", "hash10x-b200")
+    s1, s2 = str(tmp_path / "s1.hash"), str(tmp_path / "s2.hash")
+    binding.write_hash(ix, s1)
+    r = subprocess.run([exe, "-B", "20", "--readHash", s1, "--hashDepthRange", "2", "5", "-ct", "2", "--cluster", "10", "200",
+                        "--codeStats", "--writeHash", s2], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "  clustered codes 10 to 200" in r.stdout
+    hf = hashfile.parse(s2)
+    assert np.array_equal(hf.blkNSub, c2[1]) and np.array_equal(hf.clusRaw, c2[0])
+    assert np.array_equal(hf.blkPointToMin.view(np.uint64), c2[2].view(np.uint64))

@@ -56,4 +56,4 @@ def test_cluster_needs_the_gpu_index(orc, tmp_path):
     assert r.returncode == 0 and "!! you must set hashDepthRange before cluster" in r.stdout
     r = subprocess.run([_exe(), "-B", "20", "--readHash", str(tmp_path / "a.hash"), "--hashDepthRange", "1", "50",
                         "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
-    assert r.returncode != 0 and "FATAL ERROR: --cluster runs on the index that --readFQB left on the GPU" in r.stderr
+    assert r.returncode != 0 and "FATAL ERROR: --cluster runs on the GPU-resident index" in r.stderr
