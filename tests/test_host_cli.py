@@ -54,6 +54,9 @@ def test_cluster_needs_the_gpu_index(orc, tmp_path):
     r = subprocess.run([_exe(), "-B", "20", "--readHash", str(tmp_path / "a.hash"), "--cluster", "0", "0"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "!! you must set hashDepthRange before cluster" in r.stdout
+    import hash10x_b200
+    if hash10x_b200.load_library().h10x_gpu_device_count() > 0:
+        return          # with a GPU the read index is loaded onto it and --cluster runs (tests/test_gpu_cluster.py)
     r = subprocess.run([_exe(), "-B", "20", "--readHash", str(tmp_path / "a.hash"), "--hashDepthRange", "1", "50",
                         "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "FATAL ERROR: --cluster runs on the GPU-resident index" in r.stderr
