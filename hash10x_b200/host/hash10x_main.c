@@ -6,11 +6,12 @@
  * errors are "FATAL ERROR: ...\n" on stderr with exit(-1) (utils.c:18-29).  --readFQB runs on the
  * GPU through libh10xgpu.so (include/h10x_gpu.h) - there is no CPU build in this program - and
  * leaves the same state behind (hash table, values, depths, block table, ClusterHash lists,
- * hash->code lists) for --writeHash, --hashStats, --codeStats and --hashDepthRange, which are O(bins)
- * / O(hashes) host passes exactly as in the reference.  --readHash loads a .hash file written by
- * either program.  --cluster (with -ct) runs on the GPU too, on the index --readFQB left there.  The research
- * probes (--clusterReport, --cribBuild, --hashExplore, ...) are out of scope and die with a
- * message saying so.
+ * hash->code lists) for --writeHash, --hashStats and --codeStats, which are O(bins) / O(blocks) host report
+ * passes exactly as in the reference.  --hashDepthRange and --cluster (with -ct) run on the GPU on the resident
+ * index and have no CPU version here.  --readHash loads a .hash file written by either program and, when a CUDA
+ * device is present, moves the index onto it so that the two commands serve read-then-cluster sessions too.  The
+ * research probes (--clusterReport, --cribBuild, --hashExplore, ...) are out of scope and
+ * die with a message saying so.
  */
 #define _GNU_SOURCE
 #include "h10x_gpu.h"
@@ -239,22 +240,15 @@ static int hashRangeMin = 0, hashRangeMax = 0 ;
 static uint16_t **goodHashes = 0 ;
 static int *nGoodHashes = 0 ;
 
-typedef struct { uint32_t depth ; uint16_t idx ; } GoodKey ;
 static void resetDerived (void)	/* a new index: the reference's initialise() starts over too (and leaks, hash10x.c:1099-1118) */
 { free (hashWithinRange) ; hashWithinRange = 0 ; hashRangeMin = hashRangeMax = 0 ;
   free (goodHashes) ; goodHashes = 0 ; free (nGoodHashes) ; nGoodHashes = 0 ;	/* the lists themselves: context slab or small leaks */
 }
 
-static int cmpGood (const void *a, const void *b)
-{ const GoodKey *x = a, *y = b ;
-  if (x->depth != y->depth) return x->depth < y->depth ? -1 : 1 ;
-  return (int) x->idx - (int) y->idx ;	/* glibc qsort is a stable merge sort: ties keep list order */
-}
-
 static void hashDepthRange (int min, int max)
 { if (!haveIndex) die ("cluster code called without setting hashDepthRange") ;
-  uint32_t i, c ;
-  if (ctx && indexFromGpu)	/* the index is still resident on the GPU: build the lists there */
+  uint32_t c ;
+  if (ctx && indexFromGpu)	/* the index is resident on the GPU: build the lists there */
     { char err[512] ; h10x_good_hashes g ;
       int st = h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
       if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
@@ -273,34 +267,8 @@ static void hashDepthRange (int min, int max)
       timeUpdate (outFile) ; fflush (outFile) ;
       return ;
     }
-  if (!(hashWithinRange && min == hashRangeMin && max == hashRangeMax))
-    { if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
-      for (i = 0 ; i < ix.hashNumber ; ++i)	/* flags are only ever set, as in the reference */
-	{ int n = (int) ix.hashDepth[i] ; if (n >= min && n < max) hashWithinRange[i] = 1 ; }
-      hashRangeMin = min ; hashRangeMax = max ;
-    }
-  goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;
-  nGoodHashes = calloc (ix.nBlocksMax, sizeof (int)) ;
-  GoodKey *keys = malloc (65536 * sizeof (GoodKey)) ;
-  for (c = 0 ; c < ix.nBlocksMax ; ++c)
-    { uint32_t nh = c ? ix.blkNHash[c] : 0 ;
-      if (nh > 65535)
-	{ nGoodHashes[c] = 0 ; goodHashes[c] = calloc (1, 2) ;
-	  fprintf (stderr, "ignoring barcode %d - too many hashes %d > %d\n", (int) c, (int) nh, 65535) ;
-	  continue ;
-	}
-      const h10x_cluster_hash *ch = ix.clusHash + ix.blkOff[c] ;
-      int n = 0 ;
-      for (i = 0 ; i < nh ; ++i)
-	if (hashWithinRange[ch[i].hash]) { keys[n].depth = ix.hashDepth[ch[i].hash] ; keys[n].idx = (uint16_t) i ; ++n ; }
-      qsort (keys, n, sizeof (GoodKey), cmpGood) ;
-      goodHashes[c] = malloc ((n ? n : 1) * 2) ;
-      for (i = 0 ; i < (uint32_t) n ; ++i) goodHashes[c][i] = keys[i].idx ;
-      nGoodHashes[c] = n ;
-    }
-  free (keys) ;
-  printf ("  made goodHashes arrays for hash range %d to %d\n  ", hashRangeMin, hashRangeMax) ;
-  timeUpdate (outFile) ; fflush (outFile) ;
+  /* no GPU-resident index (no CUDA device after --readHash, or a multi-GPU build): this program has no CPU version */
+  die ("--hashDepthRange runs on the GPU-resident index (--readFQB on one GPU, or --readHash with a GPU present); after a multi-GPU build write the index with --writeHash and read it back with --readHash") ;
 }
 
 /* ---- --cluster codeMin codeMax: hash10x.c:1241-1261, on the GPU (h10x_gpu_cluster) ---- */

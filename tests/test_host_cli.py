@@ -47,8 +47,8 @@ def test_read_hash_stats_and_rewrite_match_the_reference(orc, tmp_path):
 
 
 def test_cluster_needs_the_gpu_index(orc, tmp_path):
-    """--cluster after --readHash: the good lists exist (host --hashDepthRange) but there is no resident GPU index and
-    no CPU clustering in this program, so it dies saying so rather than falling back."""
+    """--hashDepthRange / --cluster after --readHash without a CUDA device: there is no resident GPU index and no CPU
+    version of either in this program, so it dies saying so rather than falling back."""
     assert orc.build_and_write(orc.synth_fqb(orc.synth_params(seed=3, n_barcodes=12, pairs_min=3, pairs_max=20)),
                                str(tmp_path / "a.hash"), B=20) == 0
     r = subprocess.run([_exe(), "-B", "20", "--readHash", str(tmp_path / "a.hash"), "--cluster", "0", "0"],
@@ -59,4 +59,4 @@ def test_cluster_needs_the_gpu_index(orc, tmp_path):
         return          # with a GPU the read index is loaded onto it and --cluster runs (tests/test_gpu_cluster.py)
     r = subprocess.run([_exe(), "-B", "20", "--readHash", str(tmp_path / "a.hash"), "--hashDepthRange", "1", "50",
                         "--cluster", "0", "0"], capture_output=True, text=True, timeout=600)
-    assert r.returncode != 0 and "FATAL ERROR: --cluster runs on the GPU-resident index" in r.stderr
+    assert r.returncode != 0 and "FATAL ERROR: --hashDepthRange runs on the GPU-resident index" in r.stderr
