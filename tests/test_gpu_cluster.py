@@ -175,3 +175,27 @@ def test_loaded_index_clusters_like_a_built_one(orc, gpu_lib, tmp_path):
     hf = hashfile.parse(s2)
     assert np.array_equal(hf.blkNSub, c2[1]) and np.array_equal(hf.clusRaw, c2[0])
     assert np.array_equal(hf.blkPointToMin.view(np.uint64), c2[2].view(np.uint64))
+
+
+def _cluster_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cluster.json")) as f:
+        return sorted(json.load(f).items())
+
+
+@pytest.mark.parametrize("name,d", _cluster_golden())
+def test_gpu_reproduces_reference_cluster_golden(gpu_lib, name, d):
+    """the committed digests of the REFERENCE's --hashDepthRange + --cluster output (tests/golden/make_golden_cluster.py)
+    against the CUDA path alone - no oracle involved, no /root/reference needed on the GPU box"""
+    import zlib
+    crc = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF      # noqa: E731
+    recs = np.fromfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".fqb"), np.uint32)
+    with _gpu(B=d["params"]["B"]) as g:
+        got = g.build_host(recs)
+        assert (int(got.nBlocksMax), int(got.nHashes)) == (d["nBlocksMax"], d["nHashes"])
+        g.depth_range(*d["depth_range"])
+        clus, nsub, ptm, _ms = g.cluster(d["codes"][0], d["codes"][1], d["clusterThreshold"])
+    sub = ((clus >> np.uint64(48)) & np.uint64(0xFF)).astype(np.uint8)
+    assert crc(nsub) == d["crc_blkNSub"] and crc(ptm) == d["crc_pointToMin"] and crc(sub) == d["crc_clusSub"]
+    assert crc(clus & np.uint64(0x00FFFFFFFFFFFFFF)) == d["crc_clusRaw"]
+    assert int(nsub.sum()) == d["sub_clusters"] and int((sub > 0).sum()) == d["clustered_entries"]

@@ -243,3 +243,24 @@ def test_cluster_twice_carries_state_like_the_reference(orc, tmp_path):
     assert np.array_equal(ref.blkNSub, nsub)
     assert np.array_equal(ref.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
     assert np.array_equal(ref.clusRaw, clus)
+
+
+def _cluster_golden():
+    with open(os.path.join(GOLD, "golden_cluster.json")) as f:
+        return sorted(json.load(f).items())
+
+
+@pytest.mark.parametrize("name,d", _cluster_golden())
+def test_oracle_reproduces_reference_cluster_golden(orc, name, d):
+    """golden_cluster.json (tests/golden/make_golden_cluster.py: the reference's own --readFQB / --readHash ...
+    --hashDepthRange --cluster --writeHash) against the oracle's build + good lists + clustering"""
+    crc = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF      # noqa: E731
+    recs = np.fromfile(os.path.join(GOLD, name + ".fqb"), np.uint32)
+    ix = orc.build(recs, B=d["params"]["B"])
+    assert (int(ix.nBlocksMax), int(ix.nHashes)) == (d["nBlocksMax"], d["nHashes"])
+    _w, goff, good = orc.good_hashes(ix, *d["depth_range"])
+    clus, nsub, ptm = orc.cluster(ix, goff, good, d["codes"][0], d["codes"][1], d["clusterThreshold"])
+    sub = ((clus >> np.uint64(48)) & np.uint64(0xFF)).astype(np.uint8)
+    assert crc(nsub) == d["crc_blkNSub"] and crc(ptm) == d["crc_pointToMin"] and crc(sub) == d["crc_clusSub"]
+    assert crc(clus & np.uint64(0x00FFFFFFFFFFFFFF)) == d["crc_clusRaw"]
+    assert int(nsub.sum()) == d["sub_clusters"] and int((sub > 0).sum()) == d["clustered_entries"]
