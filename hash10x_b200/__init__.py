@@ -7,4 +7,5 @@ calls the same C ABI through ctypes and never computes anything itself.  There i
 fallback: importing works anywhere, but every build call raises without the library and a GPU.
 """
 from .binding import (Hash10xGPU, H10xError, Index, Params, lib_path, load_library,  # noqa: F401
-                      factor1_from_seed, DEFAULT_FACTOR1)
+                      factor1_from_seed, DEFAULT_FACTOR1, FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES,
+                      FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL)

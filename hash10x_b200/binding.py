@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_FACTOR1 = 0x49308BB9003CB3AD  # -r 17
 
 H10X_NSTAGES = 12
-FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES, FLAG_GENERIC_ONLY = 1, 2, 4, 8
+FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES, FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL = 1, 2, 4, 8, 16
 
 
 class H10xError(RuntimeError):
@@ -44,7 +44,13 @@ class CStats(C.Structure):
                 ("nRecords", C.c_uint64), ("nMoshes", C.c_uint64), ("nHashes", C.c_uint64),
                 ("nBins", C.c_uint64), ("nBlocks", C.c_uint64), ("algorithmicBytes", C.c_uint64),
                 ("kernelLaunches", C.c_uint64), ("fusedBlocks", C.c_uint64),
-                ("genericBlocks", C.c_uint64), ("peakDeviceBytes", C.c_uint64)]
+                ("genericBlocks", C.c_uint64), ("peakDeviceBytes", C.c_uint64), ("tailPath", C.c_uint64)]
+
+
+class CDigest(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("hashIndex", "hashValue", "hashDepth", "blkNRead", "blkNHash", "clusHash",
+                                          "codes", "codeOff", "codesMissing", "codesUnordered")] + \
+               [("haveTable", C.c_int32), ("haveBins", C.c_int32), ("haveCodes", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CDistInfo(C.Structure):
@@ -100,6 +106,7 @@ def load_library():
     L.h10x_gpu_build_host.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_build_file.argtypes = [vp, cp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_stats.argtypes = [vp, C.POINTER(CStats)]
+    L.h10x_gpu_index_digest.argtypes = [vp, u64, u64, C.c_int, C.POINTER(CDigest), cp, sz]
     L.h10x_index_free.argtypes = [C.POINTER(CIndex)]
     L.h10x_host_alloc.restype = vp
     L.h10x_host_alloc.argtypes = [sz]
@@ -334,6 +341,14 @@ class Hash10xGPU:
         d = {f: getattr(cs, f) for f, _ in CStats._fields_ if f != "msStage"}
         d["msStage"] = {self.lib.h10x_stage_name(i).decode(): cs.msStage[i] for i in range(H10X_NSTAGES)}
         return d
+
+    def digest(self, block_base=0, entry_base=0, with_block_zero=True):
+        """h10x_gpu_index_digest of the resident index -> dict of ints (see include/h10x_gpu.h)"""
+        d = CDigest()
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_index_digest(self.ctx, block_base, entry_base, 1 if with_block_zero else 0,
+                                                   C.byref(d), err, len(err)), err)
+        return {f: int(getattr(d, f)) for f, _ in CDigest._fields_ if f != "reserved"}
 
     def record_moshes(self, recs):
         """K1 alone: per-record mosh hashes in generation order -> (offsets[n+1], hashes)."""

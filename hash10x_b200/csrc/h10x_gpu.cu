@@ -18,6 +18,7 @@
 #include "h10x_cluster.cuh"
 #include "h10x_bucket.cuh"
 #include "h10x_subcluster.cuh"
+#include "h10x_tail.cuh"
 
 #include <cub/cub.cuh>
 
@@ -445,6 +446,37 @@ __global__ void k_table_insert (uint32_t hashNumber, const uint64_t *__restrict_
     }
 }
 
+/* every (block, bin) of the ClusterHash lists must stand in the bin's barcode list: one CTA per block, a binary
+   search per entry (the lists are ascending); counts the misses */
+__global__ void k_check_codes (uint32_t nBlocksMax, const uint64_t *__restrict__ blkOff, const uint32_t *__restrict__ blkNHash,
+			       const uint64_t *__restrict__ clus, const uint64_t *__restrict__ codeOff, const uint32_t *__restrict__ codes,
+			       unsigned long long *__restrict__ missing)
+{ unsigned long long bad = 0 ;
+  for (uint32_t b = 1 + blockIdx.x ; b < nBlocksMax ; b += gridDim.x)
+    { const uint32_t n = blkNHash[b] ;
+      const uint64_t off = blkOff[b] ;
+      for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x)
+	{ const uint32_t id = (uint32_t) clus[off + i] ;
+	  uint64_t lo = codeOff[id], hi = codeOff[id + 1] ;
+	  while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1) ; if (codes[mid] < b) lo = mid + 1 ; else hi = mid ; }
+	  if (lo >= codeOff[id + 1] || codes[lo] != b) ++bad ;
+	}
+    }
+  if (bad) atomicAdd (missing, bad) ;
+}
+
+/* each bin's list strictly ascending and as long as its depth */
+__global__ void k_check_ascending (const uint64_t *__restrict__ codeOff, const uint32_t *__restrict__ codes,
+				   const uint32_t *__restrict__ depth, uint32_t hashNumber, unsigned long long *__restrict__ unordered)
+{ unsigned long long bad = 0 ;
+  for (uint64_t id = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ; id < hashNumber ; id += (uint64_t) gridDim.x * blockDim.x)
+    { const uint64_t a = codeOff[id], b = codeOff[id + 1] ;
+      if (b - a != depth[id]) ++bad ;
+      for (uint64_t i = a + 1 ; i < b ; ++i) if (codes[i] <= codes[i - 1]) ++bad ;
+    }
+  if (bad) atomicAdd (unordered, bad) ;
+}
+
 /* ------------------------------------------------------------------ host: parameters */
 
 static uint64_t inv64 (uint64_t a)	/* inverse of odd a modulo 2^64 (Newton) */
@@ -552,6 +584,281 @@ struct HostTrace {
     t0 = t1 ;
   }
 } ;
+
+/* ------------------------------------------------------------------ host: the hand-written tail (h10x_tail.cuh) */
+
+static int bits_for (uint64_t maxValue) { int b = 1 ; while (b < 64 && (maxValue >> b)) ++b ; return b ; }
+
+/* sub-range / range geometry for H entries whose q = hash / w is at most `top`; false = the packed 64-bit entry
+   does not fit or the keys are too coarse to be cut into shared-memory pieces (the library path runs instead) */
+static bool tail_geometry (uint64_t H, uint64_t top, uint32_t maxBlock, TailGeom &g)
+{ g.sortBits = bits_for (top) ;
+  g.blkBits = bits_for (maxBlock) ;
+  g.eShift = g.blkBits + 16 ;
+  int rem = g.sortBits ;
+  while (rem > 0 && (double) H / (double) ((top >> rem) + 1) > H10X_SR_TARGET) --rem ;
+  if ((double) H / (double) ((top >> rem) + 1) > 0.5 * H10X_SR_CAP) return false ;	/* a handful of hash values: nothing to cut */
+  int p2 = 0 ;
+  for (;;)		/* ranges x digits must cover the sub-ranges; coarser sub-ranges when they cannot */
+    { p2 = 0 ;
+      while (rem + p2 < g.sortBits && (top >> (rem + p2)) + 1 > H10X_P1_MAX_RANGES) ++p2 ;
+      if (((uint64_t) 1 << p2) <= H10X_PART_MAX_BINS) break ;
+      ++rem ;
+    }
+  if ((double) H / (double) ((top >> rem) + 1) > 0.35 * H10X_SR_CAP) return false ;	/* twice that at the dense end */
+  g.remBits = rem ; g.p2 = p2 ; g.lowBits = rem + p2 ;
+  if (g.lowBits + g.eShift > 64) return false ;
+  g.nRanges = (uint32_t) ((top >> g.lowBits) + 1) ;
+  g.nSub = g.nRanges << p2 ;
+  return true ;
+}
+
+__global__ void k_job_starts (uint64_t n, uint32_t nJobs, uint64_t chunk, uint64_t *__restrict__ jobStart)
+{ uint32_t j = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (j <= nJobs) jobStart[j] = (j == nJobs) ? n : min (n, (uint64_t) j * chunk) ;
+}
+
+__global__ void k_u64_to_u32 (const uint64_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ; if (i < n) out[i] = (uint32_t) in[i] ; }
+
+static int device_sms (h10x_ctx *c)
+{ int nSM = 148 ; CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, c->P.device)) ; return nSM ; }
+
+/* the scatter kernel for a digit width: 16 warps per CTA above 512 digits (its shared memory then allows two CTAs
+   per SM anyway), 8 warps and up to four CTAs below */
+template <class L>
+static void part_scatter_launch (h10x_ctx *c, cudaStream_t s, L ld, const uint64_t *jobStart, uint32_t nJobs, uint32_t nBins,
+				 uint64_t strideBin, uint64_t strideJob, const uint32_t *off, uint64_t *out, uint32_t grid)
+{ if (nBins > 512)
+    { auto fn = k_part_scatter<L, 16, 8, 2> ;
+      const size_t smem = h10x_part_smem (nBins, 16) ;
+      CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+      LAUNCH (c, fn, grid, 16 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out) ;
+    }
+  else
+    { auto fn = k_part_scatter<L, 8, 8, 4> ;
+      const size_t smem = h10x_part_smem (nBins, 8) ;
+      CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+      LAUNCH (c, fn, grid, 8 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out) ;
+    }
+}
+
+template <class L>
+static uint32_t part_resident_ctas (h10x_ctx *c, uint32_t nBins)
+{ int occ = 1 ;
+  if (nBins > 512)
+    { auto fn = k_part_scatter<L, 16, 8, 2> ;
+      CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_part_smem (nBins, 16))) ;
+      CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, 512, h10x_part_smem (nBins, 16))) ;
+    }
+  else
+    { auto fn = k_part_scatter<L, 8, 8, 4> ;
+      CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_part_smem (nBins, 8))) ;
+      CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, 256, h10x_part_smem (nBins, 8))) ;
+    }
+  return (uint32_t) (device_sms (c) * std::max (occ, 1)) ;
+}
+
+/* one stable partition pass over n elements seen through `ld`: out[] = the elements grouped by digit, each group
+   in input order.  Jobs are equal chunks of the input, one per resident CTA. */
+template <class L>
+static void part_pass (h10x_ctx *c, cudaStream_t s, L ld, uint64_t n, uint32_t nBins, uint64_t *out)
+{ if (!n) return ;
+  MemTrack *mt = &c->mt ;
+  const uint64_t tile = (uint64_t) (nBins > 512 ? 16 : 8) * 32 * 8 ;
+  /* one job per resident CTA: the scatter runs as a single wave */
+  uint32_t nJobs = (uint32_t) std::min<uint64_t> (part_resident_ctas<L> (c, nBins), (n + tile - 1) / tile) ;
+  uint64_t chunk = (n + nJobs - 1) / nJobs ;
+  chunk = (chunk + tile - 1) / tile * tile ;
+  nJobs = (uint32_t) ((n + chunk - 1) / chunk) ;
+  DBuf<uint64_t> jobStart ((size_t) nJobs + 1, s, mt) ;
+  LAUNCH (c, k_job_starts, gridFor (nJobs + 1, 256), 256, 0, s, n, nJobs, chunk, jobStart.p) ;
+  const size_t nh = (size_t) nBins * nJobs ;
+  DBuf<uint32_t> hist (nh + 1, s, mt) ;
+  CK (cudaMemsetAsync (hist.p + nh, 0, 4, s)) ;
+  LAUNCH (c, k_part_hist<L>, nJobs, 512, (size_t) nBins * 4, s, ld, jobStart.p, nJobs, nBins, (uint64_t) nJobs, (uint64_t) 1, hist.p) ;
+  cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, hist.p, hist.p, nh + 1, s) ; }) ;
+  part_scatter_launch (c, s, ld, jobStart.p, nJobs, nBins, (uint64_t) nJobs, (uint64_t) 1, hist.p, out, nJobs) ;
+}
+
+struct TailSrc {	/* what the mosh stages left behind */
+  uint32_t nProcBlk, blkBase ;
+  const uint64_t *srcOff ; const uint32_t *blkCnt ; const uint64_t *scratch, *gHash ; const uint32_t *gRec, *blkStart ;
+  uint64_t wInvFull, wDiv ;
+} ;
+
+/* P1: the entries, range-major, as packed words (stage "dedup") */
+static void tail_p1 (h10x_ctx *c, cudaStream_t s, const TailGeom &g, const TailSrc &in, uint64_t H,
+		     DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart)
+{ MemTrack *mt = &c->mt ;
+  const int nSM = device_sms (c) ;
+  uint32_t G = (uint32_t) (((uint64_t) in.nProcBlk * g.nRanges + ((1u << 24) - 1)) >> 24) ;
+  if (G < 1) G = 1 ;
+  const uint32_t nTiles = (in.nProcBlk + G - 1) / G ;
+  const size_t nc = (size_t) g.nRanges * nTiles ;
+  DBuf<uint32_t> cnt (nc + 1, s, mt) ;
+  CK (cudaMemsetAsync (cnt.p + nc, 0, 4, s)) ;
+  LAUNCH (c, k_p1_count, std::min<uint32_t> (nTiles, (uint32_t) nSM * 8), 256, (size_t) g.nRanges * 4, s, in.nProcBlk, G, nTiles,
+	  g.nRanges, g.lowBits, in.srcOff, in.blkCnt, in.scratch, in.gHash, in.wInvFull, cnt.p) ;
+  cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, cnt.p, cnt.p, nc + 1, s) ; }) ;
+  rangeStart.alloc ((size_t) g.nRanges + 1, s, mt) ;
+  LAUNCH (c, k_p1_range_start, gridFor (g.nRanges + 1, 256), 256, 0, s, g.nRanges, nTiles, cnt.p, H, rangeStart.p) ;
+  B.alloc (H, s, mt) ;
+  const size_t smem = (size_t) g.nRanges * (8 * H10X_RING_STRIDE + 12) + 16 ;
+  CK (cudaFuncSetAttribute (k_p1_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+  const uint32_t grid = std::min<uint32_t> (nTiles, (uint32_t) nSM) ;
+  LAUNCH (c, k_p1_place, grid, H10X_P1_THREADS, smem, s, in.nProcBlk, G, nTiles, g.nRanges, g.lowBits, g.eShift, in.srcOff,
+	  in.blkCnt, cnt.p, in.scratch, in.gHash, in.gRec, in.blkStart, in.blkBase, in.wInvFull, B.p) ;
+}
+
+/* P2, sub-range sort, bin ids, codes, ClusterHash lists: everything after P1.  Leaves hashValue / hashDepth /
+   hashNumber / codeOff / codes / clus in the context; returns the number of bins. */
+static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint64_t H, uint64_t wDiv,
+			   DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart)
+{ MemTrack *mt = &c->mt ;
+  const h10x_params &P = c->P ;
+  const int nSM = device_sms (c) ;
+  const uint32_t blkMask = (uint32_t) ((((uint64_t) 1) << g.blkBits) - 1) ;
+  DBuf<uint64_t> A ;
+  DBuf<uint32_t> srStart ((size_t) g.nSub + 1, s, mt), stage, nHeads ((size_t) g.nSub + 1, s, mt) ;
+  uint32_t D = 0 ;
+  { StageTimer tm (c, s, ST_HASHSORT) ;
+    if (g.p2 > 0)
+      { const uint32_t nBins = 1u << g.p2 ;
+	LoadWord ld = { B.p, g.eShift + g.remBits, nBins - 1u, ~(uint64_t) 0 } ;
+	CK (cudaMemsetAsync (srStart.p + g.nSub, 0, 4, s)) ;
+	LAUNCH (c, k_part_hist<LoadWord>, std::min<uint32_t> (g.nRanges, (uint32_t) nSM * 8), 512, (size_t) nBins * 4, s, ld, rangeStart.p,
+		g.nRanges, nBins, (uint64_t) 1, (uint64_t) nBins, srStart.p) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, srStart.p, srStart.p, (size_t) g.nSub + 1, s) ; }) ;
+	A.alloc (H, s, mt) ;
+	part_scatter_launch (c, s, ld, rangeStart.p, g.nRanges, nBins, (uint64_t) 1, (uint64_t) nBins, srStart.p, A.p,
+			     std::min<uint32_t> (g.nRanges, part_resident_ctas<LoadWord> (c, nBins))) ;
+	B.release () ;
+      }
+    else
+      { LAUNCH (c, k_u64_to_u32, gridFor (g.nSub + 1, 256), 256, 0, s, rangeStart.p, g.nSub + 1, srStart.p) ;
+	A.swap (B) ;
+      }
+    rangeStart.release () ;
+    /* sub-range sort + first entries */
+    stage.alloc (H, s, mt) ;
+    DBuf<uint32_t> overList ((size_t) g.nSub, s, mt), jobList ((size_t) g.nSub, s, mt) ; DBuf<unsigned int> counters (3, s, mt) ;
+    CK (cudaMemsetAsync (counters.p, 0, 12, s)) ;
+    CK (cudaMemsetAsync (nHeads.p, 0, 4 * ((size_t) g.nSub + 1), s)) ;
+    SrArgs sa ;
+    sa.A = A.p ; sa.srStart = srStart.p ; sa.stage = stage.p ; sa.nHeads = nHeads.p ; sa.overList = overList.p ; sa.jobList = jobList.p ;
+    sa.nOver = counters.p ; sa.ticket = counters.p + 1 ; sa.nJobs = counters.p + 2 ; sa.nSub = g.nSub ;
+    sa.cap = H10X_SR_CAP ;
+    if (const char *e = getenv ("H10X_SR_CAP")) { long v = atol (e) ; if (v >= 1 && v < (long) H10X_SR_CAP) sa.cap = (uint32_t) v ; }	/* tests: force the big-sub-range path */
+    sa.groupCap = std::min<uint32_t> (H10X_SR_GROUP, sa.cap) ; sa.maxLog = (uint32_t) std::min (2, g.p2) ;
+    sa.eShift = g.eShift ; sa.remBits = g.remBits ;
+    LAUNCH (c, k_sr_jobs, gridFor (((uint64_t) g.nSub + 3) / 4, 256), 256, 0, s, sa) ;
+    const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (H10X_SR_THREADS / 32) * 2 << H10X_SR_DIGIT) + 16 ;
+    CK (cudaFuncSetAttribute (k_sr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+    int occ = 1 ;
+    CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_sr_sort, H10X_SR_THREADS, smem)) ;
+    if (occ < 1) occ = 1 ;
+    LAUNCH (c, k_sr_sort, std::min<uint32_t> (g.nSub, (uint32_t) (nSM * occ)), H10X_SR_THREADS, smem, s, sa) ;
+    unsigned int nOver = 0 ;
+    CK (cudaMemcpyAsync (&nOver, counters.p, 4, cudaMemcpyDeviceToHost, s)) ;
+    CK (cudaStreamSynchronize (s)) ;
+    if (nOver)
+      { std::vector<uint32_t> over (nOver), st2 ((size_t) g.nSub + 1) ;
+	CK (cudaMemcpyAsync (over.data (), overList.p, 4 * (size_t) nOver, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaMemcpyAsync (st2.data (), srStart.p, 4 * ((size_t) g.nSub + 1), cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	for (uint32_t j : over)
+	  { const uint64_t n = st2[j + 1] - st2[j] ;
+	    DBuf<uint64_t> tmp (n, s, mt) ;
+	    /* the whole word orders a sub-range: q bits, then block (one entry per (hash, block)) */
+	    cubCall (c, s, [&] (void *t, size_t &b)
+	      { return cub::DeviceRadixSort::SortKeys (t, b, A.p + st2[j], tmp.p, n, 16, g.eShift + g.remBits, s) ; }) ;
+	    CK (cudaMemcpyAsync (A.p + st2[j], tmp.p, 8 * n, cudaMemcpyDeviceToDevice, s)) ;
+	    LAUNCH (c, k_sr_heads_big, 1, 512, 0, s, sa, j) ;
+	  }
+	c->stats.genericBlocks += 0 ;
+      }
+  }
+  DBuf<uint32_t> segStart, idOfSeg ;
+  { StageTimer tm (c, s, ST_BINIDS) ;
+    DBuf<uint32_t> binBase ((size_t) g.nSub + 1, s, mt) ;
+    cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, nHeads.p, binBase.p, (size_t) g.nSub + 1, s) ; }) ;
+    CK (cudaMemcpyAsync (&D, binBase.p + g.nSub, 4, cudaMemcpyDeviceToHost, s)) ;
+    CK (cudaStreamSynchronize (s)) ;
+    if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
+      throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
+    segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
+    DBuf<uint64_t> fkey (D, s, mt), fkey2 (D, s, mt), hvHash (D, s, mt) ;
+    LAUNCH (c, k_heads_compact, (uint32_t) std::min<uint64_t> (((uint64_t) g.nSub * 32 + 255) / 256, (uint64_t) nSM * 16), 256, 0, s, g.nSub,
+	    srStart.p, nHeads.p, binBase.p, stage.p, A.p, g.eShift, g.lowBits, g.p2, blkMask, wDiv, segStart.p, fkey.p, hvHash.p) ;
+    const uint32_t H32 = (uint32_t) H ;
+    CK (cudaMemcpyAsync (segStart.p + D, &H32, 4, cudaMemcpyHostToDevice, s)) ;	/* pageable source: copied before the call returns */
+    stage.release () ; nHeads.release () ; binBase.release () ; srStart.release () ;
+    /* bins stand in hash order; the id order is (first block, hash): stable passes on the first block */
+    const int b1 = g.blkBits <= 9 ? g.blkBits : (g.blkBits + 1) / 2, b2 = g.blkBits - b1 ;
+    if (b1 > 11) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^22 barcode blocks") ;
+    const uint64_t *sorted = nullptr ;
+    { LoadWord l1 = { fkey.p, 32, (1u << b1) - 1u, ~(uint64_t) 0 } ;
+      part_pass (c, s, l1, D, 1u << b1, fkey2.p) ;
+      sorted = fkey2.p ;
+      if (b2 > 0)
+	{ LoadWord l2 = { fkey2.p, 32 + b1, (1u << b2) - 1u, ~(uint64_t) 0 } ;
+	  part_pass (c, s, l2, D, 1u << b2, fkey.p) ;
+	  sorted = fkey.p ;
+	}
+    }
+    c->hashNumber = D + 1 ;
+    c->hashValue.alloc ((size_t) D + 1, s, mt) ;
+    c->hashDepth.alloc ((size_t) D + 2, s, mt) ;	/* one spare 0 so the scan yields codeOff[hashNumber] */
+    CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+    CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
+    CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
+    LAUNCH (c, k_bins_by_rank_e, gridFor (D, 256), 256, 0, s, D, sorted, segStart.p, hvHash.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+  }
+  early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ;
+  early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ;
+  const size_t hn = c->hashNumber ;
+  DBuf<uint64_t> idRead (H, s, mt) ;
+  { StageTimer tm (c, s, ST_CODES) ;
+    c->codeOff.alloc (hn + 1, s, mt) ;
+    c->codes.alloc (H, s, mt) ;
+    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
+    cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+    LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, idOfSeg.p, A.p, blkMask,
+	    c->codeOff.p, c->codes.p, idRead.p) ;
+  }
+  A.release () ; segStart.release () ; idOfSeg.release () ;
+  if (!(P.flags & H10X_FLAG_NO_CODES))
+    { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
+  c->clus.alloc (H, s, mt) ;
+  { StageTimer tm (c, s, ST_CLUSTERS) ;
+    /* stable partition of the bin-major (id, read) words by block number, lowest digit first.  The block bits
+       not yet used ride in the free top 16 bits of the word. */
+    const int nP = (g.blkBits + 9) / 10 ;	/* 512-1024 digits per pass: the rings absorb everything; with few digits most
+						   entries overflow them and take the slow direct path (3 passes of 6-7 bits: 50 ms) */
+    int bits[4] = { 0, 0, 0, 0 } ;
+    for (int i = 0, left = g.blkBits ; i < nP ; ++i) { bits[i] = (left + (nP - i) - 1) / (nP - i) ; left -= bits[i] ; }
+    LoadCodes l1 = { c->codes.p, idRead.p, (1u << bits[0]) - 1u, bits[0] } ;
+    if (nP == 1) part_pass (c, s, l1, H, 1u << bits[0], c->clus.p) ;
+    else
+      { DBuf<uint64_t> X (H, s, mt), Y ;
+	part_pass (c, s, l1, H, 1u << bits[0], X.p) ;
+	idRead.release () ;
+	uint64_t *src = X.p ;
+	int shift = 48 ;
+	for (int i = 1 ; i < nP ; ++i)
+	  { const bool last = (i == nP - 1) ;
+	    uint64_t *dst = last ? c->clus.p : (src == X.p ? (Y.alloc (H, s, mt), Y.p) : X.p) ;
+	    LoadWord lw = { src, shift, (1u << bits[i]) - 1u, last ? 0x0000ffffffffffffull : ~(uint64_t) 0 } ;
+	    part_pass (c, s, lw, H, 1u << bits[i], dst) ;
+	    shift += bits[i] ; src = dst ;
+	  }
+      }
+  }
+  if (P.flags & H10X_FLAG_NO_CODES) { c->codes.release () ; c->codeOff.release () ; }
+  early_pull (c, s, SLOT_CLUS, c->clus.p, 8 * H) ;
+  return D ;
+}
 
 static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
 		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
@@ -839,15 +1146,27 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   /* single-GPU: bucket-major (key, value) pairs (h10x_bucket.cuh); multi-GPU: block-major hash / read / block arrays */
   int blkBits = 1 ; while (((uint64_t) 1 << blkBits) < (uint64_t) nBlk + 2) ++blkBits ;
   const int nbBits = sortBits > 32 ? sortBits - 32 : 0 ;
-  const bool bucketed = !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
+  /* single-GPU: the hand-written tail (h10x_tail.cuh) whenever its packed 64-bit entry fits; the library-sort tail
+     of round 1 stays as the general path (multi-GPU, very wide hashes) and as a cross-check (H10X_FLAG_LEGACY_TAIL) */
+  TailGeom tg ; memset (&tg, 0, sizeof (tg)) ;
+  const uint64_t topQ = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
+  const bool tail2 = !dist && H > 0 && !(P.flags & H10X_FLAG_LEGACY_TAIL) && !getenv ("H10X_LEGACY_TAIL")
+    && tail_geometry (H, topQ, blkBase + nProcBlk, tg) ;
+  c->stats.tailPath = tail2 ? 2 : 1 ;
+  const bool bucketed = !tail2 && !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
   uint32_t nBuck = 1 ;
   std::vector<uint64_t> hBucketBase ;
   DBuf<uint64_t> eHash, eBR, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk, key32 ;
+  DBuf<uint64_t> tailB, tailRangeStart ;
   if (dist) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
-  else if (!bucketed) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
+  else if (!bucketed && !tail2) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
-    if (bucketed)
+    if (tail2)
+      { TailSrc in = { nProcBlk, blkBase, srcOff.p, blkCnt.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, wInvFull, wDiv } ;
+	tail_p1 (c, s, tg, in, H, tailB, tailRangeStart) ;
+      }
+    else if (bucketed)
       { uint64_t top = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
 	nBuck = (uint32_t) (top >> 32) + 1 ;
 	const size_t nCnt = (size_t) nBuck * nProcBlk ;
@@ -883,8 +1202,9 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   if (dist) entryId.alloc (H, s, mt) ;
   DBuf<uint32_t> se, segIncl, segStart, idOfSeg, sk ;
   DBuf<uint64_t> sv ;
-  if (!bucketed) segIncl.alloc (H, s, mt) ;
-  if (bucketed)
+  if (!bucketed && !tail2) segIncl.alloc (H, s, mt) ;
+  if (tail2) D = tail_rest (c, s, tg, H, wDiv, tailB, tailRangeStart) ;
+  else if (bucketed)
     { sk.alloc (H, s, mt) ; sv.alloc (H, s, mt) ;
       { StageTimer tm (c, s, ST_HASHSORT) ;
 	const int endBit = std::min (32, sortBits) ;
@@ -983,7 +1303,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       dist_bins (c, s, 0, nullptr, nullptr, nullptr, 0, segStart.p, nullptr, nBlkGlobal, nullptr, D, wDiv) ;
     }
 
-  if (!dist) { early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ; early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ; }
+  if (!dist && !tail2) { early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ; early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ; }
   tr.mark ("bins-enq") ;
   /* ---------------- hash -> code CSR ---------------- */
   if (dist)
@@ -997,7 +1317,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       CK (cudaMemcpyAsync (c->localCodeOff.p, segStart.p, 4 * ((size_t) Dl + 1), cudaMemcpyDeviceToDevice, s)) ;
       if (H) LAUNCH (c, k_gather_u32, gridFor (H, 256), 256, 0, s, H, se.p, entryBlk.p, c->localCodes.p) ;
     }
-  else
+  else if (!tail2)
     { /* codes (bin-major block lists) are needed as the sort key even under H10X_FLAG_NO_CODES */
       size_t hn = c->hashNumber ;
       DBuf<uint64_t> idRead (H, s, mt) ;
@@ -1911,6 +2231,49 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 
 int h10x_gpu_stats (h10x_ctx *c, h10x_stats *out)
 { if (!c || !out) return H10X_ERR_BAD_PARAM ; *out = c->stats ; return H10X_OK ; }
+
+/* position-salted sum digests (h10x_digest.h) of the resident index, computed where it lies; and the check that
+   codes[] is exactly the transposition of the ClusterHash lists (fillHashTable, hash10x.c:317-347) */
+int h10x_gpu_index_digest (h10x_ctx *c, uint64_t blockBase, uint64_t entryBase, int withBlockZero, h10x_digest *out,
+			   char *err, size_t errlen)
+{ if (!c || !out || !c->haveIndex) { set_err (err, errlen, "no index resident") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      CK (cudaStreamSynchronize (s)) ;
+      const size_t hn = c->hashNumber, nb = c->nBlocksMax, H = c->nHashes ;
+      unsigned long long *acc = nullptr ;
+      CK (cudaMalloc ((void**) &acc, 16 * sizeof (unsigned long long))) ;
+      struct Free { void *p ; ~Free () { cudaFree (p) ; } } freer { acc } ;
+      CK (cudaMemsetAsync (acc, 0, 16 * sizeof (unsigned long long), s)) ;
+      const int grid = 148 * 8 ;
+      const uint64_t all = ~(uint64_t) 0 ;
+      if (c->hashIndex.p) k_digest<uint32_t><<<grid, 256, 0, s>>> (c->hashIndex.p, (uint64_t) 1 << c->P.B, 0, all, acc + 0) ;
+      if (c->hashValue.p) k_digest<uint64_t><<<grid, 256, 0, s>>> (c->hashValue.p, hn, 0, all, acc + 1) ;
+      if (c->hashDepth.p) k_digest<uint32_t><<<grid, 256, 0, s>>> (c->hashDepth.p, hn, 0, all, acc + 2) ;
+      const size_t i0 = withBlockZero ? 0 : 1 ;
+      if (nb > i0)
+	{ k_digest<uint32_t><<<grid, 256, 0, s>>> (c->blkNRead.p + i0, nb - i0, blockBase + i0, all, acc + 3) ;
+	  k_digest<uint32_t><<<grid, 256, 0, s>>> (c->blkNHash.p + i0, nb - i0, blockBase + i0, all, acc + 4) ;
+	}
+      if (H) k_digest<uint64_t><<<grid, 256, 0, s>>> (c->clus.p, H, entryBase, H10X_DG_CLUS_MASK, acc + 5) ;
+      if (c->codes.p && c->codeOff.p && !c->dist)
+	{ if (H) k_digest<uint32_t><<<grid, 256, 0, s>>> (c->codes.p, H, 0, all, acc + 6) ;
+	  k_digest<uint64_t><<<grid, 256, 0, s>>> (c->codeOff.p, hn + 1, 0, all, acc + 7) ;
+	  k_check_codes<<<(unsigned) std::min<size_t> (nb, 148 * 16), 256, 0, s>>> ((uint32_t) nb, c->blkOff.p, c->blkNHash.p, c->clus.p, c->codeOff.p, c->codes.p, acc + 8) ;
+	  if (H > 1) k_check_ascending<<<grid, 256, 0, s>>> (c->codeOff.p, c->codes.p, c->hashDepth.p, (uint32_t) hn, acc + 9) ;
+	  out->haveCodes = 1 ;
+	}
+      CK (cudaGetLastError ()) ;
+      unsigned long long h[16] ;
+      CK (cudaMemcpyAsync (h, acc, sizeof (h), cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      out->hashIndex = h[0] ; out->hashValue = h[1] ; out->hashDepth = h[2] ; out->blkNRead = h[3] ; out->blkNHash = h[4] ;
+      out->clusHash = h[5] ; out->codes = h[6] ; out->codeOff = h[7] ; out->codesMissing = h[8] ; out->codesUnordered = h[9] ;
+      out->haveTable = c->hashIndex.p ? 1 : 0 ; out->haveBins = c->hashValue.p ? 1 : 0 ;
+    }) ;
+}
 
 void *h10x_host_alloc (size_t bytes)
 { void *p = nullptr ; if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError () ; return nullptr ; } return p ; }

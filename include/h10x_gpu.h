@@ -54,6 +54,7 @@ typedef struct h10x_params {
 #define H10X_FLAG_NO_TABLE	2u	/* skip hashIndex[] materialisation (hashIndex stays NULL) */
 #define H10X_FLAG_NO_CODES	4u	/* skip the hash->code CSR (fillHashTable) */
 #define H10X_FLAG_GENERIC_ONLY	8u	/* force the generic (global-memory) sort path for every block */
+#define H10X_FLAG_LEGACY_TAIL	16u	/* group / transpose with the library radix sort (round-1 tail) instead of h10x_tail.cuh */
 
 /* ClusterHash of hash10x.c:35-43, 8 bytes; subCluster and flags are written as 0 */
 typedef struct h10x_cluster_hash {
@@ -104,6 +105,7 @@ typedef struct h10x_stats {
   uint64_t kernelLaunches ;	/* kernels launched by the last build (ours + CUB's) */
   uint64_t fusedBlocks, genericBlocks ;	/* barcode blocks taken by each mosh path */
   uint64_t peakDeviceBytes ;
+  uint64_t tailPath ;		/* 2 = hand-written tail (h10x_tail.cuh), 1 = library-sort tail */
 } h10x_stats ;
 
 typedef struct h10x_ctx h10x_ctx ;
@@ -149,6 +151,22 @@ int h10x_gpu_build_file (h10x_ctx *ctx, const char *path, h10x_index *out, char 
 int h10x_gpu_load_index (h10x_ctx *ctx, const h10x_index *host, char *err, size_t errlen) ;
 
 int h10x_gpu_stats (h10x_ctx *ctx, h10x_stats *out) ;
+
+/* Verification of the resident index at sizes where copying it out would dominate: position-salted sum digests
+   (hash10x_b200/csrc/h10x_digest.h: sum over i of mix(mix(base+i) ^ A[i]) mod 2^64) of every array that
+   writeHashFile stores (hash10x.c:244-267), computed on the device.  A rank of a multi-GPU build passes the global
+   number of its block 0 (blockBase) and of its first ClusterHash entry (entryBase) and withBlockZero = 0 on all
+   ranks but the first; the per-rank digests then simply add up to the digest of the stitched arrays.  On a
+   single-GPU index codesMissing / codesUnordered also count (block, bin) pairs of the ClusterHash lists absent from
+   the bin's barcode list, and bins whose list is not strictly ascending or not hashDepth long: both 0 means
+   codes[] is exactly what fillHashTable (hash10x.c:317-347) builds. */
+typedef struct h10x_digest {
+  uint64_t hashIndex, hashValue, hashDepth, blkNRead, blkNHash, clusHash, codes, codeOff ;
+  uint64_t codesMissing, codesUnordered ;
+  int32_t haveTable, haveBins, haveCodes, reserved ;
+} h10x_digest ;
+int h10x_gpu_index_digest (h10x_ctx *ctx, uint64_t blockBase, uint64_t entryBase, int withBlockZero, h10x_digest *out,
+			   char *err, size_t errlen) ;
 
 /* "next" row: --hashDepthRange on the index resident after a single-GPU build.
    hashWithinRangeBuild (hash10x.c:528-539): within[bin] is SET when min <= depth < max (flags accumulate over

@@ -72,6 +72,10 @@ def lib():
         L.orc_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_cluster_stale_labels.restype = C.c_uint64
+        L.orc_digest_u32.restype = C.c_uint64
+        L.orc_digest_u32.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_digest_u64.restype = C.c_uint64
+        L.orc_digest_u64.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
         L.synth_layout.restype = C.c_uint64
         L.synth_layout.argtypes = [C.POINTER(SynthParams), C.c_void_p]
         L.synth_fill.argtypes = [C.POINTER(SynthParams), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -285,3 +289,24 @@ def run_reference(fqb_path, hash_path=None, B=24, extra=(), k=None, w=None, r=No
         cmd += ["--writeHash", hash_path]
     cmd += list(extra)
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+def digest(a, base=0, mask=0xFFFFFFFFFFFFFFFF):
+    """position-salted sum digest (hash10x_b200/csrc/h10x_digest.h) of a uint32 / uint64 array on the host"""
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32:
+        return int(lib().orc_digest_u32(a.ctypes.data, a.size, base))
+    assert a.dtype == np.uint64, a.dtype
+    return int(lib().orc_digest_u64(a.ctypes.data, a.size, base, mask))
+
+
+def index_digests(ix):
+    """the digests h10x_gpu_index_digest reports, computed from an Index on the host"""
+    d = {"hashValue": digest(ix.hashValue), "hashDepth": digest(ix.hashDepth), "blkNRead": digest(ix.blkNRead),
+         "blkNHash": digest(ix.blkNHash), "clusHash": digest(ix.clus, mask=0x0000FFFFFFFFFFFF)}
+    if getattr(ix, "hashIndex", None) is not None:
+        d["hashIndex"] = digest(ix.hashIndex)
+    if getattr(ix, "codes", None) is not None:
+        d["codes"] = digest(ix.codes)
+        d["codeOff"] = digest(ix.codeOff)
+    return d
