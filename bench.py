@@ -10,6 +10,13 @@ left in HBM) with CUDA events; `e2e` times the same build through the C ABI's ho
 N=1 workload is BASELINE.json configs[2] ("1 Gb diploid genome at 60x, ~200M read pairs, 24 GB
 FQB, -B 28, 1xB200"), the largest single-GPU configuration; inputs are far larger than the 126 MB L2.
 
+After the timed region the index that was just built is CHECKED: h10x_gpu_index_digest (device-side
+position-salted sums of every array writeHashFile stores) against tests/golden/golden_scale.json, which holds the
+same digests of the `.hash` the UNMODIFIED reference binary wrote for the same data set ("parity" in the line;
+at N > 1 the per-rank digests add up to the digest of the stitched arrays).  At N=1 the line also carries
+`weak_base` (the same build on one GPU's share of the N>1 workload, so that the 1->8 curve can be read on one
+workload), and the rows that follow the build on the resident index: --hashDepthRange and --cluster.
+
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/hash10x compiled from
 the unmodified reference; the oracle port if that binary is missing) on a bounded sample of the same
 workload on this box's host cores.  --readFQB is single-threaded in the reference even with -DOMP.
@@ -27,6 +34,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json's metric, verbatim, in BOTH arms (the driver divides one arm's value by the other's only when
+# metric, unit and direction agree)
+METRIC = "read pairs/sec through --readFQB minhash+index build; % of HBM roofline"
+UNIT = "read pairs/s"
+
 WORKLOADS = {
     # name: genome, barcodes, pairs/barcode range, molecules, mol len, snp period, err rate, B
     "1gb": dict(genome_len=1_000_000_000, n_barcodes=500_000, pairs_min=300, pairs_max=500,
@@ -36,6 +48,7 @@ WORKLOADS = {
                      "per pair and the reference itself dies with 'hashTableSize is too small' at -B 28)"),
     "yeast": dict(genome_len=12_000_000, n_barcodes=10_000, pairs_min=150, pairs_max=350,
                   mol_per_barcode=10, mol_len=50_000, snp_period=500, err_rate=0.004, B=24, read_len=151,
+                  depth_range=(10, 100),
                   desc="BASELINE configs[1]: synthetic yeast-scale diploid (12 Mb, ~2.5M read pairs, 10k barcodes, 60x), -B 24"),
     "gb10th": dict(genome_len=100_000_000, n_barcodes=50_000, pairs_min=300, pairs_max=500,
                    mol_per_barcode=10, mol_len=50_000, snp_period=1000, err_rate=0.0005, B=26, read_len=160,
@@ -135,10 +148,19 @@ def cpu_sample(orc, wl, sample_pairs):
     nb = int(np.searchsorted(off, sample_pairs, side="left"))
     nb = max(2, min(nb, p.nBarcodes))
     r1 = int(off[nb])
-    return orc.synth_fqb(p, 0, r1), nb
+    return orc.synth_fqb(p, 0, r1), nb, n
 
 
-def time_reference(orc, recs, B, threads_note=True):
+def _run(cmd):
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference failed: " + (r.stderr or r.stdout)[-300:])
+    return dt
+
+
+def time_reference(orc, recs, B):
     """Seconds for the reference's --readFQB step on recs; kind 'reference' when oracle/_ref exists."""
     exe = orc.ref_binary("hash10x")
     if exe is None:
@@ -148,12 +170,52 @@ def time_reference(orc, recs, B, threads_note=True):
     with tempfile.NamedTemporaryFile(suffix=".fqb", dir=shm) as f:
         recs.tofile(f)
         f.flush()
-        t0 = time.perf_counter()
-        r = subprocess.run([exe, "-B", str(B), "--readFQB", f.name], capture_output=True, text=True)
-        dt = time.perf_counter() - t0
-    if r.returncode != 0:
-        raise RuntimeError("reference failed: " + r.stderr[-300:])
+        dt = _run([exe, "-B", str(B), "--readFQB", f.name])
     return dt, "reference", "oracle/_ref/hash10x (unmodified reference, gcc -O3), wall clock of `-B %d --readFQB`" % B
+
+
+def cluster_like_for_like(orc, gpu_factory, torch, gsynth, stream):
+    """--hashDepthRange + --cluster on BASELINE configs[1] (the README's yeast case, where the reference quotes
+    '5 minutes'): the whole data set on the GPU and on the host's cores with the reference's -DOMP build (its only
+    OpenMP region is this loop, hash10x.c:1247).  The CPU commands run on a `.hash` the reference wrote, each timed
+    as the difference of two command chains."""
+    wl = WORKLOADS["yeast"]
+    dmin, dmax, ct = wl["depth_range"] + (5,)
+    p = synth_params(gsynth, wl, seed=3)
+    n, off = gsynth.layout(p)
+    fq = torch.empty(n * 30, dtype=torch.int32, device="cuda:%d" % torch.cuda.current_device())
+    gsynth.fill_device(p, off, 0, n, fq.data_ptr())
+    torch.cuda.synchronize()
+    out = {"workload": wl["desc"], "pairs": int(n), "hashDepthRange": [dmin, dmax], "clusterThreshold": ct}
+    with gpu_factory(wl["B"]) as g:
+        g.build_device(fq.data_ptr(), n, stream.cuda_stream)
+        t0 = time.perf_counter()
+        n_good = g.depth_range(dmin, dmax, copy=False)
+        t1 = time.perf_counter()
+        _c, nsub, _p, ms_kernel = g.cluster(0, 0, ct, copy=False)
+        out.update({"build_ms": g.stats()["msTotal"], "good_hashes": int(n_good), "depth_range_ms": (t1 - t0) * 1e3,
+                    "cluster_ms": ms_kernel, "sub_clusters": int(nsub.sum())})
+    exe, omp = orc.ref_binary("hash10x"), orc.ref_binary("hash10x_omp")
+    if exe and omp:
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        with tempfile.TemporaryDirectory(dir=shm) as d:
+            path, hsh = os.path.join(d, "y.fqb"), os.path.join(d, "y.hash")
+            host = torch.empty(n * 30, dtype=torch.int32)
+            host.copy_(fq)
+            host.numpy().tofile(path)
+            t_build = _run([exe, "-B", str(wl["B"]), "--readFQB", path, "--writeHash", hsh])
+            base = [omp, "-B", str(wl["B"]), "--readHash", hsh]
+            t_a = _run(base)
+            t_b = _run(base + ["--hashDepthRange", str(dmin), str(dmax)])
+            t_c = _run(base + ["--hashDepthRange", str(dmin), str(dmax), "-ct", str(ct), "--cluster", "0", "0"])
+        out["cpu_baseline"] = {"binary": "oracle/_ref/hash10x_omp (-DOMP -fopenmp)", "threads": os.cpu_count(),
+                               "readFQB_writeHash_s": t_build, "hashDepthRange_s": max(t_b - t_a, 0.0),
+                               "cluster_s": max(t_c - t_b, 0.0),
+                               "how": "wall clock of `--readHash ... <command>` minus the same chain without the command"}
+        if out["cpu_baseline"]["cluster_s"] > 0:
+            out["cluster_speedup_vs_omp"] = out["cpu_baseline"]["cluster_s"] * 1e3 / max(ms_kernel, 1e-6)
+    del fq
+    return out
 
 
 def run_reference_arm(args, wl):
@@ -161,37 +223,121 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    recs, nb = cpu_sample(orc, wl, args.cpu_pairs)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    recs, nb, n_total = cpu_sample(orc, wl, args.cpu_pairs)
     pairs = recs.shape[0]
     times = []
-    kind = sample = None
+    kind = how = None
     for i in range(args.warmup + args.steps):
         dt, kind, how = time_reference(orc, recs, wl["B"])
         if i >= args.warmup:
             times.append(dt)
     dt = sum(times) / len(times)
     val = pairs / dt
-    sample = "first %d barcode runs = %d read pairs of the workload per step; %s" % (nb, pairs, how)
-    line = {"impl": "reference", "metric": "read pairs/sec through --readFQB minhash+index build",
-            "value": val, "unit": "read pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+    full_pairs = n_total * world
+    sample = ("first %d barcode runs = %d read pairs (%.2f %% of the %d pairs of the configuration) per step; %s; "
+              "at this rate the whole configuration takes %.0f s on one core"
+              % (nb, pairs, 100.0 * pairs / full_pairs, full_pairs, how, full_pairs / val))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "B": wl["B"], "k": 21, "w": 31},
-            "cpu_baseline": {"value": val, "unit": "read pairs/s", "cores": 1, "kind": kind, "sample": sample,
+            "config": {"workload": wl["desc"], "B": wl["B"], "k": 21, "w": 31,
+                       "sample_pairs": int(pairs), "config_pairs": int(full_pairs),
+                       "extrapolated_config_seconds": full_pairs / val},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                              "host_cores": os.cpu_count(),
                              "note": "--readFQB is single-threaded in the reference, also with -DOMP (hash10x.c:1247 is the only omp pragma)"},
-            "e2e": {"value": val, "unit": "read pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------- GPU arm
 
-def run_ours(args, wl):
-    import ctypes as C
+def load_golden(key):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "golden_scale.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+DIGEST_ARRAYS = ("hashIndex", "hashValue", "hashDepth", "blkNRead", "blkNHash", "clusHash")
+
+
+def parity_check(g, stats, dist, torch, dev, rank, world, golden_key, cut_by_pairs):
+    """Digest of the index that was just timed against the reference binary's (tests/golden/golden_scale.json)."""
     import numpy as np
+    mask = (1 << 64) - 1
+    if world == 1:
+        dg = g.digest()
+        tot = {k: dg[k] for k in DIGEST_ARRAYS}
+        counts = {"nHashes": stats["nHashes"], "hashNumber": stats["nBins"] + 1, "nBlocksMax": stats["nBlocks"] + 1,
+                  "nReads": stats["nRecords"]}
+        extra = {"codesMissing": dg["codesMissing"], "codesUnordered": dg["codesUnordered"], "haveCodes": dg["haveCodes"]}
+    else:
+        info = g.dist_info(download=False)
+        mine = torch.tensor([stats["nHashes"]], dtype=torch.int64, device=dev)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        entry_base = int(sum(int(x[0]) for x in allh[:rank]))
+        dg = g.digest(block_base=info["blockBase"], entry_base=entry_base, with_block_zero=(rank == 0))
+        vec = [dg[k] for k in DIGEST_ARRAYS]
+        t = torch.tensor(np.array(vec, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)        # two's complement: the sum wraps like the digest's
+        summed = t.cpu().numpy().view(np.uint64)
+        tot = {k: int(summed[i]) & mask for i, k in enumerate(DIGEST_ARRAYS)}
+        counts = {"nHashes": int(info["nHashesGlobal"]), "nBlocksMax": int(info["nBlocksGlobal"]) + 1,
+                  "nReads": int(info["nReadsGlobal"]), "hashNumber": None}
+        nb = torch.tensor([stats["nBins"] + 1 if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        counts["hashNumber"] = int(nb[0])
+        extra = {}
+    out = {"checked": False, "digest": "sum over i of mix(mix(pos_i) ^ value_i) mod 2^64 (hash10x_b200/csrc/h10x_digest.h) of "
+           + ", ".join(DIGEST_ARRAYS) + "; computed on the device by h10x_gpu_index_digest after the timed region",
+           "digest_of": {k: "%016x" % v for k, v in tot.items()}}
+    out.update(extra)
+    gold = None if cut_by_pairs else load_golden(golden_key)
+    if gold is None:
+        out["reason"] = ("workload cut by --pairs: no golden" if cut_by_pairs else
+                         "no golden digests for '%s' in tests/golden/golden_scale.json (the reference needs more host memory "
+                         "than the authoring container has for this size)" % golden_key)
+        if extra:
+            out["invariants_ok"] = bool(extra["haveCodes"] and extra["codesMissing"] == 0 and extra["codesUnordered"] == 0)
+        return out
+    bad = [k for k in DIGEST_ARRAYS if "%016x" % tot[k] != gold["dg_" + k]]
+    bad += [k for k in ("nHashes", "hashNumber", "nBlocksMax", "nReads") if counts[k] != gold[k]]
+    if extra and not (extra["haveCodes"] and extra["codesMissing"] == 0 and extra["codesUnordered"] == 0):
+        bad.append("codes")
+    out.update({"checked": True, "ok": not bad, "mismatch": bad, "golden": "tests/golden/golden_scale.json[%s]" % golden_key,
+                "golden_made_by": gold.get("made_by"), "reference_wall_s": gold.get("reference_wall_s")})
+    return out
+
+
+def timed_builds(g, torch, stream, build, warmup, steps, barrier):
+    """W untimed + K timed device-resident builds; CUDA events on the launching stream."""
+    for _ in range(warmup):
+        build()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms, launches, lib_ms = {}, 0, 0.0
+    e0.record(stream)
+    for _ in range(steps):
+        build()
+        s = g.stats()
+        lib_ms += s["msTotal"]
+        launches += s["kernelLaunches"]
+        for k_, v in s["msStage"].items():
+            stage_ms[k_] = stage_ms.get(k_, 0.0) + v
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1), stage_ms, launches, lib_ms
+
+
+def run_ours(args, wl, wl_name):
     import torch
     import hash10x_b200
     from hash10x_b200 import synth as gsynth
+    from hash10x_b200 import shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,24 +348,30 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
-    # --- synthetic FQB generated in HBM: ONE data set (same genome), each rank a contiguous barcode range ---
-    from hash10x_b200 import shard
-    p = synth_params(gsynth, wl, seed=3)
-    if args.pairs:
-        mean = (wl["pairs_min"] + wl["pairs_max"]) / 2
-        p.nBarcodes = max(2, int(args.pairs / mean))
-    p.nBarcodes *= world                     # weak scaling: the per-GPU share stays fixed
-    _n_total, off = gsynth.layout(p)
-    cut = shard.plan_shards(off, world)
-    r0, r1 = shard.shard_records(off, cut, rank)
-    n_rec = r1 - r0
-    fqb = torch.empty(n_rec * 30, dtype=torch.int32, device=dev)
-    gsynth.fill_device(p, off, r0, r1, fqb.data_ptr())
-    torch.cuda.synchronize()
-
-    g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local)
     stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_input(w, mult, r, nranks):
+        """ONE data set (same genome); each rank a contiguous barcode range of it, generated in HBM"""
+        p = synth_params(gsynth, w, seed=3)
+        if args.pairs:
+            mean = (w["pairs_min"] + w["pairs_max"]) / 2
+            p.nBarcodes = max(2, int(args.pairs / mean))
+        p.nBarcodes *= mult                  # weak scaling: the per-GPU share stays fixed
+        _n, off = gsynth.layout(p)
+        cut = shard.plan_shards(off, nranks)
+        r0, r1 = shard.shard_records(off, cut, r)
+        t = torch.empty((r1 - r0) * 30, dtype=torch.int32, device=dev)
+        gsynth.fill_device(p, off, r0, r1, t.data_ptr())
+        torch.cuda.synchronize()
+        return t, r1 - r0
+
+    fqb, n_rec = make_input(wl, world, rank, world)
+    g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local)
     if world > 1:
         g.dist_init(rank, world, shard.share_unique_id(dist, rank, hash10x_b200.Hash10xGPU.dist_unique_id))
 
@@ -229,11 +381,6 @@ def run_ours(args, wl):
         else:
             g.build_device(fqb.data_ptr(), n_rec, stream.cuda_stream)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # --- value: device-resident build, CUDA events on the launching stream ---
     sampler = ClockSampler(local, enabled=not args.no_clocks)
     sampler.start()
@@ -241,29 +388,32 @@ def run_ours(args, wl):
         build_resident()
     barrier()
     sampler.window()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {}
-    launches = 0
-    e0.record(stream)
-    lib_ms = 0.0
-    for _ in range(args.steps):
-        t_py = time.perf_counter()
-        build_resident()
-        if os.environ.get("H10X_TRACE"):
-            print("py-trace build call %.3f ms" % ((time.perf_counter() - t_py) * 1e3), file=sys.stderr)
-        s = g.stats()
-        lib_ms += s["msTotal"]
-        launches += s["kernelLaunches"]
-        for k_, v in s["msStage"].items():
-            stage_ms[k_] = stage_ms.get(k_, 0.0) + v
-    e1.record(stream)
-    barrier()
+    ms, stage_ms, launches, lib_ms = timed_builds(g, torch, stream, build_resident, 0, args.steps, barrier)
     clocks = sampler.summary()
-    ms = e0.elapsed_time(e1)
     stats = g.stats()
     ms, total_pairs = shard.job_time_and_units(dist, torch, ms, n_rec, dev)
     ms_step = ms / args.steps
     value = total_pairs / (ms_step * 1e-3)
+
+    # --- parity of what was just timed ---
+    golden_key = wl_name if world == 1 else "%sx%d" % (wl_name, world)
+    parity = parity_check(g, stats, dist, torch, dev, rank, world, golden_key, bool(args.pairs))
+
+    # --- the rows after the build, on the index still resident (N=1): --hashDepthRange, --cluster ---
+    nxt = None
+    if world == 1 and not args.no_next:
+        dmin, dmax, ct = wl.get("depth_range", (30, 100)) + (5,)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_good = g.depth_range(dmin, dmax, copy=False)
+        t1 = time.perf_counter()
+        _c, nsub, _p, ms_kernel = g.cluster(0, 0, ct, copy=False)
+        t2 = time.perf_counter()
+        nxt = {"hashDepthRange": [dmin, dmax], "clusterThreshold": ct, "good_hashes": int(n_good),
+               "depth_range_ms": (t1 - t0) * 1e3, "cluster_ms": ms_kernel, "cluster_ms_incl_d2h": (t2 - t1) * 1e3,
+               "sub_clusters": int(nsub.sum()), "clustered_blocks": int((nsub > 0).sum()),
+               "note": "h10x_gpu_depth_range / h10x_gpu_cluster (hash10x.c:528-539,738-766 / 770-868) on the index the timed "
+                       "build left in HBM; depth_range_ms includes the D2H of the good-hash lists, cluster_ms is the kernel"}
 
     # --- e2e: the C ABI's host entry point, H2D + build + D2H inside the timed region ---
     e2e = None
@@ -275,6 +425,7 @@ def run_ours(args, wl):
         del fqb
         torch.cuda.empty_cache()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
         def build_e2e():
             if world > 1:
                 g.build_host_dist_ptr(host, n_rec)
@@ -297,12 +448,36 @@ def run_ours(args, wl):
             d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H + 8 * (hn + 1) + 4 * H
         else:       # rank 0: table + values + depths + its blocks and ClusterHash lists (hash->code parts stay resident)
             d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H
-        e2e = {"value": total_pairs / dt, "unit": "read pairs/s", "h2d_bytes_per_step": n_rec * 120,
+        e2e = {"value": total_pairs / dt, "unit": UNIT, "h2d_bytes_per_step": n_rec * 120,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "bytes_are": "rank 0's, per step",
                "api": ("h10x_gpu_build_host" if world == 1 else "h10x_gpu_build_host_dist") +
                       " (include/h10x_gpu.h): pinned host FQB -> index arrays in pinned host memory"}
         del host_t
+    else:
+        del fqb
+    torch.cuda.empty_cache()
+
+    # --- weak_base: at N=1, the same build on one GPU's share of the N>1 workload ---
+    weak_base = None
+    if world == 1 and not args.no_weak_base and not args.pairs and wl_name != "human8":
+        wb = WORKLOADS["human8"]
+        g.close()
+        fq2, n2 = make_input(wb, 1, 0, 1)
+        g = hash10x_b200.Hash10xGPU(B=wb["B"], device=local)
+
+        def build_wb():
+            g.build_device(fq2.data_ptr(), n2, stream.cuda_stream)
+        ms2, st2, _l2, _ = timed_builds(g, torch, stream, build_wb, 1, 2, barrier)
+        s2 = g.stats()
+        par2 = parity_check(g, s2, None, torch, dev, 0, 1, "human8", False)
+        weak_base = {"workload": wb["desc"], "pairs": int(n2), "B": wb["B"], "ms_per_step": ms2 / 2,
+                     "value": n2 / (ms2 / 2 * 1e-3), "unit": UNIT, "steps": 2, "warmup": 1,
+                     "stage_ms": {k_: v / 2 for k_, v in st2.items() if v}, "parity": par2,
+                     "note": "`bench.py --gpus N` (N > 1) runs N of these shares of one human-scale data set: divide the N-GPU "
+                             "value by N times this one for the same-workload weak-scaling efficiency"}
+        del fq2
+        torch.cuda.empty_cache()
 
     if rank != 0:
         g.close()
@@ -315,25 +490,39 @@ def run_ours(args, wl):
     dom = max(stage_ms.items(), key=lambda kv: kv[1])
     R, M, H, D, nB = stats["nRecords"], stats["nMoshes"], stats["nHashes"], stats["nBins"], stats["nBlocks"]
     stage_bytes = {   # algorithmic bytes of each stage per build (DESIGN.md "kernels")
-        "moshes": 120 * R + 12 * M, "fused": 120 * R + 8 * H, "blocksort": 24 * M, "dedup": 8 * H + 12 * H,
-        "hashsort": 24 * H, "binids": 4 * H + 40 * D, "entryids": 8 * H, "codes": 20 * H + 12 * D,
-        "clusters": 12 * H + 8 * H, "table": (4 << wl["B"]) + 12 * D, "runs": 4 * R * 3, "other": 0}
+        "moshes": 120 * R + 12 * M, "fused": 120 * R + 8 * H, "blocksort": 24 * M, "dedup": 8 * H + 8 * H,
+        "hashsort": 32 * H, "binids": 36 * D, "entryids": 8 * H, "codes": 20 * H + 12 * D,
+        "clusters": 12 * H + 8 * H + 16 * H, "table": (4 << wl["B"]) + 12 * D, "runs": 4 * R * 3, "other": 0}
     dom_ms = dom[1] / args.steps
     dom_bytes = stage_bytes.get(dom[0], 0)
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
-    try:        # DRAM bytes of the fused kernel from the committed ncu capture, scaled per read pair
-        with open(os.path.join(ROOT, "profiles", "r01_fused_traffic.json")) as f:
+    traffic = alu = None
+    try:        # DRAM bytes and ALU-pipe instructions of the fused kernel from the committed ncu captures, per read pair
+        with open(os.path.join(ROOT, "profiles", "r02_fused_kernel.json")) as f:
             tj = json.load(f)
         if dom[0] == "fused":
             traffic = tj["dram_bytes_per_pair"] * R
+            alu = tj
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                "traffic_source": "profiles/r01_fused_traffic.json (ncu dram__bytes_read+write at 50M pairs) x pairs" if traffic else None,
-                "note": "the fused kernel is bound by the integer pipes (ncu: ALU 59 %, FMA/IMAD 42 %, issue 74 %, DRAM 7 %), see profiles/README.md",
+                "traffic_source": "profiles/r02_fused_kernel.json (ncu dram__bytes_read+write of the two fused launches at this workload) x pairs" if traffic else None,
                 "ms_per_launch_group": dom_ms, "share_of_step": dom_ms / ms_step}
+    rooflines = [roofline]
+    if alu is not None:
+        # the fused kernel's real bound: the 16-lane-per-scheduler integer ALU pipe (64 lanes per SM and clock)
+        sm_clock = (clocks.get("sm_mhz") or 1965) * 1e6
+        ops = alu["alu_pipe_thread_instructions_per_pair"] * R
+        peak_ops = 148 * 64 * sm_clock
+        ach_ops = ops / (dom_ms * 1e-3)
+        rooflines.append({"bound": "int_alu", "kernel": "fused", "achieved": ach_ops / 1e12, "peak": peak_ops / 1e12,
+                          "unit": "T thread-instructions/s on the ALU pipe", "frac": ach_ops / peak_ops,
+                          "per_pair": alu["alu_pipe_thread_instructions_per_pair"], "source": alu.get("alu_source"),
+                          "note": "SURVEY 8d expected HBM to bind this stage; ncu shows the integer pipes do (ALU %s %%, FMA/IMAD %s %%, "
+                                  "issue %s %%, DRAM %s %%): its 120 R + 8 H bytes would take ~6 ms at the HBM peak"
+                                  % (alu.get("alu_pct"), alu.get("fma_pct"), alu.get("issue_pct"), alu.get("dram_pct"))})
+        roofline["note"] = "bound by the integer ALU pipe, not HBM: see roofline_int_alu"
     pipe_ach = stats["algorithmicBytes"] / (ms_step * 1e-3) / 1e9
     pipeline = {"bound": "hbm", "algorithmic_bytes": stats["algorithmicBytes"],
                 "bytes_per_pair": stats["algorithmicBytes"] / max(1, R), "achieved": pipe_ach, "peak": peak,
@@ -344,14 +533,18 @@ def run_ours(args, wl):
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import orc          # the only use of oracle/ in this arm: the timed CPU baseline
-        recs, nb = cpu_sample(orc, wl, args.cpu_pairs)
+        recs, nb, n_total = cpu_sample(orc, wl, args.cpu_pairs)
         dt, kind, how = time_reference(orc, recs, wl["B"])
-        cpu = {"value": recs.shape[0] / dt, "unit": "read pairs/s", "cores": 1, "kind": kind,
-               "sample": "first %d barcode runs = %d read pairs of the same workload, %.1f s; %s"
-                         % (nb, recs.shape[0], dt, how), "host_cores": os.cpu_count()}
+        cpu = {"value": recs.shape[0] / dt, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "first %d barcode runs = %d read pairs (%.2f %%) of the same workload, %.1f s; %s; the whole "
+                         "configuration would take %.0f s at this rate"
+                         % (nb, recs.shape[0], 100.0 * recs.shape[0] / n_total, dt, how, n_total * dt / recs.shape[0]),
+               "host_cores": os.cpu_count()}
+        if nxt is not None:
+            nxt["like_for_like"] = cluster_like_for_like(
+                orc, lambda B: hash10x_b200.Hash10xGPU(B=B, device=local), torch, gsynth, stream)
 
-    line = {"metric": "read pairs/sec through --readFQB minhash+index build; % of HBM roofline",
-            "value": value, "unit": "read pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["desc"] + (" (cut to %d pairs per GPU by --pairs)" % n_rec if args.pairs else ""),
@@ -360,11 +553,18 @@ def run_ours(args, wl):
                        "parallelism": "1 GPU" if world == 1 else
                        "%d ranks: barcode-range shards, NCCL all-to-all-v of rank-distinct hashes to hash-range owners, "
                        "global bin ids; hashValue/hashDepth/hashIndex on rank 0" % world},
-            "roofline": roofline, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks, "lib_ms_per_step": lib_ms / args.steps,
             "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items() if v},
+            "tail": "hand-written (h10x_tail.cuh)" if stats.get("tailPath") == 2 else "library radix sort (round-1 tail)",
             "counts": {"pairs": R, "moshes": M, "block_unique_hashes": H, "bins": D, "blocks": nB,
                        "peak_device_bytes": stats["peakDeviceBytes"]}}
+    if len(rooflines) > 1:
+        line["roofline_int_alu"] = rooflines[1]
+    if nxt:
+        line["next_rows"] = nxt
+    if weak_base:
+        line["weak_base"] = weak_base
     print(json.dumps(line))
     g.close()
     if dist is not None:
@@ -383,6 +583,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-next", action="store_true", help="skip --hashDepthRange / --cluster on the resident index")
+    ap.add_argument("--no-weak-base", action="store_true", help="skip the human8 (one GPU's share of the N>1 workload) build at N=1")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample NVML clocks during the timed region")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -399,7 +601,7 @@ def main():
         if args.impl == "reference":
             run_reference_arm(args, wl)
         else:
-            run_ours(args, wl)
+            run_ours(args, wl, name)
     finally:
         sys.stdout = py_out
         sys.stdout.flush()

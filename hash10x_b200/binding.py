@@ -302,11 +302,14 @@ class Hash10xGPU:
             out["localCodes"] = pull(di.localCodes, int(off[-1]) if off.size else 0)
         return out
 
-    def depth_range(self, dmin, dmax):
-        """--hashDepthRange on the resident index -> (within u8, goodOff u64, good u16) host copies"""
+    def depth_range(self, dmin, dmax, copy=True):
+        """--hashDepthRange on the resident index -> (within u8, goodOff u64, good u16) host copies;
+        copy=False returns only the number of good hashes (the lists stay in the context's pinned arena)"""
         cg = CGood()
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_depth_range(self.ctx, dmin, dmax, C.byref(cg), err, len(err)), err)
+        if not copy:
+            return int(cg.nGood)
         return (_arr(cg.within, cg.hashNumber, np.uint8), _arr(cg.goodOff, cg.nBlocksMax + 1, np.uint64),
                 _arr(cg.good, cg.nGood, np.uint16))
 
@@ -326,12 +329,14 @@ class Hash10xGPU:
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_load_index(self.ctx, C.byref(ci), err, len(err)), err)
 
-    def cluster(self, code_min=0, code_max=0, threshold=5):
+    def cluster(self, code_min=0, code_max=0, threshold=5, copy=True):
         """--cluster codeMin codeMax (-ct threshold) on the resident index and goodHashes ->
         (clus u64 with the subCluster bytes set, nSubCluster u32, pointToMin f64, kernel ms) host copies"""
         cc = CClusters()
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_cluster(self.ctx, code_min, code_max, threshold, C.byref(cc), err, len(err)), err)
+        if not copy:
+            return (None, _arr(cc.nSubCluster, cc.nBlocksMax, np.uint32), None, cc.msKernel)
         return (_arr(cc.clusHash, cc.nHashes, np.uint64), _arr(cc.nSubCluster, cc.nBlocksMax, np.uint32),
                 _arr(cc.pointToMin, cc.nBlocksMax, np.float64), cc.msKernel)
 

@@ -5,7 +5,7 @@
  *              prefetched one pair ahead);
  *   windows    the pair's k-mers are split into chunks of 8 consecutive start positions, one chunk
  *              per lane (14 chunks of read 1, 17 of read 2 for k=21; the last chunk of a read is
- *              slid back to end at the last k-mer, its duplicates vanish in the dedup).  The three
+ *              slid back to end at the last k-mer, the k-mers it shares with the chunk before are never selected).  The three
  *              32-bit words holding a chunk's 8+k-1 bases come from the owning lanes by warp
  *              shuffle and are funnel-shifted into one 64-bit window W; its 2-bit-reversed
  *              complement WR yields the reverse-complement k-mers, so there is no per-base rolling
@@ -101,14 +101,19 @@ struct FusedArgs {
   uint32_t rowCap ;		/* keys per lane column of the staging area */
   uint32_t c1, c2 ;		/* 8-k-mer chunks of read 1 / read 2 */
   uint32_t n1, n2 ;		/* k-mers of read 1 / read 2 */
+  unsigned long long *moshCount ;	/* selected k-mers of the blocks this path completed (seqhash.c:171,189) */
 } ;
 
 /* CTAs per SM that the shared memory of a size class allows (h10x_gpu.cu, kClasses): the register budget follows it */
 __host__ __device__ constexpr int h10x_fused_ctas_per_sm (int threads)
 { return threads <= 256 ? 5 : threads <= 384 ? 4 : threads <= 512 ? 2 : 1 ; }
 
-/* K > 0: k fixed at compile time (shifts and masks become immediates); K == 0: k from hp */
-template <int THREADS, bool WODD, int K>
+/* K > 0: k fixed at compile time (shifts and masks become immediates); K == 0: k from hp.
+   WODD: w is odd and at least 3 (the host sends w = 1 and even w to the other instantiation).
+   LEAN: the block's selected keys leave unsorted and with their duplicates - the single-GPU tail (h10x_tail.cuh)
+   sorts every key once, globally, and drops the duplicates of a (hash, block) there, keeping the lowest read index
+   (k_sr_sort), so the in-CTA bucket sort + dedup below would be a second sort of the same keys. */
+template <int THREADS, bool WODD, int K, bool LEAN>
 __global__ void __launch_bounds__ (THREADS, h10x_fused_ctas_per_sm (THREADS))
 k_fused_block (FusedArgs a, HashParams hp)
 {
@@ -138,6 +143,22 @@ k_fused_block (FusedArgs a, HashParams hp)
   const uint32_t nk = isR2 ? a.n2 : a.n1 ;			/* k-mers of this read */
   const uint32_t chunk = isR2 ? lane - a.c1 : lane ;
   const uint32_t first = min (8u * chunk, nk - 8u) ;		/* the last chunk slides back: all 8 valid */
+  /* ... and its first dupSkip k-mers belong to the chunk before: they are never selected, so every selected k-mer is
+     stored once and the block's key count is its mosh count (seqhash.c:171,189).  The read ranges are fixed
+     (hash10x.c:162-163), so for a compile-time K the two tail lanes and their dupSkip are constants and the test folds
+     into the predicate input of the selection compare: no instruction in the hash loop, where a compare + add per
+     k-mer on the integer ALU pipe - the kernel's limiter - cost 14 ms of 79 at the 1 Gb workload */
+  const uint32_t dupSkip = 8u * chunk - first ;
+  constexpr int KN1 = K ? H10X_R1_LEN - K + 1 : 8, KN2 = K ? H10X_R2_LEN - K + 1 : 8 ;
+  constexpr int KC1 = (KN1 + 7) / 8, KC2 = (KN2 + 7) / 8 ;
+  constexpr int KD1 = 8 * (KC1 - 1) - (KN1 - 8), KD2 = 8 * (KC2 - 1) - (KN2 - 8) ;
+  const bool notTail1 = lane != (uint32_t) (KC1 - 1), notTail2 = lane != (uint32_t) (KC1 + KC2 - 1) ;
+  const bool notTail = notTail1 && notTail2 ;
+  /* WODD: the hash loop tests only the high word, q_hi < limHi1 = wLim_hi + 1 - every multiple of w passes, and so does
+     one other k-mer in 2^32; each lane then re-tests its few stored keys exactly before they are counted.  One
+     compare per k-mer instead of two, and the tail lanes' limit for their shared k-mers is simply 0. */
+  const uint32_t limHi1 = (uint32_t) (wLim >> 32) + 1u ;
+  const uint32_t limT = notTail ? limHi1 : 0u, limT1 = notTail1 ? limHi1 : 0u, limT2 = notTail2 ? limHi1 : 0u ;
   const uint32_t p0 = (isR2 ? H10X_R2_START : H10X_R1_START) + first ;	/* unpacked position of k-mer 0 */
   const uint32_t wi = p0 >> 4, sh = 2 * (p0 & 15) ;
   const uint32_t base = isR2 ? 15u : 0u ;
@@ -193,8 +214,21 @@ k_fused_block (FusedArgs a, HashParams hp)
 	      uint64_t pq = h10x_mul64 (rlo, rhi, flo, fhi) ;
 	      uint64_t m = (pf < pq ? pf : pq) & (((uint64_t) TOPHI << 32) | TOPLO) ;	/* canonical hash << SH */
 	      uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
-	      bool sel = q <= wLim ;
-	      if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
+		      bool sel ;
+		      if constexpr (WODD && K > 0)
+			{ const uint32_t qhi = (uint32_t) (q >> 32) ;
+			  sel = qhi < ((j < KD1 && j < KD2) ? limT : (j < KD1) ? limT1 : (j < KD2) ? limT2 : limHi1) ;
+			}
+		      else
+			{ sel = q <= wLim ;
+			  if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
+			  if constexpr (K > 0)
+			    { if (j < KD1 && j < KD2) sel = sel && notTail ;
+			      else if (j < KD1) sel = sel && notTail1 ;
+			      else if (j < KD2) sel = sel && notTail2 ;
+			    }
+			  else sel = sel && (uint32_t) j >= dupSkip ;
+			}
 	      if (sel)	/* low SH bits of m are 0, so the read index simply drops in (an add, issued as IMAD: FMA pipe) */
 		{ uint32_t klo ;
 		  asm ("mad.lo.u32 %0, %1, 1, %2;" : "=r" (klo) : "r" (pr), "r" ((uint32_t) m)) ;
@@ -203,12 +237,45 @@ k_fused_block (FusedArgs a, HashParams hp)
 		}
 	    }
 	}
+      if constexpr (WODD && K > 0)	/* the exact test of the lane's stored keys; a failing one (1 in 2^32 k-mers) is squeezed out */
+	{ uint32_t v = 0 ;
+	  for (uint32_t i = 0 ; i < cnt ; ++i)
+	    { const uint64_t key = col[(size_t) i * THREADS] ;
+	      const uint64_t m = key & (((uint64_t) TOPHI << 32) | TOPLO) ;
+	      if (h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) <= wLim)
+		{ if (v != i) col[(size_t) v * THREADS] = key ;
+		  ++v ;
+		}
+	    }
+	  cnt = v ;
+	}
       if (over) sBad = 1 ;
       if (cnt) atomicAdd (&sCount, cnt) ;
       __syncthreads () ;
 
       uint32_t n = sCount ;
       bool bad = sBad != 0 || n > a.cap ;
+      if constexpr (LEAN)
+	{ /* ---- the keys as they are: lane columns -> shared memory -> one contiguous piece of the scratch slab ---- */
+	  if (!bad)
+	    { cur[t] = cnt ;		/* nbuck >= THREADS */
+	      __syncthreads () ;
+	      cta_exclusive_scan<THREADS> (cur, THREADS, warpTmp) ;
+	      uint64_t *dst = S + cur[t] ;
+	      for (uint32_t i = 0 ; i < cnt ; ++i) dst[i] = col[(size_t) i * THREADS] ;
+	      if (n == 0) { if (t == 0) S[0] = 0 ; n = 1 ; }	/* hash10x.c:167-168: the phantom entry of an empty block */
+	      if (t == 0) sBase = atomicAdd (a.cursor, (unsigned long long) n) ;
+	      __syncthreads () ;
+	      if (sBase + n > a.scratchCap) bad = true ;
+	      else for (uint32_t i = t ; i < n ; i += THREADS) a.scratch[sBase + i] = S[i] ;
+	    }
+	  if (t == 0)
+	    { if (bad) { a.blkCnt[blk] = H10X_BLK_FALLBACK ; a.srcOff[blk] = 0 ; }
+	      else { a.blkCnt[blk] = n ; a.srcOff[blk] = sBase | ((uint64_t) SH << 56) ; atomicAdd (a.moshCount, (unsigned long long) sCount) ; }
+	    }
+	  __syncthreads () ;
+	  continue ;
+	}
       if (!bad)
 	{ /* ---- bucket histogram on the top hash bits ---- */
 	  for (uint32_t i = 0 ; i < cnt ; ++i) atomicAdd (&start[(uint32_t) (col[(size_t) i * THREADS] >> buckShift)], 1u) ;
@@ -265,7 +332,7 @@ k_fused_block (FusedArgs a, HashParams hp)
 	}
       if (t == 0)
 	{ if (bad) { a.blkCnt[blk] = H10X_BLK_FALLBACK ; a.srcOff[blk] = 0 ; }
-	  else { a.blkCnt[blk] = U ; a.srcOff[blk] = sBase | ((uint64_t) SH << 56) ; }
+	  else { a.blkCnt[blk] = U ; a.srcOff[blk] = sBase | ((uint64_t) SH << 56) ; atomicAdd (a.moshCount, (unsigned long long) sCount) ; }
 	}
       __syncthreads () ;
     }

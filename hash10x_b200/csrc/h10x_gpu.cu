@@ -712,15 +712,18 @@ static void tail_p1 (h10x_ctx *c, cudaStream_t s, const TailGeom &g, const TailS
 }
 
 /* P2, sub-range sort, bin ids, codes, ClusterHash lists: everything after P1.  Leaves hashValue / hashDepth /
-   hashNumber / codeOff / codes / clus in the context; returns the number of bins. */
-static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint64_t H, uint64_t wDiv,
-			   DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart)
+   hashNumber / codeOff / codes / clus in the context; returns the number of bins.  H comes in as the number of
+   entries P1 placed and leaves as the number of (hash, block) pairs: the sub-range sort drops the duplicates a lean
+   fused kernel left in, blkDupHost[b] = how many of (global, 1-based) block b's. */
+static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint64_t &H, uint64_t wDiv,
+			   DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart, uint32_t nBlkNumbers, std::vector<uint32_t> &blkDupHost)
 { MemTrack *mt = &c->mt ;
   const h10x_params &P = c->P ;
   const int nSM = device_sms (c) ;
   const uint32_t blkMask = (uint32_t) ((((uint64_t) 1) << g.blkBits) - 1) ;
   DBuf<uint64_t> A ;
-  DBuf<uint32_t> srStart ((size_t) g.nSub + 1, s, mt), stage, nHeads ((size_t) g.nSub + 1, s, mt) ;
+    DBuf<uint32_t> srStart ((size_t) g.nSub + 1, s, mt), stage, nHeads ((size_t) g.nSub + 1, s, mt), srCount ((size_t) g.nSub, s, mt) ;
+  DBuf<uint32_t> blkDup ((size_t) nBlkNumbers + 1, s, mt) ; DBuf<unsigned long long> nDup (1, s, mt) ;
   uint32_t D = 0 ;
   { StageTimer tm (c, s, ST_HASHSORT) ;
     if (g.p2 > 0)
@@ -744,14 +747,18 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     stage.alloc (H, s, mt) ;
     DBuf<uint32_t> overList ((size_t) g.nSub, s, mt), jobList ((size_t) g.nSub, s, mt) ; DBuf<unsigned int> counters (3, s, mt) ;
     CK (cudaMemsetAsync (counters.p, 0, 12, s)) ;
-    CK (cudaMemsetAsync (nHeads.p, 0, 4 * ((size_t) g.nSub + 1), s)) ;
+        CK (cudaMemsetAsync (nHeads.p, 0, 4 * ((size_t) g.nSub + 1), s)) ;
+    CK (cudaMemsetAsync (srCount.p, 0, 4 * (size_t) g.nSub, s)) ;
+    CK (cudaMemsetAsync (blkDup.p, 0, 4 * ((size_t) nBlkNumbers + 1), s)) ;
+    CK (cudaMemsetAsync (nDup.p, 0, 8, s)) ;
     SrArgs sa ;
     sa.A = A.p ; sa.srStart = srStart.p ; sa.stage = stage.p ; sa.nHeads = nHeads.p ; sa.overList = overList.p ; sa.jobList = jobList.p ;
     sa.nOver = counters.p ; sa.ticket = counters.p + 1 ; sa.nJobs = counters.p + 2 ; sa.nSub = g.nSub ;
     sa.cap = H10X_SR_CAP ;
     if (const char *e = getenv ("H10X_SR_CAP")) { long v = atol (e) ; if (v >= 1 && v < (long) H10X_SR_CAP) sa.cap = (uint32_t) v ; }	/* tests: force the big-sub-range path */
     sa.groupCap = std::min<uint32_t> (H10X_SR_GROUP, sa.cap) ; sa.maxLog = (uint32_t) std::min (2, g.p2) ;
-    sa.eShift = g.eShift ; sa.remBits = g.remBits ;
+        sa.eShift = g.eShift ; sa.remBits = g.remBits ;
+    sa.srCount = srCount.p ; sa.blkDup = blkDup.p ; sa.nDup = nDup.p ; sa.blkMask = blkMask ;
     LAUNCH (c, k_sr_jobs, gridFor (((uint64_t) g.nSub + 3) / 4, 256), 256, 0, s, sa) ;
     const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (H10X_SR_THREADS / 32) * 2 << H10X_SR_DIGIT) + 16 ;
     CK (cudaFuncSetAttribute (k_sr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
@@ -770,16 +777,21 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
 	for (uint32_t j : over)
 	  { const uint64_t n = st2[j + 1] - st2[j] ;
 	    DBuf<uint64_t> tmp (n, s, mt) ;
-	    /* the whole word orders a sub-range: q bits, then block (one entry per (hash, block)) */
+	    /* the whole word orders a sub-range: q bits, then block, then read (the lowest read of a (hash, block) first) */
 	    cubCall (c, s, [&] (void *t, size_t &b)
-	      { return cub::DeviceRadixSort::SortKeys (t, b, A.p + st2[j], tmp.p, n, 16, g.eShift + g.remBits, s) ; }) ;
+	      { return cub::DeviceRadixSort::SortKeys (t, b, A.p + st2[j], tmp.p, n, 0, g.eShift + g.remBits, s) ; }) ;
 	    CK (cudaMemcpyAsync (A.p + st2[j], tmp.p, 8 * n, cudaMemcpyDeviceToDevice, s)) ;
 	    LAUNCH (c, k_sr_heads_big, 1, 512, 0, s, sa, j) ;
 	  }
-	c->stats.genericBlocks += 0 ;
-      }
+	      }
+    unsigned long long dups = 0 ;
+    blkDupHost.assign ((size_t) nBlkNumbers + 1, 0) ;
+    CK (cudaMemcpyAsync (&dups, nDup.p, 8, cudaMemcpyDeviceToHost, s)) ;
+    CK (cudaMemcpyAsync (blkDupHost.data (), blkDup.p, 4 * ((size_t) nBlkNumbers + 1), cudaMemcpyDeviceToHost, s)) ;
+    CK (cudaStreamSynchronize (s)) ;
+    H -= dups ;
   }
-  DBuf<uint32_t> segStart, idOfSeg ;
+    DBuf<uint32_t> segStart, segLen, idOfSeg ;
   { StageTimer tm (c, s, ST_BINIDS) ;
     DBuf<uint32_t> binBase ((size_t) g.nSub + 1, s, mt) ;
     cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, nHeads.p, binBase.p, (size_t) g.nSub + 1, s) ; }) ;
@@ -787,13 +799,12 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     CK (cudaStreamSynchronize (s)) ;
     if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
       throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
-    segStart.alloc ((size_t) D + 1, s, mt) ; idOfSeg.alloc (D, s, mt) ;
+        segStart.alloc (D, s, mt) ; segLen.alloc (D, s, mt) ; idOfSeg.alloc (D, s, mt) ;
     DBuf<uint64_t> fkey (D, s, mt), fkey2 (D, s, mt), hvHash (D, s, mt) ;
     LAUNCH (c, k_heads_compact, (uint32_t) std::min<uint64_t> (((uint64_t) g.nSub * 32 + 255) / 256, (uint64_t) nSM * 16), 256, 0, s, g.nSub,
-	    srStart.p, nHeads.p, binBase.p, stage.p, A.p, g.eShift, g.lowBits, g.p2, blkMask, wDiv, segStart.p, fkey.p, hvHash.p) ;
-    const uint32_t H32 = (uint32_t) H ;
-    CK (cudaMemcpyAsync (segStart.p + D, &H32, 4, cudaMemcpyHostToDevice, s)) ;	/* pageable source: copied before the call returns */
-    stage.release () ; nHeads.release () ; binBase.release () ; srStart.release () ;
+	    	    srStart.p, nHeads.p, srCount.p, binBase.p, stage.p, A.p, g.eShift, g.lowBits, g.p2, blkMask, wDiv, segStart.p, segLen.p,
+	    fkey.p, hvHash.p) ;
+    stage.release () ; nHeads.release () ; binBase.release () ; srStart.release () ; srCount.release () ;
     /* bins stand in hash order; the id order is (first block, hash): stable passes on the first block */
     const int b1 = g.blkBits <= 9 ? g.blkBits : (g.blkBits + 1) / 2, b2 = g.blkBits - b1 ;
     if (b1 > 11) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^22 barcode blocks") ;
@@ -813,7 +824,7 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
     CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
     CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-    LAUNCH (c, k_bins_by_rank_e, gridFor (D, 256), 256, 0, s, D, sorted, segStart.p, hvHash.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+        LAUNCH (c, k_bins_by_rank_e, gridFor (D, 256), 256, 0, s, D, sorted, segLen.p, hvHash.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
   }
   early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ;
   early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ;
@@ -824,10 +835,10 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     c->codes.alloc (H, s, mt) ;
     cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
     cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
-    LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, idOfSeg.p, A.p, blkMask,
+        LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, segLen.p, idOfSeg.p, A.p, blkMask,
 	    c->codeOff.p, c->codes.p, idRead.p) ;
   }
-  A.release () ; segStart.release () ; idOfSeg.release () ;
+    A.release () ; segStart.release () ; segLen.release () ; idOfSeg.release () ;
   if (!(P.flags & H10X_FLAG_NO_CODES))
     { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
   c->clus.alloc (H, s, mt) ;
@@ -988,8 +999,31 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   static const FusedClass kClasses[5] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 }, { 5632, 2048, 11, 384, 48 },
 					  { 12288, 4096, 12, 512, 64 }, { 24576, 8192, 13, 1024, 64 } } ;
   const int nClasses = 5 ;
-  DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
+    DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
   uint64_t nFused = 0 ;
+  DBuf<uint64_t> gHash ; DBuf<uint32_t> gRec ;
+  uint64_t G = 0 ; size_t gCap = 0 ;
+  /* the global sort runs on hash / w: exact division = multiplication by w^-1 mod 2^64 (w odd part) and a
+     shift (power-of-two part); quotients of multiples keep the order and need fewer radix passes */
+  const uint64_t wInvFull = c->hp.wTz ? 1 : c->hp.wInv ;
+  const uint64_t wDiv = c->hp.wTz ? 1 : (uint64_t) P.w ;
+  const uint64_t topQ = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
+  /* single-GPU: the hand-written tail (h10x_tail.cuh) whenever its packed 64-bit entry fits; the library-sort tail
+     of round 1 stays as the general path (multi-GPU, very wide hashes) and as a cross-check (H10X_FLAG_LEGACY_TAIL).
+     The hand-written tail sorts every key itself, so the fused kernel then runs LEAN (no in-CTA sort / dedup); should
+     the real key count turn the tail's geometry down after all, the mosh stage is repeated the classic way. */
+  TailGeom tg ; memset (&tg, 0, sizeof (tg)) ;
+  const bool tailWanted = !dist && !(P.flags & H10X_FLAG_LEGACY_TAIL) && !getenv ("H10X_LEGACY_TAIL") ;
+  bool tail2 = false, lean = false ;
+  for (int attempt = 0 ; ; ++attempt)
+  {
+  lean = tailWanted && attempt == 0 && !getenv ("H10X_NO_LEAN") ;
+  if (lean)
+    { TailGeom te ; const double perPairE = (double) (n1 + n2) / (double) P.w ;
+      lean = tail_geometry ((uint64_t) (perPairE * 1.1 * nProc) + nProcBlk + 1, topQ, blkBase + nProcBlk, te) ;
+    }
+  std::fill (hCnt.begin (), hCnt.end (), H10X_BLK_FALLBACK) ;
+  H = 0 ; totalMoshes = 0 ; nFused = 0 ; G = 0 ;
   if (fusedOK)
     { StageTimer tm (c, s, ST_FUSED) ;
       std::vector<uint32_t> lists[5] ;
@@ -1002,14 +1036,14 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    if (need <= kClasses[ci].cap && (int) kClasses[ci].lb <= 2 * P.k) { lists[ci].push_back (p) ; break ; }
 	}
       uint64_t scratchCap = (uint64_t) (perPair * 1.15 * nProc) + (1u << 20) ;
-      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (1, s, mt) ; work.alloc (nClasses, s, mt) ;
-      CK (cudaMemsetAsync (cursor.p, 0, 8, s)) ;
+      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (2, s, mt) ; work.alloc (nClasses, s, mt) ;	/* cursor[1]: mosh count */
+      CK (cudaMemsetAsync (cursor.p, 0, 16, s)) ;
       CK (cudaMemsetAsync (work.p, 0, 4 * nClasses, s)) ;
       CK (cudaMemsetAsync (blkCnt.p, 0xff, 4 * ((size_t) nProcBlk + 1), s)) ;
       int nSM = 148 ;
       CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, P.device)) ;
       std::vector<DBuf<uint32_t>> dLists (nClasses) ;
-      const bool wodd = (c->hp.wTz == 0) ;
+            const bool wodd = (c->hp.wTz == 0 && P.w >= 3) ;
       const bool k21 = (P.k == 21 && wodd) ;
       /* pass 1: grids and the staging area they need (launches run one after another and share it) */
       uint32_t grid[5] = { 0, 0, 0, 0, 0 } ; size_t smemB[5] ; size_t stageKeys = 0 ;
@@ -1017,11 +1051,13 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       for (int ci = 0 ; ci < nClasses ; ++ci)
 	{ const FusedClass &fc = kClasses[ci] ;
 	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) fc.nbuck + 1) + 16 ;
-#define FUSED_FN(T) (k21 ? (const void*) k_fused_block<T, true, 21> : wodd ? (const void*) k_fused_block<T, true, 0> \
-		     : (const void*) k_fused_block<T, false, 0>)
+#define FUSED_FN1(T, L) (k21 ? (const void*) k_fused_block<T, true, 21, L> : wodd ? (const void*) k_fused_block<T, true, 0, L> \
+		     : (const void*) k_fused_block<T, false, 0, L>)
+#define FUSED_FN(T) (lean ? FUSED_FN1 (T, true) : FUSED_FN1 (T, false))
 	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 384 ? FUSED_FN (384)
 	    : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
 #undef FUSED_FN
+#undef FUSED_FN1
 	  if (lists[ci].empty ()) continue ;
 	  CK (cudaFuncSetAttribute (fn[ci], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemB[ci])) ;
 	  int occ = 1 ;
@@ -1040,23 +1076,24 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	  fa.fqb = fqb ; fa.list = dLists[ci].p ; fa.blkStart = dBlkStart.p ; fa.stage = stage.p ; fa.scratch = scratch.p ;
 	  fa.cursor = cursor.p ; fa.work = work.p + ci ; fa.scratchCap = scratchCap ; fa.srcOff = srcOff.p ; fa.blkCnt = blkCnt.p ;
 	  fa.nList = (uint32_t) lists[ci].size () ; fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.rowCap = fc.rowCap ;
-	  fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ;
+	  fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ; fa.moshCount = cursor.p + 1 ;
 	  HashParams hpv = c->hp ;
 	  void *args[2] = { (void*) &fa, (void*) &hpv } ;
 	  CK (cudaLaunchKernel (fn[ci], dim3 (grid[ci]), dim3 (fc.threads), args, smemB[ci], s)) ;
 	  ++c->launches ;
 	}
       CK (cudaMemcpyAsync (hCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
+      unsigned long long fusedMoshes = 0 ;
+      CK (cudaMemcpyAsync (&fusedMoshes, cursor.p + 1, 8, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies above */
+      totalMoshes += fusedMoshes ;
       for (uint32_t p = 0 ; p < nProcBlk ; ++p) if (hCnt[p] != H10X_BLK_FALLBACK) ++nFused ;
     }
   c->stats.fusedBlocks = nFused ; c->stats.genericBlocks = nProcBlk - nFused ;
   tr.mark ("fused") ;
 
   /* -- generic path for whatever the fused path did not take: global-memory segmented sort -- */
-  DBuf<uint64_t> gHash ; DBuf<uint32_t> gRec ;
-  uint64_t G = 0 ; size_t gCap = 0 ;
-  auto ensureG = [&] (uint64_t need)
+    auto ensureG = [&] (uint64_t need)
     { if (need <= gCap) return ;
       size_t cap = std::max<size_t> ((size_t) need, gCap + gCap / 2) ;
       DBuf<uint64_t> nh (cap, s, mt) ; DBuf<uint32_t> nr (cap, s, mt) ;
@@ -1087,10 +1124,12 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, ph.p, phOff.p, (size_t) nblk + 1, s) ; }) ;
 	LAUNCH (c, k_seg_off, gridFor (nblk + 1, 256), 256, 0, s, dBlkStart.p, p0, nblk, r0, off2.p, phOff.p, ph.p, segOff.p,
 		(uint64_t*) nullptr, (uint32_t*) nullptr) ;
+	uint32_t rawMoshes = 0 ;	/* without the phantom entries of empty blocks */
 	CK (cudaMemcpyAsync (&Mb, segOff.p + nblk, 4, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaMemcpyAsync (&rawMoshes, off2.p + 2 * (size_t) nb, 4, cudaMemcpyDeviceToHost, s)) ;
 	CK (cudaStreamSynchronize (s)) ;
+	totalMoshes += rawMoshes ;
       }
-      totalMoshes += Mb ;
       DBuf<uint64_t> keys (Mb, s, mt), keysS (Mb, s, mt) ;
       DBuf<uint32_t> vals (Mb, s, mt), valsS (Mb, s, mt) ;
       { StageTimer tm (c, s, ST_MOSHES) ;
@@ -1131,28 +1170,22 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       G += Hb ;
     }
 
-  tr.mark ("generic") ;
-  /* the global sort runs on hash / w: exact division = multiplication by w^-1 mod 2^64 (w odd part) and a
-     shift (power-of-two part); quotients of multiples keep the order and need fewer radix passes */
-  const uint64_t wInvFull = c->hp.wTz ? 1 : c->hp.wInv ;
-  const uint64_t wDiv = c->hp.wTz ? 1 : (uint64_t) P.w ;
+    tr.mark ("generic") ;
+  for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
+  hBlkOff[nProcBlk] = H ;
+  tail2 = tailWanted && H > 0 && tail_geometry (H, topQ, blkBase + nProcBlk, tg) ;
+  if (lean && !tail2) { scratch.release () ; stage.release () ; work.release () ; cursor.release () ; continue ; }
+  break ;
+  }
   int sortBits = 2 * P.k ;
   { uint64_t top = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ; sortBits = 1 ; while (sortBits < 64 && (top >> sortBits)) ++sortBits ; }
   /* -- final placement in block order: eHash / eRead / entryBlk -- */
-  for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
-  hBlkOff[nProcBlk] = H ;
-  c->nHashes = H ;
+    c->nHashes = H ;
   if (H >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 block-unique hashes on one device") ;
   /* single-GPU: bucket-major (key, value) pairs (h10x_bucket.cuh); multi-GPU: block-major hash / read / block arrays */
   int blkBits = 1 ; while (((uint64_t) 1 << blkBits) < (uint64_t) nBlk + 2) ++blkBits ;
   const int nbBits = sortBits > 32 ? sortBits - 32 : 0 ;
-  /* single-GPU: the hand-written tail (h10x_tail.cuh) whenever its packed 64-bit entry fits; the library-sort tail
-     of round 1 stays as the general path (multi-GPU, very wide hashes) and as a cross-check (H10X_FLAG_LEGACY_TAIL) */
-  TailGeom tg ; memset (&tg, 0, sizeof (tg)) ;
-  const uint64_t topQ = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
-  const bool tail2 = !dist && H > 0 && !(P.flags & H10X_FLAG_LEGACY_TAIL) && !getenv ("H10X_LEGACY_TAIL")
-    && tail_geometry (H, topQ, blkBase + nProcBlk, tg) ;
-  c->stats.tailPath = tail2 ? 2 : 1 ;
+    c->stats.tailPath = tail2 ? 2 : 1 ;
   const bool bucketed = !tail2 && !dist && nbBits <= 8 && sortBits + blkBits <= 64 && H < 0x7fffffffull && H > 0 ;
   uint32_t nBuck = 1 ;
   std::vector<uint64_t> hBucketBase ;
@@ -1193,7 +1226,6 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       }
   }
   scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
-  if (!totalMoshes) totalMoshes = H ;
 
   tr.mark ("place") ;
   /* ---------------- bins: ids, values, depths ---------------- */
@@ -1203,7 +1235,16 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   DBuf<uint32_t> se, segIncl, segStart, idOfSeg, sk ;
   DBuf<uint64_t> sv ;
   if (!bucketed && !tail2) segIncl.alloc (H, s, mt) ;
-  if (tail2) D = tail_rest (c, s, tg, H, wDiv, tailB, tailRangeStart) ;
+    if (tail2)
+    { std::vector<uint32_t> blkDup ;
+      D = tail_rest (c, s, tg, H, wDiv, tailB, tailRangeStart, blkBase + nProcBlk, blkDup) ;
+      /* per-block unique counts, now that the duplicates are gone */
+      uint64_t run = 0 ;
+      for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = run ; hCnt[p] -= blkDup[blkBase + p + 1] ; run += hCnt[p] ; }
+      hBlkOff[nProcBlk] = run ;
+      if (run != H) throw H10xError (H10X_ERR_CUDA, "internal: duplicate count mismatch in the grouping tail") ;
+      c->nHashes = H ;
+    }
   else if (bucketed)
     { sk.alloc (H, s, mt) ; sv.alloc (H, s, mt) ;
       { StageTimer tm (c, s, ST_HASHSORT) ;

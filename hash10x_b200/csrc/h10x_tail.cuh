@@ -340,6 +340,10 @@ struct SrArgs {
   const uint32_t *srStart ;	/* nSub + 1 */
   uint32_t *stage ;		/* first entries (global positions) of sub-range j's hashes, at stage[srStart[j] ..) */
   uint32_t *nHeads ;		/* nSub + 1 (the last one stays 0 for the scan) */
+  uint32_t *srCount ;		/* nSub: entries a job kept (a lean fused kernel leaves the duplicates of a (hash, block) in) */
+  uint32_t *blkDup ;		/* per (global, 1-based) block number: entries dropped as duplicates */
+  unsigned long long *nDup ;	/* ... in total */
+  uint32_t blkMask ;
   uint32_t *overList ;		/* sub-ranges left to the library sort */
   uint32_t *jobList ;		/* first sub-range | log2 (sub-ranges) << 30 */
   unsigned int *nOver ;
@@ -481,17 +485,34 @@ k_sr_sort (SrArgs a)
 	  __syncthreads () ;		/* the counters are cleared again by the next pass */
 	}
       __syncthreads () ;
-      /* first entry of every hash: q's kept bits change (the sub-range fixes the bits above) */
-      uint32_t cntHead = 0 ;
+      /* one entry per (hash, block): equal ones stand side by side (the passes above are stable and the entries came
+	 block-ascending), the lowest read index is kept (hash10x.c:166-172: the stable qsort leaves the first-generated
+	 mosh of a hash first).  First entry of every hash: q's kept bits change (the sub-range fixes the bits above). */
+      uint32_t cntFH = 0 ;		/* kept entries | heads << 16 (n <= cap < 2^16) */
       const uint32_t perT = (n + H10X_SR_THREADS - 1) / H10X_SR_THREADS ;
       const uint32_t l0 = min (t * perT, n), l1 = min (l0 + perT, n) ;
-      for (uint32_t i = l0 ; i < l1 ; ++i) cntHead += (i == 0 || (src[i] >> a.eShift) != (src[i - 1] >> a.eShift)) ? 1u : 0u ;
-      uint32_t total ;
-      uint32_t at = sr_cta_exclusive_scan (cntHead, warpTmp, total) ;
       for (uint32_t i = l0 ; i < l1 ; ++i)
-	if (i == 0 || (src[i] >> a.eShift) != (src[i - 1] >> a.eShift)) a.stage[st + at++] = st + i ;
-      if (t == 0) a.nHeads[j] = total ;
-      if (passes) for (uint32_t i = t ; i < n ; i += H10X_SR_THREADS) g[i] = src[i] ;
+	{ const uint64_t e = src[i], p = i ? src[i - 1] : 0 ;
+	  if (i == 0 || (e >> 16) != (p >> 16)) cntFH += 1u + ((i == 0 || (e >> a.eShift) != (p >> a.eShift)) ? 0x10000u : 0u) ;
+	}
+      uint32_t total ;
+      const uint32_t at = sr_cta_exclusive_scan (cntFH, warpTmp, total) ;
+      uint32_t atF = at & 0xffffu, atH = at >> 16 ;
+      for (uint32_t i = l0 ; i < l1 ; ++i)
+	{ const uint64_t e = src[i], p = i ? src[i - 1] : 0 ;
+	  if (i == 0 || (e >> 16) != (p >> 16))
+	    { uint32_t r = (uint32_t) e & 0xffffu ;
+	      for (uint32_t k = i + 1 ; k < n && (src[k] >> 16) == (e >> 16) ; ++k) r = min (r, (uint32_t) src[k] & 0xffffu) ;
+	      dst[atF] = (e & ~(uint64_t) 0xffffu) | r ;
+	      if (i == 0 || (e >> a.eShift) != (p >> a.eShift)) a.stage[st + atH++] = st + atF ;
+	      ++atF ;
+	    }
+	  else atomicAdd (&a.blkDup[(uint32_t) (e >> 16) & a.blkMask], 1u) ;
+	}
+      __syncthreads () ;
+      const uint32_t nF = total & 0xffffu ;
+      if (t == 0) { a.nHeads[j] = total >> 16 ; a.srCount[j] = nF ; if (nF != n) atomicAdd (a.nDup, (unsigned long long) (n - nF)) ; }
+      for (uint32_t i = t ; i < nF ; i += H10X_SR_THREADS) g[i] = dst[i] ;
     }
 }
 
@@ -499,17 +520,22 @@ k_sr_sort (SrArgs a)
 __global__ void k_sr_heads_big (SrArgs a, uint32_t j)
 { __shared__ uint32_t warpTmp[33] ;
   const uint32_t st = a.srStart[j], n = a.srStart[j + 1] - st ;
-  const uint64_t *g = a.A + st ;
-  uint32_t done = 0 ;
+  uint64_t *g = a.A + st ;		/* sorted on the whole word: (hash, block, read) */
+  uint32_t doneF = 0, doneH = 0 ;
   for (uint32_t c0 = 0 ; c0 < n ; c0 += blockDim.x)
     { const uint32_t i = c0 + threadIdx.x ;
-      const bool head = i < n && (i == 0 || (g[i] >> a.eShift) != (g[i - 1] >> a.eShift)) ;
+      const uint64_t e = i < n ? g[i] : 0, p = (i && i < n) ? g[i - 1] : 0 ;
+      const bool first = i < n && (i == 0 || (e >> 16) != (p >> 16)) ;
+      const bool head = first && (i == 0 || (e >> a.eShift) != (p >> a.eShift)) ;
       uint32_t total ;
-      const uint32_t at = sr_cta_exclusive_scan (head ? 1u : 0u, warpTmp, total) ;
-      if (head) a.stage[st + done + at] = st + i ;
-      done += total ;
+      const uint32_t at = sr_cta_exclusive_scan ((first ? 1u : 0u) | (head ? 0x10000u : 0u), warpTmp, total) ;	/* barriers: all have read */
+      if (first) g[doneF + (at & 0xffffu)] = e ;	/* at or before i; the first of a group carries the lowest read index */
+      else if (i < n) atomicAdd (&a.blkDup[(uint32_t) (e >> 16) & a.blkMask], 1u) ;
+      if (head) a.stage[st + doneH + (at >> 16)] = st + doneF + (at & 0xffffu) ;
+      doneF += total & 0xffffu ; doneH += total >> 16 ;
+      __syncthreads () ;
     }
-  if (threadIdx.x == 0) a.nHeads[j] = done ;
+  if (threadIdx.x == 0) { a.nHeads[j] = doneH ; a.srCount[j] = doneF ; if (doneF != n) atomicAdd (a.nDup, (unsigned long long) (n - doneF)) ; }
 }
 
 /* ---------------------------------------------------------------- bins in hash order -> ids */
@@ -517,21 +543,23 @@ __global__ void k_sr_heads_big (SrArgs a, uint32_t j)
 /* one warp per sub-range: its hashes' first positions move to their place in the global (hash-ordered) bin list;
    the bin's hash value and its sort key (first block << 32 | bin) come from the first entry */
 __global__ void k_heads_compact (uint32_t nSub, const uint32_t *__restrict__ srStart, const uint32_t *__restrict__ nHeads,
-				 const uint32_t *__restrict__ binBase, const uint32_t *__restrict__ stage,
+				 const uint32_t *__restrict__ srCount, const uint32_t *__restrict__ binBase, const uint32_t *__restrict__ stage,
 				 const uint64_t *__restrict__ A, int eShift, int lowBits, int p2, uint32_t blkMask, uint64_t wMul,
-				 uint32_t *__restrict__ segStart, uint64_t *__restrict__ fkey, uint64_t *__restrict__ hvHash)
+				 uint32_t *__restrict__ segStart, uint32_t *__restrict__ segLen, uint64_t *__restrict__ fkey,
+				 uint64_t *__restrict__ hvHash)
 { const uint32_t lane = threadIdx.x & 31 ;
   const uint64_t nw = ((uint64_t) gridDim.x * blockDim.x) >> 5 ;
   for (uint64_t j = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ; j < nSub ; j += nw)
     { const uint32_t nh = nHeads[j] ;
       if (!nh) continue ;
-      const uint32_t bb = binBase[j], st = srStart[j] ;
+      const uint32_t bb = binBase[j], st = srStart[j], end = st + srCount[j] ;
       const uint64_t qTop = (lowBits >= 64) ? 0 : ((uint64_t) (j >> p2) << lowBits) ;
       for (uint32_t x = lane ; x < nh ; x += 32)
 	{ const uint32_t pos = stage[st + x] ;
 	  const uint64_t E = A[pos] ;
 	  const uint32_t s = bb + x ;
 	  segStart[s] = pos ;
+	  segLen[s] = ((x + 1 < nh) ? stage[st + x + 1] : end) - pos ;	/* the job's kept entries are contiguous from st */
 	  fkey[s] = ((uint64_t) ((uint32_t) (E >> 16) & blkMask) << 32) | s ;
 	  hvHash[s] = (qTop | (E >> eShift)) * wMul ;
 	}
@@ -539,7 +567,7 @@ __global__ void k_heads_compact (uint32_t nSub, const uint32_t *__restrict__ srS
 }
 
 /* rank r in (first block, hash) order is bin id r + 1 (hash10x.c:147) */
-__global__ void k_bins_by_rank_e (uint32_t nSeg, const uint64_t *__restrict__ sortedKey, const uint32_t *__restrict__ segStart,
+__global__ void k_bins_by_rank_e (uint32_t nSeg, const uint64_t *__restrict__ sortedKey, const uint32_t *__restrict__ segLen,
 				  const uint64_t *__restrict__ hvHash, uint32_t *__restrict__ idOfSeg,
 				  uint64_t *__restrict__ hashValue, uint32_t *__restrict__ hashDepth)
 { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x ;
@@ -547,11 +575,12 @@ __global__ void k_bins_by_rank_e (uint32_t nSeg, const uint64_t *__restrict__ so
   const uint32_t s = (uint32_t) sortedKey[r], id = r + 1u ;
   idOfSeg[s] = id ;
   hashValue[id] = hvHash[s] ;
-  hashDepth[id] = segStart[s + 1] - segStart[s] ;	/* one entry per (block, hash): hash10x.c:178 */
+  hashDepth[id] = segLen[s] ;	/* one entry per (block, hash): hash10x.c:178 */
 }
 
 /* fillHashTable (hash10x.c:317-347) + the transposed view: as k_codes_seg_kv, on E words */
-__global__ void k_codes_seg_e (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ idOfSeg,
+__global__ void k_codes_seg_e (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ segLen,
+			       const uint32_t *__restrict__ idOfSeg,
 			       const uint64_t *__restrict__ A, uint32_t blkMask, const uint64_t *__restrict__ codeOff,
 			       uint32_t *__restrict__ codes, uint64_t *__restrict__ idRead)
 { const uint32_t lane = threadIdx.x & 31 ;
@@ -562,7 +591,7 @@ __global__ void k_codes_seg_e (uint32_t nSeg, const uint32_t *__restrict__ segSt
   uint32_t myI0 = 0, myN = 0, myId = 0 ; uint64_t myDst = 0 ;
   if (lane < cnt)
     { const uint32_t s = (uint32_t) s0 + lane ;
-      myI0 = segStart[s] ; myN = segStart[s+1] - myI0 ; myId = idOfSeg[s] ; myDst = codeOff[myId] ;
+      myI0 = segStart[s] ; myN = segLen[s] ; myId = idOfSeg[s] ; myDst = codeOff[myId] ;
     }
   uint32_t i0 = __shfl_sync (0xffffffffu, myI0, 0), n = __shfl_sync (0xffffffffu, myN, 0) ;
   uint64_t cur = (lane < n) ? A[(uint64_t) i0 + lane] : 0 ;

@@ -254,3 +254,42 @@ def test_random_small_inputs_match_oracle(orc, gpu_lib):
         assert np.array_equal(got.codes, want.codes) and np.array_equal(got.clus, want.clus)
         n_ok += 1
     assert n_ok >= 20 and n_err >= 5
+
+
+def test_mosh_count_is_the_raw_selection_count(orc, gpu_lib):
+    # stats.nMoshes = selected k-mers of the processed blocks (seqhash.c:171,189), before the per-block dedup
+    p = orc.synth_params(seed=31, n_barcodes=12, pairs_min=20, pairs_max=300)
+    recs = orc.synth_fqb(p)
+    n, off = orc.synth_layout(p)
+    want = sum(len(orc.record_moshes(rec)[0]) for rec in recs[:int(off[-2])])     # the last run is never hashed
+    for flags in (0, 8):
+        with _gpu(B=20, flags=flags) as g:
+            g.build_host(recs)
+            st = g.stats()
+        assert st["nMoshes"] == want, flags
+        assert st["nHashes"] < st["nMoshes"]
+
+
+def test_tail_big_sub_ranges_and_deep_bins(orc, gpu_lib, monkeypatch):
+    # the hand-written tail: sub-ranges beyond the shared-memory sort's capacity go through the library sort +
+    # k_sr_heads_big (forced here by a tiny capacity), and a hash held by every block (poly-A read pairs) makes one
+    # very deep bin; both must give the oracle's index
+    rng = np.random.default_rng(23)
+    p = orc.synth_params(seed=29, n_barcodes=150, pairs_min=10, pairs_max=120, genome_len=60_000, mol_len=5_000)
+    recs = orc.synth_fqb(p)
+    n, off = orc.synth_layout(p)
+    parts = []
+    for b in range(150):                      # one poly-A pair at the end of every barcode run: hash 0 in every block
+        run = recs[int(off[b]):int(off[b + 1])]
+        polyA = fqbtools.const_records(int(run[0, 0]), 1, 0, 0)
+        polyA[0, 0] = run[0, 0]
+        parts += [run, polyA]
+    deep = np.concatenate(parts)
+    want, got, st = _compare(orc, deep, B=21)
+    assert st["tailPath"] == 2
+    z = int(np.where(got.hashValue[1:] == 0)[0][0]) + 1
+    assert got.hashDepth[z] == 149
+    monkeypatch.setenv("H10X_SR_CAP", "48")
+    want, got, st = _compare(orc, deep, B=21)
+    assert st["tailPath"] == 2
+    want, got, st = _compare(orc, recs, B=21)
