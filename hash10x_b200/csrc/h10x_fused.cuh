@@ -157,7 +157,17 @@ k_fused_block (FusedArgs a, HashParams hp)
   /* WODD: the hash loop tests only the high word, q_hi < limHi1 = wLim_hi + 1 - every multiple of w passes, and so does
      one other k-mer in 2^32; each lane then re-tests its few stored keys exactly before they are counted.  One
      compare per k-mer instead of two, and the tail lanes' limit for their shared k-mers is simply 0. */
-  const uint32_t limHi1 = (uint32_t) (wLim >> 32) + 1u ;
+  /* ... and, for K > 16 (SH < 32), on an estimate of that word that is at most 2^(32-SH) - 1 below it: with
+     H = m_hi 2^tb + t (t = the tb = 32 - SH hash bits of the low word), q_hi = bits tb .. tb+31 of H w^-1
+     = lo32 (m_hi ilo + t (ihi << SH) + floor (t ilo / 2^tb)), and floor (t ilo / 2^tb) = t (ilo >> tb) + e, 0 <= e < t:
+     two plain multiply-adds instead of a wide one and two - the 64-bit multiplies are what saturates the SM here
+     (ncu: fmaheavy pipe 86 %, IMAD.WIDE / IMAD.HI take 4 of its cycles, IMAD 2).  The estimate gets the bias 2^tb so that
+     e never wraps it below zero, and so does the limit. */
+  constexpr bool QFAST = WODD && K > 16 ;
+  constexpr int TB = QFAST ? 2 * K - 32 : 1 ;
+  const uint32_t qK = QFAST ? (ihi << (32 - TB)) + (ilo >> TB) : 0u ;
+  const uint32_t qBias = QFAST ? (1u << TB) : 0u ;
+  const uint32_t limHi1 = (uint32_t) (wLim >> 32) + 1u + qBias ;
   const uint32_t limT = notTail ? limHi1 : 0u, limT1 = notTail1 ? limHi1 : 0u, limT2 = notTail2 ? limHi1 : 0u ;
   const uint32_t p0 = (isR2 ? H10X_R2_START : H10X_R1_START) + first ;	/* unpacked position of k-mer 0 */
   const uint32_t wi = p0 >> 4, sh = 2 * (p0 & 15) ;
@@ -178,7 +188,8 @@ k_fused_block (FusedArgs a, HashParams hp)
       const uint32_t *rec0 = a.fqb + (size_t) H10X_REC_WORDS * r0 ;
 
       /* ---- hash loop: no atomics, no divergence; selected keys go to the lane's column ---- */
-      uint32_t cnt = 0 ; bool over = false ;
+      uint32_t off = 0 ; bool over = false ;	/* byte offset of the next free slot of the lane's column (slot i at col[i * THREADS]): the
+						   address is then an add with carry, where index * stride would be one more wide multiply */
       uint32_t wordNext = (wid < nRead && lane < H10X_REC_WORDS) ? __ldcs (rec0 + (size_t) H10X_REC_WORDS * wid + lane) : 0u ;
       for (uint32_t pr = wid ; pr < nRead ; pr += THREADS / 32)
 	{ const uint32_t word = wordNext ;
@@ -192,7 +203,7 @@ k_fused_block (FusedArgs a, HashParams hp)
 	  if (!laneActive) continue ;
 	  const uint32_t Whi = __funnelshift_l (w1, w0, sh), Wlo = __funnelshift_l (w2, w1, sh) ;	/* bases p0..p0+31 */
 	  const uint32_t WRhi = h10x_swap_pairs_not (__brev (Wlo)), WRlo = h10x_swap_pairs_not (__brev (Whi)) ;
-	  if (cnt + 8 > a.rowCap) { over = true ; cnt = 0 ; }
+	  if (off + 8u * 8u * THREADS > a.rowCap * (8u * THREADS)) { over = true ; off = 0 ; }
 #pragma unroll
 	  for (int j = 0 ; j < 8 ; ++j)
 	    { const int c = SH - 2 * j ;		/* (W >> c) & mask: k-mer j, first base on top */
@@ -212,31 +223,39 @@ k_fused_block (FusedArgs a, HashParams hp)
 		 two hashes are equal and either may be taken, so one mask after the min is enough */
 	      uint64_t pf = h10x_mul64 (hlo, hhi, flo, fhi) ;
 	      uint64_t pq = h10x_mul64 (rlo, rhi, flo, fhi) ;
-	      uint64_t m = (pf < pq ? pf : pq) & (((uint64_t) TOPHI << 32) | TOPLO) ;	/* canonical hash << SH */
-	      uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
-		      bool sel ;
-		      if constexpr (WODD && K > 0)
-			{ const uint32_t qhi = (uint32_t) (q >> 32) ;
-			  sel = qhi < ((j < KD1 && j < KD2) ? limT : (j < KD1) ? limT1 : (j < KD2) ? limT2 : limHi1) ;
+	      if constexpr (QFAST)
+		{ const bool lt = pf < pq ;
+		  const uint32_t mhi = lt ? (uint32_t) (pf >> 32) : (uint32_t) (pq >> 32), mlo = lt ? (uint32_t) pf : (uint32_t) pq ;
+		  const uint32_t tq = mlo >> (32 - TB) ;
+		  uint32_t est ;
+		  asm ("mad.lo.u32 %0, %1, %2, %3;" : "=r" (est) : "r" (mhi), "r" (ilo), "r" (qBias)) ;
+		  asm ("mad.lo.u32 %0, %1, %2, %0;" : "+r" (est) : "r" (tq), "r" (qK)) ;
+		  if (est < ((j < KD1 && j < KD2) ? limT : (j < KD1) ? limT1 : (j < KD2) ? limT2 : limHi1))
+		    { *(uint64_t*) ((char*) col + off) = ((uint64_t) mhi << 32) | ((tq << (32 - TB)) + pr) ;	/* hash << SH | read index */
+		      off += 8u * THREADS ;
+		    }
+		}
+	      else
+		{ uint64_t m = (pf < pq ? pf : pq) & (((uint64_t) TOPHI << 32) | TOPLO) ;	/* canonical hash << SH */
+		  uint64_t q = h10x_mul64 ((uint32_t) m, (uint32_t) (m >> 32), ilo, ihi) ;
+		  bool sel ;
+		  if constexpr (WODD && K > 0)
+		    sel = (uint32_t) (q >> 32) < ((j < KD1 && j < KD2) ? limT : (j < KD1) ? limT1 : (j < KD2) ? limT2 : limHi1) ;
+		  else
+		    { sel = q <= wLim ;
+		      if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
+		      if constexpr (K > 0)
+			{ if (j < KD1 && j < KD2) sel = sel && notTail ;
+			  else if (j < KD1) sel = sel && notTail1 ;
+			  else if (j < KD2) sel = sel && notTail2 ;
 			}
-		      else
-			{ sel = q <= wLim ;
-			  if (!WODD) sel = sel && ((m & tzMaskSh) == 0) ;
-			  if constexpr (K > 0)
-			    { if (j < KD1 && j < KD2) sel = sel && notTail ;
-			      else if (j < KD1) sel = sel && notTail1 ;
-			      else if (j < KD2) sel = sel && notTail2 ;
-			    }
-			  else sel = sel && (uint32_t) j >= dupSkip ;
-			}
-	      if (sel)	/* low SH bits of m are 0, so the read index simply drops in (an add, issued as IMAD: FMA pipe) */
-		{ uint32_t klo ;
-		  asm ("mad.lo.u32 %0, %1, 1, %2;" : "=r" (klo) : "r" (pr), "r" ((uint32_t) m)) ;
-		  col[(size_t) cnt * THREADS] = (m & 0xffffffff00000000ull) | klo ;
-		  asm ("mad.lo.u32 %0, %0, 1, 1;" : "+r" (cnt)) ;
+		      else sel = sel && (uint32_t) j >= dupSkip ;
+		    }
+		  if (sel) { *(uint64_t*) ((char*) col + off) = (m & 0xffffffff00000000ull) | ((uint32_t) m + pr) ; off += 8u * THREADS ; }
 		}
 	    }
 	}
+      uint32_t cnt = off / (8u * THREADS) ;
       if constexpr (WODD && K > 0)	/* the exact test of the lane's stored keys; a failing one (1 in 2^32 k-mers) is squeezed out */
 	{ uint32_t v = 0 ;
 	  for (uint32_t i = 0 ; i < cnt ; ++i)
