@@ -371,7 +371,9 @@ def run_ours(args, wl, wl_name):
         return t, r1 - r0
 
     fqb, n_rec = make_input(wl, world, rank, world)
-    g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local)
+        # FLAG_LAZY_CODES: as hash10x-b200 creates its context - the hash->code lists stay resident for --cluster and are not
+    # part of what h10x_gpu_build_host copies back (no host command of the --readFQB ... --writeHash chain reads them)
+    g = hash10x_b200.Hash10xGPU(B=wl["B"], device=local, flags=hash10x_b200.FLAG_LAZY_CODES)
     if world > 1:
         g.dist_init(rank, world, shard.share_unique_id(dist, rank, hash10x_b200.Hash10xGPU.dist_unique_id))
 
@@ -445,14 +447,17 @@ def run_ours(args, wl, wl_name):
         s = g.stats()
         hn, H, nbm = s["nBins"] + 1, s["nHashes"], s["nBlocks"] + 1
         if world == 1:
-            d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H + 8 * (hn + 1) + 4 * H
+                        d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H
         else:       # rank 0: table + values + depths + its blocks and ClusterHash lists (hash->code parts stay resident)
             d2h = (4 << wl["B"]) + 8 * hn + 4 * hn + 4 * nbm + 4 * nbm + 8 * (nbm + 1) + 8 * H
         e2e = {"value": total_pairs / dt, "unit": UNIT, "h2d_bytes_per_step": n_rec * 120,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "bytes_are": "rank 0's, per step",
                "api": ("h10x_gpu_build_host" if world == 1 else "h10x_gpu_build_host_dist") +
-                      " (include/h10x_gpu.h): pinned host FQB -> index arrays in pinned host memory"}
+                                            " (include/h10x_gpu.h): pinned host FQB -> index arrays in pinned host memory (hashIndex, hashValue, "
+                      "hashDepth, block table, ClusterHash lists = everything writeHashFile, hash10x.c:244-267, writes; the "
+                      "hash->code lists stay resident, H10X_FLAG_LAZY_CODES, as in hash10x-b200); the file goes up in slabs "
+                      "and the fused kernel hashes the slabs that have landed"}
         del host_t
     else:
         del fqb

@@ -8,4 +8,4 @@ fallback: importing works anywhere, but every build call raises without the libr
 """
 from .binding import (Hash10xGPU, H10xError, Index, Params, lib_path, load_library,  # noqa: F401
                       factor1_from_seed, DEFAULT_FACTOR1, FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES,
-                      FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL)
+                      FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL, FLAG_LAZY_CODES)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_FACTOR1 = 0x49308BB9003CB3AD  # -r 17
 
 H10X_NSTAGES = 12
-FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES, FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL = 1, 2, 4, 8, 16
+FLAG_WIDE_B, FLAG_NO_TABLE, FLAG_NO_CODES, FLAG_GENERIC_ONLY, FLAG_LEGACY_TAIL, FLAG_LAZY_CODES = 1, 2, 4, 8, 16, 32
 
 
 class H10xError(RuntimeError):
@@ -103,6 +103,7 @@ def load_library():
     L.h10x_gpu_build_device.argtypes = [vp, vp, u64, vp, cp, sz]
     L.h10x_gpu_index_device.argtypes = [vp, C.POINTER(CIndex)]
     L.h10x_gpu_download.argtypes = [vp, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_download_codes.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_build_host.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_build_file.argtypes = [vp, cp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_stats.argtypes = [vp, C.POINTER(CStats)]
@@ -207,6 +208,15 @@ class Hash10xGPU:
             return Index(ci, self.lib) if want_index else (ci.hashNumber, ci.nHashes, ci.nBlocksMax)
         finally:
             self.lib.h10x_index_free(C.byref(ci))
+
+    def download_codes(self):
+        """fillHashTable()'s lists of the resident index -> (codeOff u64, codes u32) host copies: what a context created
+        with FLAG_LAZY_CODES leaves out of build_host / download"""
+        ci = CIndex()
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_download_codes(self.ctx, C.byref(ci), err, len(err)), err)
+        s = self.stats()
+        return _arr(ci.codeOff, s["nBins"] + 2, np.uint64), _arr(ci.codes, s["nHashes"], np.uint32)
 
     def build_file(self, path):
         ci = CIndex()

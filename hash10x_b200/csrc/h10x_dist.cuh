@@ -78,6 +78,8 @@ struct DistState {
   int rank = 0, nranks = 1 ;
   ncclComm_t comm = nullptr ;
   int pushState = 0 ;		/* 0 untried, 1 peer stores work, -1 fall back to ncclSend/ncclRecv */
+  bool owesAgreement = false ;	/* the peers will wait for this rank's word at the next dist_agree (dist_bins' entry): a rank
+				   that fails before it must still deliver it, or the others block in the collective for ever */
   PeerMap peers[H10X_MAX_RANKS] ;
   std::vector<cudaStream_t> copyStreams ;
   /* results of the last distributed build */

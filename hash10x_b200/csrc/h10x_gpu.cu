@@ -35,6 +35,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <deque>
 
 /* ------------------------------------------------------------------ errors / memory */
 
@@ -127,6 +128,7 @@ struct h10x_ctx {
   /* multi-GPU (h10x_dist.cuh) */
   bool slabClamped = false ;	/* the slab already takes all free device memory */
   /* host-buffer builds start the D2H of an index array as soon as it is final, on a second stream */
+    cudaStream_t ulStream = 0 ;	/* ... and copy the file up in slabs on a third one while the fused kernel hashes the slabs that landed */
   bool earlyDl = false ; cudaStream_t dlStream = 0 ; bool slotDone[9] = { false, false, false, false, false, false, false, false, false } ;
   DBuf<uint8_t> within ;	/* --hashDepthRange flags per bin; only ever set (hash10x.c:535) until the next build */
   /* goodHashes of the last --hashDepthRange (hash10x.c:722-766), resident for --cluster; ClusterBlock.nSubCluster /
@@ -207,6 +209,18 @@ __global__ void k_run_flags (const uint32_t *__restrict__ fqb, uint32_t n, uint3
   uint32_t w0 = fqb[(size_t) H10X_REC_WORDS * i] ;
   uint32_t prev = i ? fqb[(size_t) H10X_REC_WORDS * (i - 1)] : ~w0 ;
   flag[i] = (w0 != prev) ? 1u : 0u ;
+  if (w0 == 0) *anyZero = 1 ;
+}
+
+/* the same for records r0 .. r0 + n - 1 of a file whose earlier records are resident: flag[i - r0] */
+__global__ void k_run_flags_at (const uint32_t *__restrict__ fqb, uint32_t r0, uint32_t n, uint32_t *__restrict__ flag,
+				int *__restrict__ anyZero)
+{ uint32_t j = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (j >= n) return ;
+  const uint32_t i = r0 + j ;
+  uint32_t w0 = fqb[(size_t) H10X_REC_WORDS * i] ;
+  uint32_t prev = i ? fqb[(size_t) H10X_REC_WORDS * (i - 1)] : ~w0 ;
+  flag[j] = (w0 != prev) ? 1u : 0u ;
   if (w0 == 0) *anyZero = 1 ;
 }
 
@@ -828,6 +842,15 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
   }
   early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ;
   early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ;
+  /* hashIndex[] only needs the values in id order: built here, its copy to the host runs beside the stages below */
+  if (!(P.flags & H10X_FLAG_NO_TABLE))
+    { StageTimer tm (c, s, ST_TABLE) ;
+      const size_t tableSize = (size_t) 1 << P.B ;
+      c->hashIndex.alloc (tableSize, s, mt) ;
+      CK (cudaMemsetAsync (c->hashIndex.p, 0, 4 * tableSize, s)) ;
+      if (D) LAUNCH (c, k_table_insert, gridFor (D, 256), 256, 0, s, c->hashNumber, c->hashValue.p, c->hashIndex.p, P.B) ;
+      early_pull (c, s, SLOT_INDEX, c->hashIndex.p, 4 * tableSize) ;
+    }
   const size_t hn = c->hashNumber ;
   DBuf<uint64_t> idRead (H, s, mt) ;
   { StageTimer tm (c, s, ST_CODES) ;
@@ -839,7 +862,7 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
 	    c->codeOff.p, c->codes.p, idRead.p) ;
   }
     A.release () ; segStart.release () ; segLen.release () ; idOfSeg.release () ;
-  if (!(P.flags & H10X_FLAG_NO_CODES))
+    if (!(P.flags & (H10X_FLAG_NO_CODES | H10X_FLAG_LAZY_CODES)))
     { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
   c->clus.alloc (H, s, mt) ;
   { StageTimer tm (c, s, ST_CLUSTERS) ;
@@ -876,8 +899,134 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul) ;
 static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_t mine[4], std::vector<uint32_t> &all) ;
 
+/* ------------------------------------------------------------------ host: the fused mosh stage (h10x_fused.cuh) */
+
+struct FusedClass { uint32_t cap, nbuck, lb, threads, rowCap ; } ;
+/* shared memory per CTA = 8 * cap + 4 * nbuck (+ 1 KB the driver reserves): 5, 5, 4, 2 and 1 CTAs per SM */
+static const FusedClass kClasses[5] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 }, { 5632, 2048, 11, 384, 48 },
+					{ 12288, 4096, 12, 512, 64 }, { 24576, 8192, 13, 1024, 64 } } ;
+static const int kNClasses = 5 ;
+
+/* Everything the fused kernel's launches of one build share: kernel variants, grids, the staging area, the scratch
+   slab the block lists go to and its cursor.  A launch takes a list of blocks per size class; the blocks of a build
+   may come in several launches (h10x_gpu_build_host hashes each slab of the file while the next one is copied). */
+struct FusedEngine {
+  bool ready = false, lean = false ;
+  int n1 = 0, n2 = 0, c1 = 0, c2 = 0 ;
+  double perPair = 0 ;
+  const void *fn[5] ; size_t smemB[5] ; uint32_t maxGrid[5] ;
+  DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
+  uint64_t scratchCap = 0 ; uint32_t workUsed = 0, workCap = 0 ;
+  std::deque<DBuf<uint32_t>> dLists ;
+
+  static bool usable (const h10x_params &P)
+  { const int n1 = H10X_R1_LEN - P.k + 1, n2 = H10X_R2_LEN - P.k + 1 ;
+    return !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && (n1 + 7) / 8 + (n2 + 7) / 8 <= 32 && n1 >= 8 ;
+  }
+  /* nProc: records of the blocks that will be hashed; nLaunchGroups: how many times launch () may be called */
+  void init (h10x_ctx *c, cudaStream_t s, bool lean_, uint64_t nProc, uint32_t nLaunchGroups)
+  { const h10x_params &P = c->P ; MemTrack *mt = &c->mt ;
+    lean = lean_ ;
+    n1 = H10X_R1_LEN - P.k + 1 ; n2 = H10X_R2_LEN - P.k + 1 ; c1 = (n1 + 7) / 8 ; c2 = (n2 + 7) / 8 ;
+    perPair = (double) (n1 + n2) / (double) P.w ;	/* expected moshes per read pair */
+    scratchCap = (uint64_t) (perPair * 1.15 * nProc) + (1u << 20) ;
+    workCap = nLaunchGroups * kNClasses ; workUsed = 0 ;
+    scratch.alloc (scratchCap, s, mt) ; cursor.alloc (2, s, mt) ; work.alloc (workCap, s, mt) ;	/* cursor[1]: mosh count */
+    CK (cudaMemsetAsync (cursor.p, 0, 16, s)) ;
+    CK (cudaMemsetAsync (work.p, 0, 4 * (size_t) workCap, s)) ;
+    int nSM = 148 ;
+    CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, P.device)) ;
+    const bool wodd = (c->hp.wTz == 0 && P.w >= 3) ;
+    const bool k21 = (P.k == 21 && wodd) ;
+    size_t stageKeys = 0 ;
+    for (int ci = 0 ; ci < kNClasses ; ++ci)
+      { const FusedClass &fc = kClasses[ci] ;
+	smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) fc.nbuck + 1) + 16 ;
+#define FUSED_FN1(T, L) (k21 ? (const void*) k_fused_block<T, true, 21, L> : wodd ? (const void*) k_fused_block<T, true, 0, L> \
+		     : (const void*) k_fused_block<T, false, 0, L>)
+#define FUSED_FN(T) (lean ? FUSED_FN1 (T, true) : FUSED_FN1 (T, false))
+	fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 384 ? FUSED_FN (384)
+	  : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
+#undef FUSED_FN
+#undef FUSED_FN1
+	CK (cudaFuncSetAttribute (fn[ci], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemB[ci])) ;
+	int occ = 1 ;
+	CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn[ci], (int) fc.threads, smemB[ci])) ;
+	if (occ < 1) occ = 1 ;
+	maxGrid[ci] = (uint32_t) nSM * (uint32_t) occ ;
+	stageKeys = std::max<size_t> (stageKeys, (size_t) maxGrid[ci] * fc.threads * fc.rowCap) ;
+      }
+    stage.alloc (stageKeys, s, mt) ;	/* launches run one after another and share it */
+    ready = true ;
+  }
+  /* size class of a block of nRead read pairs, -1: not for this path */
+  int classOf (const h10x_params &P, uint32_t nRead) const
+  { const double e = perPair * nRead, need = e * 1.12 + 6.0 * sqrt (e) + 16.0 ;
+    if (((uint64_t) nRead >> (64 - 2 * P.k)) != 0) return -1 ;	/* read index must fit under the hash bits */
+    for (int ci = 0 ; ci < kNClasses ; ++ci)
+      if (need <= kClasses[ci].cap && (int) kClasses[ci].lb <= 2 * P.k) return ci ;
+    return -1 ;
+  }
+  void launch (h10x_ctx *c, cudaStream_t s, const std::vector<uint32_t> lists[5], const uint32_t *fqb, const uint32_t *blkStart,
+	       uint64_t *srcOff, uint32_t *blkCnt)
+  { if (workUsed + kNClasses > workCap) throw H10xError (H10X_ERR_CUDA, "internal: fused launch groups exhausted") ;
+    for (int ci = 0 ; ci < kNClasses ; ++ci)
+      { if (lists[ci].empty ()) continue ;
+	const FusedClass &fc = kClasses[ci] ;
+	dLists.emplace_back () ;
+	DBuf<uint32_t> &dl = dLists.back () ;
+	dl.alloc (lists[ci].size (), s, &c->mt) ;
+	CK (cudaMemcpyAsync (dl.p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
+	FusedArgs fa ;
+	fa.fqb = fqb ; fa.list = dl.p ; fa.blkStart = blkStart ; fa.stage = stage.p ; fa.scratch = scratch.p ;
+	fa.cursor = cursor.p ; fa.work = work.p + workUsed + ci ; fa.scratchCap = scratchCap ; fa.srcOff = srcOff ; fa.blkCnt = blkCnt ;
+	fa.nList = (uint32_t) lists[ci].size () ; fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.rowCap = fc.rowCap ;
+	fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ; fa.moshCount = cursor.p + 1 ;
+	HashParams hpv = c->hp ;
+	void *args[2] = { (void*) &fa, (void*) &hpv } ;
+	const uint32_t grid = (uint32_t) std::min<size_t> (lists[ci].size (), maxGrid[ci]) ;
+	CK (cudaLaunchKernel (fn[ci], dim3 (grid), dim3 (fc.threads), args, smemB[ci], s)) ;
+	++c->launches ;
+      }
+    workUsed += kNClasses ;
+  }
+  void release ()
+  { scratch.release () ; stage.release () ; work.release () ; cursor.release () ; dLists.clear () ; ready = false ; }
+  void swap (FusedEngine &o)
+  { std::swap (ready, o.ready) ; std::swap (lean, o.lean) ; std::swap (n1, o.n1) ; std::swap (n2, o.n2) ; std::swap (c1, o.c1) ;
+    std::swap (c2, o.c2) ; std::swap (perPair, o.perPair) ;
+    for (int i = 0 ; i < 5 ; ++i) { std::swap (fn[i], o.fn[i]) ; std::swap (smemB[i], o.smemB[i]) ; std::swap (maxGrid[i], o.maxGrid[i]) ; }
+    scratch.swap (o.scratch) ; stage.swap (o.stage) ; cursor.swap (o.cursor) ; work.swap (o.work) ;
+    std::swap (scratchCap, o.scratchCap) ; std::swap (workUsed, o.workUsed) ; std::swap (workCap, o.workCap) ; dLists.swap (o.dLists) ;
+  }
+} ;
+
+/* What h10x_gpu_build_host's streamed front half hands to build_device_impl: the barcode runs of the whole file and
+   the fused kernel's lists of every run but the last, produced slab by slab while the file was still being copied.
+   Runs are blocks unless a barcode word is 0 (simulate_chunks); then, or when the tail's geometry turns the lean
+   lists down, the lists are dropped and the classic stages run. */
+struct Prefuse {
+  bool valid = false, anyZero = false ;
+  uint32_t nRuns = 0 ;
+  std::vector<uint32_t> runStart ;	/* nRuns + 1 */
+  DBuf<uint32_t> dBlkStart ;		/* the same on the device */
+  DBuf<uint64_t> srcOff ; DBuf<uint32_t> blkCnt ;	/* per run */
+  FusedEngine eng ;
+} ;
+
+static bool tail_geometry (uint64_t H, uint64_t top, uint32_t maxBlock, TailGeom &g) ;
+static bool lean_wanted (h10x_ctx *c, bool dist, uint64_t nProc, uint32_t nBlocks)
+{ const h10x_params &P = c->P ;
+  if (dist || (P.flags & H10X_FLAG_LEGACY_TAIL) || getenv ("H10X_LEGACY_TAIL") || getenv ("H10X_NO_LEAN")) return false ;
+  const uint64_t wDiv = c->hp.wTz ? 1 : (uint64_t) P.w ;
+  const uint64_t topQ = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
+  const double perPair = (double) (H10X_R1_LEN + H10X_R2_LEN - 2 * P.k + 2) / (double) P.w ;
+  TailGeom te ;
+  return tail_geometry ((uint64_t) (perPair * 1.1 * nProc) + nBlocks + 1, topQ, nBlocks, te) ;
+}
+
 static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile, cudaStream_t s, bool reset = true,
-			       bool dist = false)
+			       bool dist = false, Prefuse *pre = nullptr)
 {
   const h10x_params &P = c->P ;
   HostTrace tr ;
@@ -948,8 +1097,33 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   } ;
 
   /* multi-GPU: ranks own consecutive barcode-run ranges; agree on errors and on global block numbers */
-  bool lastRank = true ; uint32_t blkBase = 0, nBlkGlobal = 0 ;
-  if (!dist) doRuns () ;
+    bool lastRank = true ; uint32_t blkBase = 0, nBlkGlobal = 0 ;
+  bool blkInclReady = true ;		/* the per-record block numbers, which only the generic mosh path reads */
+  bool preRuns = false ;
+  if (pre && pre->valid && !pre->anyZero && nRec && !dist)
+    { /* the streamed front half found the runs already; blocks are the runs (no barcode word is 0) */
+      for (uint32_t r = 0 ; r < pre->nRuns ; ++r)
+	{ uint64_t st = pre->runStart[r], len = pre->runStart[r+1] - st ;
+	  if (len >= (uint64_t) P.chunkSize && (P.N == 0 || st + (uint64_t) P.chunkSize < (uint64_t) P.N))
+	    throw H10xError (H10X_ERR_CHUNK_TOO_SMALL, "chunkSize too small") ;
+	}
+      bt.nBlk = pre->nRuns ; bt.start = pre->runStart ;
+      dBlkStart.swap (pre->dBlkStart) ;
+      blkInclReady = false ; preRuns = true ;
+    }
+    else if (pre)
+    { pre->valid = false ; pre->eng.release () ; pre->srcOff.release () ; pre->blkCnt.release () ; pre->dBlkStart.release () ; }
+  auto ensureBlkIncl = [&] ()
+    { if (blkInclReady) return ;
+      DBuf<uint32_t> flag (nRec, s, mt) ;
+      CK (cudaMemsetAsync (flag.p, 0, 4 * (size_t) nRec, s)) ;
+      LAUNCH (c, k_flags_from_starts, gridFor (bt.nBlk, 256), 256, 0, s, dBlkStart.p, bt.nBlk, flag.p) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveSum (t, b, flag.p, blkIncl.p, nRec, s) ; }) ;
+      CK (cudaStreamSynchronize (s)) ;
+      blkInclReady = true ;
+    } ;
+  if (preRuns) {}
+  else if (!dist) doRuns () ;
   else
     { int localErr = 0 ;
       try { doRuns () ; }
@@ -963,7 +1137,9 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       if (!localErr && (nRec == 0 || P.N != 0 || sawZeroBarcode)) localErr = H10X_ERR_UNSUPPORTED ;
       const uint32_t mine[4] = { bt.nBlk, words[0], words[1], nRec } ;
       std::vector<uint32_t> all ;
+      c->dist->owesAgreement = false ;
       dist_agree (c, s, localErr, mine, all) ;		/* throws the same error on every rank */
+      c->dist->owesAgreement = true ;			/* the next one is at the entry of dist_bins */
       const int R = c->dist->rank, NR = c->dist->nranks ;
       uint64_t readsGlobal = 0 ;
       for (int r = 0 ; r < NR ; ++r)
@@ -973,6 +1149,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	    throw H10xError (H10X_ERR_UNSUPPORTED, "multi-GPU shards must be cut at barcode-run boundaries") ;
 	}
       lastRank = (R == NR - 1) ;
+      if (const char *e = getenv ("H10X_TEST_FAIL_RANK"))	/* tests: a rank-local failure between two agreements */
+	if (atoi (e) == R) throw H10xError (H10X_ERR_UNSUPPORTED, "forced failure (H10X_TEST_FAIL_RANK)") ;
       c->dist->blockBase = blkBase ; c->dist->nBlocksGlobal = nBlkGlobal ; c->dist->nReadsGlobal = readsGlobal ;
     }
 
@@ -990,16 +1168,10 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   std::vector<uint32_t> hCnt ((size_t) nProcBlk + 1, H10X_BLK_FALLBACK) ;
   uint64_t H = 0, totalMoshes = 0 ;
 
-  /* -- fused path: one CTA per block, everything in shared memory (h10x_fused.cuh) -- */
-  const int n1 = H10X_R1_LEN - P.k + 1, n2 = H10X_R2_LEN - P.k + 1 ;
-  const int c1 = (n1 + 7) / 8, c2 = (n2 + 7) / 8 ;
-  const bool fusedOK = !(P.flags & H10X_FLAG_GENERIC_ONLY) && P.k >= 13 && P.k <= 23 && c1 + c2 <= 32 && n1 >= 8 && nProcBlk > 0 ;
-  struct FusedClass { uint32_t cap, nbuck, lb, threads, rowCap ; } ;
-  /* shared memory per CTA = 8 * cap + 4 * nbuck (+ 1 KB the driver reserves): 5, 5, 4, 2 and 1 CTAs per SM */
-  static const FusedClass kClasses[5] = { { 1024, 512, 9, 128, 32 }, { 4096, 2048, 11, 256, 48 }, { 5632, 2048, 11, 384, 48 },
-					  { 12288, 4096, 12, 512, 64 }, { 24576, 8192, 13, 1024, 64 } } ;
-  const int nClasses = 5 ;
-    DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
+    /* -- fused path: one CTA per block, everything in shared memory (h10x_fused.cuh) -- */
+  const bool fusedOK = FusedEngine::usable (P) && nProcBlk > 0 ;
+  FusedEngine eng ;
+  DBuf<uint64_t> &scratch = eng.scratch ;
   uint64_t nFused = 0 ;
   DBuf<uint64_t> gHash ; DBuf<uint32_t> gRec ;
   uint64_t G = 0 ; size_t gCap = 0 ;
@@ -1017,75 +1189,32 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   bool tail2 = false, lean = false ;
   for (int attempt = 0 ; ; ++attempt)
   {
-  lean = tailWanted && attempt == 0 && !getenv ("H10X_NO_LEAN") ;
-  if (lean)
-    { TailGeom te ; const double perPairE = (double) (n1 + n2) / (double) P.w ;
-      lean = tail_geometry ((uint64_t) (perPairE * 1.1 * nProc) + nProcBlk + 1, topQ, blkBase + nProcBlk, te) ;
-    }
+  const bool usePre = attempt == 0 && preRuns && pre->eng.ready && fusedOK ;
+  lean = usePre ? pre->eng.lean : (attempt == 0 && lean_wanted (c, dist, nProc, blkBase + nProcBlk)) ;
   std::fill (hCnt.begin (), hCnt.end (), H10X_BLK_FALLBACK) ;
   H = 0 ; totalMoshes = 0 ; nFused = 0 ; G = 0 ;
-  if (fusedOK)
+  if (usePre)
+    { /* the lists of every run but the last are there already (and the last run is never hashed) */
+      eng.swap (pre->eng) ; srcOff.swap (pre->srcOff) ; blkCnt.swap (pre->blkCnt) ;
+    }
+  else if (fusedOK)
     { StageTimer tm (c, s, ST_FUSED) ;
+      eng.release () ;
+      eng.init (c, s, lean, nProc, 1) ;
       std::vector<uint32_t> lists[5] ;
-      const double perPair = (double) (n1 + n2) / (double) P.w ;	/* expected moshes per read pair */
       for (uint32_t p = 0 ; p < nProcBlk ; ++p)
-	{ uint32_t nRead = bt.start[p+1] - bt.start[p] ;
-	  double e = perPair * nRead, need = e * 1.12 + 6.0 * sqrt (e) + 16.0 ;
-	  if (((uint64_t) nRead >> (64 - 2 * P.k)) != 0) continue ;	/* read index must fit under the hash bits */
-	  for (int ci = 0 ; ci < nClasses ; ++ci)
-	    if (need <= kClasses[ci].cap && (int) kClasses[ci].lb <= 2 * P.k) { lists[ci].push_back (p) ; break ; }
+	{ const int ci = eng.classOf (P, bt.start[p+1] - bt.start[p]) ;
+	  if (ci >= 0) lists[ci].push_back (p) ;
 	}
-      uint64_t scratchCap = (uint64_t) (perPair * 1.15 * nProc) + (1u << 20) ;
-      scratch.alloc (scratchCap, s, mt) ; cursor.alloc (2, s, mt) ; work.alloc (nClasses, s, mt) ;	/* cursor[1]: mosh count */
-      CK (cudaMemsetAsync (cursor.p, 0, 16, s)) ;
-      CK (cudaMemsetAsync (work.p, 0, 4 * nClasses, s)) ;
       CK (cudaMemsetAsync (blkCnt.p, 0xff, 4 * ((size_t) nProcBlk + 1), s)) ;
-      int nSM = 148 ;
-      CK (cudaDeviceGetAttribute (&nSM, cudaDevAttrMultiProcessorCount, P.device)) ;
-      std::vector<DBuf<uint32_t>> dLists (nClasses) ;
-            const bool wodd = (c->hp.wTz == 0 && P.w >= 3) ;
-      const bool k21 = (P.k == 21 && wodd) ;
-      /* pass 1: grids and the staging area they need (launches run one after another and share it) */
-      uint32_t grid[5] = { 0, 0, 0, 0, 0 } ; size_t smemB[5] ; size_t stageKeys = 0 ;
-      const void *fn[5] ;
-      for (int ci = 0 ; ci < nClasses ; ++ci)
-	{ const FusedClass &fc = kClasses[ci] ;
-	  smemB[ci] = (size_t) fc.cap * 8 + 4 * ((size_t) fc.nbuck + 1) + 16 ;
-#define FUSED_FN1(T, L) (k21 ? (const void*) k_fused_block<T, true, 21, L> : wodd ? (const void*) k_fused_block<T, true, 0, L> \
-		     : (const void*) k_fused_block<T, false, 0, L>)
-#define FUSED_FN(T) (lean ? FUSED_FN1 (T, true) : FUSED_FN1 (T, false))
-	  fn[ci] = fc.threads == 128 ? FUSED_FN (128) : fc.threads == 256 ? FUSED_FN (256) : fc.threads == 384 ? FUSED_FN (384)
-	    : fc.threads == 512 ? FUSED_FN (512) : FUSED_FN (1024) ;
-#undef FUSED_FN
-#undef FUSED_FN1
-	  if (lists[ci].empty ()) continue ;
-	  CK (cudaFuncSetAttribute (fn[ci], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemB[ci])) ;
-	  int occ = 1 ;
-	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn[ci], (int) fc.threads, smemB[ci])) ;
-	  if (occ < 1) occ = 1 ;
-	  grid[ci] = (uint32_t) std::min<size_t> (lists[ci].size (), (size_t) nSM * occ) ;
-	  stageKeys = std::max<size_t> (stageKeys, (size_t) grid[ci] * fc.threads * fc.rowCap) ;
-	}
-      stage.alloc (stageKeys, s, mt) ;
-      for (int ci = 0 ; ci < nClasses ; ++ci)
-	{ if (lists[ci].empty ()) continue ;
-	  const FusedClass &fc = kClasses[ci] ;
-	  dLists[ci].alloc (lists[ci].size (), s, mt) ;
-	  CK (cudaMemcpyAsync (dLists[ci].p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
-	  FusedArgs fa ;
-	  fa.fqb = fqb ; fa.list = dLists[ci].p ; fa.blkStart = dBlkStart.p ; fa.stage = stage.p ; fa.scratch = scratch.p ;
-	  fa.cursor = cursor.p ; fa.work = work.p + ci ; fa.scratchCap = scratchCap ; fa.srcOff = srcOff.p ; fa.blkCnt = blkCnt.p ;
-	  fa.nList = (uint32_t) lists[ci].size () ; fa.cap = fc.cap ; fa.nbuck = fc.nbuck ; fa.lb = fc.lb ; fa.rowCap = fc.rowCap ;
-	  fa.c1 = c1 ; fa.c2 = c2 ; fa.n1 = n1 ; fa.n2 = n2 ; fa.moshCount = cursor.p + 1 ;
-	  HashParams hpv = c->hp ;
-	  void *args[2] = { (void*) &fa, (void*) &hpv } ;
-	  CK (cudaLaunchKernel (fn[ci], dim3 (grid[ci]), dim3 (fc.threads), args, smemB[ci], s)) ;
-	  ++c->launches ;
-	}
-      CK (cudaMemcpyAsync (hCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
+      eng.launch (c, s, lists, fqb, dBlkStart.p, srcOff.p, blkCnt.p) ;
+      CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies of launch () */
+    }
+  if (fusedOK)
+    { CK (cudaMemcpyAsync (hCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
       unsigned long long fusedMoshes = 0 ;
-      CK (cudaMemcpyAsync (&fusedMoshes, cursor.p + 1, 8, cudaMemcpyDeviceToHost, s)) ;
-      CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies above */
+      CK (cudaMemcpyAsync (&fusedMoshes, eng.cursor.p + 1, 8, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
       totalMoshes += fusedMoshes ;
       for (uint32_t p = 0 ; p < nProcBlk ; ++p) if (hCnt[p] != H10X_BLK_FALLBACK) ++nFused ;
     }
@@ -1109,7 +1238,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       uint32_t p0 = q0, p1 = p0 + 1 ;
       while (p1 < nProcBlk && hCnt[p1] == H10X_BLK_FALLBACK && bt.start[p1+1] - bt.start[p0] <= batchRecs) ++p1 ;
       q0 = p1 ;
-      uint32_t r0 = bt.start[p0], nb = bt.start[p1] - r0, nblk = p1 - p0 ;
+            uint32_t r0 = bt.start[p0], nb = bt.start[p1] - r0, nblk = p1 - p0 ;
+      ensureBlkIncl () ;
       if ((uint64_t) nb * 237 > 0x7fffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "barcode block too large for the generic path") ;
       DBuf<uint32_t> cnt2 ((size_t) 2 * nb + 1, s, mt), off2 ((size_t) 2 * nb + 1, s, mt) ;
       DBuf<uint32_t> ph ((size_t) nblk + 1, s, mt), phOff ((size_t) nblk + 1, s, mt), segOff ((size_t) nblk + 1, s, mt) ;
@@ -1174,7 +1304,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = H ; H += hCnt[p] ; }
   hBlkOff[nProcBlk] = H ;
   tail2 = tailWanted && H > 0 && tail_geometry (H, topQ, blkBase + nProcBlk, tg) ;
-  if (lean && !tail2) { scratch.release () ; stage.release () ; work.release () ; cursor.release () ; continue ; }
+    if (lean && !tail2) { eng.release () ; continue ; }
   break ;
   }
   int sortBits = 2 * P.k ;
@@ -1225,7 +1355,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	CK (cudaStreamSynchronize (s)) ;	/* hBlkOff is read by the async copy */
       }
   }
-  scratch.release () ; stage.release () ; work.release () ; cursor.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
+    eng.release () ; gHash.release () ; gRec.release () ; srcOff.release () ; blkCnt.release () ;
 
   tr.mark ("place") ;
   /* ---------------- bins: ids, values, depths ---------------- */
@@ -1377,7 +1507,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       se.release () ; sk.release () ; sv.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ;
       eHash.release () ; eBR.release () ;
       /* the block sort below only reads codes[]: its copy to the host runs beside the sort */
-      if (!(P.flags & H10X_FLAG_NO_CODES))
+            if (!(P.flags & (H10X_FLAG_NO_CODES | H10X_FLAG_LAZY_CODES)))
 	{ early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
       c->clus.alloc (H, s, mt) ;
       if (H)
@@ -1450,7 +1580,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   entryId.release () ; eRead.release () ; entryBlk.release () ;
 
   /* ---------------- hashIndex[] ---------------- */
-  if (!(P.flags & H10X_FLAG_NO_TABLE) && c->hashValue.p)
+  if (!(P.flags & H10X_FLAG_NO_TABLE) && c->hashValue.p && !c->hashIndex.p)
     { StageTimer tm (c, s, ST_TABLE) ;
       size_t tableSize = (size_t) 1 << P.B ;
       c->hashIndex.alloc (tableSize, s, mt) ;
@@ -1521,6 +1651,12 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
   StageTimer tm (c, s, ST_BINIDS) ;
   d->nLocalBins = Dl ;
+  /* every rank got through its own mosh stage and sort (a rank that did not reports here from dist_fail_agree, and
+     all ranks leave with its error instead of waiting for it in the collectives below) */
+  { const uint32_t none[4] = { 0, 0, 0, 0 } ; std::vector<uint32_t> all ;
+    d->owesAgreement = false ;
+    dist_agree (c, s, 0, none, all) ;
+  }
   HostTrace tr ;
   auto mark = [&] (const char *w) { if (tr.on) { cudaStreamSynchronize (s) ; tr.mark (w) ; } } ;
 
@@ -1549,7 +1685,10 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   std::vector<uint64_t> recvCnt (NR), recvOff ((size_t) NR + 1, 0) ;
   for (int r = 0 ; r < NR ; ++r) { recvCnt[r] = cntMat[(size_t) r * NR + R] ; recvOff[r+1] = recvOff[r] + recvCnt[r] ; }
   const uint64_t Ro64 = recvOff[NR] ;
-  if (Ro64 >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 rank-distinct hashes for one owner") ;
+  for (int o = 0 ; o < NR ; ++o)	/* the count matrix is the same everywhere: every rank throws, or none */
+    { uint64_t tot = 0 ; for (int r = 0 ; r < NR ; ++r) tot += cntMat[(size_t) r * NR + o] ;
+      if (tot >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 rank-distinct hashes for one owner") ;
+    }
   const uint32_t Ro = (uint32_t) Ro64 ;
 
   mark ("d3-counts") ;
@@ -1934,7 +2073,8 @@ void h10x_gpu_destroy (h10x_ctx *c)
 { if (!c) return ;
   cudaSetDevice (c->P.device) ;
   if (c->own) cudaStreamSynchronize (c->own) ;
-  if (c->dlStream) { cudaStreamSynchronize (c->dlStream) ; cudaStreamDestroy (c->dlStream) ; c->dlStream = 0 ; }
+    if (c->dlStream) { cudaStreamSynchronize (c->dlStream) ; cudaStreamDestroy (c->dlStream) ; c->dlStream = 0 ; }
+  if (c->ulStream) { cudaStreamSynchronize (c->ulStream) ; cudaStreamDestroy (c->ulStream) ; c->ulStream = 0 ; }
   if (c->dist)
     { for (int r = 0 ; r < H10X_MAX_RANKS ; ++r)
 	if (c->dist->peers[r].mapped && c->dist->peers[r].viaIpc) cudaIpcCloseMemHandle (c->dist->peers[r].mapped) ;
@@ -2015,14 +2155,103 @@ int h10x_gpu_download (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
       pull ((void**) &out->blkNHash, c->blkNHash.p, 4 * nb) ;
       pull ((void**) &out->blkOff, c->blkOff.p, 8 * (nb + 1)) ;
       pull ((void**) &out->clusHash, c->clus.p, 8 * H) ;
-      pull ((void**) &out->codeOff, c->codeOff.p, c->codeOff.p ? 8 * (hn + 1) : 0) ;
-      pull ((void**) &out->codes, c->codes.p, c->codes.p ? 4 * H : 0) ;
+            const bool lazy = (c->P.flags & H10X_FLAG_LAZY_CODES) != 0 ;
+      pull ((void**) &out->codeOff, lazy ? nullptr : c->codeOff.p, c->codeOff.p ? 8 * (hn + 1) : 0) ;
+      pull ((void**) &out->codes, lazy ? nullptr : c->codes.p, c->codes.p ? 4 * H : 0) ;
       CK (cudaStreamSynchronize (s)) ;
       if (c->dlStream) CK (cudaStreamSynchronize (c->dlStream)) ;
       for (int i = 0 ; i < 9 ; ++i) c->slotDone[i] = false ;
     }) ;
   if (st != H10X_OK) memset (out, 0, sizeof (*out)) ;
   return st ;
+}
+
+/* The front half of a host-buffer build, overlapped with the copy of the file (hash10x.c:197-223 reads and hashes the
+   file chunk by chunk; here the chunks are slabs of the pinned host buffer going up on their own stream): as soon as a
+   slab has landed its barcode runs are found and the fused kernel hashes the runs that are complete, while the next
+   slabs are on their way.  What build_device_impl gets is the run table of the whole file and the per-run key lists. */
+static void prefuse_streamed (h10x_ctx *c, cudaStream_t s, const void *hostFqb, uint32_t *dFqb, uint64_t n64, Prefuse &pf)
+{ const h10x_params &P = c->P ; MemTrack *mt = &c->mt ;
+  const uint32_t n = (uint32_t) n64 ;
+  uint32_t slabRecs = 4u << 20 ;		/* 4M records = 503 MB: 9 ms of PCIe time, ~1.3 ms of hashing */
+  if (const char *e = getenv ("H10X_STREAM_SLAB")) { long v = atol (e) ; if (v >= 1) slabRecs = (uint32_t) v ; }
+  const uint32_t nSlabs = (n + slabRecs - 1) / slabRecs ;
+  std::vector<cudaEvent_t> landed (nSlabs) ;
+  for (uint32_t k = 0 ; k < nSlabs ; ++k)
+    { const uint64_t r0 = (uint64_t) k * slabRecs, nr = std::min<uint64_t> (slabRecs, n - r0) ;
+      CK (cudaMemcpyAsync (dFqb + r0 * H10X_REC_WORDS, (const char*) hostFqb + r0 * 120, nr * 120, cudaMemcpyHostToDevice, c->ulStream)) ;
+      landed[k] = ctx_event (c) ;
+      CK (cudaEventRecord (landed[k], c->ulStream)) ;
+    }
+    /* beyond that (runs of fewer than 8 read pairs on average) the classic stages take over */
+  const uint32_t runCap = std::max<uint32_t> (n / 8 + 65536, std::min<uint32_t> (slabRecs, n)) ;
+  pf.dBlkStart.alloc ((size_t) runCap + 2, s, mt) ; pf.srcOff.alloc ((size_t) runCap + 2, s, mt) ; pf.blkCnt.alloc ((size_t) runCap + 2, s, mt) ;
+  CK (cudaMemsetAsync (pf.blkCnt.p, 0xff, 4 * ((size_t) runCap + 2), s)) ;
+  DBuf<uint32_t> flag (std::min<uint32_t> (slabRecs, n), s, mt), dCount (1, s, mt) ;
+  DBuf<int> anyZero (1, s, mt) ;
+  CK (cudaMemsetAsync (anyZero.p, 0, sizeof (int), s)) ;
+  pf.runStart.clear () ; pf.nRuns = 0 ;
+  uint32_t done = 0 ;		/* runs handed to the fused kernel */
+  bool ok = true ;
+  for (uint32_t k = 0 ; k < nSlabs ; ++k)
+    { const uint32_t r0 = k * slabRecs, nr = std::min<uint32_t> (slabRecs, n - r0) ;
+            CK (cudaStreamWaitEvent (s, landed[k], 0)) ;
+      if (ok && (uint64_t) pf.nRuns + nr > (uint64_t) runCap) ok = false ;	/* the selection below may write a start per record */
+      if (!ok) continue ;
+      LAUNCH (c, k_run_flags_at, gridFor (nr, 256), 256, 0, s, dFqb, r0, nr, flag.p, anyZero.p) ;
+      cub::CountingInputIterator<uint32_t> recNo (r0) ;
+      cubCall (c, s, [&] (void *t, size_t &b)
+	{ return cub::DeviceSelect::Flagged (t, b, recNo, flag.p, pf.dBlkStart.p + pf.nRuns, dCount.p, (int) nr, s) ; }) ;
+      
+      uint32_t cnt = 0 ;
+      CK (cudaMemcpyAsync (&cnt, dCount.p, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      
+      pf.runStart.resize ((size_t) pf.nRuns + cnt) ;
+      if (cnt)
+	{ CK (cudaMemcpyAsync (pf.runStart.data () + pf.nRuns, pf.dBlkStart.p + pf.nRuns, 4 * (size_t) cnt, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaStreamSynchronize (s)) ;
+	}
+      pf.nRuns += cnt ;
+      if (!pf.eng.ready)
+	{ if (!FusedEngine::usable (P)) { ok = false ; continue ; }
+	  const uint32_t runsGuess = (uint32_t) std::min<uint64_t> ((uint64_t) pf.nRuns * nSlabs * 3 / 2 + 16, 0x7fffffffull) ;
+	  pf.eng.init (c, s, lean_wanted (c, false, n, runsGuess), n, nSlabs + 1) ;
+	}
+      if (pf.nRuns > done + 1)		/* run i is complete once run i + 1 has started */
+	{ std::vector<uint32_t> lists[5] ;
+	  for (uint32_t r = done ; r + 1 < pf.nRuns ; ++r)
+	    { const int ci = pf.eng.classOf (P, pf.runStart[r + 1] - pf.runStart[r]) ;
+	      if (ci >= 0) lists[ci].push_back (r) ;
+	    }
+	  pf.eng.launch (c, s, lists, dFqb, pf.dBlkStart.p, pf.srcOff.p, pf.blkCnt.p) ;
+	  CK (cudaStreamSynchronize (s)) ;	/* the lists are read by the async copies of launch (); the slab after this one is on its way */
+	  done = pf.nRuns - 1 ;
+	}
+    }
+  int hAnyZero = 0 ;
+  CK (cudaMemcpyAsync (&hAnyZero, anyZero.p, 4, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaMemcpyAsync (pf.dBlkStart.p + pf.nRuns, &n, 4, cudaMemcpyHostToDevice, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  pf.runStart.push_back (n) ;
+  pf.anyZero = hAnyZero != 0 ;
+  pf.valid = ok && pf.nRuns > 0 ;
+  if (!pf.valid) { pf.eng.release () ; pf.srcOff.release () ; pf.blkCnt.release () ; pf.dBlkStart.release () ; }
+}
+
+int h10x_gpu_download_codes (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)
+{ if (!c || !out || !c->haveIndex) { set_err (err, errlen, "no index resident") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->codes.p || !c->codeOff.p) { set_err (err, errlen, "the hash->code lists were not built (H10X_FLAG_NO_CODES)") ; return H10X_ERR_BAD_PARAM ; }
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      const size_t hn = c->hashNumber, H = c->nHashes ;
+      out->codeOff = (uint64_t*) host_slot (c, SLOT_CODEOFF, 8 * (hn + 1)) ;
+      out->codes = (uint32_t*) host_slot (c, SLOT_CODES, 4 * H) ;
+      CK (cudaMemcpyAsync (out->codeOff, c->codeOff.p, 8 * (hn + 1), cudaMemcpyDeviceToHost, s)) ;
+      if (H) CK (cudaMemcpyAsync (out->codes, c->codes.p, 4 * H, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+    }) ;
 }
 
 int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_index *out, char *err, size_t errlen)
@@ -2033,12 +2262,19 @@ int h10x_gpu_build_host (h10x_ctx *c, const void *fqb, uint64_t nRecords, h10x_i
       /* only the first N records are ever looked at (hash10x.c:202,207) */
       uint64_t n = (c->P.N > 0 && (uint64_t) c->P.N < nRecords) ? (uint64_t) c->P.N : nRecords ;
       with_slab (c, s, slab_estimate (c->P, n, true), [&] ()
-	{ reset_result (c) ;
+		{ reset_result (c) ;
 	  DBuf<uint32_t> d ((size_t) n * H10X_REC_WORDS, s, &c->mt) ;
-	  if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
 	  if (!c->dlStream) CK (cudaStreamCreateWithFlags (&c->dlStream, cudaStreamNonBlocking)) ;
+	  Prefuse pf ;
+	  const bool streamed = !c->dist && n > 0 && n < 0xffffffffull && FusedEngine::usable (c->P) && !getenv ("H10X_NO_STREAM") ;
+	  if (streamed)
+	    { if (!c->ulStream) CK (cudaStreamCreateWithFlags (&c->ulStream, cudaStreamNonBlocking)) ;
+	      try { prefuse_streamed (c, s, fqb, d.p, n, pf) ; }
+	      catch (...) { cudaStreamSynchronize (c->ulStream) ; throw ; }
+	    }
+	  else if (n) CK (cudaMemcpyAsync (d.p, fqb, (size_t) n * 120, cudaMemcpyHostToDevice, s)) ;
 	  c->earlyDl = true ;
-	  try { build_device_impl (c, d.p, n, s, false) ; }
+	  try { build_device_impl (c, d.p, n, s, false, false, streamed ? &pf : nullptr) ; }
 	  catch (...) { c->earlyDl = false ; cudaStreamSynchronize (c->dlStream) ; throw ; }
 	  c->earlyDl = false ;
 	}) ;
@@ -2346,6 +2582,15 @@ int h10x_dist_init (h10x_ctx *c, int rank, int nranks, const void *id128, char *
     }) ;
 }
 
+/* a rank-local failure between two agreements of a distributed build: hand the error to the peers, who are (or will
+   be) waiting at the next one.  Not after a CUDA error - the context cannot run a collective any more. */
+static void dist_fail_agree (h10x_ctx *c, cudaStream_t s, int code)
+{ if (!c->dist || !c->dist->owesAgreement || code == H10X_ERR_CUDA) return ;
+  c->dist->owesAgreement = false ;
+  try { const uint32_t none[4] = { 0, 0, 0, 0 } ; std::vector<uint32_t> all ; dist_agree (c, s, code, none, all) ; }
+  catch (...) {}
+}
+
 int h10x_gpu_build_device_dist (h10x_ctx *c, const void *d_fqb, uint64_t nRecords, void *stream, char *err, size_t errlen)
 { if (!c || !c->dist || !c->dist->comm) { set_err (err, errlen, "h10x_dist_init has not been called") ; return H10X_ERR_BAD_PARAM ; }
   int st = guarded (err, errlen, [&] ()
@@ -2357,7 +2602,10 @@ int h10x_gpu_build_device_dist (h10x_ctx *c, const void *d_fqb, uint64_t nRecord
       if (c->mt.cap < est && !c->slabClamped) { reset_result (c) ; slab_resize (c, est) ; }
       try { build_device_impl (c, (const uint32_t*) d_fqb, nRecords, s, true, true) ; }
       catch (const SlabFull &f)
-	{ throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ; }
+	{ dist_fail_agree (c, s, H10X_ERR_NOMEM) ;
+	  throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ;
+	}
+      catch (const H10xError &e) { dist_fail_agree (c, s, e.code) ; throw ; }
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (stream ? (cudaStream_t) stream : c->own) ; cudaGetLastError () ; c->haveIndex = false ; }
   return st ;
@@ -2378,7 +2626,10 @@ int h10x_gpu_build_host_dist (h10x_ctx *c, const void *fqb, uint64_t nRecords, h
 	  build_device_impl (c, d.p, nRecords, s, false, true) ;
 	}
       catch (const SlabFull &f)
-	{ throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ; }
+	{ dist_fail_agree (c, s, H10X_ERR_NOMEM) ;
+	  throw H10xError (H10X_ERR_NOMEM, "device workspace too small in a distributed build (need " + std::to_string (f.need) + " bytes)") ;
+	}
+      catch (const H10xError &e) { dist_fail_agree (c, s, e.code) ; throw ; }
     }) ;
   if (st != H10X_OK) { cudaStreamSynchronize (c->own) ; cudaGetLastError () ; c->haveIndex = false ; return st ; }
   return h10x_gpu_download (c, out, err, errlen) ;

@@ -102,6 +102,7 @@ static void readFQB (const char *path)
   p.k = params.k ; p.w = params.w ; p.B = params.B ; p.N = params.N ; p.chunkSize = params.chunkSize ;
   p.factor1 = h10x_factor1_from_seed (params.r) ;
   p.device = getenv ("H10X_DEVICE") ? atoi (getenv ("H10X_DEVICE")) : 0 ;
+  p.flags = H10X_FLAG_LAZY_CODES ;	/* no command below reads hashCodes on the host: --cluster runs where they are */
   printf ("  reading and processing sorted fqb file with chunkSize %d", params.chunkSize) ;
   if (params.N) printf (", first %d records", params.N) ;
   printf ("\n") ;

@@ -55,6 +55,10 @@ typedef struct h10x_params {
 #define H10X_FLAG_NO_CODES	4u	/* skip the hash->code CSR (fillHashTable) */
 #define H10X_FLAG_GENERIC_ONLY	8u	/* force the generic (global-memory) sort path for every block */
 #define H10X_FLAG_LEGACY_TAIL	16u	/* group / transpose with the library radix sort (round-1 tail) instead of h10x_tail.cuh */
+#define H10X_FLAG_LAZY_CODES	32u	/* the hash->code CSR is built and stays resident (--cluster reads it there), but
+					   h10x_gpu_build_host / h10x_gpu_download leave codes / codeOff NULL in the host index:
+					   no host command of the --readFQB ... --writeHash chain reads them (the reference's
+					   writeHashFile, hash10x.c:244-267, does not either); h10x_gpu_download_codes fetches them */
 
 /* ClusterHash of hash10x.c:35-43, 8 bytes; subCluster and flags are written as 0 */
 typedef struct h10x_cluster_hash {
@@ -136,6 +140,10 @@ int h10x_gpu_index_device (h10x_ctx *ctx, h10x_index *out) ;
 /* copy the resident index to pinned host memory owned by the context (pinned = 2): the arrays stay
    valid until the next download/build_host/build_file on this context or its destruction */
 int h10x_gpu_download (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
+
+/* fillHashTable()'s lists (hash10x.c:317-347) of the resident index -> out->codeOff / out->codes, in the context's
+   pinned arena like the arrays of h10x_gpu_download; for contexts created with H10X_FLAG_LAZY_CODES */
+int h10x_gpu_download_codes (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
 
 /* the whole seam with HOST buffers: H2D of the FQB records, build, D2H of the index */
 int h10x_gpu_build_host (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x_index *out,

@@ -83,7 +83,29 @@ def main():
         g.close()
         if world > 1:
             dist.barrier()
+    # a failure on one rank only (after the runs were agreed on) must come back as an error on every rank, not as a hang
+    os.environ["H10X_TEST_FAIL_RANK"] = str(world - 1)
+    p = orc.synth_params(seed=44, n_barcodes=4 * world, pairs_min=5, pairs_max=40)
+    n, off = orc.synth_layout(p)
+    cut = [int(round(p.nBarcodes * r / world)) for r in range(world + 1)]
+    recs = orc.synth_fqb(p, int(off[cut[rank]]), int(off[cut[rank + 1]]))
+    fqb = torch.from_numpy(recs.view(np.int32).reshape(-1).copy()).cuda()
+    g = hash10x_b200.Hash10xGPU(B=B, device=local)
+    idb = [hash10x_b200.Hash10xGPU.dist_unique_id() if rank == 0 else None]
     if world > 1:
+        dist.broadcast_object_list(idb, src=0)
+    g.dist_init(rank, world, idb[0])
+    try:
+        g.build_device_dist(fqb.data_ptr(), recs.shape[0])
+        failed = False
+    except hash10x_b200.H10xError as e:
+        failed = e.code == 8
+    del os.environ["H10X_TEST_FAIL_RANK"]
+    assert failed, "rank %d: the forced failure of rank %d did not arrive" % (rank, world - 1)
+    g.build_device_dist(fqb.data_ptr(), recs.shape[0])          # the context and the communicator are still usable
+    g.close()
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print("DIST_PARITY_OK world=%d" % world, flush=True)

@@ -293,3 +293,39 @@ def test_tail_big_sub_ranges_and_deep_bins(orc, gpu_lib, monkeypatch):
     want, got, st = _compare(orc, deep, B=21)
     assert st["tailPath"] == 2
     want, got, st = _compare(orc, recs, B=21)
+
+
+@pytest.mark.parametrize("slab", [1, 97, 5000])
+def test_streamed_host_build_matches_oracle(orc, gpu_lib, monkeypatch, slab):
+    # h10x_gpu_build_host copies the file in slabs and hashes the runs of every slab that has landed (prefuse_streamed):
+    # tiny slabs put run boundaries, slab boundaries and open runs in every relation; the index must be the oracle's
+    p = orc.synth_params(seed=41, n_barcodes=60, pairs_min=1, pairs_max=260)
+    recs = orc.synth_fqb(p)
+    monkeypatch.setenv("H10X_STREAM_SLAB", str(slab))
+    want, got, st = _compare(orc, recs, B=20)
+    assert st["nBins"] == want.hashNumber - 1
+    # a barcode word of 0 glues runs in the reference's chunk loop: the streamed lists are dropped, the classic stages run
+    recs2 = np.concatenate([fqbtools.const_records(0, 3, 0, 1), recs])
+    _compare(orc, recs2, B=20)
+    monkeypatch.setenv("H10X_NO_STREAM", "1")
+    _compare(orc, recs, B=20)
+
+
+def test_lazy_codes(orc, gpu_lib):
+    # H10X_FLAG_LAZY_CODES: the hash->code lists stay on the device (what hash10x-b200 asks for); fetched on demand
+    import hash10x_b200
+    p = orc.synth_params(seed=43, n_barcodes=40, pairs_min=5, pairs_max=200)
+    recs = orc.synth_fqb(p)
+    want = orc.build(recs, B=20)
+    with _gpu(B=20, flags=hash10x_b200.FLAG_LAZY_CODES) as g:
+        got = g.build_host(recs)
+        assert got.codes is None and got.codeOff is None
+        assert np.array_equal(got.clus, want.clus) and np.array_equal(got.hashDepth, want.hashDepth)
+        code_off, codes = g.download_codes()
+        _gw, goff, good = g.depth_range(2, 40)          # --hashDepthRange / --cluster read the resident lists
+        clus, nsub, _ptm, _ms = g.cluster(0, 0, 2)
+    assert np.array_equal(code_off, want.codeOff) and np.array_equal(codes, want.codes)
+    _w, wgoff, wgood = orc.good_hashes(want, 2, 40)
+    wclus, wnsub, _wptm = orc.cluster(want, wgoff, wgood, 0, 0, 2)
+    assert np.array_equal(goff, wgoff) and np.array_equal(good, wgood)
+    assert np.array_equal(clus, wclus) and np.array_equal(nsub, wnsub)

@@ -9,5 +9,5 @@ def rep(s, old, new, count=1):
     m = list(re.finditer(pat, s))
     assert len(m) == count, (len(m), old[:80])
     for mm in reversed(m):
-        s = s[:mm.start()] + new.strip('\n') + s[mm.end():]
+        s = s[:mm.start()] + new.strip('\n').lstrip(' \t') + s[mm.end():]
     return s
