@@ -104,6 +104,8 @@ def load_library():
     L.h10x_gpu_index_device.argtypes = [vp, C.POINTER(CIndex)]
     L.h10x_gpu_download.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_download_codes.argtypes = [vp, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_fq2b.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.c_uint32, C.POINTER(CFq2bOut), cp, sz]
+    L.h10x_pack_barcode.argtypes = [cp, C.POINTER(C.c_uint32)]
     L.h10x_gpu_build_host.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_build_file.argtypes = [vp, cp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_stats.argtypes = [vp, C.POINTER(CStats)]
@@ -137,6 +139,12 @@ def _arr(ptr, n, dtype):
         return np.zeros(0, dtype)
     buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class CFq2bOut(C.Structure):
+    _fields_ = [("fqb", C.c_void_p), ("d_fqb", C.c_void_p), ("nRecords", C.c_uint64), ("nRead", C.c_uint64),
+                ("recWords", C.c_uint32), ("s1Len", C.c_uint32), ("s2Len", C.c_uint32), ("reserved", C.c_uint32),
+                ("nBad", C.c_uint64), ("nFixed", C.c_uint64), ("nFixBase", C.c_uint64 * 16)]
 
 
 class Index:
@@ -217,6 +225,25 @@ class Hash10xGPU:
         self._check(self.lib.h10x_gpu_download_codes(self.ctx, C.byref(ci), err, len(err)), err)
         s = self.stats()
         return _arr(ci.codeOff, s["nBins"] + 2, np.uint64), _arr(ci.codes, s["nHashes"], np.uint32)
+
+    def fq2b(self, fq1, fq2=None, whitelist=None, sort=False, host=True):
+        """fq2b (+ bsort when sort): FASTQ texts (bytes) -> (records uint32 [n, recWords] or None, stats, device pointer).
+        whitelist: packed barcodes (uint32) in file order, or None"""
+        co = CFq2bOut()
+        err = C.create_string_buffer(512)
+        wl = None if whitelist is None else np.ascontiguousarray(whitelist, dtype=np.uint32)
+        b1 = C.create_string_buffer(fq1, len(fq1)) if len(fq1) else None
+        b2 = None if fq2 is None else (C.create_string_buffer(fq2, len(fq2)) if len(fq2) else C.create_string_buffer(1))
+        st = self.lib.h10x_gpu_fq2b(self.ctx, C.cast(b1, C.c_void_p), len(fq1), C.cast(b2, C.c_void_p), 0 if fq2 is None else len(fq2),
+                                    None if wl is None else wl.ctypes.data, 0 if wl is None else wl.size,
+                                    (1 if sort else 0) | (0 if host else 2), C.byref(co), err, len(err))
+        self._check(st, err)
+        stats = dict(nRead=co.nRead, nRecords=co.nRecords, nBad=co.nBad, nFixed=co.nFixed, nFixBase=list(co.nFixBase),
+                     s1Len=co.s1Len, s2Len=co.s2Len, recWords=co.recWords)
+        recs = None
+        if host:
+            recs = _arr(co.fqb, co.nRecords * co.recWords, np.uint32).reshape(co.nRecords, max(co.recWords, 1))
+        return recs, stats, co.d_fqb
 
     def build_file(self, path):
         ci = CIndex()

@@ -128,7 +128,10 @@ struct h10x_ctx {
   /* multi-GPU (h10x_dist.cuh) */
   bool slabClamped = false ;	/* the slab already takes all free device memory */
   /* host-buffer builds start the D2H of an index array as soon as it is final, on a second stream */
-    cudaStream_t ulStream = 0 ;	/* ... and copy the file up in slabs on a third one while the fused kernel hashes the slabs that landed */
+    /* h10x_gpu_fq2b: the records of the last call and the whitelist table (2^32 words, kept while the whitelist is the same) */
+  uint32_t *fqRecs = nullptr ; void *fqHost = nullptr ; size_t fqHostCap = 0 ;
+  uint32_t *wlTable = nullptr ; uint64_t wlCount = 0, wlSum = 0 ;
+  cudaStream_t ulStream = 0 ;	/* ... and copy the file up in slabs on a third one while the fused kernel hashes the slabs that landed */
   bool earlyDl = false ; cudaStream_t dlStream = 0 ; bool slotDone[9] = { false, false, false, false, false, false, false, false, false } ;
   DBuf<uint8_t> within ;	/* --hashDepthRange flags per bin; only ever set (hash10x.c:535) until the next build */
   /* goodHashes of the last --hashDepthRange (hash10x.c:722-766), resident for --cluster; ClusterBlock.nSubCluster /
@@ -197,6 +200,7 @@ template <class F> static void cubCall (h10x_ctx *c, cudaStream_t s, F f)
 struct CastU64 { __host__ __device__ uint64_t operator() (uint32_t x) const { return (uint64_t) x ; } } ;
 
 #include "h10x_dist.cuh"
+#include "h10x_fq2b.cuh"
 
 /* ------------------------------------------------------------------ kernels: runs */
 
@@ -2075,6 +2079,9 @@ void h10x_gpu_destroy (h10x_ctx *c)
   if (c->own) cudaStreamSynchronize (c->own) ;
     if (c->dlStream) { cudaStreamSynchronize (c->dlStream) ; cudaStreamDestroy (c->dlStream) ; c->dlStream = 0 ; }
   if (c->ulStream) { cudaStreamSynchronize (c->ulStream) ; cudaStreamDestroy (c->ulStream) ; c->ulStream = 0 ; }
+  if (c->fqRecs) cudaFree (c->fqRecs) ;
+  if (c->wlTable) cudaFree (c->wlTable) ;
+  if (c->fqHost) cudaFreeHost (c->fqHost) ;
   if (c->dist)
     { for (int r = 0 ; r < H10X_MAX_RANKS ; ++r)
 	if (c->dist->peers[r].mapped && c->dist->peers[r].viaIpc) cudaIpcCloseMemHandle (c->dist->peers[r].mapped) ;
@@ -2237,6 +2244,169 @@ static void prefuse_streamed (h10x_ctx *c, cudaStream_t s, const void *hostFqb, 
   pf.anyZero = hAnyZero != 0 ;
   pf.valid = ok && pf.nRuns > 0 ;
   if (!pf.valid) { pf.eng.release () ; pf.srcOff.release () ; pf.blkCnt.release () ; pf.dBlkStart.release () ; }
+}
+
+/* ------------------------------------------------------------------ fq2b + bsort (h10x_fq2b.cuh) */
+
+int h10x_pack_barcode (const char *s, uint32_t *out)
+{ if (!s || !out || strlen (s) != 16) return -1 ;
+  uint32_t u = 0 ;
+  for (int i = 0 ; i < 16 ; ++i)
+    { const char ch = s[i] ;
+      u = (u << 2) | ((ch == 'c' || ch == 'C') ? 1u : (ch == 'g' || ch == 'G') ? 2u : (ch == 't' || ch == 'T') ? 3u : 0u) ;
+    }
+  *out = u ;
+  return 0 ;
+}
+
+struct FqFile { DBuf<char> text ; DBuf<unsigned long long> nl ; uint64_t nLines = 0, nRec = 0 ; uint32_t L = 0 ; } ;
+
+/* text -> device, newline positions, line length of the first sequence line, gzReadFastq's checks */
+static void fq_index (h10x_ctx *c, cudaStream_t s, const char *host, uint64_t n, FqFile &f, int entryMul, int entryAdd)
+{ MemTrack *mt = &c->mt ;
+  f.text.alloc (n + 1, s, mt) ;
+  if (n) CK (cudaMemcpyAsync (f.text.p, host, n, cudaMemcpyHostToDevice, s)) ;
+  f.nl.alloc (n / 2 + 4, s, mt) ;		/* at most every other byte is a newline of a well-formed entry (checked below) */
+  DBuf<unsigned long long> dCount (1, s, mt) ;
+  unsigned long long cnt = 0 ;
+  if (n)
+    { /* a text with more newlines than n/2 is malformed; count first so that the selection cannot overrun */
+      FqIsNewline pred = { f.text.p } ;
+      cub::CountingInputIterator<unsigned long long> pos (0ull) ;
+      cub::TransformInputIterator<unsigned long long, FqNlCount, cub::CountingInputIterator<unsigned long long>> ones (pos, FqNlCount { f.text.p }) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceReduce::Sum (t, b, ones, dCount.p, (::cuda::std::int64_t) n, s) ; }) ;
+      CK (cudaMemcpyAsync (&cnt, dCount.p, 8, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      if (cnt > n / 2 + 4) throw H10xError (H10X_ERR_IO, "fastq id line for entry " + std::to_string (entryAdd) + " does not start with @") ;
+      cubCall (c, s, [&] (void *t, size_t &b)
+	{ return cub::DeviceSelect::If (t, b, pos, f.nl.p, dCount.p, (::cuda::std::int64_t) n, pred, s) ; }) ;
+    }
+  f.nLines = cnt ; f.nRec = cnt / 4 ;
+  char last = '\n' ;
+  unsigned long long first2[2] = { 0, 0 } ;
+  if (n) CK (cudaMemcpyAsync (&last, f.text.p + (n - 1), 1, cudaMemcpyDeviceToHost, s)) ;
+  if (cnt >= 2) CK (cudaMemcpyAsync (first2, f.nl.p, 16, cudaMemcpyDeviceToHost, s)) ;
+  CK (cudaStreamSynchronize (s)) ;
+  if ((cnt & 3) || last != '\n')	/* the reference dies inside the unfinished entry; which message depends on where it stops */
+    throw H10xError (H10X_ERR_IO, "truncated fastq entry " + std::to_string ((long long) f.nRec * entryMul + entryAdd)) ;
+  f.L = f.nRec ? (uint32_t) (first2[1] - first2[0] - 1) : 0 ;
+  if (f.nRec && (f.L == 0 || f.L > 1023)) throw H10xError (H10X_ERR_IO, "fastq sequence lines of 1..1023 bases expected (fq2b.c:142)") ;
+  if (f.nRec)
+    { DBuf<unsigned long long> dErr (1, s, mt) ;
+      CK (cudaMemsetAsync (dErr.p, 0xff, 8, s)) ;
+      LAUNCH (c, k_fq_check, gridFor (f.nRec, 256), 256, 0, s, f.text.p, f.nl.p, f.nRec, f.L, dErr.p) ;
+      unsigned long long e = 0 ;
+      CK (cudaMemcpyAsync (&e, dErr.p, 8, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      if (e != ~0ull)
+	{ const long long entry = (long long) (e >> 3) * entryMul + entryAdd ; const int code = (int) (e & 7) ;
+	  const std::string en = std::to_string (entry) ;
+	  throw H10xError (H10X_ERR_IO, code == FQ_ERR_ID ? "fastq id line for entry " + en + " does not start with @"
+			   : code == FQ_ERR_SEQ ? "fastq entry " + en + " seq line does not end in \\n"
+			   : code == FQ_ERR_PLUS ? "bad + fastq line entry " + en
+			   : "fastq entry " + en + " qual line does not end in \\n") ;
+	}
+    }
+}
+
+int h10x_gpu_fq2b (h10x_ctx *c, const char *fq1, uint64_t n1, const char *fq2, uint64_t n2,
+		   const uint32_t *whitelist, uint64_t nWhitelist, uint32_t flags, h10x_fq2b_out *out, char *err, size_t errlen)
+{ if (!c || !out || (!fq1 && n1) || (!fq2 && n2) || (!whitelist && nWhitelist)) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  if (nWhitelist >= (1ull << 24)) { set_err (err, errlen, "more than 2^24-1 whitelist barcodes") ; return H10X_ERR_UNSUPPORTED ; }
+  memset (out, 0, sizeof (*out)) ;
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      /* the whitelist table outlives the call: 16 GiB are not worth re-filling for every chunk of a run */
+      if (whitelist)
+	{ uint64_t sum = 1469598103934665603ull ;
+	  for (uint64_t i = 0 ; i < nWhitelist ; ++i) sum = (sum ^ whitelist[i]) * 1099511628211ull ;
+	  if (!c->wlTable || c->wlCount != nWhitelist || c->wlSum != sum)
+	    { if (!c->wlTable) CK (cudaMalloc (&c->wlTable, (size_t) 4 << 32)) ;
+	      CK (cudaMemsetAsync (c->wlTable, 0, (size_t) 4 << 32, s)) ;
+	      uint32_t *dWl = nullptr ;
+	      CK (cudaMalloc (&dWl, 4 * (size_t) (nWhitelist ? nWhitelist : 1))) ;
+	      CK (cudaMemcpyAsync (dWl, whitelist, 4 * (size_t) nWhitelist, cudaMemcpyHostToDevice, s)) ;
+	      if (nWhitelist) LAUNCH (c, k_wl_build, gridFor (nWhitelist * 64, 256), 256, 0, s, dWl, nWhitelist, c->wlTable) ;
+	      CK (cudaStreamSynchronize (s)) ;
+	      cudaFree (dWl) ;
+	      c->wlCount = nWhitelist ; c->wlSum = sum ;
+	    }
+	}
+      if (c->fqRecs) { cudaFree (c->fqRecs) ; c->fqRecs = nullptr ; }
+      with_slab (c, s, 3 * (n1 + n2) + ((size_t) 64 << 20), [&] ()
+	{ MemTrack *mt = &c->mt ;
+	  if (c->fqRecs) { cudaFree (c->fqRecs) ; c->fqRecs = nullptr ; }
+	  FqFile f1, f2 ;
+	  fq_index (c, s, fq1, n1, f1, fq2 ? 2 : 1, 1) ;
+	  if (fq2)
+	    { fq_index (c, s, fq2, n2, f2, 2, 2) ;
+	      if (f2.nRec < f1.nRec) throw H10xError (H10X_ERR_IO, "second fastq file terminated early at " + std::to_string (f2.nRec)) ;
+	    }
+	  const uint64_t nRec = f1.nRec ;
+	  const uint32_t w1 = (f1.L + 15) / 16 + (f1.L + 31) / 32, w2 = fq2 ? (f2.L + 15) / 16 + (f2.L + 31) / 32 : 0 ;
+	  const uint32_t recWords = w1 + w2 ;
+	  out->nRead = nRec ; out->recWords = recWords ; out->s1Len = f1.L ; out->s2Len = fq2 ? f2.L : 0 ;
+	  if (nRec >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 fastq entries in one call") ;
+	  DBuf<uint32_t> recs ((size_t) nRec * recWords, s, mt) ;
+	  if (nRec)
+	    { LAUNCH (c, k_fq_pack, gridFor (nRec * w1, 256), 256, 0, s, f1.text.p, f1.nl.p, nRec, f1.L, recWords, 0u, recs.p) ;
+	      if (fq2) LAUNCH (c, k_fq_pack, gridFor (nRec * w2, 256), 256, 0, s, f2.text.p, f2.nl.p, nRec, f2.L, recWords, w1, recs.p) ;
+	    }
+	  f1.text.release () ; f1.nl.release () ; f2.text.release () ; f2.nl.release () ;
+	  /* barcode correction; the kept records, in input order */
+	  uint64_t nKeep = nRec ;
+	  DBuf<unsigned long long> idx ;
+	  if (whitelist && nRec)
+	    { DBuf<uint32_t> keep (nRec, s, mt) ; DBuf<FqStats> st (1, s, mt) ; DBuf<unsigned long long> dN (1, s, mt) ;
+	      CK (cudaMemsetAsync (st.p, 0, sizeof (FqStats), s)) ;
+	      LAUNCH (c, k_wl_apply, gridFor (nRec, 256), 256, 0, s, recs.p, nRec, recWords, c->wlTable, keep.p, st.p) ;
+	      idx.alloc (nRec, s, mt) ;
+	      cub::CountingInputIterator<unsigned long long> pos (0ull) ;
+	      cubCall (c, s, [&] (void *t, size_t &b)
+		{ return cub::DeviceSelect::Flagged (t, b, pos, keep.p, idx.p, dN.p, (::cuda::std::int64_t) nRec, s) ; }) ;
+	      FqStats hs ; unsigned long long hn = 0 ;
+	      CK (cudaMemcpyAsync (&hs, st.p, sizeof (FqStats), cudaMemcpyDeviceToHost, s)) ;
+	      CK (cudaMemcpyAsync (&hn, dN.p, 8, cudaMemcpyDeviceToHost, s)) ;
+	      CK (cudaStreamSynchronize (s)) ;
+	      nKeep = hn ; out->nBad = hs.nBad ; out->nFixed = hs.nFixed ;
+	      for (int i = 0 ; i < 16 ; ++i) out->nFixBase[i] = hs.nFixBase[i] ;
+	    }
+	  out->nRecords = nKeep ;
+	  CK (cudaMalloc (&c->fqRecs, 4 * (size_t) (nKeep ? nKeep : 1) * (recWords ? recWords : 1))) ;
+	  if (nKeep)
+	    { DBuf<uint64_t> wa, wb ;
+	      const uint64_t *order = nullptr ;
+	      if (flags & H10X_FQ2B_SORT)
+		{ wa.alloc (nKeep, s, mt) ; wb.alloc (nKeep, s, mt) ;
+		  LAUNCH (c, k_fq_sort_words, gridFor (nKeep, 256), 256, 0, s, recs.p, recWords, idx.p, nKeep, wa.p) ;
+		  /* least significant digit first, four stable passes of 8 bits over the byte-swapped first word */
+		  uint64_t *src = wa.p, *dst = wb.p ;
+		  for (int p = 0 ; p < 4 ; ++p)
+		    { LoadWord ld = { src, 32 + 8 * p, 255u, ~(uint64_t) 0 } ;
+		      part_pass (c, s, ld, nKeep, 256u, dst) ;
+		      std::swap (src, dst) ;
+		    }
+		  order = src ;
+		}
+	      LAUNCH (c, k_fq_gather, gridFor (nKeep * 32, 256), 256, 0, s, recs.p, recWords, idx.p, order, nKeep, c->fqRecs) ;
+	      CK (cudaStreamSynchronize (s)) ;
+	    }
+	}) ;
+      out->d_fqb = c->fqRecs ;
+      if (!(flags & H10X_FQ2B_NO_HOST))
+	{ const size_t bytes = 4 * (size_t) out->nRecords * out->recWords ;
+	  if (c->fqHostCap < bytes || !c->fqHost)
+	    { if (c->fqHost) cudaFreeHost (c->fqHost) ;
+	      c->fqHost = nullptr ; c->fqHostCap = 0 ;
+	      CK (cudaHostAlloc (&c->fqHost, bytes ? bytes : 1, cudaHostAllocDefault)) ;
+	      c->fqHostCap = bytes ? bytes : 1 ;
+	    }
+	  if (bytes) CK (cudaMemcpyAsync (c->fqHost, c->fqRecs, bytes, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaStreamSynchronize (s)) ;
+	  out->fqb = c->fqHost ;
+	}
+    }) ;
 }
 
 int h10x_gpu_download_codes (h10x_ctx *c, h10x_index *out, char *err, size_t errlen)

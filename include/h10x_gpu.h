@@ -141,6 +141,30 @@ int h10x_gpu_index_device (h10x_ctx *ctx, h10x_index *out) ;
    valid until the next download/build_host/build_file on this context or its destruction */
 int h10x_gpu_download (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
 
+/* ---- fq2b + bsort on the device (fq2b.c:108-178; README.md:25-26): the stage that produces the FQB file ----
+   fq1 / fq2: the two UNCOMPRESSED FASTQ texts in host memory (fq2 may be NULL: single reads); the reference reads
+   them through zlib, which stays a host matter.  whitelist: the 10x barcode list as packed 16-mers in file order
+   (h10x_pack_barcode), NULL = no barcode correction (fq2b without -10x).  Records whose barcode has no whitelist entry
+   within one mismatch are dropped, the others get the corrected barcode (fq2b.c:98-104, 159).  The records stay on the
+   device (out->d_fqb, valid until the next h10x_gpu_fq2b or destroy) so that h10x_gpu_build_device can follow, and are
+   copied to pinned host memory owned by ctx (out->fqb) unless H10X_FQ2B_NO_HOST.  A malformed entry gives H10X_ERR_IO
+   with gzReadFastq's message (fq2b.c:180-208). */
+typedef struct h10x_fq2b_out {
+  void *fqb ;			/* nRecords * recWords little-endian U32, host */
+  void *d_fqb ;			/* the same, device */
+  uint64_t nRecords ;		/* records written */
+  uint64_t nRead ;		/* entries read from fq1 */
+  uint32_t recWords ;		/* (s1Len+15)/16 + (s1Len+31)/32 [+ the same for s2Len]: 30 for 145..160-bp pairs */
+  uint32_t s1Len, s2Len, reserved ;
+  uint64_t nBad, nFixed, nFixBase[16] ;	/* the counters fq2b prints (fq2b.c:168-177) */
+} h10x_fq2b_out ;
+#define H10X_FQ2B_SORT		1u	/* group the records by barcode as `bsort -k 4 -r <record bytes>` does: by their first 4 bytes, stable */
+#define H10X_FQ2B_NO_HOST	2u	/* leave out->fqb NULL */
+int h10x_gpu_fq2b (h10x_ctx *ctx, const char *fq1, uint64_t n1, const char *fq2, uint64_t n2,
+		   const uint32_t *whitelist, uint64_t nWhitelist, uint32_t flags, h10x_fq2b_out *out, char *err, size_t errlen) ;
+/* seqPack (fq2b.c:33-42) of one 16-base barcode line of the whitelist file; -1 if it is not 16 characters */
+int h10x_pack_barcode (const char *s16, uint32_t *out) ;
+
 /* fillHashTable()'s lists (hash10x.c:317-347) of the resident index -> out->codeOff / out->codes, in the context's
    pinned arena like the arrays of h10x_gpu_download; for contexts created with H10X_FLAG_LAZY_CODES */
 int h10x_gpu_download_codes (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;

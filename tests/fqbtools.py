@@ -67,3 +67,25 @@ def mixed_records(words, counts, kinds, seed):
             r2 = np.tile([2, 3], 76)[:151]
             out.append(np.tile(make_record(w, r1, r2), (n, 1)))
     return np.concatenate(out).astype(np.uint32)
+
+
+def fastq_from_fqb(recs, read_len):
+    """the two FASTQ texts fq2b would have packed into these records (fq2b.c:33-61: the last partial word of a line is
+    right-aligned; quality bit 1 -> 'I', 0 -> '#'); read_len bases per read"""
+    ws, wq = (read_len + 15) // 16, (read_len + 31) // 32
+    assert recs.shape[1] == 2 * (ws + wq)
+
+    def unpack(words, bits, n):
+        per = 32 // bits
+        out = []
+        for i, u in enumerate(words):
+            k = per if (i + 1 < len(words)) else n - per * i
+            out += [(int(u) >> (bits * (k - 1 - j))) & ((1 << bits) - 1) for j in range(k)]
+        return out
+    f1, f2 = [], []
+    for r, rec in enumerate(recs):
+        for f, o, tag in ((f1, 0, b"1"), (f2, ws + wq, b"2")):
+            s = bytes(b"ACGT"[x] for x in unpack(rec[o:o + ws], 2, read_len))
+            q = bytes(b"#I"[x] for x in unpack(rec[o + ws:o + ws + wq], 1, read_len))
+            f.append(b"@r%d %s\n" % (r, tag) + s + b"\n+\n" + q + b"\n")
+    return b"".join(f1), b"".join(f2)
