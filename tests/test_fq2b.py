@@ -105,3 +105,36 @@ def test_gpu_fq2b_errors_are_the_references(gpu_lib):
             with pytest.raises(hash10x_b200.H10xError) as got:
                 gp.fq2b(a, b, None)
             assert got.value.code == 5 and got.value.msg == want.value.text, (got.value.msg, want.value.text)
+
+
+@pytest.mark.gpu
+def test_fq2b_cli_matches_reference_binary(gpu_lib, tmp_path):
+    # hash10x_b200/bin/fq2b-b200 against oracle/_ref/fq2b (the unmodified reference, when it travelled with the snapshot;
+    # the golden CRC otherwise): the same .fqb bytes and the same report on stderr; -sort adds the bsort step
+    import subprocess
+    exe = os.path.join(ROOT, "hash10x_b200", "bin", "fq2b-b200")
+    ref = os.path.join(ROOT, "oracle", "_ref", "fq2b")
+    g = GOLD["cases"]["pairs151_wl"]
+    c = g["params"]
+    wl = fo.synth_whitelist(*c["wl"])
+    f1, f2 = fo.synth_fastq(c["seed"], c["n"], c["l1"], c["l2"], wl)
+    p1, p2, pw = tmp_path / "r1.fq", tmp_path / "r2.fq", tmp_path / "wl.txt"
+    p1.write_bytes(f1)
+    p2.write_bytes(f2)
+    pw.write_text("".join(s + "\n" for s in wl))
+    r = subprocess.run([exe, "-10x", str(pw), "-o", str(tmp_path / "a.fqb"), str(p1), str(p2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    data = (tmp_path / "a.fqb").read_bytes()
+    assert "%08x" % zlib.crc32(data) == g["crc32"]
+    assert r.stderr.splitlines()[-4:] == g["stderr"]
+    if os.path.exists(ref):
+        rr = subprocess.run([ref, "-10x", str(pw), "-o", str(tmp_path / "b.fqb"), str(p1), str(p2)], capture_output=True, text=True)
+        assert rr.returncode == 0 and (tmp_path / "b.fqb").read_bytes() == data and rr.stderr == r.stderr
+    rs = subprocess.run([exe, "-10x", str(pw), "-sort", "-o", str(tmp_path / "s.fqb"), str(p1), str(p2)], capture_output=True, text=True)
+    assert rs.returncode == 0, rs.stderr
+    srt = np.frombuffer((tmp_path / "s.fqb").read_bytes(), dtype="<u4").reshape(-1, 30)
+    assert np.array_equal(srt, fo.bsort(np.frombuffer(data, dtype="<u4").reshape(-1, 30)))
+    # a malformed entry dies with the reference's text
+    p1.write_bytes(f1.replace(b"\n+\n", b"\n-\n", 1))
+    rb = subprocess.run([exe, "-o", str(tmp_path / "c.fqb"), str(p1), str(p2)], capture_output=True, text=True)
+    assert rb.returncode != 0 and "FATAL ERROR: bad + fastq line entry 1" in rb.stderr
