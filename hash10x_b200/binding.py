@@ -104,6 +104,7 @@ def load_library():
     L.h10x_gpu_index_device.argtypes = [vp, C.POINTER(CIndex)]
     L.h10x_gpu_download.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_download_codes.argtypes = [vp, C.POINTER(CIndex), cp, sz]
+    L.h10x_gpu_dist_global_codes.argtypes = [vp, cp, sz]
     L.h10x_gpu_fq2b.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.c_uint32, C.POINTER(CFq2bOut), cp, sz]
     L.h10x_pack_barcode.argtypes = [cp, C.POINTER(C.c_uint32)]
     L.h10x_gpu_build_host.argtypes = [vp, vp, u64, C.POINTER(CIndex), cp, sz]
@@ -223,8 +224,10 @@ class Hash10xGPU:
         ci = CIndex()
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_download_codes(self.ctx, C.byref(ci), err, len(err)), err)
-        s = self.stats()
-        return _arr(ci.codeOff, s["nBins"] + 2, np.uint64), _arr(ci.codes, s["nHashes"], np.uint32)
+        ix = CIndex()
+        self.lib.h10x_gpu_index_device(self.ctx, C.byref(ix))
+        code_off = _arr(ci.codeOff, ix.hashNumber + 1, np.uint64)
+        return code_off, _arr(ci.codes, int(code_off[-1]), np.uint32)
 
     def fq2b(self, fq1, fq2=None, whitelist=None, sort=False, host=True):
         """fq2b (+ bsort when sort): FASTQ texts (bytes) -> (records uint32 [n, recWords] or None, stats, device pointer).
@@ -318,6 +321,11 @@ class Hash10xGPU:
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_build_host_dist(self.ctx, ptr, n, C.byref(ci), err, len(err)), err)
         return ci.hashNumber, ci.nHashes, ci.nBlocksMax
+
+    def dist_global_codes(self):
+        """collective: hashDepth and the whole hash->code CSR on every rank, so that depth_range / cluster work per rank"""
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_dist_global_codes(self.ctx, err, len(err)), err)
 
     def dist_info(self, download=True):
         di = CDistInfo()

@@ -34,6 +34,7 @@ struct NcclApi {
   decltype (&ncclRecv) Recv = nullptr ;
   decltype (&ncclAllGather) AllGather = nullptr ;
   decltype (&ncclAllReduce) AllReduce = nullptr ;
+  decltype (&ncclBroadcast) Broadcast = nullptr ;
   decltype (&ncclGetErrorString) GetErrorString = nullptr ;
   bool load (std::string &why)
   { if (handle) return true ;
@@ -43,7 +44,7 @@ struct NcclApi {
 #define H10X_SYM(field, name) field = (decltype (field)) dlsym (handle, name) ; if (!field) { why = "NCCL symbol missing: " name ; return false ; }
     H10X_SYM (GetUniqueId, "ncclGetUniqueId") H10X_SYM (CommInitRank, "ncclCommInitRank") H10X_SYM (CommDestroy, "ncclCommDestroy")
     H10X_SYM (GroupStart, "ncclGroupStart") H10X_SYM (GroupEnd, "ncclGroupEnd") H10X_SYM (Send, "ncclSend") H10X_SYM (Recv, "ncclRecv")
-    H10X_SYM (AllGather, "ncclAllGather") H10X_SYM (AllReduce, "ncclAllReduce") H10X_SYM (GetErrorString, "ncclGetErrorString")
+    H10X_SYM (AllGather, "ncclAllGather") H10X_SYM (AllReduce, "ncclAllReduce") H10X_SYM (Broadcast, "ncclBroadcast") H10X_SYM (GetErrorString, "ncclGetErrorString")
 #undef H10X_SYM
     return true ;
   }
@@ -78,6 +79,7 @@ struct DistState {
   int rank = 0, nranks = 1 ;
   ncclComm_t comm = nullptr ;
   int pushState = 0 ;		/* 0 untried, 1 peer stores work, -1 fall back to ncclSend/ncclRecv */
+  bool globalCodes = false ;	/* h10x_gpu_dist_global_codes ran: hashDepth and the whole hash->code CSR are on this rank too */
   bool owesAgreement = false ;	/* the peers will wait for this rank's word at the next dist_agree (dist_bins' entry): a rank
 				   that fails before it must still deliver it, or the others block in the collective for ever */
   PeerMap peers[H10X_MAX_RANKS] ;
@@ -88,6 +90,22 @@ struct DistState {
 } ;
 
 /* ---- kernels ---- */
+
+/* fillHashTable (hash10x.c:317-347) over the ranks' pieces: rank r's part of bin binId[j] goes behind the parts of the
+   ranks before it (fill[] counts them; ranks own ascending block ranges, so every list ends up ascending).  A warp per
+   local bin; the pieces of the ranks are placed one kernel after the other. */
+__global__ void k_place_piece (uint32_t nBins, const uint32_t *__restrict__ binId, const uint32_t *__restrict__ off,
+			       const uint32_t *__restrict__ piece, const uint64_t *__restrict__ codeOff, uint32_t *__restrict__ fill,
+			       uint32_t *__restrict__ codes)
+{ const uint32_t lane = threadIdx.x & 31 ;
+  const uint64_t j = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+  if (j >= nBins) return ;
+  const uint32_t bin = binId[j], o = off[j], n = off[j + 1] - o ;
+  const uint64_t dst = codeOff[bin] + fill[bin] ;
+  for (uint32_t x = lane ; x < n ; x += 32) codes[dst + x] = piece[o + x] ;
+  __syncwarp () ;
+  if (lane == 0) fill[bin] += n ;
+}
 
 /* rank-distinct hashes from the sorted entries: value, number of local blocks, first (global) block */
 __global__ void k_local_distinct (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sh,

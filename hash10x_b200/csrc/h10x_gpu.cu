@@ -1141,7 +1141,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
       if (!localErr && (nRec == 0 || P.N != 0 || sawZeroBarcode)) localErr = H10X_ERR_UNSUPPORTED ;
       const uint32_t mine[4] = { bt.nBlk, words[0], words[1], nRec } ;
       std::vector<uint32_t> all ;
-      c->dist->owesAgreement = false ;
+      c->dist->owesAgreement = false ; c->dist->globalCodes = false ;
       dist_agree (c, s, localErr, mine, all) ;		/* throws the same error on every rank */
       c->dist->owesAgreement = true ;			/* the next one is at the entry of dist_bins */
       const int R = c->dist->rank, NR = c->dist->nranks ;
@@ -2415,7 +2415,7 @@ int h10x_gpu_download_codes (h10x_ctx *c, h10x_index *out, char *err, size_t err
   return guarded (err, errlen, [&] ()
     { CK (cudaSetDevice (c->P.device)) ;
       cudaStream_t s = c->own ;
-      const size_t hn = c->hashNumber, H = c->nHashes ;
+      const size_t hn = c->hashNumber, H = c->codes.n ;	/* after h10x_gpu_dist_global_codes: all ranks' pairs */
       out->codeOff = (uint64_t*) host_slot (c, SLOT_CODEOFF, 8 * (hn + 1)) ;
       out->codes = (uint32_t*) host_slot (c, SLOT_CODES, 4 * H) ;
       CK (cudaMemcpyAsync (out->codeOff, c->codeOff.p, 8 * (hn + 1), cudaMemcpyDeviceToHost, s)) ;
@@ -2535,7 +2535,8 @@ int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *e
 }
 
 int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen)
-{ if (!c || !out || !c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+{ if (!c || !out || !c->haveIndex || (c->dist && !c->dist->globalCodes))
+    { set_err (err, errlen, "no index resident (after a distributed build: h10x_gpu_dist_global_codes first)") ; return H10X_ERR_BAD_PARAM ; }
   memset (out, 0, sizeof (*out)) ;
   return guarded (err, errlen, [&] ()
     { CK (cudaSetDevice (c->P.device)) ;
@@ -2589,7 +2590,8 @@ int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out
 int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out, char *err, size_t errlen)
 { if (!c || !out) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
   memset (out, 0, sizeof (*out)) ;
-  if (!c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->haveIndex || (c->dist && !c->dist->globalCodes))
+    { set_err (err, errlen, "no index resident (after a distributed build: h10x_gpu_dist_global_codes first)") ; return H10X_ERR_BAD_PARAM ; }
   if (!c->haveGood) { set_err (err, errlen, "you must set hashDepthRange before cluster") ; return H10X_ERR_BAD_PARAM ; }	/* hash10x.c:1258 */
   if (!c->codes.p || !c->codeOff.p) { set_err (err, errlen, "the hash->code lists were not built (H10X_FLAG_NO_CODES)") ; return H10X_ERR_BAD_PARAM ; }
   if (clusterThreshold < 1) { set_err (err, errlen, "clusterThreshold must be at least 1") ; return H10X_ERR_BAD_PARAM ; }
@@ -2618,7 +2620,8 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_subcluster, H10X_SC_THREADS, H10X_SC_DYN_SMEM)) ;
 	  if (occ < 1) throw H10xError (H10X_ERR_CUDA, "k_subcluster does not fit on this device") ;
 	  uint32_t cap = 1024 ; int lg = 10 ;
-	  while (cap < 2 * (uint64_t) nb && lg < 31) { cap <<= 1 ; ++lg ; }
+	  const uint64_t nbAll = c->dist ? (uint64_t) c->dist->nBlocksGlobal + 2 : nb ;	/* barcodes a block can share hashes with */
+	  while (cap < 2 * nbAll && lg < 31) { cap <<= 1 ; ++lg ; }
 	  /* per CTA: the global table, 32 warps of deep-bin counters, bin depth / offset, the per-step results, and the
 	     global-memory versions of the per-step arrays and read labels for blocks that do not fit in shared memory */
 	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_WARPS * 65536 * 4 + (size_t) 2 * 65536 * 4 + (size_t) 6 * 65536 * 4
@@ -2650,6 +2653,7 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	  a.goodOff = c->goodOffD.p ; a.good = c->goodD.p ;
 	  a.nSub = c->blkNSub.p ; a.pointToMin = c->blkPtm.p ;
 	  a.codeMin = (uint32_t) codeMin ; a.codeMax = (uint32_t) codeMax ; a.threshold = clusterThreshold ;
+	  a.codeBase = c->dist ? c->dist->blockBase : 0u ;
 	  CK (cudaEventRecord (evA, s)) ;
 	  LAUNCH (c, k_subcluster, grid, H10X_SC_THREADS, H10X_SC_DYN_SMEM, s, a) ;
 	  CK (cudaEventRecord (evB, s)) ;
@@ -2749,6 +2753,55 @@ int h10x_dist_init (h10x_ctx *c, int rank, int nranks, const void *id128, char *
       ncclUniqueId id ; memcpy (&id, id128, sizeof (id)) ;
       NCK (gNccl.CommInitRank (&c->dist->comm, nranks, id, rank)) ;
       c->dist->rank = rank ; c->dist->nranks = nranks ;
+    }) ;
+}
+
+int h10x_gpu_dist_global_codes (h10x_ctx *c, char *err, size_t errlen)
+{ if (!c || !c->dist || !c->dist->comm || !c->haveIndex) { set_err (err, errlen, "no distributed index resident") ; return H10X_ERR_BAD_PARAM ; }
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      DistState *d = c->dist ;
+      const int R = d->rank, NR = d->nranks ;
+      const size_t hn = c->hashNumber ;
+      /* local allocations first, then one agreement: nobody enters a broadcast that a peer cannot follow */
+      int localErr = 0 ;
+      DBuf<uint32_t> fill ;
+      try
+	{ if (R != 0 || !c->hashDepth.p) c->hashDepth.alloc (hn + 1, s, mt) ;
+	  c->codeOff.alloc (hn + 1, s, mt) ; fill.alloc (hn, s, mt) ;
+	}
+      catch (const SlabFull&) { localErr = H10X_ERR_NOMEM ; }
+      const uint32_t mine[4] = { d->nLocalBins, (uint32_t) c->nHashes, 0, 0 } ;
+      std::vector<uint32_t> all ;
+      dist_agree (c, s, localErr, mine, all) ;
+      uint64_t Hg = 0 ; uint32_t maxBins = 0, maxH = 0 ;
+      for (int r = 0 ; r < NR ; ++r) { Hg += all[4*r + 1] ; maxBins = std::max (maxBins, all[4*r]) ; maxH = std::max (maxH, all[4*r + 1]) ; }
+      if (Hg >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 (block, hash) pairs over all ranks") ;
+      DBuf<uint32_t> tBin, tOff, tCodes ;
+      try { c->codes.alloc (Hg, s, mt) ; tBin.alloc (maxBins, s, mt) ; tOff.alloc ((size_t) maxBins + 1, s, mt) ; tCodes.alloc (maxH, s, mt) ; }
+      catch (const SlabFull&) { localErr = H10X_ERR_NOMEM ; }
+      dist_agree (c, s, localErr, mine, all) ;
+      /* depths from rank 0, offsets by the same scan as a single-GPU build */
+      NCK (gNccl.Broadcast (c->hashDepth.p, c->hashDepth.p, hn, ncclUint32, 0, d->comm, s)) ;
+      CK (cudaMemsetAsync (c->hashDepth.p + hn, 0, 4, s)) ;
+      cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+      CK (cudaMemsetAsync (fill.p, 0, 4 * hn, s)) ;
+      for (int r = 0 ; r < NR ; ++r)
+	{ const uint32_t nb = all[4*r], nh = all[4*r + 1] ;
+	  const uint32_t *bin = (r == R) ? c->localBinId.p : tBin.p, *off = (r == R) ? c->localCodeOff.p : tOff.p,
+	    *piece = (r == R) ? c->localCodes.p : tCodes.p ;
+	  NCK (gNccl.GroupStart ()) ;
+	  if (nb) NCK (gNccl.Broadcast (bin, (void*) bin, nb, ncclUint32, r, d->comm, s)) ;
+	  NCK (gNccl.Broadcast (off, (void*) off, (size_t) nb + 1, ncclUint32, r, d->comm, s)) ;
+	  if (nh) NCK (gNccl.Broadcast (piece, (void*) piece, nh, ncclUint32, r, d->comm, s)) ;
+	  NCK (gNccl.GroupEnd ()) ;
+	  if (nb) LAUNCH (c, k_place_piece, gridFor ((uint64_t) nb * 32, 256), 256, 0, s, nb, bin, off, piece, c->codeOff.p, fill.p, c->codes.p) ;
+	}
+      CK (cudaStreamSynchronize (s)) ;
+      d->globalCodes = true ;
     }) ;
 }
 

@@ -54,6 +54,7 @@ struct SubClusterArgs {
   const uint64_t *goodOff ; const uint16_t *good ;
   uint32_t *nSub ; double *pointToMin ;
   uint32_t codeMin, codeMax ; int threshold ;
+  uint32_t codeBase ;			/* codes[] holds global block numbers, this context's block b is codeBase + b (0 on one GPU) */
   unsigned int *work ;			/* ticket counter */
   unsigned long long *table ;		/* per CTA: tableCap entries (barcode << 32 | stamp << 16 | minShare), zeroed once */
   uint32_t tableCap, tableShift ;	/* power of two >= 2 * blocks; shift = 32 - log2 (tableCap) */
@@ -139,6 +140,7 @@ k_subcluster (SubClusterArgs a)
       const uint32_t code = a.codeMin + sTicket ;
       __syncthreads () ;
       if (code >= a.codeMax) break ;
+      const uint32_t self = code + a.codeBase ;	/* this block's number in codes[]: global after a multi-GPU build */
 
       unsigned long long *ch = a.clus + a.blkOff[code] ;
       const uint16_t *g = a.good + a.goodOff[code] ;
@@ -183,18 +185,18 @@ k_subcluster (SubClusterArgs a)
 		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
 			{ nc[q] = __shfl_sync (0xffffffffu, myNc, q0 + q) ; off[q] = __shfl_sync (0xffffffffu, myOff, q0 + q) ; }
 #pragma unroll
-		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)	/* `code` stands for "no barcode here": it is skipped anyway */
-			{ cja[q] = lane < nc[q] ? a.codes[(size_t) off[q] + lane] : code ;
-			  cjb[q] = lane + 32 < nc[q] ? a.codes[(size_t) off[q] + 32 + lane] : code ;
+		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)	/* `self` stands for "no barcode here": it is skipped anyway */
+			{ cja[q] = lane < nc[q] ? a.codes[(size_t) off[q] + lane] : self ;
+			  cjb[q] = lane + 32 < nc[q] ? a.codes[(size_t) off[q] + 32 + lane] : self ;
 			}
 #pragma unroll
 		      for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
 			{ const uint32_t i = c0 + q0 + q ;
-			  if (cja[q] != code) sc_table_min (tab, mask, shift, inSmem, stamp, cja[q], i + 1, &sClaims, &sOverflow, limit) ;
-			  if (cjb[q] != code) sc_table_min (tab, mask, shift, inSmem, stamp, cjb[q], i + 1, &sClaims, &sOverflow, limit) ;
+			  if (cja[q] != self) sc_table_min (tab, mask, shift, inSmem, stamp, cja[q], i + 1, &sClaims, &sOverflow, limit) ;
+			  if (cjb[q] != self) sc_table_min (tab, mask, shift, inSmem, stamp, cjb[q], i + 1, &sClaims, &sOverflow, limit) ;
 			  for (uint32_t j = lane + 64 ; j < nc[q] ; j += 32)
 			    { const uint32_t cj = a.codes[(size_t) off[q] + j] ;
-			      if (cj != code) sc_table_min (tab, mask, shift, inSmem, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
+			      if (cj != self) sc_table_min (tab, mask, shift, inSmem, stamp, cj, i + 1, &sClaims, &sOverflow, limit) ;
 			    }
 			}
 		    }
@@ -217,8 +219,8 @@ k_subcluster (SubClusterArgs a)
 		    { ncs[q] = __shfl_sync (0xffffffffu, myNc, q0 + q) ; off[q] = __shfl_sync (0xffffffffu, myOff, q0 + q) ; }
 #pragma unroll
 		  for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
-		    { cja[q] = lane < ncs[q] ? a.codes[(size_t) off[q] + lane] : code ;
-		      cjb[q] = lane + 32 < ncs[q] ? a.codes[(size_t) off[q] + 32 + lane] : code ;
+		    { cja[q] = lane < ncs[q] ? a.codes[(size_t) off[q] + lane] : self ;
+		      cjb[q] = lane + 32 < ncs[q] ? a.codes[(size_t) off[q] + 32 + lane] : self ;
 		    }
 #pragma unroll
 		  for (int q = 0 ; q < H10X_SC_GROUP ; ++q)
@@ -231,7 +233,7 @@ k_subcluster (SubClusterArgs a)
 			{ for (uint32_t j = lane ; j < nc ; j += 32)
 			    { const uint32_t cj = j < 32 ? cja[q] : j < 64 ? cjb[q] : cl[j] ;
 			      uint32_t v = 0xffffu ;
-			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (cj != self) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
 			      vbuf[w][j] = (uint16_t) v ;
 			    }
 			  __syncwarp () ;
@@ -251,14 +253,14 @@ k_subcluster (SubClusterArgs a)
 			{ for (uint32_t j = lane ; j < nc ; j += 32)
 			    { const uint32_t cj = cl[j] ;
 			      uint32_t v = 0xffffu ;
-			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (cj != self) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
 			      if (v != 0xffffu) { atomicAdd (cnt + v, 1u) ; ++tot ; }
 			    }
 			  __syncwarp () ;
 			  for (uint32_t j = lane ; j < nc ; j += 32)
 			    { const uint32_t cj = cl[j] ;
 			      uint32_t v = 0xffffu ;
-			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (cj != self) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
 			      if (v != 0xffffu)
 				{ const uint32_t c = __ldcg (cnt + v) ;
 				  if (c > bMax || (c == bMax && v < bBest)) { bMax = c ; bBest = v ; }
@@ -268,7 +270,7 @@ k_subcluster (SubClusterArgs a)
 			  for (uint32_t j = lane ; j < nc ; j += 32)	/* leave the counters zero for the next step */
 			    { const uint32_t cj = cl[j] ;
 			      uint32_t v = 0xffffu ;
-			      if (cj != code) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
+			      if (cj != self) { v = sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u ; if (v >= i) v = 0xffffu ; }
 			      if (v != 0xffffu) cnt[v] = 0 ;
 			    }
 			}
@@ -361,7 +363,7 @@ k_subcluster (SubClusterArgs a)
 		  cAt = 0 ;
 		  for (uint32_t j = lane ; j < nc ; j += 32)
 		    { const uint32_t cj = cl[j] ;
-		      if (cj != code && sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u == cm) ++cAt ;
+		      if (cj != self && sc_table_get (tab, mask, shift, inSmem, stamp, cj) - 1u == cm) ++cAt ;
 		    }
 #pragma unroll
 		  for (int d = 16 ; d ; d >>= 1) cAt += __shfl_xor_sync (0xffffffffu, cAt, d) ;

@@ -37,6 +37,25 @@ static char *slurp (const char *path, uint64_t *n)
   return buf ;
 }
 
+/* the reference compares the id lines of the two files entry by entry and reports the first pair that differs
+   (fq2b.c:152-157); ids are host business: four lines per entry, found with memchr */
+static void checkIds (const char *t1, uint64_t n1, const char *t2, uint64_t n2)
+{ const char *p1 = t1, *e1 = t1 + n1, *p2 = t2, *e2 = t2 + n2 ;
+  while (p1 < e1 && p2 < e2)
+    { const char *a = memchr (p1, '\n', (size_t) (e1 - p1)), *b = memchr (p2, '\n', (size_t) (e2 - p2)) ;
+      if (!a || !b) return ;
+      if (a - p1 != b - p2 || memcmp (p1, p2, (size_t) (a - p1)))
+	{ fprintf (stderr, "proceeding despite paired read ids not matching, e.g. %.*s %.*s\n", (int) (a - p1), p1, (int) (b - p2), p2) ;
+	  return ;
+	}
+      for (int k = 0 ; k < 3 ; ++k)
+	{ a = memchr (a + 1, '\n', (size_t) (e1 - a - 1)) ; b = memchr (b + 1, '\n', (size_t) (e2 - b - 1)) ;
+	  if (!a || !b) return ;
+	}
+      p1 = a + 1 ; p2 = b + 1 ;
+    }
+}
+
 int main (int argc, char *argv[])
 { FILE *fout = stdout ;
   uint32_t *wl = 0 ; uint64_t nWl = 0 ; const char *wlName = 0 ;
@@ -86,6 +105,7 @@ int main (int argc, char *argv[])
   h10x_fq2b_out o ;
   int st = h10x_gpu_fq2b (ctx, t1, n1, t2, n2, wl, nWl, flags, &o, err, sizeof (err)) ;
   if (st) die ("%s", err) ;
+  if (t2) checkIds (t1, n1, t2, n2) ;
   if (o.nRecords && fwrite (o.fqb, 4 * (size_t) o.recWords, o.nRecords, fout) != o.nRecords) die ("write error") ;
   if (fout != stdout) fclose (fout) ;
   int n = (int) o.nRecords ;

@@ -268,6 +268,13 @@ int h10x_gpu_build_device_dist (h10x_ctx *ctx, const void *d_fqb, uint64_t nReco
 /* the same with this rank's records in HOST memory: H2D, collective build, D2H of this rank's arrays */
 int h10x_gpu_build_host_dist (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, h10x_index *out,
 			      char *err, size_t errlen) ;
+
+/* Collective, after a distributed build: every rank receives hashDepth[] and the WHOLE hash -> code lists
+   (fillHashTable, hash10x.c:317-347, over all ranks' barcode blocks: codes[] then holds global block numbers), so that
+   h10x_gpu_depth_range and h10x_gpu_cluster (hash10x.c:528-539, 738-868) run on each rank for its own blocks - codeMin /
+   codeMax and the arrays they return are in the rank's local block numbering, block b of rank r being global block
+   blockBase + b (h10x_gpu_dist_info).  Needs fewer than 2^32 (block, hash) pairs over all ranks. */
+int h10x_gpu_dist_global_codes (h10x_ctx *ctx, char *err, size_t errlen) ;
 int h10x_gpu_dist_info (h10x_ctx *ctx, h10x_dist_info *out) ;
 /* the whole seam on nGpus GPUs of this node from ONE process (a thread and a context per GPU, devices
    p->device .. p->device+nGpus-1): the file is cut at barcode-run boundaries, every GPU builds its range and

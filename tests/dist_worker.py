@@ -45,7 +45,14 @@ def main():
         g.build_device_dist(fqb.data_ptr(), recs.shape[0])
         ix = g.download()
         info = g.dist_info()
+        # the rows that follow the build, per rank on its own blocks: --hashDepthRange and --cluster need every bin's depth
+        # and its barcodes on ALL ranks (hash10x.c:528-539, 738-868)
+        g.dist_global_codes()
+        _within, goff, good = g.depth_range(2, 40)
+        cclus, nsub, ptm, _ms = g.cluster(0, 0, 2)
+        gcoff, gcodes = g.download_codes()
         piece = dict(rank=rank, blkNRead=ix.blkNRead, blkNHash=ix.blkNHash, clus=ix.clus, info=info,
+                     goff=goff, good=good, cclus=cclus, nsub=nsub, ptm=ptm, gcoff=gcoff, gcodes=gcodes,
                      hashNumber=ix.hashNumber, hashValue=ix.hashValue if rank == 0 else None,
                      hashDepth=ix.hashDepth if rank == 0 else None, hashIndex=ix.hashIndex if rank == 0 else None)
         pieces = [None] * world
@@ -79,7 +86,21 @@ def main():
             for x in range(1, hn):
                 got = np.concatenate(lists[x]) if lists[x] else np.zeros(0, np.uint32)
                 assert np.array_equal(got, want.codes[int(want.codeOff[x]):int(want.codeOff[x + 1])]), x
-            print("dist case %d ok: %d ranks, %d bins, %d hashes" % (case, world, hn - 1, clus.size), flush=True)
+            # every rank holds the whole hash->code CSR; good lists / sub-clusters of the ranks' blocks, put end to end, are
+            # what the oracle gets for the whole data set
+            _w, wgoff, wgood = orc.good_hashes(want, 2, 40)
+            wclus, wnsub, wptm = orc.cluster(want, wgoff, wgood, 0, 0, 2)
+            for pc in pieces:
+                assert np.array_equal(pc["gcoff"], want.codeOff) and np.array_equal(pc["gcodes"], want.codes), pc["rank"]
+            ggood = np.concatenate([pc["good"] for pc in pieces])
+            gsizes = np.concatenate([[0]] + [np.diff(pc["goff"].astype(np.int64))[1:] for pc in pieces])
+            assert np.array_equal(ggood, wgood) and np.array_equal(gsizes, np.diff(wgoff.astype(np.int64)))
+            assert np.array_equal(np.concatenate([pc["cclus"] for pc in pieces]), wclus)
+            assert np.array_equal(np.concatenate([[0]] + [pc["nsub"][1:] for pc in pieces]).astype(np.uint32), wnsub)
+            gptm = np.concatenate([[0.0]] + [pc["ptm"][1:] for pc in pieces])
+            assert np.array_equal(gptm.view(np.uint64), wptm.view(np.uint64))
+            print("dist case %d ok: %d ranks, %d bins, %d hashes, %d good, %d sub-clusters" %
+                  (case, world, hn - 1, clus.size, wgood.size, int(wnsub.sum())), flush=True)
         g.close()
         if world > 1:
             dist.barrier()
