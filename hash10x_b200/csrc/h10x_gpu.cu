@@ -36,6 +36,7 @@
 #include <string>
 #include <vector>
 #include <deque>
+#include <functional>
 
 /* ------------------------------------------------------------------ errors / memory */
 
@@ -918,7 +919,7 @@ struct FusedEngine {
   bool ready = false, lean = false ;
   int n1 = 0, n2 = 0, c1 = 0, c2 = 0 ;
   double perPair = 0 ;
-  const void *fn[5] ; size_t smemB[5] ; uint32_t maxGrid[5] ;
+  const void *fn[5] = { nullptr, nullptr, nullptr, nullptr, nullptr } ; size_t smemB[5] = { 0, 0, 0, 0, 0 } ; uint32_t maxGrid[5] = { 0, 0, 0, 0, 0 } ;
   DBuf<uint64_t> scratch, stage ; DBuf<unsigned long long> cursor ; DBuf<unsigned int> work ;
   uint64_t scratchCap = 0 ; uint32_t workUsed = 0, workCap = 0 ;
   std::deque<DBuf<uint32_t>> dLists ;
@@ -2864,7 +2865,20 @@ int h10x_gpu_build_host_dist (h10x_ctx *c, const void *fqb, uint64_t nRecords, h
    host index (block table and ClusterHash slabs concatenate in rank order; rank 0 holds the bin table).
    The hash->code lists stay distributed (codes / codeOff are NULL): --writeHash, --hashStats, --codeStats
    and --hashDepthRange do not read them, and readHashFile rebuilds them anyway (hash10x.c:269-315). */
-int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path, h10x_index *out, char *err, size_t errlen)
+
+/* ------------------------------------------------------------------ a multi-GPU session: build, then the commands that follow */
+
+struct h10x_multi {
+  std::vector<h10x_ctx*> ctxs ;		/* one per GPU, rank order = block order */
+  std::vector<uint32_t> nbLocal ;	/* nBlocksMax of every rank (its blocks are 1 .. nbLocal - 1) */
+  std::vector<uint64_t> hLocal ;
+  uint32_t nb = 0, hn = 0 ; uint64_t H = 0 ;
+  /* stitched results, owned by the session */
+  std::vector<uint8_t> within ; std::vector<uint64_t> goodOff ; std::vector<uint16_t> good ;
+  std::vector<uint64_t> clus ; std::vector<uint32_t> nSub ; std::vector<double> ptm ;
+} ;
+
+static int multi_build_file (const h10x_params *p, int nGpus, const char *path, h10x_index *out, h10x_multi **session, char *err, size_t errlen)
 { if (!p || !path || !out || nGpus < 1) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
   memset (out, 0, sizeof (*out)) ;
   int nDev = h10x_gpu_device_count () ;
@@ -2949,6 +2963,8 @@ int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path
       if (!st && failedEarly.load () == 0)
 	{ st = h10x_gpu_build_device_dist (ctxs[r], dFqb[r], n, nullptr, e, sizeof (e)) ;
 	  if (!st) st = h10x_gpu_download (ctxs[r], &parts[r], e, sizeof (e)) ;
+	  /* a session goes on to --hashDepthRange / --cluster: every rank needs the depths and the whole hash->code CSR */
+	  if (!st && session) st = h10x_gpu_dist_global_codes (ctxs[r], e, sizeof (e)) ;
 	}
       else if (!st) { st = H10X_ERR_IO ; snprintf (e, sizeof (e), "another rank failed before the build") ; }
       status[r] = st ; msgs[r] = e ;
@@ -2986,12 +3002,101 @@ int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path
 	out->blkOff[nb] = H ;
 	out->pinned = 0 ; out->onDevice = 0 ;
       }) ;
-  for (int r = 0 ; r < used ; ++r)
-    { if (dFqb[r]) { cudaSetDevice (p->device + r) ; cudaFree (dFqb[r]) ; }
-      if (ctxs[r]) h10x_gpu_destroy (ctxs[r]) ;
+  for (int r = 0 ; r < used ; ++r) if (dFqb[r]) { cudaSetDevice (p->device + r) ; cudaFree (dFqb[r]) ; }
+  if (!st && session)
+    { h10x_multi *m = new h10x_multi ;
+      m->ctxs = ctxs ; m->nb = out->nBlocksMax ; m->H = out->nHashes ; m->hn = out->hashNumber ;
+      for (int r = 0 ; r < used ; ++r) { m->nbLocal.push_back (parts[r].nBlocksMax) ; m->hLocal.push_back (parts[r].nHashes) ; }
+      *session = m ;
     }
+  else
+    for (int r = 0 ; r < used ; ++r) if (ctxs[r]) h10x_gpu_destroy (ctxs[r]) ;
   if (st) { h10x_index_free (out) ; memset (out, 0, sizeof (*out)) ; }
   return st ;
+}
+
+
+int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path, h10x_index *out, char *err, size_t errlen)
+{ return multi_build_file (p, nGpus, path, out, nullptr, err, errlen) ; }
+
+int h10x_multi_build_file (const h10x_params *p, int nGpus, const char *path, h10x_multi **session, h10x_index *out,
+			   char *err, size_t errlen)
+{ if (!session) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  *session = nullptr ;
+  return multi_build_file (p, nGpus, path, out, session, err, errlen) ;
+}
+
+void h10x_multi_destroy (h10x_multi *m)
+{ if (!m) return ;
+  for (h10x_ctx *c : m->ctxs) if (c) h10x_gpu_destroy (c) ;
+  delete m ;
+}
+
+/* one thread per rank; the first failure is reported */
+static int multi_each (h10x_multi *m, char *err, size_t errlen, const std::function<int (int, char*, size_t)> &f)
+{ const int n = (int) m->ctxs.size () ;
+  std::vector<int> status (n, H10X_OK) ; std::vector<std::string> msgs (n) ;
+  std::vector<std::thread> th ;
+  for (int r = 0 ; r < n ; ++r)
+    th.emplace_back ([&, r] () { char e[512] = "" ; status[r] = f (r, e, sizeof (e)) ; msgs[r] = e ; }) ;
+  for (auto &t : th) t.join () ;
+  for (int r = 0 ; r < n ; ++r) if (status[r]) { set_err (err, errlen, msgs[r].c_str ()) ; return status[r] ; }
+  return H10X_OK ;
+}
+
+int h10x_multi_depth_range (h10x_multi *m, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen)
+{ if (!m || !out) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  const int n = (int) m->ctxs.size () ;
+  std::vector<h10x_good_hashes> part (n) ;
+  int st = multi_each (m, err, errlen, [&] (int r, char *e, size_t el) { return h10x_gpu_depth_range (m->ctxs[r], dmin, dmax, &part[r], e, el) ; }) ;
+  if (st) return st ;
+  return guarded (err, errlen, [&] ()
+    { m->within.assign (part[0].within, part[0].within + m->hn) ;	/* the same on every rank: depths are global */
+      m->goodOff.assign ((size_t) m->nb + 1, 0) ; m->good.clear () ;
+      uint32_t b = 1 ;
+      for (int r = 0 ; r < n ; ++r)
+	{ const h10x_good_hashes &g = part[r] ;
+	  for (uint32_t i = 1 ; i < m->nbLocal[r] ; ++i, ++b) m->goodOff[b] = m->good.size () + (g.goodOff[i] - g.goodOff[1]) ;
+	  m->good.insert (m->good.end (), g.good + g.goodOff[1], g.good + g.goodOff[m->nbLocal[r]]) ;
+	}
+      m->goodOff[0] = 0 ; m->goodOff[m->nb] = m->good.size () ;
+      out->within = m->within.data () ; out->goodOff = m->goodOff.data () ; out->good = m->good.data () ;
+      out->nGood = m->good.size () ; out->hashNumber = m->hn ; out->nBlocksMax = m->nb ;
+    }) ;
+}
+
+int h10x_multi_cluster (h10x_multi *m, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out, char *err, size_t errlen)
+{ if (!m || !out) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  if (!codeMin) codeMin = 1 ;
+  if (!codeMax) codeMax = (int) m->nb ;
+  if (codeMin < 1 || codeMax > (int) m->nb) { set_err (err, errlen, "code range outside the barcode blocks") ; return H10X_ERR_BAD_PARAM ; }
+  const int n = (int) m->ctxs.size () ;
+  std::vector<h10x_clusters> part (n) ;
+  std::vector<uint32_t> base (n + 1, 0) ;
+  for (int r = 0 ; r < n ; ++r) base[r + 1] = base[r] + m->nbLocal[r] - 1 ;
+  int st = multi_each (m, err, errlen, [&] (int r, char *e, size_t el)
+    { /* global blocks base[r] + 1 .. base[r + 1] are this rank's blocks 1 .. nbLocal - 1; an empty local range still
+	 returns the rank's arrays (codeMax == codeMin launches nothing) */
+      long lo = std::max<long> ((long) codeMin - (long) base[r], 1), hi = std::min<long> ((long) codeMax - (long) base[r], (long) m->nbLocal[r]) ;
+      if (hi < lo) hi = lo ;
+      return h10x_gpu_cluster (m->ctxs[r], (int) lo, (int) hi, clusterThreshold, &part[r], e, el) ;
+    }) ;
+  if (st) return st ;
+  return guarded (err, errlen, [&] ()
+    { m->clus.resize (m->H ? m->H : 1) ; m->nSub.assign (m->nb, 0) ; m->ptm.assign (m->nb, 0.0) ;
+      uint64_t e = 0 ; uint32_t b = 1 ; float ms = 0 ;
+      for (int r = 0 ; r < n ; ++r)
+	{ const h10x_clusters &q = part[r] ;
+	  if (m->hLocal[r]) memcpy (m->clus.data () + e, q.clusHash, 8 * m->hLocal[r]) ;
+	  e += m->hLocal[r] ;
+	  for (uint32_t i = 1 ; i < m->nbLocal[r] ; ++i, ++b) { m->nSub[b] = q.nSubCluster[i] ; m->ptm[b] = q.pointToMin[i] ; }
+	  ms = std::max (ms, (float) q.msKernel) ;
+	}
+      out->clusHash = (h10x_cluster_hash*) m->clus.data () ; out->nSubCluster = m->nSub.data () ; out->pointToMin = m->ptm.data () ;
+      out->nBlocksMax = m->nb ; out->nHashes = m->H ; out->msKernel = ms ;
+    }) ;
 }
 
 int h10x_gpu_dist_info (h10x_ctx *c, h10x_dist_info *out)

@@ -27,6 +27,7 @@ static FILE *outFile ;
 static h10x_index ix ;		/* the state --readFQB / --readHash leave behind */
 static int haveIndex = 0, indexFromGpu = 0 ;
 static h10x_ctx *ctx = 0 ;
+static h10x_multi *multi = 0 ;	/* --gpus N: one context per GPU, kept for --hashDepthRange / --cluster */
 static long totalAllocated = 0 ;
 
 static void resetDerived (void) ;	/* drops what --hashDepthRange built on the previous index */
@@ -110,8 +111,9 @@ static void readFQB (const char *path)
   resetDerived () ;		/* the good lists may point into the context's memory */
   if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
   int st ;
-  if (params.gpus > 1)		/* one thread and one context per GPU, NCCL inside the library */
-    st = h10x_gpu_build_file_multi (&p, params.gpus, path, &ix, err, sizeof (err)) ;
+  if (multi) { h10x_multi_destroy (multi) ; multi = 0 ; }
+  if (params.gpus > 1)		/* one thread and one context per GPU, NCCL inside the library; the contexts stay for the commands below */
+    st = h10x_multi_build_file (&p, params.gpus, path, &multi, &ix, err, sizeof (err)) ;
   else
     { if (!(ctx = h10x_gpu_create (&p, err, sizeof (err)))) die ("%s", err) ;
       st = h10x_gpu_build_file (ctx, path, &ix, err, sizeof (err)) ;
@@ -120,7 +122,7 @@ static void readFQB (const char *path)
   else if (st == H10X_ERR_CHUNK_TOO_SMALL) die ("chunkSize too small") ;
   else if (st == H10X_ERR_IO) die ("file read problem") ;
   else if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
-  haveIndex = 1 ; indexFromGpu = (params.gpus <= 1) ;
+  haveIndex = 1 ; indexFromGpu = 1 ;
   totalAllocated += ((long) 4 << ix.B) + 12L * ix.hashNumber + 12L * (long) ix.nHashes ;
 
   int nBarcodes = (int) ix.nBlocksMax - 1, i ;
@@ -161,6 +163,7 @@ static void readHash (const char *path)
   fprintf (outFile, "  filled hash table: %ld hashes from %d barcodes in %d bins\n", nHashes, (int) ix.nBlocksMax, (int) ix.hashNumber) ;
   /* with a GPU the index moves there as well, so that --hashDepthRange and --cluster run on it as after --readFQB */
   if (ctx) { h10x_gpu_destroy (ctx) ; ctx = 0 ; }
+  if (multi) { h10x_multi_destroy (multi) ; multi = 0 ; }
   if (h10x_gpu_device_count () > 0)
     { h10x_params p ;
       memset (&p, 0, sizeof (p)) ;
@@ -249,9 +252,10 @@ static void resetDerived (void)	/* a new index: the reference's initialise() sta
 static void hashDepthRange (int min, int max)
 { if (!haveIndex) die ("cluster code called without setting hashDepthRange") ;
   uint32_t c ;
-  if (ctx && indexFromGpu)	/* the index is resident on the GPU: build the lists there */
+  if ((ctx || multi) && indexFromGpu)	/* the index is resident on the GPU(s): build the lists there */
     { char err[512] ; h10x_good_hashes g ;
-      int st = h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
+      int st = multi ? h10x_multi_depth_range (multi, min, max, &g, err, sizeof (err))
+	: h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
       if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
       if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
       memcpy (hashWithinRange, g.within, ix.hashNumber) ;
@@ -268,8 +272,8 @@ static void hashDepthRange (int min, int max)
       timeUpdate (outFile) ; fflush (outFile) ;
       return ;
     }
-  /* no GPU-resident index (no CUDA device after --readHash, or a multi-GPU build): this program has no CPU version */
-  die ("--hashDepthRange runs on the GPU-resident index (--readFQB on one GPU, or --readHash with a GPU present); after a multi-GPU build write the index with --writeHash and read it back with --readHash") ;
+  /* no GPU-resident index (no CUDA device after --readHash): this program has no CPU version */
+  die ("--hashDepthRange runs on the GPU-resident index (--readFQB, or --readHash with a GPU present)") ;
 }
 
 /* ---- --cluster codeMin codeMax: hash10x.c:1241-1261, on the GPU (h10x_gpu_cluster) ---- */
@@ -279,12 +283,13 @@ static void clusterCodes (int codeMin, int codeMax)
       if (outFile != stdout) fprintf (stderr, "!! you must set hashDepthRange before cluster\n") ;
       return ;
     }
-  if (!(ctx && indexFromGpu))
-    die ("--cluster runs on the GPU-resident index (--readFQB on one GPU, or --readHash with a GPU present): there is no CPU clustering in this program") ;
+  if (!((ctx || multi) && indexFromGpu))
+    die ("--cluster runs on the GPU-resident index (--readFQB, or --readHash with a GPU present): there is no CPU clustering in this program") ;
   if (!codeMin) codeMin = 1 ;
   if (!codeMax) codeMax = (int) ix.nBlocksMax ;
   char err[512] ; h10x_clusters cl ;
-  int st = h10x_gpu_cluster (ctx, codeMin, codeMax, params.clusterThreshold, &cl, err, sizeof (err)) ;
+  int st = multi ? h10x_multi_cluster (multi, codeMin, codeMax, params.clusterThreshold, &cl, err, sizeof (err))
+    : h10x_gpu_cluster (ctx, codeMin, codeMax, params.clusterThreshold, &cl, err, sizeof (err)) ;
   if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
   if (ix.pinned == 0)		/* an index h10x_read_hash malloc'ed: keep its own arrays (h10x_index_free frees them) */
     { size_t nb = ix.nBlocksMax ;
@@ -387,5 +392,6 @@ int main (int argc, char *argv[])
   fprintf (outFile, "total resources used: ") ; timeTotal (outFile) ;
   if (outFile != stdout) { printf ("total resources used: ") ; timeTotal (stdout) ; }
   if (ctx) h10x_gpu_destroy (ctx) ;
+  if (multi) h10x_multi_destroy (multi) ;
   return 0 ;
 }

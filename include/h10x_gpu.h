@@ -282,6 +282,19 @@ int h10x_gpu_dist_info (h10x_ctx *ctx, h10x_dist_info *out) ;
    NULL: the hash->code lists remain distributed and no command of the --readFQB ... --writeHash chain reads them. */
 int h10x_gpu_build_file_multi (const h10x_params *p, int nGpus, const char *path, h10x_index *out,
 			       char *err, size_t errlen) ;
+
+/* The same build as a SESSION: the per-GPU contexts stay alive (with hashDepth and the whole hash->code CSR on every
+   GPU, h10x_gpu_dist_global_codes), so that the commands hash10x chains after --readFQB run on all GPUs too, each on
+   its own barcode blocks: --hashDepthRange (hash10x.c:528-539, 738-766) and --cluster (hash10x.c:770-868).  Block
+   numbers, good lists and ClusterHash entries come back stitched in the global numbering of the one-GPU calls; the
+   arrays belong to the session and are valid until its next call of the same kind. */
+typedef struct h10x_multi h10x_multi ;
+int h10x_multi_build_file (const h10x_params *p, int nGpus, const char *path, h10x_multi **session, h10x_index *out,
+			   char *err, size_t errlen) ;
+int h10x_multi_depth_range (h10x_multi *session, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen) ;
+int h10x_multi_cluster (h10x_multi *session, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out,
+			char *err, size_t errlen) ;
+void h10x_multi_destroy (h10x_multi *session) ;
 int h10x_gpu_memcpy_d2h (h10x_ctx *ctx, void *dst, const void *src, size_t bytes) ;
 
 /* moshes of each record without the index build (the K1 stage alone), for parity tests of

@@ -199,3 +199,31 @@ def test_gpu_reproduces_reference_cluster_golden(gpu_lib, name, d):
     assert crc(nsub) == d["crc_blkNSub"] and crc(ptm) == d["crc_pointToMin"] and crc(sub) == d["crc_clusSub"]
     assert crc(clus & np.uint64(0x00FFFFFFFFFFFFFF)) == d["crc_clusRaw"]
     assert int(nsub.sum()) == d["sub_clusters"] and int((sub > 0).sum()) == d["clustered_entries"]
+
+
+def test_cli_multi_gpu_depth_range_and_cluster(orc, gpu_lib, tmp_path):
+    """--gpus N --readFQB --hashDepthRange -ct --cluster --writeHash: the commands that follow the build run on every GPU
+    for its own barcode blocks (h10x_multi_*); the .hash carries the oracle's nSubCluster / pointToMin / subCluster bytes,
+    also for a cluster range that starts and ends inside different GPUs' block ranges"""
+    import hash10x_b200
+    n = gpu_lib.h10x_gpu_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = os.path.join(os.path.dirname(hash10x_b200.__file__), "bin", "hash10x-b200")
+    recs = _cluster_case(orc, 36, 300, 100, 250, 200_000, 20_000, 4)
+    fqb = str(tmp_path / "a.fqb")
+    recs.tofile(fqb)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, 4, 400)
+    for g in sorted({2, min(n, 8)}):
+        for cmin, cmax in ((0, 0), (40, 260)):
+            out = str(tmp_path / ("g%d_%d.hash" % (g, cmin)))
+            r = subprocess.run([exe, "--gpus", str(g), "-B", "20", "--readFQB", fqb, "--hashDepthRange", "4", "400", "-ct", "3",
+                                "--cluster", str(cmin), str(cmax), "--writeHash", out], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr
+            clus, nsub, ptm = orc.cluster(ix, goff, good, cmin, cmax, 3)
+            hf = hashfile.parse(out)
+            assert np.array_equal(hf.blkNSub, nsub), (g, cmin)
+            assert np.array_equal(hf.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+            assert np.array_equal(hf.clusRaw, clus)
+            hashfile.assert_strict_equal(hashfile.from_index(ix), hf, table=True)
