@@ -417,6 +417,31 @@ def run_ours(args, wl, wl_name):
                "note": "h10x_gpu_depth_range / h10x_gpu_cluster (hash10x.c:528-539,738-766 / 770-868) on the index the timed "
                        "build left in HBM; depth_range_ms includes the D2H of the good-hash lists, cluster_ms is the kernel"}
 
+    if world > 1 and not args.no_next:
+        # the same rows on N GPUs: every rank first receives hashDepth and the whole hash->code CSR (one collective),
+        # then filters and clusters its own barcode blocks; times are the slowest rank's
+        dmin, dmax, ct = wl.get("depth_range", (30, 100)) + (5,)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        g.dist_global_codes()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        n_good = g.depth_range(dmin, dmax, copy=False)
+        t2 = time.perf_counter()
+        _c, nsub, _p, ms_kernel = g.cluster(0, 0, ct, copy=False)
+        t3 = time.perf_counter()
+        tmax = torch.tensor([t1 - t0, t2 - t1, t3 - t2, ms_kernel * 1e-3], dtype=torch.float64, device=dev)
+        tot = torch.tensor([int(n_good), int(nsub.sum()), int((nsub > 0).sum())], dtype=torch.int64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        nxt = {"hashDepthRange": [dmin, dmax], "clusterThreshold": ct, "good_hashes": int(tot[0]),
+               "global_codes_ms": float(tmax[0]) * 1e3, "depth_range_ms": float(tmax[1]) * 1e3,
+               "cluster_ms": float(tmax[3]) * 1e3, "cluster_ms_incl_d2h": float(tmax[2]) * 1e3,
+               "sub_clusters": int(tot[1]), "clustered_blocks": int(tot[2]),
+               "note": "h10x_gpu_dist_global_codes (collective: hashDepth + the whole hash->code CSR on every rank), then "
+                       "h10x_gpu_depth_range / h10x_gpu_cluster per rank on its own barcode blocks; slowest rank's times"}
+
     # --- e2e: the C ABI's host entry point, H2D + build + D2H inside the timed region ---
     e2e = None
     if not args.no_e2e:

@@ -22,7 +22,7 @@
 #include <string.h>
 #include <sys/resource.h>
 
-static struct { int k, w, r, B, N, chunkSize, clusterThreshold, gpus ; } params ;
+static struct { int k, w, r, B, N, chunkSize, clusterThreshold, gpus, wideB ; } params ;
 static FILE *outFile ;
 static h10x_index ix ;		/* the state --readFQB / --readHash leave behind */
 static int haveIndex = 0, indexFromGpu = 0 ;
@@ -83,6 +83,7 @@ static void usage (void)
   fprintf (stderr, "   --hashStats : distribution of hash counts and summary info\n") ;
   fprintf (stderr, "   --codeStats : distribution of barcode/cluster sizes and summary info\n") ;
   fprintf (stderr, "   --gpuStats : per-stage device times and roofline bytes of the last --readFQB\n") ;
+  fprintf (stderr, "   --wideB : accept -B 31 to 34 (hash10x-b200 only; README.md:55)\n") ;
   fprintf (stderr, "   --help : print this usage message\n") ;
 }
 
@@ -90,7 +91,9 @@ static void usage (void)
 static void initialise (int k, int w, int r, int B)
 { if (k <= 0 || w <= 0) die ("k %d, w %d must be > 0; run without args for usage", k, w) ;
   if (k >= 32) die ("seqhash k %d must be between 1 and 32\n", k) ;
-  if (B < 20 || B > 30) die ("hashTableBits %d out of range 20-30", B) ;
+  /* hash10x.c:1107 stops at 30; README.md:55 and moshset.c:17 speak of up to 34: --wideB opts into 31..34 (a 8..64 GiB
+     hashIndex), with the same table algorithm, which the reference's own binary cannot read back */
+  if (B < 20 || B > (params.wideB ? 34 : 30)) die ("hashTableBits %d out of range 20-%d", B, params.wideB ? 34 : 30) ;
   if (haveIndex) { h10x_index_free (&ix) ; memset (&ix, 0, sizeof (ix)) ; haveIndex = 0 ; }
   fprintf (outFile, "hash10x initialised with k = %d, w = %d, random seed = %d, hashtable bits = %d\n", k, w, r, B) ;
 }
@@ -103,7 +106,7 @@ static void readFQB (const char *path)
   p.k = params.k ; p.w = params.w ; p.B = params.B ; p.N = params.N ; p.chunkSize = params.chunkSize ;
   p.factor1 = h10x_factor1_from_seed (params.r) ;
   p.device = getenv ("H10X_DEVICE") ? atoi (getenv ("H10X_DEVICE")) : 0 ;
-  p.flags = H10X_FLAG_LAZY_CODES ;	/* no command below reads hashCodes on the host: --cluster runs where they are */
+  p.flags = H10X_FLAG_LAZY_CODES | (params.wideB ? H10X_FLAG_WIDE_B : 0) ;	/* no command below reads hashCodes on the host: --cluster runs where they are */
   printf ("  reading and processing sorted fqb file with chunkSize %d", params.chunkSize) ;
   if (params.N) printf (", first %d records", params.N) ;
   printf ("\n") ;
@@ -349,6 +352,7 @@ int main (int argc, char *argv[])
       else if (ARGMATCH ("-N", 2)) params.N = atoi (argv[-1]) ;
       else if (ARGMATCH ("-c", 2)) params.chunkSize = atoi (argv[-1]) ;
       else if (ARGMATCH ("--gpus", 2)) params.gpus = atoi (argv[-1]) ;	/* new: GPUs used by --readFQB */
+      else if (ARGMATCH ("--wideB", 1)) params.wideB = 1 ;			/* new: accept -B 31..34 */
       else if (ARGMATCH ("-t", 2) || ARGMATCH ("--threads", 2))
 	fprintf (stderr, "  can't set thread number - not compiled with OMP\n") ;
       else if (ARGMATCH ("-o", 2) || ARGMATCH ("--output", 2))

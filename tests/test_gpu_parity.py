@@ -329,3 +329,26 @@ def test_lazy_codes(orc, gpu_lib):
     wclus, wnsub, _wptm = orc.cluster(want, wgoff, wgood, 0, 0, 2)
     assert np.array_equal(goff, wgoff) and np.array_equal(good, wgood)
     assert np.array_equal(clus, wclus) and np.array_equal(nsub, wnsub)
+
+
+def test_wide_table_B31(orc, gpu_lib):
+    # H10X_FLAG_WIDE_B (hash10x-b200 --wideB): -B 31..34 as README.md:55 / moshset.c:17 describe.  Bin ids, values, depths
+    # and lists do not depend on B (they equal the B = 30 oracle's); the 8 GiB hashIndex is the table the oracle's
+    # restatement of hashIndexFind (hash10x.c:139-152) fills when it is allowed 31 bits
+    import psutil
+    import hash10x_b200
+    if psutil.virtual_memory().available < (56 << 30):
+        pytest.skip("needs about 40 GB of host memory for the two 8 GiB tables and their copies")
+    p = orc.synth_params(seed=47, n_barcodes=30, pairs_min=10, pairs_max=150)
+    recs = orc.synth_fqb(p)
+    want30 = orc.build(recs, B=30)
+    with pytest.raises(hash10x_b200.H10xError):
+        _gpu(B=31)
+    with _gpu(B=31, flags=hash10x_b200.FLAG_WIDE_B) as g:
+        got = g.build_host(recs)
+    assert np.array_equal(got.hashValue, want30.hashValue) and np.array_equal(got.hashDepth, want30.hashDepth)
+    assert np.array_equal(got.clus, want30.clus) and np.array_equal(got.codes, want30.codes)
+    assert got.hashIndex.size == 1 << 31
+    del want30
+    want31 = orc.build(recs, B=31, maxB=34)
+    assert want31.status == 0 and np.array_equal(got.hashIndex, want31.hashIndex)
