@@ -129,7 +129,9 @@ struct h10x_ctx {
   /* multi-GPU (h10x_dist.cuh) */
   bool slabClamped = false ;	/* the slab already takes all free device memory */
   /* host-buffer builds start the D2H of an index array as soon as it is final, on a second stream */
-    /* h10x_gpu_fq2b: the records of the last call and the whitelist table (2^32 words, kept while the whitelist is the same) */
+    /* h10x_gpu_histogram / h10x_gpu_crib_build results (host) */
+  std::vector<int> histHost, cribHist ; std::vector<uint8_t> cribType ; std::vector<int16_t> cribChr ; std::vector<uint16_t> cribPos ;
+  /* h10x_gpu_fq2b: the records of the last call and the whitelist table (2^32 words, kept while the whitelist is the same) */
   uint32_t *fqRecs = nullptr ; void *fqHost = nullptr ; size_t fqHostCap = 0 ;
   uint32_t *wlTable = nullptr ; uint64_t wlCount = 0, wlSum = 0 ;
   cudaStream_t ulStream = 0 ;	/* ... and copy the file up in slabs on a third one while the fused kernel hashes the slabs that landed */
@@ -202,6 +204,7 @@ struct CastU64 { __host__ __device__ uint64_t operator() (uint32_t x) const { re
 
 #include "h10x_dist.cuh"
 #include "h10x_fq2b.cuh"
+#include "h10x_crib.cuh"
 
 /* ------------------------------------------------------------------ kernels: runs */
 
@@ -2245,6 +2248,96 @@ static void prefuse_streamed (h10x_ctx *c, cudaStream_t s, const void *hostFqb, 
   pf.anyZero = hAnyZero != 0 ;
   pf.valid = ok && pf.nRuns > 0 ;
   if (!pf.valid) { pf.eng.release () ; pf.srcOff.release () ; pf.blkCnt.release () ; pf.dBlkStart.release () ; }
+}
+
+/* ------------------------------------------------------------------ --hashStats / --codeStats / --cribBuild (h10x_crib.cuh) */
+
+int h10x_gpu_histogram (h10x_ctx *c, int which, const int **hist, int *n, char *err, size_t errlen)
+{ if (!c || !hist || !n || !c->haveIndex || which < 0 || which > 2) { set_err (err, errlen, "no index resident") ; return H10X_ERR_BAD_PARAM ; }
+  const uint32_t *v = which == 0 ? c->hashDepth.p : which == 1 ? c->blkNHash.p : c->blkNSub.p ;
+  const uint64_t cnt = which == 0 ? c->hashNumber : c->nBlocksMax ;
+  if (!v) { set_err (err, errlen, which == 2 ? "no sub-clusters yet" : "array not resident on this rank") ; return H10X_ERR_BAD_PARAM ; }
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      DBuf<uint32_t> dTop (1, s, mt) ;
+      CK (cudaMemsetAsync (dTop.p, 0, 4, s)) ;
+      const unsigned grid = (unsigned) std::min<uint64_t> (gridFor (cnt, 256), (uint64_t) device_sms (c) * 8) ;
+      LAUNCH (c, k_max_u32, grid, 256, 0, s, v, cnt, dTop.p) ;
+      uint32_t top = 0 ;
+      CK (cudaMemcpyAsync (&top, dTop.p, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      DBuf<int> dHist ((size_t) top + 1, s, mt) ;
+      CK (cudaMemsetAsync (dHist.p, 0, 4 * ((size_t) top + 1), s)) ;
+      LAUNCH (c, k_hist_u32, grid, 256, 0, s, v, cnt, top + 1, dHist.p) ;
+      c->histHost.resize ((size_t) top + 1) ;
+      CK (cudaMemcpyAsync (c->histHost.data (), dHist.p, 4 * ((size_t) top + 1), cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      *hist = c->histHost.data () ; *n = (int) top + 1 ;
+    }) ;
+}
+
+int h10x_gpu_crib_build (h10x_ctx *c, const uint8_t *g1, const uint64_t *off1, uint32_t nSeq1,
+			 const uint8_t *g2, const uint64_t *off2, uint32_t nSeq2, h10x_crib *out, char *err, size_t errlen)
+{ if (!c || !out || !c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->hashIndex.p || !c->hashValue.p || !c->hashDepth.p) { set_err (err, errlen, "the bin table is not resident (H10X_FLAG_NO_TABLE)") ; return H10X_ERR_BAD_PARAM ; }
+  if ((nSeq1 && (!g1 || !off1)) || (nSeq2 && (!g2 || !off2))) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  memset (out, 0, sizeof (*out)) ;
+  return guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      const uint32_t hn = c->hashNumber ;
+      DBuf<uint32_t> cnt[2] ; DBuf<unsigned long long> first[2] ; DBuf<CribCounts> cc (2, s, mt) ;
+      CK (cudaMemsetAsync (cc.p, 0, 2 * sizeof (CribCounts), s)) ;
+      CribCounts hcc[2] ;
+      for (int g = 0 ; g < 2 ; ++g)
+	{ const uint8_t *codes = g ? g2 : g1 ; const uint64_t *off = g ? off2 : off1 ; const uint32_t nSeq = g ? nSeq2 : nSeq1 ;
+	  cnt[g].alloc (hn, s, mt) ; first[g].alloc (hn, s, mt) ;
+	  CK (cudaMemsetAsync (cnt[g].p, 0, 4 * (size_t) hn, s)) ;
+	  CK (cudaMemsetAsync (first[g].p, 0xff, 8 * (size_t) hn, s)) ;
+	  const uint64_t total = nSeq ? off[nSeq] : 0 ;
+	  if (total)
+	    { DBuf<uint8_t> dCodes (total, s, mt) ; DBuf<uint64_t> dOff ((size_t) nSeq + 1, s, mt) ;
+	      CK (cudaMemcpyAsync (dCodes.p, codes, total, cudaMemcpyHostToDevice, s)) ;
+	      CK (cudaMemcpyAsync (dOff.p, off, 8 * ((size_t) nSeq + 1), cudaMemcpyHostToDevice, s)) ;
+	      const unsigned grid = (unsigned) std::min<uint64_t> (gridFor (total, 256), (uint64_t) device_sms (c) * 16) ;
+	      LAUNCH (c, k_crib_scan, grid, 256, 0, s, dCodes.p, total, dOff.p, nSeq, c->hp, c->hashIndex.p, c->P.B, c->hashValue.p,
+		      cnt[g].p, first[g].p, cc.p + g) ;
+	      CK (cudaStreamSynchronize (s)) ;		/* the staging buffers go out of scope */
+	    }
+	  out->nSeq[g] = (int32_t) nSeq ;
+	}
+      CK (cudaMemcpyAsync (hcc, cc.p, sizeof (hcc), cudaMemcpyDeviceToHost, s)) ;
+      /* the groups' histograms by bin depth */
+      DBuf<uint32_t> dTop (1, s, mt) ;
+      CK (cudaMemsetAsync (dTop.p, 0, 4, s)) ;
+      LAUNCH (c, k_max_u32, (unsigned) std::min<uint64_t> (gridFor (hn, 256), (uint64_t) device_sms (c) * 8), 256, 0, s, c->hashDepth.p, (uint64_t) hn, dTop.p) ;
+      uint32_t top = 0 ;
+      CK (cudaMemcpyAsync (&top, dTop.p, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      const uint32_t histLen = top + 1 ;
+      DBuf<int> dHist ((size_t) 4 * histLen, s, mt) ; DBuf<uint8_t> dType (hn, s, mt) ; DBuf<int16_t> dChr (hn, s, mt) ; DBuf<uint16_t> dPos (hn, s, mt) ;
+      CK (cudaMemsetAsync (dHist.p, 0, 16 * (size_t) histLen, s)) ;
+      LAUNCH (c, k_crib_classify, gridFor (hn, 256), 256, 0, s, hn, cnt[0].p, first[0].p, cnt[1].p, first[1].p, c->hashDepth.p, histLen,
+	      dType.p, dChr.p, dPos.p, dHist.p) ;
+      c->cribHist.resize ((size_t) 4 * histLen) ; c->cribType.resize (hn) ; c->cribChr.resize (hn) ; c->cribPos.resize (hn) ;
+      CK (cudaMemcpyAsync (c->cribHist.data (), dHist.p, 16 * (size_t) histLen, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaMemcpyAsync (c->cribType.data (), dType.p, hn, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaMemcpyAsync (c->cribChr.data (), dChr.p, 2 * (size_t) hn, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaMemcpyAsync (c->cribPos.data (), dPos.p, 2 * (size_t) hn, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      out->hashNumber = hn ; out->histLen = (int32_t) histLen ;
+      out->type = c->cribType.data () ; out->chr = c->cribChr.data () ; out->pos = c->cribPos.data () ;
+      for (int g = 0 ; g < 2 ; ++g) { out->nPresent[g] = (int32_t) hcc[g].nPresent ; out->nAbsent[g] = (int32_t) hcc[g].nAbsent ; }
+      for (int t = 0 ; t < 4 ; ++t)
+	{ const int *h = c->cribHist.data () + (size_t) t * histLen ;
+	  out->hist[t] = h ;
+	  int mx = 0 ; for (uint32_t d = 0 ; d < histLen ; ++d) if (h[d]) mx = (int) d + 1 ;
+	  out->histMax[t] = mx ;
+	}
+    }) ;
 }
 
 /* ------------------------------------------------------------------ fq2b + bsort (h10x_fq2b.cuh) */

@@ -83,6 +83,7 @@ static void usage (void)
   fprintf (stderr, "   --hashStats : distribution of hash counts and summary info\n") ;
   fprintf (stderr, "   --codeStats : distribution of barcode/cluster sizes and summary info\n") ;
   fprintf (stderr, "   --gpuStats : per-stage device times and roofline bytes of the last --readFQB\n") ;
+  fprintf (stderr, "   --cribBuild <genome1.fa> <genome2.fa>: match to genomic hashes (runs on the GPU)\n") ;
   fprintf (stderr, "   --wideB : accept -B 31 to 34 (hash10x-b200 only; README.md:55)\n") ;
   fprintf (stderr, "   --help : print this usage message\n") ;
 }
@@ -223,7 +224,10 @@ static int *countHist (const uint32_t *v, uint32_t n, int *maxOut)
 /* hashDepthHist hash10x.c:377-386: over all of hashDepth, dummy bin 0 included */
 static void hashStats (void)
 { if (!haveIndex || ix.hashNumber <= 1) { fprintf (stderr, "  no hash list to print stats for\n") ; return ; }
-  int max ; int *a = countHist (ix.hashDepth, ix.hashNumber, &max) ;
+  int max ; const int *d ; char err[512] ;
+  if (ctx && indexFromGpu && !h10x_gpu_histogram (ctx, 0, &d, &max, err, sizeof (err)))	/* counted where the index is */
+    { histogramReport ("HASH_COUNT", d, max) ; return ; }
+  int *a = countHist (ix.hashDepth, ix.hashNumber, &max) ;
   histogramReport ("HASH_COUNT", a, max) ;
   free (a) ;
 }
@@ -231,7 +235,14 @@ static void hashStats (void)
 /* codeSizeHist hash10x.c:388-402: over all blocks, dummy block 0 and the unhashed last one included */
 static void codeStats (void)
 { if (!haveIndex || !ix.nBlocksMax) { fprintf (stderr, "  no barcodes to print stats for\n") ; return ; }
-  int max ; int *a = countHist (ix.blkNHash, ix.nBlocksMax, &max) ;
+  int max ; int *a ; const int *d ; char err[512] ;
+  if (ctx && indexFromGpu && !h10x_gpu_histogram (ctx, 1, &d, &max, err, sizeof (err)))
+    { histogramReport ("CODE_SIZE", d, max) ;
+      if (ix.blkNSubCluster && !h10x_gpu_histogram (ctx, 2, &d, &max, err, sizeof (err)) && max > 1)
+	histogramReport ("CODE_CLUSTER", d, max) ;
+      return ;
+    }
+  a = countHist (ix.blkNHash, ix.nBlocksMax, &max) ;
   histogramReport ("CODE_SIZE", a, max) ;
   free (a) ;
   if (ix.blkNSubCluster)	/* only once some block has sub-clusters: arrayMax(clusterHist) > 1, hash10x.c:401 */
@@ -310,6 +321,77 @@ static void clusterCodes (int codeMin, int codeMax)
   if (outFile != stdout) printf ("  clustered codes %d to %d\n", codeMin, codeMax) ;
 }
 
+/* ---- --cribBuild genome1.fa genome2.fa: cribBuild hash10x.c:426-510, on the GPU (h10x_gpu_crib_build) ---- */
+
+/* readSequence (readseq.c:63-157) as cribAddGenome calls it (dna2indexConv with N -> 0, no id, hash10x.c:433-434),
+   sequence after sequence until one comes back empty; the codes of all sequences back to back */
+static void readGenome (FILE *f, uint8_t **codesOut, uint64_t **offOut, uint32_t *nSeqOut)
+{ size_t cap = (size_t) 1 << 24, n = 0, offCap = 1024 ;
+  uint8_t *codes = malloc (cap) ; uint64_t *off = malloc (8 * offCap) ;
+  uint32_t nSeq = 0 ; int line = 1, c ;
+  if (!codes || !off) die ("myalloc failure") ;
+  off[0] = 0 ;
+  for (;;)
+    { size_t start = n ; int bad = 0 ;
+      c = getc (f) ;
+      if (c == '>') { while ((c = getc (f)) != EOF && c != '\n') ; ++line ; }
+      else if (c != EOF) ungetc (c, f) ;
+      while ((c = getc (f)) != EOF)
+	{ int v ;
+	  if (c == '>') { ungetc (c, f) ; break ; }
+	  switch (c)
+	    { case 'A': case 'a': case 'N': case 'n': v = 0 ; break ;
+	      case 'C': case 'c': v = 1 ; break ;
+	      case 'G': case 'g': v = 2 ; break ;
+	      case 'T': case 't': v = 3 ; break ;
+	      case '\n': ++line ; v = -1 ; break ;
+	      case ' ': case '\t': v = -1 ; break ;
+	      default: v = -2 ;
+	    }
+	  if (v == -2)
+	    { fprintf (stderr, "Bad char 0x%x = '%c' at line %d, base %d\n", c, c, line, (int) (n - start)) ; bad = 1 ; break ; }
+	  if (v < 0) continue ;
+	  if (n == cap) { cap *= 2 ; if (!(codes = realloc (codes, cap))) die ("myalloc failure") ; }
+	  codes[n++] = (uint8_t) v ;
+	}
+      if (bad) { n = start ; break ; }		/* readSequence returns 0: the walk over this genome ends */
+      if (n == start) break ;
+      if (nSeq + 2 > offCap) { offCap *= 2 ; if (!(off = realloc (off, 8 * offCap))) die ("myalloc failure") ; }
+      off[++nSeq] = n ;
+    }
+  fclose (f) ;
+  *codesOut = codes ; *offOut = off ; *nSeqOut = nSeq ;
+}
+
+static void printCribStats (const int *a, int max)		/* printArrayStats hash10x.c:457-468 */
+{ int i, sum = 0, min = -1 ;
+  double total = 0 ;
+  for (i = 0 ; i < max ; ++i)
+    if (a[i]) { sum += a[i] ; total += a[i] * i ; if (min == -1) min = i ; }
+  fprintf (outFile, "  %d mean %.1f min %d max %d\n", sum, total / sum, min, max - 1) ;
+}
+
+static void cribBuild (FILE *f1, FILE *f2)
+{ if (!(ctx && indexFromGpu)) die ("--cribBuild runs on the GPU-resident index (--readFQB on one GPU, or --readHash with a GPU present)") ;
+  uint8_t *g[2] ; uint64_t *off[2] ; uint32_t nSeq[2] ; int i ;
+  readGenome (f1, &g[0], &off[0], &nSeq[0]) ;
+  readGenome (f2, &g[1], &off[1], &nSeq[1]) ;
+  char err[512] ; h10x_crib cb ;
+  int st = h10x_gpu_crib_build (ctx, g[0], off[0], nSeq[0], g[1], off[1], nSeq[1], &cb, err, sizeof (err)) ;
+  if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+  for (i = 0 ; i < 2 ; ++i)
+    { fprintf (outFile, "  read %d known and %d unknown hashes from %d sequences in crib genome\n", cb.nPresent[i], cb.nAbsent[i], cb.nSeq[i]) ;
+      if (outFile != stdout)
+	printf ("  read %d known and %d unknown hashes from %d sequences in crib genome\n", cb.nPresent[i], cb.nAbsent[i], cb.nSeq[i]) ;
+    }
+  fprintf (outFile, "  crib matches\n") ;
+  fprintf (outFile, "    hom  ") ; printCribStats (cb.hist[2], cb.histMax[2]) ;
+  fprintf (outFile, "    het  ") ; printCribStats (cb.hist[1], cb.histMax[1]) ;
+  fprintf (outFile, "    mul ") ; printCribStats (cb.hist[3], cb.histMax[3]) ;
+  fprintf (outFile, "    err ") ; printCribStats (cb.hist[0], cb.histMax[0]) ;
+  for (i = 0 ; i < 2 ; ++i) { free (g[i]) ; free (off[i]) ; }
+}
+
 static void gpuStats (void)
 { h10x_stats s ; int i ;
   if (!ctx || !indexFromGpu || h10x_gpu_stats (ctx, &s)) { fprintf (stderr, "  no GPU build to report\n") ; return ; }
@@ -378,13 +460,19 @@ int main (int argc, char *argv[])
       else if (ARGMATCH ("--hashDepthRange", 3)) hashDepthRange (atoi (argv[-2]), atoi (argv[-1])) ;
       else if (ARGMATCH ("-ct", 2) || ARGMATCH ("--clusterThreshold", 2)) params.clusterThreshold = atoi (argv[-1]) ;
       else if (ARGMATCH ("--cluster", 3)) clusterCodes (atoi (argv[-2]), atoi (argv[-1])) ;
+      else if (ARGMATCH ("--cribBuild", 3))
+	{ FILE *f1, *f2 ;
+	  if (!(f1 = fopen (argv[-2], "r"))) die ("failed to open .fa file %s", argv[-2]) ;
+	  if (!(f2 = fopen (argv[-1], "r"))) die ("failed to open .fa file %s", argv[-1]) ;
+	  cribBuild (f1, f2) ;
+	}
       else if (ARGMATCH ("--hashStats", 1)) hashStats () ;
       else if (ARGMATCH ("--codeStats", 1)) codeStats () ;
       else if (ARGMATCH ("--gpuStats", 1)) gpuStats () ;
       else if (ARGMATCH ("--help", 1)) usage () ;
       else if (ARGMATCH ("--quit", 1) || ARGMATCH ("--exit", 1)) break ;
       else if (!strcmp (*argv, "--clusterReport") || !strcmp (*argv, "--clusterSplit")
-	       || !strcmp (*argv, "--cribBuild") || !strcmp (*argv, "--cribSummary") || !strcmp (*argv, "--hashInfo")
+	       || !strcmp (*argv, "--cribSummary") || !strcmp (*argv, "--hashInfo")
 	       || !strcmp (*argv, "--hashExplore") || !strcmp (*argv, "--doubleShared") || !strcmp (*argv, "--codeExplore")
 	       || !strcmp (*argv, "--errorFix") || !strcmp (*argv, "--shareScan") || !strcmp (*argv, "--interactive"))
 	die ("command %s is outside the scope of hash10x-b200: write the index with --writeHash and run it in hash10x --readHash", *argv) ;

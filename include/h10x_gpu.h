@@ -141,6 +141,27 @@ int h10x_gpu_index_device (h10x_ctx *ctx, h10x_index *out) ;
    valid until the next download/build_host/build_file on this context or its destruction */
 int h10x_gpu_download (h10x_ctx *ctx, h10x_index *out, char *err, size_t errlen) ;
 
+/* ---- --hashStats / --codeStats / --cribBuild on the resident index ("next" row f4; hash10x.c:351-402, 426-510) ----
+   h10x_gpu_histogram: the count-per-value array that hashDepthHist (which = 0: over hashDepth[0 .. hashNumber), dummy bin
+   included), codeSizeHist (1: over the blocks' nHash) and its cluster part (2: over nSubCluster, after --cluster) hand to
+   histogramReport; *n = largest value + 1.  The array is owned by the context, valid until the next call. */
+int h10x_gpu_histogram (h10x_ctx *ctx, int which, const int **hist, int *n, char *err, size_t errlen) ;
+
+/* cribBuild (hash10x.c:470-510): g1 / g2 = the two genomes as base codes 0..3, one byte per base, sequences back to back
+   (off[s] .. off[s+1]), as readSequence + cribAddGenome's conversion deliver them (N -> 0).  Per bin: cribType
+   (0 err, 1 htA, 2 htB, 3 hom, 4 mul), CribInfo.chr / .pos; per genome the counters of the report line; hist[g] =
+   bins of group g (0 err, 1 het, 2 hom, 3 mul) by bin depth, histMax[g] = the reference's arrayMax of that array.
+   Arrays are owned by the context, valid until the next call or build. */
+typedef struct h10x_crib {
+  uint32_t hashNumber ;
+  int32_t histLen ;
+  uint8_t *type ; int16_t *chr ; uint16_t *pos ;
+  int32_t nPresent[2], nAbsent[2], nSeq[2] ;
+  const int *hist[4] ; int32_t histMax[4] ;
+} h10x_crib ;
+int h10x_gpu_crib_build (h10x_ctx *ctx, const uint8_t *g1, const uint64_t *off1, uint32_t nSeq1,
+			 const uint8_t *g2, const uint64_t *off2, uint32_t nSeq2, h10x_crib *out, char *err, size_t errlen) ;
+
 /* ---- fq2b + bsort on the device (fq2b.c:108-178; README.md:25-26): the stage that produces the FQB file ----
    fq1 / fq2: the two UNCOMPRESSED FASTQ texts in host memory (fq2 may be NULL: single reads); the reference reads
    them through zlib, which stays a host matter.  whitelist: the 10x barcode list as packed 16-mers in file order

@@ -94,3 +94,46 @@ def test_cli_multi_gpu_matches_reference(orc, gpu_lib, tmp_path):
         ha, hb = hashfile.parse(str(tmp_path / "ref.hash")), hashfile.parse(str(tmp_path / ("gpu%d.hash" % g)))
         assert ha.size == hb.size
         hashfile.assert_strict_equal(ha, hb, table=True)
+
+
+def test_cli_crib_build_and_stats_match_reference(orc, gpu_lib, tmp_path):
+    """--cribBuild genome1.fa genome2.fa (hash10x.c:426-510) and --hashStats / --codeStats counted on the device
+    (h10x_gpu_crib_build, h10x_gpu_histogram): the reference's report lines, for genomes made of the reads themselves
+    (hom), of reads only one genome has (het), of repeated pieces (mul), with N, lower case, wrapped lines and a
+    sequence shorter than k"""
+    import fqbtools
+    ref = orc.ref_binary("hash10x")
+    if ref is None:
+        pytest.skip("oracle/_ref/hash10x not built")
+    p = orc.synth_params(seed=71, n_barcodes=30, pairs_min=10, pairs_max=120, read_len=151)
+    recs = orc.synth_fqb(p)
+    recs.tofile(str(tmp_path / "in.fqb"))
+    _f1, f2 = fqbtools.fastq_from_fqb(recs, 151)
+    reads = f2.split(b"\n")[1::4]
+    rng = np.random.default_rng(5)
+
+    def fasta(chunks, wrap):
+        out = []
+        for i, c in enumerate(chunks):
+            out.append(b">chr%d some description" % (i + 1))
+            out += [c[j:j + wrap] for j in range(0, len(c), wrap)]
+        return b"\n".join(out) + b"\n"
+    a = b"".join(reads[0:300])
+    b = b"".join(reads[300:500])
+    c = b"".join(reads[500:600])
+    g1 = fasta([a, b + b"NNNN" + b[:3000].lower(), b"ACGTACGT", c], 60)          # b's head twice: mul; a tiny sequence
+    g2 = fasta([a[:20000] + b"N" * 7 + bytes(rng.choice(list(b"ACGT"), 5000).tolist()), b[4000:], b"".join(reads[600:700])], 71)
+    (tmp_path / "g1.fa").write_bytes(g1)
+    (tmp_path / "g2.fa").write_bytes(g2)
+    chain = ["-B", "20", "--readFQB", "in.fqb", "--cribBuild", "g1.fa", "g2.fa", "--hashStats", "--codeStats"]
+    ra, rb = _run(ref, chain, str(tmp_path)), _run(CLI, chain, str(tmp_path))
+    assert ra.returncode == 0 and rb.returncode == 0, (ra.stderr, rb.stderr)
+    la, lb = _clean(ra.stdout), _clean(rb.stdout)
+    assert any("known and" in x for x in la) and any(x.startswith("    hom") for x in la)
+    assert la == lb
+    # a bad character ends that genome's walk with the reference's message
+    (tmp_path / "g3.fa").write_bytes(g1.replace(b"NNNN", b"NN*N"))
+    chain = ["-B", "20", "--readFQB", "in.fqb", "--cribBuild", "g3.fa", "g2.fa"]
+    ra, rb = _run(ref, chain, str(tmp_path)), _run(CLI, chain, str(tmp_path))
+    assert ra.returncode == rb.returncode == 0 and _clean(ra.stdout) == _clean(rb.stdout)
+    assert [x for x in ra.stderr.splitlines() if x.startswith("Bad char")] == [x for x in rb.stderr.splitlines() if x.startswith("Bad char")]
