@@ -97,9 +97,18 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   if (fread (name, 4, 1, f) != 1 || fread (&version, 4, 1, f) != 1 || fread (&chSize, 2, 1, f) != 1
       || fread (&cbSize, 2, 1, f) != 1) { seterr (err, errlen, "read fail 0") ; goto fail ; }
   if (strcmp (name, "10XH")) { seterr (err, errlen, "not a 10X hash file") ; goto fail ; }
-  if (version != 2) { seterr (err, errlen, "hash file version mismatch: only version 2 is supported") ; goto fail ; }
-  if (chSize != 8) { seterr (err, errlen, "ClusterHash structure size mismatch") ; goto fail ; }
-  if (cbSize != 32) { seterr (err, errlen, "ClusterBlock structure size mismatch") ; goto fail ; }
+  if (version > 2)		/* hash10x.c:277-278; files of version 1 (hashValue as an Array) are read as the reference reads them */
+    { char msg[96] ; snprintf (msg, sizeof (msg), "hash file version mismatch: file %d > code %d", (int) version, 2) ;
+      seterr (err, errlen, msg) ; goto fail ;
+    }
+  if (chSize != 8)
+    { char msg[96] ; snprintf (msg, sizeof (msg), "ClusterHash structure size mismatch: file %d != code %d", (int) chSize, 8) ;
+      seterr (err, errlen, msg) ; goto fail ;
+    }
+  if (cbSize != 32)
+    { char msg[96] ; snprintf (msg, sizeof (msg), "ClusterBlock structure size mismatch: file %d != code %d", (int) cbSize, 32) ;
+      seterr (err, errlen, msg) ; goto fail ;
+    }
   if (fread (&B, 4, 1, f) != 1) { seterr (err, errlen, "read fail 1") ; goto fail ; }
   if (B != wantB)
     { char msg[96] ; snprintf (msg, sizeof (msg), "incompatible hash table size: rerun with -B %d", B) ;
@@ -110,10 +119,21 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
     if (!(out->hashIndex = malloc (tableSize * 4))) { st = H10X_ERR_NOMEM ; goto fail ; }
     if (fread (out->hashIndex, 4, tableSize, f) != tableSize) { seterr (err, errlen, "read fail 2") ; goto fail ; }
   }
-  if (fread (&out->hashNumber, 4, 1, f) != 1) { seterr (err, errlen, "failed to read hashNumber") ; goto fail ; }
-  if (!(out->hashValue = malloc ((size_t) out->hashNumber * 8 + 8))) { st = H10X_ERR_NOMEM ; goto fail ; }
-  if (fread (out->hashValue, 8, out->hashNumber, f) != out->hashNumber)
-    { seterr (err, errlen, "failed to read hashValue") ; goto fail ; }
+  if (version == 1)		/* hash10x.c:285-291: an Array of U64, hashNumber = its max */
+    { if (fread (&a, sizeof (a), 1, f) != 1 || a.size != 8 || a.dim < a.max || a.max < 0)
+	{ seterr (err, errlen, "failed to read hashValue array") ; goto fail ; }
+      out->hashNumber = (uint32_t) a.max ;
+      if (!(out->hashValue = malloc ((size_t) a.dim * 8 + 8))) { st = H10X_ERR_NOMEM ; goto fail ; }
+      if (fread (out->hashValue, 8, a.dim, f) != (size_t) a.dim) { seterr (err, errlen, "failed to read hashValue array") ; goto fail ; }
+    }
+  else
+    { if (fread (&out->hashNumber, 4, 1, f) != 1) { seterr (err, errlen, "failed to read hashNumber") ; goto fail ; }
+      if (!(out->hashValue = malloc ((size_t) out->hashNumber * 8 + 8))) { st = H10X_ERR_NOMEM ; goto fail ; }
+      if (fread (out->hashValue, 8, out->hashNumber, f) != out->hashNumber)
+	{ seterr (err, errlen, "failed to read hashValue") ; goto fail ; }
+    }
+  if (out->hashNumber < 1 || (uint64_t) out->hashNumber > ((uint64_t) 1 << B))
+    { seterr (err, errlen, "hashNumber outside the table") ; goto fail ; }
   /* hashDepth Array */
   if (fread (&a, sizeof (a), 1, f) != 1 || a.size != 4 || a.dim < a.max || a.max < 0)
     { seterr (err, errlen, "failed to read hashDepth array") ; goto fail ; }
@@ -141,6 +161,22 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   }
   if (!(out->clusHash = malloc (out->nHashes * 8 + 8))) { st = H10X_ERR_NOMEM ; goto fail ; }
   if (fread (out->clusHash, 8, out->nHashes, f) != out->nHashes) { seterr (err, errlen, "read fail 3") ; goto fail ; }
+  /* The reference trusts the file.  Here its arrays go on to index device memory (k_good_mark by bin, k_subcluster's
+     256 labels per block, the reads of a block), so what the commands rely on is checked once: every entry names an
+     existing bin and a read of its block, no block claims more than 255 sub-clusters, and the depths add up to the entries. */
+  { uint64_t depthSum = 0, e ; uint32_t b ;
+    for (b = 1 ; b < out->hashNumber ; ++b) depthSum += out->hashDepth[b] ;
+    if (depthSum != out->nHashes) { seterr (err, errlen, "inconsistent hash file: bin depths do not add up to the entries") ; goto fail ; }
+    for (b = 1 ; b < out->nBlocksMax ; ++b)
+      { uint32_t nr = out->blkNRead[b] ? out->blkNRead[b] : 1 ;
+	if (out->blkNSubCluster[b] > 255) { seterr (err, errlen, "inconsistent hash file: more than 255 sub-clusters in a block") ; goto fail ; }
+	for (e = out->blkOff[b] ; e < out->blkOff[b + 1] ; ++e)
+	  { const h10x_cluster_hash *ch = &out->clusHash[e] ;
+	    if (ch->hash >= out->hashNumber || ch->read >= nr)	/* a stale subCluster label above nSubCluster is legal: it counts as 0 */
+	      { seterr (err, errlen, "inconsistent hash file: a ClusterHash entry is out of range") ; goto fail ; }
+	  }
+      }
+  }
   free (cb) ;
   fclose (f) ;
   return H10X_OK ;

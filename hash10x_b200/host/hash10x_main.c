@@ -272,10 +272,13 @@ static void hashDepthRange (int min, int max)
 	: h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
       if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
       if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
+      if (!hashWithinRange) die ("myalloc failure") ;
       memcpy (hashWithinRange, g.within, ix.hashNumber) ;
       hashRangeMin = min ; hashRangeMax = max ;
+      free (goodHashes) ; free (nGoodHashes) ;		/* the tables of an earlier --hashDepthRange (the lists are the context's) */
       goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;
       nGoodHashes = calloc (ix.nBlocksMax, sizeof (int)) ;
+      if (!hashWithinRange || !goodHashes || !nGoodHashes) die ("myalloc failure") ;
       for (c = 0 ; c < ix.nBlocksMax ; ++c)
 	{ if (c && ix.blkNHash[c] > 65535)
 	    fprintf (stderr, "ignoring barcode %d - too many hashes %d > %d\n", (int) c, (int) ix.blkNHash[c], 65535) ;

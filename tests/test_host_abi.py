@@ -95,8 +95,28 @@ def test_hash_writer_reader_roundtrip_and_reference_layout(orc, tmp_path):
     assert np.array_equal(got.hashValue, ix.hashValue) and np.array_equal(got.clus, ix.clus)
     assert np.array_equal(got.hashDepth, ix.hashDepth) and np.array_equal(got.blkOff, ix.blkOff)
     bad = str(tmp_path / "bad.hash")
-    open(bad, "wb").write(b"nope" + open(a, "rb").read()[4:])
+    raw = open(a, "rb").read()
+    open(bad, "wb").write(b"nope" + raw[4:])
     assert L.h10x_read_hash(bad.encode(), 20, C.byref(ci), err, 256) != 0 and b"not a 10X hash file" in err.value
+    # version 1 files carry hashValue as an Array (hash10x.c:285-291): read like the reference reads them; newer ones die
+    # with its message
+    import struct
+    t = 16 + 4 * (1 << 20)
+    hn = struct.unpack_from("<I", raw, t)[0]
+    arr = struct.pack("<QQiiii", 0, 0, hn, 8, hn, 0)          # array header: magic, base, dim, size, max, pad
+    magic = raw[t + 4 + 8 * hn:t + 4 + 8 * hn + 8]            # the magic of the hashDepth Array that follows
+    v1 = raw[:4] + struct.pack("<I", 1) + raw[8:t] + magic + arr[8:] + raw[t + 4:]
+    open(bad, "wb").write(v1)
+    assert L.h10x_read_hash(bad.encode(), 20, C.byref(ci), err, 256) == 0, err.value
+    got1 = binding.Index(ci, L)
+    L.h10x_index_free(C.byref(ci))
+    assert got1.hashNumber == ix.hashNumber and np.array_equal(got1.hashValue, ix.hashValue) and np.array_equal(got1.clus, ix.clus)
+    open(bad, "wb").write(raw[:4] + struct.pack("<I", 3) + raw[8:])
+    assert L.h10x_read_hash(bad.encode(), 20, C.byref(ci), err, 256) != 0 and b"hash file version mismatch: file 3 > code 2" in err.value
+    # a file whose entries point outside the bins is refused instead of indexing device memory with them
+    e0 = len(raw) - 8 * int(ix.nHashes)
+    open(bad, "wb").write(raw[:e0] + struct.pack("<I", ix.hashNumber + 5) + raw[e0 + 4:])
+    assert L.h10x_read_hash(bad.encode(), 20, C.byref(ci), err, 256) != 0 and b"inconsistent hash file" in err.value
 
 
 def test_synth_generator_is_deterministic_and_well_formed(orc):
