@@ -729,7 +729,9 @@ static void tail_p1 (h10x_ctx *c, cudaStream_t s, const TailGeom &g, const TailS
   const size_t smem = (size_t) g.nRanges * (8 * H10X_RING_STRIDE + 12) + 16 ;
   CK (cudaFuncSetAttribute (k_p1_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
   const uint32_t grid = std::min<uint32_t> (nTiles, (uint32_t) nSM) ;
-  LAUNCH (c, k_p1_place, grid, H10X_P1_THREADS, smem, s, in.nProcBlk, G, nTiles, g.nRanges, g.lowBits, g.eShift, in.srcOff,
+  uint32_t flushEvery = 2 ;	/* measured at the 1 Gb workload: 21.0 ms every block, 20.1 every second, 23.9 every fourth (ring overflows) */
+  if (const char *e = getenv ("H10X_P1_FLUSH")) { long v = atol (e) ; if (v >= 1 && v <= 64) flushEvery = (uint32_t) v ; }
+  LAUNCH (c, k_p1_place, grid, H10X_P1_THREADS, smem, s, flushEvery, in.nProcBlk, G, nTiles, g.nRanges, g.lowBits, g.eShift, in.srcOff,
 	  in.blkCnt, cnt.p, in.scratch, in.gHash, in.gRec, in.blkStart, in.blkBase, in.wInvFull, B.p) ;
 }
 
@@ -782,12 +784,16 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
         sa.eShift = g.eShift ; sa.remBits = g.remBits ;
     sa.srCount = srCount.p ; sa.blkDup = blkDup.p ; sa.nDup = nDup.p ; sa.blkMask = blkMask ;
     LAUNCH (c, k_sr_jobs, gridFor (((uint64_t) g.nSub + 3) / 4, 256), 256, 0, s, sa) ;
-    const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (H10X_SR_THREADS / 32) * 2 << H10X_SR_DIGIT) + 16 ;
-    CK (cudaFuncSetAttribute (k_sr_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+    int srThreads = H10X_SR_THREADS_DEFAULT ;
+    if (const char *e = getenv ("H10X_SR_THREADS")) { long v = atol (e) ; if (v == 256 || v == 512) srThreads = (int) v ; }
+    if (const char *e = getenv ("H10X_SR_GROUP")) { long v = atol (e) ; if (v >= 1) sa.groupCap = std::min<uint32_t> ((uint32_t) v, sa.cap) ; }
+    const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (srThreads / 32) * 2 << H10X_SR_DIGIT) + 16 ;
+    auto srFn = srThreads == 256 ? k_sr_sort<256> : k_sr_sort<512> ;
+    CK (cudaFuncSetAttribute (srFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
     int occ = 1 ;
-    CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_sr_sort, H10X_SR_THREADS, smem)) ;
+    CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, srFn, srThreads, smem)) ;
     if (occ < 1) occ = 1 ;
-    LAUNCH (c, k_sr_sort, std::min<uint32_t> (g.nSub, (uint32_t) (nSM * occ)), H10X_SR_THREADS, smem, s, sa) ;
+    LAUNCH (c, srFn, std::min<uint32_t> (g.nSub, (uint32_t) (nSM * occ)), srThreads, smem, s, sa) ;
     unsigned int nOver = 0 ;
     CK (cudaMemcpyAsync (&nOver, counters.p, 4, cudaMemcpyDeviceToHost, s)) ;
     CK (cudaStreamSynchronize (s)) ;

@@ -35,7 +35,7 @@
 #include <stdint.h>
 
 #define H10X_SR_CAP 5120u		/* entries of a sub-range the shared-memory sort takes */
-#define H10X_SR_THREADS 512
+#define H10X_SR_THREADS_DEFAULT 512
 #define H10X_SR_TARGET 1400.0		/* average sub-range size aimed at; min(hashF, hashR) is not uniform (density 2(1-x)), so the
 					   low sub-ranges hold twice the average and the high ones next to nothing: k_sr_jobs joins
 					   aligned pairs / quads of sub-ranges into sort jobs of up to H10X_SR_GROUP entries */
@@ -141,7 +141,7 @@ __device__ __forceinline__ void h10x_ring_drain (uint32_t nStreams, uint32_t nTh
 #define H10X_P1_THREADS 1024
 #define H10X_P1_PF 3
 __global__ void __launch_bounds__ (H10X_P1_THREADS, 1)
-k_p1_place (uint32_t nProcBlk, uint32_t G, uint32_t nTiles, uint32_t nRanges, int lowBits, int eShift,
+k_p1_place (uint32_t flushEvery, uint32_t nProcBlk, uint32_t G, uint32_t nTiles, uint32_t nRanges, int lowBits, int eShift,
 	    const uint64_t *__restrict__ srcOff, const uint32_t *__restrict__ blkCnt, const uint32_t *__restrict__ off,
 	    const uint64_t *__restrict__ scratch, const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gRec,
 	    const uint32_t *__restrict__ blkStart, uint32_t blkBase, uint64_t wInvFull, uint64_t *__restrict__ out)
@@ -205,8 +205,10 @@ k_p1_place (uint32_t nProcBlk, uint32_t G, uint32_t nTiles, uint32_t nRanges, in
 	  else
 	    for (uint32_t i = t ; i < n ; i += H10X_P1_THREADS) place (gHash[o + i], gRec[o + i] - r0) ;
 	  __syncthreads () ;
-	  h10x_ring_flush (nRanges, H10X_P1_THREADS, baseOld, base, first, ring, out) ;	/* also: baseOld = base */
-	  __syncthreads () ;
+	  if ((blk - b0) % flushEvery == flushEvery - 1 || blk + 1 == b1)
+	    { h10x_ring_flush (nRanges, H10X_P1_THREADS, baseOld, base, first, ring, out) ;	/* also: baseOld = base */
+	      __syncthreads () ;
+	    }
 	}
       h10x_ring_drain (nRanges, H10X_P1_THREADS, base, first, ring, out) ;
     }
@@ -398,7 +400,8 @@ __device__ __forceinline__ uint32_t sr_cta_exclusive_scan (uint32_t v, uint32_t 
   return r ;
 }
 
-__global__ void __launch_bounds__ (H10X_SR_THREADS, 2)
+template <int H10X_SR_THREADS>
+__global__ void __launch_bounds__ (H10X_SR_THREADS, 1024 / H10X_SR_THREADS)
 k_sr_sort (SrArgs a)
 { extern __shared__ __align__ (16) unsigned char srRaw[] ;
   constexpr int NW = H10X_SR_THREADS / 32 ;
