@@ -143,6 +143,17 @@ __global__ void k_push_distinct (uint32_t nSeg, const uint32_t *__restrict__ seg
   a.first[o][dst] = entryBlk[se[i]] ;
 }
 
+/* the same push when the rank-distinct triples already exist (hand-written tail: k_heads_compact leaves them) */
+__global__ void k_push_triples (uint32_t nSeg, const uint64_t *__restrict__ dHash, const uint32_t *__restrict__ dDepth,
+				const uint32_t *__restrict__ dFirst, PushArgs a)
+{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (s >= nSeg) return ;
+  int o = 0 ;
+  while (o + 1 < a.nranks && (uint64_t) s >= a.sendOff[o + 1]) ++o ;
+  uint64_t dst = a.dstOff[o] + ((uint64_t) s - a.sendOff[o]) ;
+  a.hash[o][dst] = dHash[s] ; a.depth[o][dst] = dDepth[s] ; a.first[o][dst] = dFirst[s] ;
+}
+
 /* off[o] = first segment whose hash reaches thr[o]; the segment hashes are sh[segStart[s]] * wMul, ascending */
 __global__ void k_lower_bounds_seg (const uint32_t *__restrict__ segStart, const uint64_t *__restrict__ sh, uint64_t wMul,
 				    uint32_t n, const uint64_t *__restrict__ thr, uint32_t nThr, uint64_t *__restrict__ off)
@@ -179,6 +190,139 @@ __global__ void k_owner_merge (uint32_t nSeg, const uint32_t *__restrict__ segSt
   atomicAdd (&newCnt[first], 1u) ;
 }
 
+/* ---- owner merge without a sort --------------------------------------------------------------------------------------
+   What an owner receives is NR runs (one per source rank), each already ascending in hash.  Instead of radix-sorting
+   the concatenation over all 2k bits (6 library passes over 12 B) the runs are MERGED tile by tile:
+     - every S-th element of every run is a splitter candidate; the (few) candidates are sorted and every NR-th one is a
+       tile boundary, so a tile [B_t, B_t+1) holds on average NR*S elements and provably fewer than 3 NR S: a run has
+       fewer than S elements between two of its own candidates, a tile holds at most NR candidates plus up to NR - 1 more
+       whose value equals its lower boundary, and k candidates of a run inside a tile mean at most k + 1 such stretches
+       (rank-distinct hashes: no run holds a value twice);
+     - k_merge_bounds finds, per tile and run, where the tile starts in the run (binary search);
+     - k_owner_merge_tiles loads the <= NR pieces of a tile into shared memory; an element's place in the merged order is
+       its index in its own piece plus, for every other piece, the number of smaller elements there (ties: the lower source
+       rank first) - binary searches in shared memory; equal hashes then stand side by side: depth = sum, first block =
+       min (hash10x.c:178 / :147 seen from the owner), and every received copy learns the number of its bin (segOf).
+   Two launches: COUNT (bins per tile), scan, WRITE.  Everything read or written in global memory is a contiguous piece. */
+#define H10X_MERGE_CAP 4096u
+#define H10X_MERGE_THREADS 256
+
+struct MergeArgs {
+  const uint64_t *rHash ; const uint32_t *rDepth, *rFirst ;	/* the receive arrays, run r at [recvOff[r], recvOff[r+1]) */
+  uint64_t recvOff[H10X_MAX_RANKS + 1] ;
+  const uint32_t *bnd ;		/* (nTiles + 1) * nranks: start of tile t inside run r (relative to the run) */
+  uint32_t *tileBins ;		/* COUNT: bins of tile t; WRITE: exclusive scan of it = first bin of tile t */
+  uint64_t *gHash ; uint32_t *gDepth, *gFirst, *newCnt, *segOf ;
+  unsigned int *overflow ;
+  uint32_t nTiles ; int nranks ;
+} ;
+
+__global__ void k_merge_candidates (MergeArgs a, uint32_t S, const uint32_t *__restrict__ candOff, uint64_t *__restrict__ cand)
+{ const int r = blockIdx.y ;
+  const uint64_t n = a.recvOff[r + 1] - a.recvOff[r] ;
+  const uint64_t nc = n ? (n - 1) / S : 0 ;
+  for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ; j < nc ; j += (uint64_t) gridDim.x * blockDim.x)
+    cand[candOff[r] + j] = a.rHash[a.recvOff[r] + (j + 1) * S] ;
+}
+
+/* bnd[t * NR + r] = first element of run r that is >= B_t;  B_0 = 0, B_t = candSorted[t * NR - 1], B_nTiles = infinity */
+__global__ void k_merge_bounds (MergeArgs a, const uint64_t *__restrict__ candSorted, uint32_t nCand, uint32_t *__restrict__ bnd)
+{ const uint64_t x = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x ;
+  const uint64_t tot = ((uint64_t) a.nTiles + 1) * a.nranks ;
+  if (x >= tot) return ;
+  const uint32_t t = (uint32_t) (x / a.nranks) ; const int r = (int) (x % a.nranks) ;
+  const uint64_t *h = a.rHash + a.recvOff[r] ;
+  const uint32_t n = (uint32_t) (a.recvOff[r + 1] - a.recvOff[r]) ;
+  uint32_t lo = 0, hi = n ;
+  if (t == 0) hi = 0 ;
+  else if (t == a.nTiles) lo = n ;
+  else
+    { const uint64_t B = candSorted[min ((uint64_t) t * a.nranks - 1, (uint64_t) nCand - 1)] ;
+      while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2 ; if (h[mid] < B) lo = mid + 1 ; else hi = mid ; }
+    }
+  bnd[x] = lo ;
+}
+
+static inline size_t h10x_merge_smem (bool write) { return (size_t) H10X_MERGE_CAP * (write ? 18 : 10) ; }
+
+template <bool WRITE>
+__global__ void __launch_bounds__ (H10X_MERGE_THREADS)
+k_owner_merge_tiles (MergeArgs a)
+{ extern __shared__ __align__ (16) unsigned char mergeRaw[] ;
+  uint64_t *hs = (uint64_t*) mergeRaw ;			/* CAP: the pieces, run after run */
+  uint16_t *order = (uint16_t*) (hs + H10X_MERGE_CAP) ;	/* CAP: merged position -> slot in hs[] */
+  uint32_t *dep = (uint32_t*) (order + H10X_MERGE_CAP), *fst = dep + H10X_MERGE_CAP ;	/* CAP each, WRITE only */
+  __shared__ uint32_t pStart[H10X_MAX_RANKS + 1], pSrc[H10X_MAX_RANKS], warpTmp[33] ;
+  const uint32_t t = threadIdx.x ;
+  const int NR = a.nranks ;
+  constexpr uint32_t PER = H10X_MERGE_CAP / H10X_MERGE_THREADS ;
+  for (uint32_t tile = blockIdx.x ; tile < a.nTiles ; tile += gridDim.x)
+    { __syncthreads () ;
+      if (t == 0)
+	{ uint32_t run = 0 ;
+	  for (int r = 0 ; r < NR ; ++r)
+	    { const uint32_t lo = a.bnd[(size_t) tile * NR + r], hi = a.bnd[(size_t) (tile + 1) * NR + r] ;
+	      pStart[r] = run ; pSrc[r] = lo ; run += hi - lo ;
+	    }
+	  pStart[NR] = run ;
+	}
+      __syncthreads () ;
+      const uint32_t n = pStart[NR] ;
+      if (n > H10X_MERGE_CAP) { if (t == 0) atomicExch (a.overflow, 1u) ; continue ; }	/* cannot happen (bound above); the host re-runs with the sort */
+      for (int r = 0 ; r < NR ; ++r)
+	{ const uint32_t ps = pStart[r], len = pStart[r + 1] - ps ;
+	  const uint64_t g0 = a.recvOff[r] + pSrc[r] ;
+	  for (uint32_t x = t ; x < len ; x += H10X_MERGE_THREADS)
+	    { hs[ps + x] = a.rHash[g0 + x] ;
+	      if (WRITE) { dep[ps + x] = a.rDepth[g0 + x] ; fst[ps + x] = a.rFirst[g0 + x] ; }
+	    }
+	}
+      __syncthreads () ;
+      for (uint32_t slot = t ; slot < n ; slot += H10X_MERGE_THREADS)
+	{ int r = 0 ; while (slot >= pStart[r + 1]) ++r ;
+	  const uint64_t h = hs[slot] ;
+	  uint32_t pos = slot - pStart[r] ;
+	  for (int q = 0 ; q < NR ; ++q)
+	    { if (q == r) continue ;
+	      uint32_t lo = pStart[q], hi = pStart[q + 1] ;
+	      if (q < r) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1 ; if (hs[mid] <= h) lo = mid + 1 ; else hi = mid ; } }
+	      else       { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1 ; if (hs[mid] <  h) lo = mid + 1 ; else hi = mid ; } }
+	      pos += lo - pStart[q] ;
+	    }
+	  order[pos] = (uint16_t) slot ;
+	}
+      __syncthreads () ;
+      /* heads of the runs of equal hash; a thread owns PER consecutive merged positions */
+      const uint32_t p0 = min (t * PER, n), p1 = min (p0 + PER, n) ;
+      uint32_t heads = 0 ;
+      for (uint32_t p = p0 ; p < p1 ; ++p) if (p == 0 || hs[order[p]] != hs[order[p - 1]]) ++heads ;
+      uint32_t total ;
+      uint32_t k = sr_cta_exclusive_scan (heads, warpTmp, total) ;	/* bins before p0 in this tile */
+      if (!WRITE) { if (t == 0) a.tileBins[tile] = total ; continue ; }
+      const uint32_t base = a.tileBins[tile] ;
+      for (uint32_t p = p0 ; p < p1 ; ++p)
+	{ const uint32_t slot = order[p] ;
+	  const bool head = (p == 0 || hs[slot] != hs[order[p - 1]]) ;
+	  if (head)
+	    { uint32_t d = dep[slot], f = fst[slot] ;
+	      for (uint32_t e = p + 1 ; e < n && hs[order[e]] == hs[slot] ; ++e) { d += dep[order[e]] ; f = min (f, fst[order[e]]) ; }
+	      const uint32_t g = base + k ;
+	      a.gHash[g] = hs[slot] ; a.gDepth[g] = d ; a.gFirst[g] = f ;
+	      atomicAdd (&a.newCnt[f], 1u) ;
+	      ++k ;
+	    }
+	  int r = 0 ; while (slot >= pStart[r + 1]) ++r ;
+	  a.segOf[a.recvOff[r] + pSrc[r] + (slot - pStart[r])] = base + k - 1 ;	/* k counts the heads up to and including p's */
+	}
+    }
+}
+
+/* answer for every received copy, in the order it was received (merge path: segOf = the copy's bin) */
+__global__ void k_answer_ids_seg (uint32_t n, const uint32_t *__restrict__ segOf, const uint32_t *__restrict__ gId, uint32_t *__restrict__ ans)
+{ uint32_t j = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (j < n) ans[j] = gId[segOf[j]] ;
+}
+
 /* per block b: all owners' new-hash counts, and those of the owners before this one */
 __global__ void k_id_base (uint32_t nB, uint32_t nranks, uint32_t rank, const uint32_t *__restrict__ newMat,
 			   uint32_t *__restrict__ colSum, uint32_t *__restrict__ below)
@@ -200,11 +344,17 @@ struct MaxOp { __host__ __device__ uint32_t operator() (uint32_t a, uint32_t b) 
    block + rank inside the group */
 __global__ void k_owner_ids (uint32_t n, const uint32_t *__restrict__ sf, const uint32_t *__restrict__ sg,
 			     const uint32_t *__restrict__ groupStart, const uint32_t *__restrict__ prefixAll,
-			     const uint32_t *__restrict__ below, uint32_t *__restrict__ gId)
+			     const uint32_t *__restrict__ below, uint32_t *__restrict__ gId,
+			     const uint64_t *__restrict__ gHash, const uint32_t *__restrict__ gDepth,
+			     uint32_t *__restrict__ sId, uint64_t *__restrict__ sHash, uint32_t *__restrict__ sDepth)
 { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ;
   if (i >= n) return ;
-  uint32_t b = sf[i] ;
-  gId[sg[i]] = 1u + prefixAll[b] + below[b] + (i - groupStart[i]) ;
+  const uint32_t b = sf[i], g = sg[i] ;
+  const uint32_t id = 1u + prefixAll[b] + below[b] + (i - groupStart[i]) ;
+  gId[g] = id ;
+  /* the same bins in id order (ascending inside an owner): what goes to rank 0, so that its scatter into hashValue[] /
+     hashDepth[] writes whole runs of consecutive ids (one run per (block, owner)) instead of single random slots */
+  sId[i] = id ; sHash[i] = gHash[g] ; sDepth[i] = gDepth[g] ;
 }
 
 /* answer for every received copy, in the order it was received */

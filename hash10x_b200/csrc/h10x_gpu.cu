@@ -29,6 +29,7 @@
 #include <cmath>
 #include <iterator>
 #include <map>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -739,8 +740,15 @@ static void tail_p1 (h10x_ctx *c, cudaStream_t s, const TailGeom &g, const TailS
    hashNumber / codeOff / codes / clus in the context; returns the number of bins.  H comes in as the number of
    entries P1 placed and leaves as the number of (hash, block) pairs: the sub-range sort drops the duplicates a lean
    fused kernel left in, blkDupHost[b] = how many of (global, 1-based) block b's. */
+static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
+		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul,
+		       const uint64_t *preHash = nullptr, const uint32_t *preDepth = nullptr, const uint32_t *preFirst = nullptr) ;
+struct TailDist { uint32_t nBlkGlobal ; } ;	/* multi-GPU build: the bins get their ids from the owners (dist_bins) */
+
 static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint64_t &H, uint64_t wDiv,
-			   DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart, uint32_t nBlkNumbers, std::vector<uint32_t> &blkDupHost)
+			   DBuf<uint64_t> &B, DBuf<uint64_t> &rangeStart, uint32_t nBlkNumbers, std::vector<uint32_t> &blkDupHost,
+			   const TailDist *td = nullptr)
 { MemTrack *mt = &c->mt ;
   const h10x_params &P = c->P ;
   const int nSM = device_sms (c) ;
@@ -819,20 +827,51 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     CK (cudaStreamSynchronize (s)) ;
     H -= dups ;
   }
-    DBuf<uint32_t> segStart, segLen, idOfSeg ;
-  { StageTimer tm (c, s, ST_BINIDS) ;
+  DBuf<uint32_t> segStart, segLen, idOfSeg, gidOfSeg, localDepth ;
+  uint32_t Dglobal = 0 ;
+  { std::unique_ptr<StageTimer> tm (new StageTimer (c, s, ST_BINIDS)) ;
     DBuf<uint32_t> binBase ((size_t) g.nSub + 1, s, mt) ;
     cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, nHeads.p, binBase.p, (size_t) g.nSub + 1, s) ; }) ;
     CK (cudaMemcpyAsync (&D, binBase.p + g.nSub, 4, cudaMemcpyDeviceToHost, s)) ;
     CK (cudaStreamSynchronize (s)) ;
-    if ((uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 */
+    if (!td && (uint64_t) D + 1 > (((uint64_t) 1 << P.B) >> 2) - 2)	/* hash10x.c:149 (multi-GPU: dist_bins, on the global count) */
       throw H10xError (H10X_ERR_TABLE_TOO_SMALL, "hashTableSize is too small") ;
-        segStart.alloc (D, s, mt) ; segLen.alloc (D, s, mt) ; idOfSeg.alloc (D, s, mt) ;
+    segStart.alloc (D, s, mt) ; segLen.alloc (D, s, mt) ; idOfSeg.alloc (D, s, mt) ;
     DBuf<uint64_t> fkey (D, s, mt), fkey2 (D, s, mt), hvHash (D, s, mt) ;
+    DBuf<uint32_t> firstBlk ;
+    if (td) firstBlk.alloc (D, s, mt) ;
     LAUNCH (c, k_heads_compact, (uint32_t) std::min<uint64_t> (((uint64_t) g.nSub * 32 + 255) / 256, (uint64_t) nSM * 16), 256, 0, s, g.nSub,
-	    	    srStart.p, nHeads.p, srCount.p, binBase.p, stage.p, A.p, g.eShift, g.lowBits, g.p2, blkMask, wDiv, segStart.p, segLen.p,
-	    fkey.p, hvHash.p) ;
+	    srStart.p, nHeads.p, srCount.p, binBase.p, stage.p, A.p, g.eShift, g.lowBits, g.p2, blkMask, wDiv, segStart.p, segLen.p,
+	    fkey.p, hvHash.p, firstBlk.p) ;
     stage.release () ; nHeads.release () ; binBase.release () ; srStart.release () ; srCount.release () ;
+    if (td)
+      { /* multi-GPU.  k_heads_compact has just left this rank's distinct hashes in ascending order with their local depth
+	   and first block: exactly what the hash-range owners want.  The global ids come back per local bin; the local
+	   lists are then laid out in id order (stable passes on the id bits), so that everything below - the local part of
+	   fillHashTable, the transposition to ClusterHash lists - is the single-GPU code. */
+	tm.reset () ;		/* dist_bins times itself under the same stage */
+	dist_bins (c, s, H, nullptr, nullptr, nullptr, D, nullptr, nullptr, td->nBlkGlobal, nullptr, Dglobal, wDiv,
+		   hvHash.p, segLen.p, firstBlk.p) ;
+	tm.reset (new StageTimer (c, s, ST_BINIDS)) ;
+	hvHash.release () ; firstBlk.release () ;
+	gidOfSeg.swap (c->localBinId) ;		/* ids by local bin, hash order */
+	LAUNCH (c, k_id_words, gridFor (D, 256), 256, 0, s, D, gidOfSeg.p, fkey.p) ;
+	const int idBits = bits_for ((uint64_t) Dglobal + 1) ;
+	const int nP = (idBits + 9) / 10 ;
+	uint64_t *src = fkey.p, *dst = fkey2.p ;
+	for (int i = 0, left = idBits, shift = 32 ; i < nP ; ++i)
+	  { const int bits = (left + (nP - i) - 1) / (nP - i) ;
+	    LoadWord lw = { src, shift, (1u << bits) - 1u, ~(uint64_t) 0 } ;
+	    part_pass (c, s, lw, D, 1u << bits, dst) ;
+	    shift += bits ; left -= bits ; std::swap (src, dst) ;
+	  }
+	c->localBinId.alloc (D, s, mt) ; localDepth.alloc ((size_t) D + 2, s, mt) ;
+	CK (cudaMemsetAsync (localDepth.p, 0, 4, s)) ;
+	CK (cudaMemsetAsync (localDepth.p + D + 1, 0, 4, s)) ;
+	LAUNCH (c, k_local_ranks, gridFor (D, 256), 256, 0, s, D, src, segLen.p, idOfSeg.p, c->localBinId.p, localDepth.p) ;
+      }
+    else
+      {
     /* bins stand in hash order; the id order is (first block, hash): stable passes on the first block */
     const int b1 = g.blkBits <= 9 ? g.blkBits : (g.blkBits + 1) / 2, b2 = g.blkBits - b1 ;
     if (b1 > 11) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^22 barcode blocks") ;
@@ -852,30 +891,48 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
     CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
     CK (cudaMemsetAsync (c->hashDepth.p + D + 1, 0, 4, s)) ;
-        LAUNCH (c, k_bins_by_rank_e, gridFor (D, 256), 256, 0, s, D, sorted, segLen.p, hvHash.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+    LAUNCH (c, k_bins_by_rank_e, gridFor (D, 256), 256, 0, s, D, sorted, segLen.p, hvHash.p, idOfSeg.p, c->hashValue.p, c->hashDepth.p) ;
+      }
   }
   early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ;
   early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ;
   /* hashIndex[] only needs the values in id order: built here, its copy to the host runs beside the stages below */
-  if (!(P.flags & H10X_FLAG_NO_TABLE))
+  if (!(P.flags & H10X_FLAG_NO_TABLE) && c->hashValue.p)	/* multi-GPU: rank 0 holds the values */
     { StageTimer tm (c, s, ST_TABLE) ;
       const size_t tableSize = (size_t) 1 << P.B ;
       c->hashIndex.alloc (tableSize, s, mt) ;
       CK (cudaMemsetAsync (c->hashIndex.p, 0, 4 * tableSize, s)) ;
-      if (D) LAUNCH (c, k_table_insert, gridFor (D, 256), 256, 0, s, c->hashNumber, c->hashValue.p, c->hashIndex.p, P.B) ;
+      if (c->hashNumber > 1) LAUNCH (c, k_table_insert, gridFor (c->hashNumber - 1, 256), 256, 0, s, c->hashNumber, c->hashValue.p, c->hashIndex.p, P.B) ;
       early_pull (c, s, SLOT_INDEX, c->hashIndex.p, 4 * tableSize) ;
     }
-  const size_t hn = c->hashNumber ;
+  const size_t hn = td ? (size_t) D + 1 : (size_t) c->hashNumber ;
   DBuf<uint64_t> idRead (H, s, mt) ;
+  const uint32_t *codesPtr = nullptr ;
   { StageTimer tm (c, s, ST_CODES) ;
-    c->codeOff.alloc (hn + 1, s, mt) ;
-    c->codes.alloc (H, s, mt) ;
-    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
-    cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
-        LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, segLen.p, idOfSeg.p, A.p, blkMask,
-	    c->codeOff.p, c->codes.p, idRead.p) ;
+    if (td)
+      { /* this rank's part of every bin's barcode list (h10x_dist.cuh): local bin j (id order) is bin localBinId[j] and
+	   holds the (global) blocks localCodes[localCodeOff[j] .. localCodeOff[j+1]), ascending */
+	DBuf<uint64_t> codeOffLocal (hn + 1, s, mt) ;
+	c->localCodes.alloc (H, s, mt) ;
+	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (localDepth.p, CastU64 ()) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, codeOffLocal.p, hn + 1, s) ; }) ;
+	LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, segLen.p, idOfSeg.p, gidOfSeg.p,
+		A.p, blkMask, codeOffLocal.p, c->localCodes.p, idRead.p) ;
+	c->localCodeOff.alloc ((size_t) D + 1, s, mt) ;
+	LAUNCH (c, k_u64_to_u32_from, gridFor ((uint64_t) D + 1, 256), 256, 0, s, codeOffLocal.p + 1, D + 1, c->localCodeOff.p) ;
+	codesPtr = c->localCodes.p ;
+      }
+    else
+      { c->codeOff.alloc (hn + 1, s, mt) ;
+	c->codes.alloc (H, s, mt) ;
+	cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> depth64 (c->hashDepth.p, CastU64 ()) ;
+	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, depth64, c->codeOff.p, hn + 1, s) ; }) ;
+	LAUNCH (c, k_codes_seg_e, gridFor (((uint64_t) D + 31) / 32 * 32, 256), 256, 0, s, D, segStart.p, segLen.p, idOfSeg.p,
+		(const uint32_t*) nullptr, A.p, blkMask, c->codeOff.p, c->codes.p, idRead.p) ;
+	codesPtr = c->codes.p ;
+      }
   }
-    A.release () ; segStart.release () ; segLen.release () ; idOfSeg.release () ;
+    A.release () ; segStart.release () ; segLen.release () ; idOfSeg.release () ; gidOfSeg.release () ; localDepth.release () ;
     if (!(P.flags & (H10X_FLAG_NO_CODES | H10X_FLAG_LAZY_CODES)))
     { early_pull (c, s, SLOT_CODEOFF, c->codeOff.p, 8 * (hn + 1)) ; early_pull (c, s, SLOT_CODES, c->codes.p, 4 * H) ; }
   c->clus.alloc (H, s, mt) ;
@@ -886,7 +943,7 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
 						   entries overflow them and take the slow direct path (3 passes of 6-7 bits: 50 ms) */
     int bits[4] = { 0, 0, 0, 0 } ;
     for (int i = 0, left = g.blkBits ; i < nP ; ++i) { bits[i] = (left + (nP - i) - 1) / (nP - i) ; left -= bits[i] ; }
-    LoadCodes l1 = { c->codes.p, idRead.p, (1u << bits[0]) - 1u, bits[0] } ;
+    LoadCodes l1 = { codesPtr, idRead.p, (1u << bits[0]) - 1u, bits[0] } ;
     if (nP == 1) part_pass (c, s, l1, H, 1u << bits[0], c->clus.p) ;
     else
       { DBuf<uint64_t> X (H, s, mt), Y ;
@@ -905,12 +962,10 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
   }
   if (P.flags & H10X_FLAG_NO_CODES) { c->codes.release () ; c->codeOff.release () ; }
   early_pull (c, s, SLOT_CLUS, c->clus.p, 8 * H) ;
-  return D ;
+  return td ? Dglobal : D ;
 }
 
-static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
-		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
-		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul) ;
+
 static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_t mine[4], std::vector<uint32_t> &all) ;
 
 /* ------------------------------------------------------------------ host: the fused mosh stage (h10x_fused.cuh) */
@@ -1031,7 +1086,7 @@ struct Prefuse {
 static bool tail_geometry (uint64_t H, uint64_t top, uint32_t maxBlock, TailGeom &g) ;
 static bool lean_wanted (h10x_ctx *c, bool dist, uint64_t nProc, uint32_t nBlocks)
 { const h10x_params &P = c->P ;
-  if (dist || (P.flags & H10X_FLAG_LEGACY_TAIL) || getenv ("H10X_LEGACY_TAIL") || getenv ("H10X_NO_LEAN")) return false ;
+  if ((P.flags & H10X_FLAG_LEGACY_TAIL) || getenv ("H10X_LEGACY_TAIL") || getenv ("H10X_NO_LEAN")) return false ;
   const uint64_t wDiv = c->hp.wTz ? 1 : (uint64_t) P.w ;
   const uint64_t topQ = (((uint64_t) 1 << (2 * P.k)) - 1) / wDiv ;
   const double perPair = (double) (H10X_R1_LEN + H10X_R2_LEN - 2 * P.k + 2) / (double) P.w ;
@@ -1199,7 +1254,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
      The hand-written tail sorts every key itself, so the fused kernel then runs LEAN (no in-CTA sort / dedup); should
      the real key count turn the tail's geometry down after all, the mosh stage is repeated the classic way. */
   TailGeom tg ; memset (&tg, 0, sizeof (tg)) ;
-  const bool tailWanted = !dist && !(P.flags & H10X_FLAG_LEGACY_TAIL) && !getenv ("H10X_LEGACY_TAIL") ;
+  const bool tailWanted = !(P.flags & H10X_FLAG_LEGACY_TAIL) && !getenv ("H10X_LEGACY_TAIL") ;
   bool tail2 = false, lean = false ;
   for (int attempt = 0 ; ; ++attempt)
   {
@@ -1335,7 +1390,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   std::vector<uint64_t> hBucketBase ;
   DBuf<uint64_t> eHash, eBR, bucketBase ; DBuf<uint16_t> eRead ; DBuf<uint32_t> entryBlk, key32 ;
   DBuf<uint64_t> tailB, tailRangeStart ;
-  if (dist) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
+  if (dist && !tail2) { eHash.alloc (H, s, mt) ; eRead.alloc (H, s, mt) ; entryBlk.alloc (H, s, mt) ; }
   else if (!bucketed && !tail2) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
@@ -1375,13 +1430,14 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   /* ---------------- bins: ids, values, depths ---------------- */
   uint32_t D = 0 ;
   DBuf<uint32_t> entryId ;
-  if (dist) entryId.alloc (H, s, mt) ;
+  if (dist && !tail2) entryId.alloc (H, s, mt) ;
   DBuf<uint32_t> se, segIncl, segStart, idOfSeg, sk ;
   DBuf<uint64_t> sv ;
   if (!bucketed && !tail2) segIncl.alloc (H, s, mt) ;
     if (tail2)
     { std::vector<uint32_t> blkDup ;
-      D = tail_rest (c, s, tg, H, wDiv, tailB, tailRangeStart, blkBase + nProcBlk, blkDup) ;
+      TailDist td = { nBlkGlobal } ;
+      D = tail_rest (c, s, tg, H, wDiv, tailB, tailRangeStart, blkBase + nProcBlk, blkDup, dist ? &td : nullptr) ;
       /* per-block unique counts, now that the duplicates are gone */
       uint64_t run = 0 ;
       for (uint32_t p = 0 ; p < nProcBlk ; ++p) { hBlkOff[p] = run ; hCnt[p] -= blkDup[blkBase + p + 1] ; run += hCnt[p] ; }
@@ -1491,7 +1547,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   if (!dist && !tail2) { early_pull (c, s, SLOT_VALUE, c->hashValue.p, 8 * (size_t) c->hashNumber) ; early_pull (c, s, SLOT_DEPTH, c->hashDepth.p, 4 * (size_t) c->hashNumber) ; }
   tr.mark ("bins-enq") ;
   /* ---------------- hash -> code CSR ---------------- */
-  if (dist)
+  if (dist && tail2) ;	/* tail_rest has left localBinId / localCodeOff / localCodes and the ClusterHash lists */
+  else if (dist)
     { /* this rank's part of every bin's barcode list: bin localBinId[j] holds the (global) blocks
 	 localCodes[localCodeOff[j] .. localCodeOff[j+1]), ascending; the full list of a bin is the
 	 concatenation over ranks in rank order, because ranks own ascending block ranges */
@@ -1538,8 +1595,8 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   se.release () ; segIncl.release () ; segStart.release () ; idOfSeg.release () ; eHash.release () ; entryBlk.release () ;
 
   /* ---------------- code -> hash lists (multi-GPU: ids came back per entry; sort inside each block) ---------------- */
-  if (dist) c->clus.alloc (H, s, mt) ;
-  if (dist && H)
+  if (dist && !tail2) c->clus.alloc (H, s, mt) ;
+  if (dist && !tail2 && H)
     { StageTimer tm (c, s, ST_CLUSTERS) ;
       struct ClusClass { uint32_t cap, threads ; } ;
       static const ClusClass kCC[3] = { { 1024, 128 }, { 4096, 256 }, { 12288, 512 } } ;
@@ -1659,7 +1716,8 @@ static void dist_agree (h10x_ctx *c, cudaStream_t s, int localErr, const uint32_
 
 static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *sh, const uint32_t *se,
 		       const uint32_t *segIncl, uint32_t Dl, const uint32_t *segStart, const uint32_t *entryBlk,
-		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul)
+		       uint32_t nBlkGlobal, uint32_t *entryId, uint32_t &Dglobal, uint64_t wMul,
+		       const uint64_t *preHash, const uint32_t *preDepth, const uint32_t *preFirst)
 {
   DistState *d = c->dist ; const int R = d->rank, NR = d->nranks ;
   MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
@@ -1674,14 +1732,29 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   HostTrace tr ;
   auto mark = [&] (const char *w) { if (tr.on) { cudaStreamSynchronize (s) ; tr.mark (w) ; } } ;
 
-  /* 2. owner = hash range: thresholds ceil (o * 2^(2k) / NR), monotone so the reference id order composes */
+  /* 2. owner = hash range, monotone in the hash so the reference id order composes.  A mosh is min (hash, hashRC) of
+	two roughly uniform values, so its density over [0, 2^2k) is 2 (1 - x), not flat: equal-width ranges would give
+	owner 0 three quarters of the bins at 2 ranks (23 % instead of 12.5 % at 8).  The thresholds are the quantiles
+	of that density, x_o = 1 - sqrt (1 - o / NR); any monotone choice is correct, this one balances the owners.
+	H10X_FLAT_OWNERS=1 restores the equal-width cut (tests run both). */
   if (NR > H10X_MAX_RANKS) throw H10xError (H10X_ERR_UNSUPPORTED, "more ranks than H10X_MAX_RANKS") ;
   std::vector<uint64_t> thr ((size_t) NR + 1) ;
+  const bool flatOwners = getenv ("H10X_FLAT_OWNERS") != nullptr ;
   for (int o = 0 ; o <= NR ; ++o)
-    { unsigned __int128 t = ((unsigned __int128) o << (2 * P.k)) + (unsigned) (NR - 1) ; thr[o] = (uint64_t) (t / (unsigned) NR) ; }
+    { if (flatOwners || o == 0 || o == NR)
+	{ unsigned __int128 t = ((unsigned __int128) o << (2 * P.k)) + (unsigned) (NR - 1) ; thr[o] = (uint64_t) (t / (unsigned) NR) ; }
+      else
+	{ const long double x = 1.0L - sqrtl (1.0L - (long double) o / (long double) NR) ;
+	  thr[o] = (uint64_t) (x * (long double) ((uint64_t) 1 << (2 * P.k))) ;	/* same bits on every rank: same code, same CPU */
+	  if (thr[o] < thr[o-1]) thr[o] = thr[o-1] ;
+	}
+    }
   DBuf<uint64_t> dThr ((size_t) NR + 1, s, mt), dSendOff ((size_t) NR + 1, s, mt) ;
   CK (cudaMemcpyAsync (dThr.p, thr.data (), 8 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
-  LAUNCH (c, k_lower_bounds_seg, 1, 64, 0, s, segStart, sh, wMul, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
+  /* the rank-distinct (hash, local depth, local first block) triples either come ready from the hand-written tail
+     (preHash / preDepth / preFirst, hash-ascending) or are read off the library-sorted entries (sh, se, segStart) */
+  if (preHash) LAUNCH (c, k_lower_bounds, 1, 64, 0, s, preHash, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
+  else LAUNCH (c, k_lower_bounds_seg, 1, 64, 0, s, segStart, sh, wMul, Dl, dThr.p, (uint32_t) NR + 1, dSendOff.p) ;
   std::vector<uint64_t> sendOff ((size_t) NR + 1) ;
   CK (cudaMemcpyAsync (sendOff.data (), dSendOff.p, 8 * ((size_t) NR + 1), cudaMemcpyDeviceToHost, s)) ;
   CK (cudaStreamSynchronize (s)) ;
@@ -1795,17 +1868,23 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	     wins (3.3 ms).  H10X_PEER_KERNEL / H10X_PEER_COPY force one. */
 	  const bool useCopy = getenv ("H10X_PEER_COPY") || (NR > 2 && !getenv ("H10X_PEER_KERNEL")) ;
 	  if (useCopy)
-	    { DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
-	      if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+	    { DBuf<uint64_t> dHash ; DBuf<uint32_t> dDepth, dFirst ;
+	      const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
+	      if (!preHash)
+		{ dHash.alloc (Dl, s, mt) ; dDepth.alloc (Dl, s, mt) ; dFirst.alloc (Dl, s, mt) ;
+		  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+		  xh = dHash.p ; xd = dDepth.p ; xf = dFirst.p ;
+		}
 	      for (int k = 1 ; k <= NR ; ++k)
 		{ int o = (R + k) % NR ;		/* start with the next rank: spread the load over the links */
 		  uint64_t n = sendCnt[o] ;
-		  peerCopy (o, pa.hash[o] + pa.dstOff[o], dHash.p + sendOff[o], 8 * n) ;
-		  peerCopy (o, pa.depth[o] + pa.dstOff[o], dDepth.p + sendOff[o], 4 * n) ;
-		  peerCopy (o, pa.first[o] + pa.dstOff[o], dFirst.p + sendOff[o], 4 * n) ;
+		  peerCopy (o, pa.hash[o] + pa.dstOff[o], xh + sendOff[o], 8 * n) ;
+		  peerCopy (o, pa.depth[o] + pa.dstOff[o], xd + sendOff[o], 4 * n) ;
+		  peerCopy (o, pa.first[o] + pa.dstOff[o], xf + sendOff[o], 4 * n) ;
 		}
 	      CK (cudaStreamSynchronize (s)) ;	/* the staging arrays go out of scope */
 	    }
+	  else if (Dl && preHash) LAUNCH (c, k_push_triples, gridFor (Dl, 256), 256, 0, s, Dl, preHash, preDepth, preFirst, pa) ;
 	  else if (Dl) LAUNCH (c, k_push_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, pa) ;
 	  /* nobody reads its receive arrays before every rank's stores have landed: the collective is
 	     enqueued behind the kernel on each rank's stream */
@@ -1814,14 +1893,19 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	}
     }
   if (!pushed)
-    { DBuf<uint64_t> dHash (Dl, s, mt) ; DBuf<uint32_t> dDepth (Dl, s, mt), dFirst (Dl, s, mt) ;
-      if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+    { DBuf<uint64_t> dHash ; DBuf<uint32_t> dDepth, dFirst ;
+      const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
+      if (!preHash)
+	{ dHash.alloc (Dl, s, mt) ; dDepth.alloc (Dl, s, mt) ; dFirst.alloc (Dl, s, mt) ;
+	  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+	  xh = dHash.p ; xd = dDepth.p ; xf = dFirst.p ;
+	}
       NCK (gNccl.GroupStart ()) ;
       for (int peer = 0 ; peer < NR ; ++peer)
 	{ if (sendCnt[peer])
-	    { NCK (gNccl.Send (dHash.p + sendOff[peer], sendCnt[peer], ncclUint64, peer, d->comm, s)) ;
-	      NCK (gNccl.Send (dDepth.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
-	      NCK (gNccl.Send (dFirst.p + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	    { NCK (gNccl.Send (xh + sendOff[peer], sendCnt[peer], ncclUint64, peer, d->comm, s)) ;
+	      NCK (gNccl.Send (xd + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
+	      NCK (gNccl.Send (xf + sendOff[peer], sendCnt[peer], ncclUint32, peer, d->comm, s)) ;
 	    }
 	  if (recvCnt[peer])
 	    { NCK (gNccl.Recv (rHash.p + recvOff[peer], recvCnt[peer], ncclUint64, peer, d->comm, s)) ;
@@ -1837,11 +1921,51 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   /* 5. owner merge: depth = sum, first block = min over the (at most NR) copies of a hash */
   const uint32_t nB2 = nBlkGlobal + 2 ;
   uint32_t Do = 0 ;
-  DBuf<uint64_t> gHash ; DBuf<uint32_t> gDepth, gFirst, oi (Ro, s, mt), oSegIncl (Ro, s, mt) ;
+  DBuf<uint64_t> gHash ; DBuf<uint32_t> gDepth, gFirst, oi, oSegIncl, segOf ;
   DBuf<uint32_t> newCnt (nB2, s, mt) ;
   CK (cudaMemsetAsync (newCnt.p, 0, 4 * (size_t) nB2, s)) ;
-  if (Ro)
-    { DBuf<uint64_t> oh (Ro, s, mt) ;
+  bool merged = false ;
+  if (Ro && !getenv ("H10X_OWNER_SORT"))
+    { /* the received runs are sorted: merge them tile by tile (h10x_dist.cuh, "owner merge without a sort") */
+      const uint32_t S = std::max<uint32_t> (16u, H10X_MERGE_CAP / (3u * (uint32_t) NR)) ;
+      std::vector<uint32_t> candOff ((size_t) NR + 1, 0) ;
+      for (int r = 0 ; r < NR ; ++r) candOff[r + 1] = candOff[r] + (uint32_t) (recvCnt[r] ? (recvCnt[r] - 1) / S : 0) ;
+      const uint32_t nCand = candOff[NR], nTiles = nCand / (uint32_t) NR + 1 ;
+      DBuf<uint32_t> dCandOff ((size_t) NR + 1, s, mt), bnd (((size_t) nTiles + 1) * NR, s, mt), tileBins ((size_t) nTiles + 1, s, mt) ;
+      DBuf<uint64_t> cand (nCand, s, mt), candS (nCand, s, mt) ; DBuf<unsigned int> ovf (1, s, mt) ;
+      MergeArgs ma ; memset (&ma, 0, sizeof (ma)) ;
+      ma.rHash = rHash.p ; ma.rDepth = rDepth.p ; ma.rFirst = rFirst.p ;
+      for (int r = 0 ; r <= NR ; ++r) ma.recvOff[r] = recvOff[r] ;
+      ma.bnd = bnd.p ; ma.tileBins = tileBins.p ; ma.newCnt = newCnt.p ; ma.overflow = ovf.p ; ma.nTiles = nTiles ; ma.nranks = NR ;
+      CK (cudaMemcpyAsync (dCandOff.p, candOff.data (), 4 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemsetAsync (ovf.p, 0, 4, s)) ;
+      CK (cudaMemsetAsync (tileBins.p + nTiles, 0, 4, s)) ;
+      if (nCand)
+	{ const uint32_t gx = (uint32_t) std::min<uint64_t> (gridFor (nCand / NR + 1, 256), 1024) ;
+	  k_merge_candidates<<<dim3 (gx, (unsigned) NR), 256, 0, s>>> (ma, S, dCandOff.p, cand.p) ; ++c->launches ;
+	  cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceRadixSort::SortKeys (t, b, cand.p, candS.p, nCand, 0, 2 * P.k, s) ; }) ;
+	}
+      LAUNCH (c, k_merge_bounds, gridFor (((uint64_t) nTiles + 1) * NR, 256), 256, 0, s, ma, candS.p, nCand, bnd.p) ;
+      const int nSM = device_sms (c) ;
+      CK (cudaFuncSetAttribute (k_owner_merge_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_merge_smem (false))) ;
+      CK (cudaFuncSetAttribute (k_owner_merge_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_merge_smem (true))) ;
+      LAUNCH (c, k_owner_merge_tiles<false>, std::min<uint32_t> (nTiles, (uint32_t) nSM * 5), H10X_MERGE_THREADS, h10x_merge_smem (false), s, ma) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, tileBins.p, tileBins.p, (size_t) nTiles + 1, s) ; }) ;
+      unsigned int over = 0 ;
+      CK (cudaMemcpyAsync (&Do, tileBins.p + nTiles, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaMemcpyAsync (&over, ovf.p, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      if (!over)
+	{ gHash.alloc (Do, s, mt) ; gDepth.alloc (Do, s, mt) ; gFirst.alloc (Do, s, mt) ; segOf.alloc (Ro, s, mt) ;
+	  ma.gHash = gHash.p ; ma.gDepth = gDepth.p ; ma.gFirst = gFirst.p ; ma.segOf = segOf.p ;
+	  LAUNCH (c, k_owner_merge_tiles<true>, std::min<uint32_t> (nTiles, (uint32_t) nSM * 3), H10X_MERGE_THREADS, h10x_merge_smem (true), s, ma) ;
+	  merged = true ;
+	}
+      else Do = 0 ;
+    }
+  if (Ro && !merged)
+    { oi.alloc (Ro, s, mt) ; oSegIncl.alloc (Ro, s, mt) ;
+      DBuf<uint64_t> oh (Ro, s, mt) ;
       DBuf<uint32_t> iota (Ro, s, mt), head (Ro, s, mt), oSegStart ;
       LAUNCH (c, k_iota, gridFor (Ro, 256), 256, 0, s, iota.p, (uint64_t) Ro) ;
       cubCall (c, s, [&] (void *t, size_t &b)
@@ -1876,7 +2000,8 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   mark ("d6-idbase") ;
   /* 7. ids of this owner's hashes: order by (first block, hash) = stable sort by first block of the
 	hash-sorted list; then the id of every received copy */
-  DBuf<uint32_t> gId (Do, s, mt), ans (Ro, s, mt) ;
+  DBuf<uint32_t> gId (Do, s, mt), ans (Ro, s, mt), sId (Do, s, mt), sDepth (Do, s, mt) ;
+  DBuf<uint64_t> sHash (Do, s, mt) ;
   if (Do)
     { DBuf<uint32_t> iota (Do, s, mt), sf (Do, s, mt), sg (Do, s, mt), headPos (Do, s, mt), groupStart (Do, s, mt) ;
       int bits = 1 ; while (((uint64_t) 1 << bits) < nB2) ++bits ;
@@ -1885,8 +2010,10 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	{ return cub::DeviceRadixSort::SortPairs (t, b, gFirst.p, sf.p, iota.p, sg.p, Do, 0, bits, s) ; }) ;
       LAUNCH (c, k_group_head, gridFor (Do, 256), 256, 0, s, sf.p, Do, headPos.p) ;
       cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::InclusiveScan (t, b, headPos.p, groupStart.p, MaxOp (), Do, s) ; }) ;
-      LAUNCH (c, k_owner_ids, gridFor (Do, 256), 256, 0, s, Do, sf.p, sg.p, groupStart.p, prefixAll.p, below.p, gId.p) ;
-      LAUNCH (c, k_answer_ids, gridFor (Ro, 256), 256, 0, s, Ro, oSegIncl.p, oi.p, gId.p, ans.p) ;
+      LAUNCH (c, k_owner_ids, gridFor (Do, 256), 256, 0, s, Do, sf.p, sg.p, groupStart.p, prefixAll.p, below.p, gId.p,
+	      gHash.p, gDepth.p, sId.p, sHash.p, sDepth.p) ;
+      if (merged) LAUNCH (c, k_answer_ids_seg, gridFor (Ro, 256), 256, 0, s, Ro, segOf.p, gId.p, ans.p) ;
+      else LAUNCH (c, k_answer_ids, gridFor (Ro, 256), 256, 0, s, Ro, oSegIncl.p, oi.p, gId.p, ans.p) ;
     }
 
   mark ("d7-ids") ;
@@ -1929,15 +2056,17 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   NCK (gNccl.AllGather (d2.p, dAll2.p, 5, ncclUint64, d->comm, s)) ;
   CK (cudaMemcpyAsync (all2.data (), dAll2.p, 40 * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
   CK (cudaStreamSynchronize (s)) ;
-  if (H) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
+  mark ("d9a-sync") ;
+  if (H && entryId) LAUNCH (c, k_entry_ids, gridFor (H, 256), 256, 0, s, H, segIncl, c->localBinId.p, se, entryId) ;
+  mark ("d9b-entryids") ;
   d->nHashesGlobal = 0 ;
   for (int r = 0 ; r < NR ; ++r) d->nHashesGlobal += all2[5*r + 1] ;
   if (pushed)
     { uint64_t before = 0 ; for (int r = 0 ; r < R ; ++r) before += all2[5*r] ;
       char *z = d->peers[0].mapped ;
-      peerCopy (0, (uint32_t*) (z + all2[2]) + before, gId.p, 4 * (size_t) Do) ;
-      peerCopy (0, (uint64_t*) (z + all2[3]) + before, gHash.p, 8 * (size_t) Do) ;
-      peerCopy (0, (uint32_t*) (z + all2[4]) + before, gDepth.p, 4 * (size_t) Do) ;
+      peerCopy (0, (uint32_t*) (z + all2[2]) + before, sId.p, 4 * (size_t) Do) ;
+      peerCopy (0, (uint64_t*) (z + all2[3]) + before, sHash.p, 8 * (size_t) Do) ;
+      peerCopy (0, (uint32_t*) (z + all2[4]) + before, sDepth.p, 4 * (size_t) Do) ;
       DBuf<uint32_t> b1 (1, s, mt), bN (NR, s, mt) ;
       CK (cudaMemsetAsync (b1.p, 0, 4, s)) ;
       NCK (gNccl.AllGather (b1.p, bN.p, 1, ncclUint32, d->comm, s)) ;	/* barrier: rank 0 scatters only complete data */
@@ -1946,9 +2075,9 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   else
     { NCK (gNccl.GroupStart ()) ;
       if (Do)
-	{ NCK (gNccl.Send (gId.p, Do, ncclUint32, 0, d->comm, s)) ;
-	  NCK (gNccl.Send (gHash.p, Do, ncclUint64, 0, d->comm, s)) ;
-	  NCK (gNccl.Send (gDepth.p, Do, ncclUint32, 0, d->comm, s)) ;
+	{ NCK (gNccl.Send (sId.p, Do, ncclUint32, 0, d->comm, s)) ;
+	  NCK (gNccl.Send (sHash.p, Do, ncclUint64, 0, d->comm, s)) ;
+	  NCK (gNccl.Send (sDepth.p, Do, ncclUint32, 0, d->comm, s)) ;
 	}
       if (R == 0)
 	{ uint64_t off = 0 ;
@@ -1964,6 +2093,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	}
       NCK (gNccl.GroupEnd ()) ;
     }
+  mark ("d9c-gather") ;
   if (R == 0 && Dglobal)
     LAUNCH (c, k_scatter_bins, gridFor (Dglobal, 256), 256, 0, s, Dglobal, tId.p, tHash.p, tDepth.p, c->hashValue.p, c->hashDepth.p) ;
   CK (cudaStreamSynchronize (s)) ;	/* sends read gId/gHash/gDepth, freed on return */

@@ -549,7 +549,7 @@ __global__ void k_heads_compact (uint32_t nSub, const uint32_t *__restrict__ srS
 				 const uint32_t *__restrict__ srCount, const uint32_t *__restrict__ binBase, const uint32_t *__restrict__ stage,
 				 const uint64_t *__restrict__ A, int eShift, int lowBits, int p2, uint32_t blkMask, uint64_t wMul,
 				 uint32_t *__restrict__ segStart, uint32_t *__restrict__ segLen, uint64_t *__restrict__ fkey,
-				 uint64_t *__restrict__ hvHash)
+				 uint64_t *__restrict__ hvHash, uint32_t *__restrict__ firstBlk /* or NULL: the first block alone (multi-GPU) */)
 { const uint32_t lane = threadIdx.x & 31 ;
   const uint64_t nw = ((uint64_t) gridDim.x * blockDim.x) >> 5 ;
   for (uint64_t j = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ; j < nSub ; j += nw)
@@ -564,6 +564,7 @@ __global__ void k_heads_compact (uint32_t nSub, const uint32_t *__restrict__ srS
 	  segStart[s] = pos ;
 	  segLen[s] = ((x + 1 < nh) ? stage[st + x + 1] : end) - pos ;	/* the job's kept entries are contiguous from st */
 	  fkey[s] = ((uint64_t) ((uint32_t) (E >> 16) & blkMask) << 32) | s ;
+	  if (firstBlk) firstBlk[s] = (uint32_t) (E >> 16) & blkMask ;
 	  hvHash[s] = (qTop | (E >> eShift)) * wMul ;
 	}
     }
@@ -581,9 +582,26 @@ __global__ void k_bins_by_rank_e (uint32_t nSeg, const uint64_t *__restrict__ so
   hashDepth[id] = segLen[s] ;	/* one entry per (block, hash): hash10x.c:178 */
 }
 
+/* multi-GPU: the global bin ids came back per local bin (hash order); the local lists are laid out in id order so that
+   the transposition passes leave every block's list sorted by id.  w = id << 32 | local bin */
+__global__ void k_id_words (uint32_t n, const uint32_t *__restrict__ gid, uint64_t *__restrict__ w)
+{ uint32_t s = blockIdx.x * blockDim.x + threadIdx.x ; if (s < n) w[s] = ((uint64_t) gid[s] << 32) | s ; }
+
+__global__ void k_local_ranks (uint32_t n, const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ segLen,
+			       uint32_t *__restrict__ rankOfSeg, uint32_t *__restrict__ idByRank, uint32_t *__restrict__ depthByRank)
+{ uint32_t r = blockIdx.x * blockDim.x + threadIdx.x ;
+  if (r >= n) return ;
+  const uint64_t w = sorted[r] ;
+  const uint32_t s = (uint32_t) w ;
+  rankOfSeg[s] = r + 1u ; idByRank[r] = (uint32_t) (w >> 32) ; depthByRank[r + 1] = segLen[s] ;
+}
+
+__global__ void k_u64_to_u32_from (const uint64_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out)
+{ uint32_t i = blockIdx.x * blockDim.x + threadIdx.x ; if (i < n) out[i] = (uint32_t) in[i] ; }
+
 /* fillHashTable (hash10x.c:317-347) + the transposed view: as k_codes_seg_kv, on E words */
 __global__ void k_codes_seg_e (uint32_t nSeg, const uint32_t *__restrict__ segStart, const uint32_t *__restrict__ segLen,
-			       const uint32_t *__restrict__ idOfSeg,
+			       const uint32_t *__restrict__ idOfSeg, const uint32_t *__restrict__ payloadId /* or NULL = idOfSeg */,
 			       const uint64_t *__restrict__ A, uint32_t blkMask, const uint64_t *__restrict__ codeOff,
 			       uint32_t *__restrict__ codes, uint64_t *__restrict__ idRead)
 { const uint32_t lane = threadIdx.x & 31 ;
@@ -595,6 +613,7 @@ __global__ void k_codes_seg_e (uint32_t nSeg, const uint32_t *__restrict__ segSt
   if (lane < cnt)
     { const uint32_t s = (uint32_t) s0 + lane ;
       myI0 = segStart[s] ; myN = segLen[s] ; myId = idOfSeg[s] ; myDst = codeOff[myId] ;
+      if (payloadId) myId = payloadId[s] ;	/* multi-GPU: lists are placed by the rank-local order, entries carry the global bin id */
     }
   uint32_t i0 = __shfl_sync (0xffffffffu, myI0, 0), n = __shfl_sync (0xffffffffu, myN, 0) ;
   uint64_t cur = (lane < n) ? A[(uint64_t) i0 + lane] : 0 ;
