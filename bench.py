@@ -581,8 +581,11 @@ def run_ours(args, wl, wl_name):
                        "pairs_per_gpu": n_rec, "barcodes_per_gpu": int(nB), "B": wl["B"], "k": 21, "w": 31,
                        "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % (n_rec * 120 / 1e9),
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d ranks: barcode-range shards, NCCL all-to-all-v of rank-distinct hashes to hash-range owners, "
-                       "global bin ids; hashValue/hashDepth/hashIndex on rank 0" % world},
+                       "%d ranks: barcode-range shards, every rank groups its own entries with the hand-written tail; the "
+                       "rank-distinct (hash, depth, first block) triples go to hash-range owners (ranges cut at the quantiles of the "
+                       "mosh density) by stores / copy engines into peer memory over NVLink (NCCL for the small collectives and as "
+                       "fallback); owners merge the sorted runs and hand out the reference's bin ids; hashValue / hashDepth / "
+                       "hashIndex on rank 0" % world},
             "roofline": roofline, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks, "lib_ms_per_step": lib_ms / args.steps,
             "stage_ms": {k_: v / args.steps for k_, v in stage_ms.items() if v},

@@ -1723,12 +1723,22 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   MemTrack *mt = &c->mt ; const h10x_params &P = c->P ;
   StageTimer tm (c, s, ST_BINIDS) ;
   d->nLocalBins = Dl ;
-  /* every rank got through its own mosh stage and sort (a rank that did not reports here from dist_fail_agree, and
-     all ranks leave with its error instead of waiting for it in the collectives below) */
-  { const uint32_t none[4] = { 0, 0, 0, 0 } ; std::vector<uint32_t> all ;
-    d->owesAgreement = false ;
-    dist_agree (c, s, 0, none, all) ;
-  }
+  /* Error protocol.  A rank-local failure (in practice: the workspace slab is full) must not leave the peers waiting in a
+     collective, so every group of data collectives below is preceded by an AGREEMENT (dist_agree: an all-gather of one
+     error word) and everything a group allocates is allocated before its agreement.  A rank that throws between two
+     agreements owes the peers its word at the next one (owesAgreement); the caller's handler delivers it
+     (dist_fail_agree) and every rank leaves with that error.  Entry agreement: every rank got through its own mosh
+     stage and grouping. */
+  const uint32_t none[4] = { 0, 0, 0, 0 } ; std::vector<uint32_t> agreed ;
+  int agreements = 0, failAt = -1 ;
+  if (const char *e = getenv ("H10X_DIST_FAIL"))	/* tests: "rank:n" = this rank runs out of workspace just before its n-th agreement */
+    { int fr = -1, fa = -1 ; if (sscanf (e, "%d:%d", &fr, &fa) == 2 && fr == R) failAt = fa ; }
+  auto agree = [&] (bool last = false)
+    { if (++agreements == failAt) throw SlabFull { 0 } ;
+      d->owesAgreement = false ; dist_agree (c, s, 0, none, agreed) ; d->owesAgreement = !last ;
+    } ;
+  DBuf<uint64_t> dThr ((size_t) NR + 1, s, mt), dSendOff ((size_t) NR + 1, s, mt), dCnt (NR, s, mt), dMat ((size_t) NR * NR, s, mt) ;
+  agree () ;
   HostTrace tr ;
   auto mark = [&] (const char *w) { if (tr.on) { cudaStreamSynchronize (s) ; tr.mark (w) ; } } ;
 
@@ -1749,7 +1759,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	  if (thr[o] < thr[o-1]) thr[o] = thr[o-1] ;
 	}
     }
-  DBuf<uint64_t> dThr ((size_t) NR + 1, s, mt), dSendOff ((size_t) NR + 1, s, mt) ;
   CK (cudaMemcpyAsync (dThr.p, thr.data (), 8 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
   /* the rank-distinct (hash, local depth, local first block) triples either come ready from the hand-written tail
      (preHash / preDepth / preFirst, hash-ascending) or are read off the library-sorted entries (sh, se, segStart) */
@@ -1764,7 +1773,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   /* 3. counts */
   std::vector<uint64_t> sendCnt (NR), cntMat ((size_t) NR * NR) ;
   for (int o = 0 ; o < NR ; ++o) sendCnt[o] = sendOff[o+1] - sendOff[o] ;
-  DBuf<uint64_t> dCnt (NR, s, mt), dMat ((size_t) NR * NR, s, mt) ;
   CK (cudaMemcpyAsync (dCnt.p, sendCnt.data (), 8 * (size_t) NR, cudaMemcpyHostToDevice, s)) ;
   NCK (gNccl.AllGather (dCnt.p, dMat.p, NR, ncclUint64, d->comm, s)) ;
   CK (cudaMemcpyAsync (cntMat.data (), dMat.p, 8 * (size_t) NR * NR, cudaMemcpyDeviceToHost, s)) ;
@@ -1784,6 +1792,11 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	memory through CUDA IPC); otherwise k_local_distinct + ncclSend/ncclRecv. */
   DBuf<uint64_t> rHash (Ro, s, mt) ; DBuf<uint32_t> rDepth (Ro, s, mt), rFirst (Ro, s, mt) ;
   c->localBinId.alloc (Dl, s, mt) ;
+  DBuf<unsigned char> dInfo (sizeof (PeerInfo), s, mt), dInfos (sizeof (PeerInfo) * (size_t) NR, s, mt) ;
+  DBuf<uint32_t> dOk (1, s, mt), dOks (NR, s, mt) ;
+  DBuf<uint64_t> dHash ; DBuf<uint32_t> dDepth, dFirst ;	/* library-sort tail: the triples are materialised here first */
+  if (!preHash) { dHash.alloc (Dl, s, mt) ; dDepth.alloc (Dl, s, mt) ; dFirst.alloc (Dl, s, mt) ; }
+  agree () ;		/* 1: the receive arrays exist everywhere */
   bool pushed = false ;
   std::vector<PeerInfo> infos (NR) ;
   /* peer copies run on side streams (copy engines) and are joined back into s */
@@ -1805,7 +1818,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       mine.offHash = (uint64_t) ((char*) rHash.p - c->mt.base) ; mine.offDepth = (uint64_t) ((char*) rDepth.p - c->mt.base) ;
       mine.offFirst = (uint64_t) ((char*) rFirst.p - c->mt.base) ;
       mine.offBinId = (uint64_t) ((char*) c->localBinId.p - c->mt.base) ;
-      DBuf<unsigned char> dInfo (sizeof (PeerInfo), s, mt), dInfos (sizeof (PeerInfo) * (size_t) NR, s, mt) ;
       CK (cudaMemcpyAsync (dInfo.p, &mine, sizeof (PeerInfo), cudaMemcpyHostToDevice, s)) ;
       NCK (gNccl.AllGather (dInfo.p, dInfos.p, sizeof (PeerInfo), ncclUint8, d->comm, s)) ;
       CK (cudaMemcpyAsync (infos.data (), dInfos.p, sizeof (PeerInfo) * (size_t) NR, cudaMemcpyDeviceToHost, s)) ;
@@ -1841,7 +1853,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	  pm.handle = infos[r].handle ; pm.pid = infos[r].pid ; pm.base = infos[r].base ;
 	}
       /* every rank must take the same path */
-      DBuf<uint32_t> dOk (1, s, mt), dOks (NR, s, mt) ;
       std::vector<uint32_t> oks (NR) ;
       CK (cudaMemcpyAsync (dOk.p, &ok, 4, cudaMemcpyHostToDevice, s)) ;
       NCK (gNccl.AllGather (dOk.p, dOks.p, 1, ncclUint32, d->comm, s)) ;
@@ -1868,11 +1879,9 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	     wins (3.3 ms).  H10X_PEER_KERNEL / H10X_PEER_COPY force one. */
 	  const bool useCopy = getenv ("H10X_PEER_COPY") || (NR > 2 && !getenv ("H10X_PEER_KERNEL")) ;
 	  if (useCopy)
-	    { DBuf<uint64_t> dHash ; DBuf<uint32_t> dDepth, dFirst ;
-	      const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
+	    { const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
 	      if (!preHash)
-		{ dHash.alloc (Dl, s, mt) ; dDepth.alloc (Dl, s, mt) ; dFirst.alloc (Dl, s, mt) ;
-		  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+		{ if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
 		  xh = dHash.p ; xd = dDepth.p ; xf = dFirst.p ;
 		}
 	      for (int k = 1 ; k <= NR ; ++k)
@@ -1893,11 +1902,9 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	}
     }
   if (!pushed)
-    { DBuf<uint64_t> dHash ; DBuf<uint32_t> dDepth, dFirst ;
-      const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
+    { const uint64_t *xh = preHash ; const uint32_t *xd = preDepth, *xf = preFirst ;
       if (!preHash)
-	{ dHash.alloc (Dl, s, mt) ; dDepth.alloc (Dl, s, mt) ; dFirst.alloc (Dl, s, mt) ;
-	  if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
+	{ if (Dl) LAUNCH (c, k_local_distinct, gridFor (Dl, 256), 256, 0, s, Dl, segStart, sh, se, entryBlk, wMul, dHash.p, dDepth.p, dFirst.p) ;
 	  xh = dHash.p ; xd = dDepth.p ; xf = dFirst.p ;
 	}
       NCK (gNccl.GroupStart ()) ;
@@ -1916,6 +1923,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       NCK (gNccl.GroupEnd ()) ;
       CK (cudaStreamSynchronize (s)) ;	/* the send buffers are freed on leaving this scope */
     }
+  dHash.release () ; dDepth.release () ; dFirst.release () ;
   mark ("d4-alltoall") ;
 
   /* 5. owner merge: depth = sum, first block = min over the (at most NR) copies of a hash */
@@ -1985,6 +1993,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   mark ("d5-merge") ;
   /* 6. global id bases from every owner's per-block new-hash counts */
   DBuf<uint32_t> newMat ((size_t) NR * nB2, s, mt), colSum (nB2, s, mt), below (nB2, s, mt), prefixAll (nB2, s, mt) ;
+  agree () ;		/* 2: every owner has merged what it received */
   NCK (gNccl.AllGather (newCnt.p, newMat.p, nB2, ncclUint32, d->comm, s)) ;
   LAUNCH (c, k_id_base, gridFor (nB2, 256), 256, 0, s, nB2, (uint32_t) NR, (uint32_t) R, newMat.p, colSum.p, below.p) ;
   cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, colSum.p, prefixAll.p, nB2, s) ; }) ;
@@ -2016,6 +2025,14 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       else LAUNCH (c, k_answer_ids, gridFor (Ro, 256), 256, 0, s, Ro, oSegIncl.p, oi.p, gId.p, ans.p) ;
     }
 
+  DBuf<uint32_t> tId, tDepth ; DBuf<uint64_t> tHash ;
+  if (R == 0)
+    { tId.alloc (Dglobal, s, mt) ; tDepth.alloc (Dglobal, s, mt) ; tHash.alloc (Dglobal, s, mt) ;
+      c->hashValue.alloc ((size_t) Dglobal + 1, s, mt) ; c->hashDepth.alloc ((size_t) Dglobal + 2, s, mt) ;
+    }
+  DBuf<uint64_t> d2 (5, s, mt), dAll2 ((size_t) 5 * NR, s, mt) ;
+  DBuf<uint32_t> b1 (1, s, mt), bN (NR, s, mt) ;
+  agree (true) ;	/* 3, the last: every owner has its ids; nothing below allocates */
   mark ("d7-ids") ;
   /* 8. reverse all-to-all-v: the bin id of every rank-distinct hash, in the order it was sent */
   if (pushed)
@@ -2037,11 +2054,8 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 
   mark ("d8-reverse") ;
   /* 9. (id, hash, depth) of every bin to rank 0, which owns hashValue / hashDepth / hashIndex */
-  DBuf<uint32_t> tId, tDepth ; DBuf<uint64_t> tHash ;
   if (R == 0)
-    { tId.alloc (Dglobal, s, mt) ; tDepth.alloc (Dglobal, s, mt) ; tHash.alloc (Dglobal, s, mt) ;
-      c->hashValue.alloc ((size_t) Dglobal + 1, s, mt) ; c->hashDepth.alloc ((size_t) Dglobal + 2, s, mt) ;
-      CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
+    { CK (cudaMemsetAsync (c->hashValue.p, 0, 8, s)) ;
       CK (cudaMemsetAsync (c->hashDepth.p, 0, 4, s)) ;
       CK (cudaMemsetAsync (c->hashDepth.p + Dglobal + 1, 0, 4, s)) ;
     }
@@ -2050,7 +2064,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
     { mine2[2] = (uint64_t) ((char*) tId.p - c->mt.base) ; mine2[3] = (uint64_t) ((char*) tHash.p - c->mt.base) ;
       mine2[4] = (uint64_t) ((char*) tDepth.p - c->mt.base) ;
     }
-  DBuf<uint64_t> d2 (5, s, mt), dAll2 ((size_t) 5 * NR, s, mt) ;
   CK (cudaMemcpyAsync (d2.p, mine2.data (), 40, cudaMemcpyHostToDevice, s)) ;
   /* this collective is also the barrier behind the reverse copies: after it every rank's localBinId is complete */
   NCK (gNccl.AllGather (d2.p, dAll2.p, 5, ncclUint64, d->comm, s)) ;
@@ -2067,7 +2080,6 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
       peerCopy (0, (uint32_t*) (z + all2[2]) + before, sId.p, 4 * (size_t) Do) ;
       peerCopy (0, (uint64_t*) (z + all2[3]) + before, sHash.p, 8 * (size_t) Do) ;
       peerCopy (0, (uint32_t*) (z + all2[4]) + before, sDepth.p, 4 * (size_t) Do) ;
-      DBuf<uint32_t> b1 (1, s, mt), bN (NR, s, mt) ;
       CK (cudaMemsetAsync (b1.p, 0, 4, s)) ;
       NCK (gNccl.AllGather (b1.p, bN.p, 1, ncclUint32, d->comm, s)) ;	/* barrier: rank 0 scatters only complete data */
       CK (cudaStreamSynchronize (s)) ;

@@ -42,6 +42,18 @@ def main():
         if world > 1:
             dist.broadcast_object_list(idb, src=0)
         g.dist_init(rank, world, idb[0])
+        if os.environ.get("H10X_DIST_FAIL"):
+            # a rank-local failure inside the bin exchange: EVERY rank must come back with that error (nobody left waiting
+            # in a collective), and the same contexts must then be able to build again
+            try:
+                g.build_device_dist(fqb.data_ptr(), recs.shape[0])
+                raise SystemExit("rank %d: the injected failure did not surface" % rank)
+            except hash10x_b200.H10xError as e:
+                assert e.code == 4, (e.code, str(e))            # H10X_ERR_NOMEM on every rank
+            del os.environ["H10X_DIST_FAIL"]
+            if world > 1:
+                dist.barrier()
+            print("rank %d: injected failure surfaced everywhere" % rank, flush=True)
         g.build_device_dist(fqb.data_ptr(), recs.shape[0])
         ix = g.download()
         info = g.dist_info()

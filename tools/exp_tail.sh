@@ -1,14 +1,17 @@
-set -x
+# usage: bash tools/exp_tail.sh TAG "ENV1=.. ENV2=.." "ENV.." ...   (one short 1 Gb bench per environment setting; '-' = none)
+TAG=$1; shift
 B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-next --no-weak-base --no-clocks"
-$B > gpurun_out/r02t_base.json 2> gpurun_out/r02t_base.err
-H10X_SR_THREADS=256 $B > gpurun_out/r02t_t256.json 2>/dev/null
-H10X_SR_GROUP=2600 $B > gpurun_out/r02t_g2600.json 2>/dev/null
-H10X_SR_GROUP=5120 $B > gpurun_out/r02t_g5120.json 2>/dev/null
-H10X_SR_THREADS=256 H10X_SR_GROUP=2600 $B > gpurun_out/r02t_t256g2600.json 2>/dev/null
-H10X_SR_THREADS=256 H10X_SR_GROUP=5120 $B > gpurun_out/r02t_t256g5120.json 2>/dev/null
-for f in gpurun_out/r02t_*.json; do python - $f <<'P'
+i=0
+for envs in "$@"; do
+  i=$((i+1)); f=gpurun_out/${TAG}_$i.json
+  if [ "$envs" = "-" ]; then envs=""; fi
+  env $envs $B > $f 2> gpurun_out/${TAG}_$i.err || tail -3 gpurun_out/${TAG}_$i.err
+  python - $f "$envs" <<'P'
 import json,sys
-d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[1], round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['stage_ms'].items()}, d['parity'].get('ok'))
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("%-40s %7.2f ms %s parity=%s" % (sys.argv[2] or "(default)", d['ms_per_step'], {k:round(v,1) for k,v in d['stage_ms'].items()}, d['parity'].get('ok')))
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
 P
 done
