@@ -619,7 +619,9 @@ static bool tail_geometry (uint64_t H, uint64_t top, uint32_t maxBlock, TailGeom
   g.blkBits = bits_for (maxBlock) ;
   g.eShift = g.blkBits + 16 ;
   int rem = g.sortBits ;
-  while (rem > 0 && (double) H / (double) ((top >> rem) + 1) > H10X_SR_TARGET) --rem ;
+  double target = H10X_SR_TARGET ;
+  if (const char *e = getenv ("H10X_SR_TARGET")) { double v = atof (e) ; if (v >= 64.0 && v <= 0.35 * H10X_SR_CAP) target = v ; }
+  while (rem > 0 && (double) H / (double) ((top >> rem) + 1) > target) --rem ;
   if ((double) H / (double) ((top >> rem) + 1) > 0.5 * H10X_SR_CAP) return false ;	/* a handful of hash values: nothing to cut */
   int p2 = 0 ;
   for (;;)		/* ranges x digits must cover the sub-ranges; coarser sub-ranges when they cannot */
@@ -628,6 +630,10 @@ static bool tail_geometry (uint64_t H, uint64_t top, uint32_t maxBlock, TailGeom
       if (((uint64_t) 1 << p2) <= H10X_PART_MAX_BINS) break ;
       ++rem ;
     }
+  /* a 1024-digit partition pass costs 20.6 ms over the 1 Gb workload's entries, a 512-digit one 17.7 (profiles/README.md):
+     one more bit goes to the shared-memory sort instead when the sub-ranges still fit */
+  if (p2 == 10 && rem + 1 <= g.sortBits && (double) H / (double) ((top >> (rem + 1)) + 1) <= 0.35 * H10X_SR_CAP && !getenv ("H10X_SR_TARGET"))
+    { ++rem ; --p2 ; }
   if ((double) H / (double) ((top >> rem) + 1) > 0.35 * H10X_SR_CAP) return false ;	/* twice that at the dense end */
   g.remBits = rem ; g.p2 = p2 ; g.lowBits = rem + p2 ;
   if (g.lowBits + g.eShift > 64) return false ;
@@ -651,18 +657,19 @@ static int device_sms (h10x_ctx *c)
    per SM anyway), 8 warps and up to four CTAs below */
 template <class L>
 static void part_scatter_launch (h10x_ctx *c, cudaStream_t s, L ld, const uint64_t *jobStart, uint32_t nJobs, uint32_t nBins,
-				 uint64_t strideBin, uint64_t strideJob, const uint32_t *off, uint64_t *out, uint32_t grid)
+				 uint64_t strideBin, uint64_t strideJob, const uint32_t *off, uint64_t *out, uint32_t grid,
+				 unsigned int *ticket = nullptr)
 { if (nBins > 512)
     { auto fn = k_part_scatter<L, 16, 8, 2> ;
       const size_t smem = h10x_part_smem (nBins, 16) ;
       CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
-      LAUNCH (c, fn, grid, 16 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out) ;
+      LAUNCH (c, fn, grid, 16 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out, ticket) ;
     }
   else
     { auto fn = k_part_scatter<L, 8, 8, 4> ;
       const size_t smem = h10x_part_smem (nBins, 8) ;
       CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
-      LAUNCH (c, fn, grid, 8 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out) ;
+      LAUNCH (c, fn, grid, 8 * 32, smem, s, ld, jobStart, nJobs, nBins, strideBin, strideJob, off, out, ticket) ;
     }
 }
 
@@ -699,7 +706,8 @@ static void part_pass (h10x_ctx *c, cudaStream_t s, L ld, uint64_t n, uint32_t n
   const size_t nh = (size_t) nBins * nJobs ;
   DBuf<uint32_t> hist (nh + 1, s, mt) ;
   CK (cudaMemsetAsync (hist.p + nh, 0, 4, s)) ;
-  LAUNCH (c, k_part_hist<L>, nJobs, 512, (size_t) nBins * 4, s, ld, jobStart.p, nJobs, nBins, (uint64_t) nJobs, (uint64_t) 1, hist.p) ;
+  LAUNCH (c, k_part_hist<L>, nJobs, 512, (size_t) nBins * 4, s, ld, jobStart.p, nJobs, nBins, (uint64_t) nJobs, (uint64_t) 1, hist.p,
+	  (unsigned int*) nullptr) ;
   cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, hist.p, hist.p, nh + 1, s) ; }) ;
   part_scatter_launch (c, s, ld, jobStart.p, nJobs, nBins, (uint64_t) nJobs, (uint64_t) 1, hist.p, out, nJobs) ;
 }
@@ -762,12 +770,15 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
       { const uint32_t nBins = 1u << g.p2 ;
 	LoadWord ld = { B.p, g.eShift + g.remBits, nBins - 1u, ~(uint64_t) 0 } ;
 	CK (cudaMemsetAsync (srStart.p + g.nSub, 0, 4, s)) ;
-	LAUNCH (c, k_part_hist<LoadWord>, std::min<uint32_t> (g.nRanges, (uint32_t) nSM * 8), 512, (size_t) nBins * 4, s, ld, rangeStart.p,
-		g.nRanges, nBins, (uint64_t) 1, (uint64_t) nBins, srStart.p) ;
+	DBuf<unsigned int> tickets (2, s, mt) ;		/* ranges are handed out in order = largest first (h10x_next_job) */
+	CK (cudaMemsetAsync (tickets.p, 0, 8, s)) ;
+	unsigned int *tk = getenv ("H10X_P2_STATIC") ? nullptr : tickets.p ;
+	LAUNCH (c, k_part_hist<LoadWord>, std::min<uint32_t> (g.nRanges, (uint32_t) nSM * 4), 512, (size_t) nBins * 4, s, ld, rangeStart.p,
+		g.nRanges, nBins, (uint64_t) 1, (uint64_t) nBins, srStart.p, tk) ;
 	cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, srStart.p, srStart.p, (size_t) g.nSub + 1, s) ; }) ;
 	A.alloc (H, s, mt) ;
 	part_scatter_launch (c, s, ld, rangeStart.p, g.nRanges, nBins, (uint64_t) 1, (uint64_t) nBins, srStart.p, A.p,
-			     std::min<uint32_t> (g.nRanges, part_resident_ctas<LoadWord> (c, nBins))) ;
+			     std::min<uint32_t> (g.nRanges, part_resident_ctas<LoadWord> (c, nBins)), tk ? tk + 1 : nullptr) ;
 	B.release () ;
       }
     else
@@ -943,6 +954,7 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
 						   entries overflow them and take the slow direct path (3 passes of 6-7 bits: 50 ms) */
     int bits[4] = { 0, 0, 0, 0 } ;
     for (int i = 0, left = g.blkBits ; i < nP ; ++i) { bits[i] = (left + (nP - i) - 1) / (nP - i) ; left -= bits[i] ; }
+    if (const char *e = getenv ("H10X_T_FIRST")) { int v = atoi (e) ; if (nP == 2 && v >= 1 && v <= 10 && g.blkBits - v >= 1 && g.blkBits - v <= 10) { bits[0] = v ; bits[1] = g.blkBits - v ; } }
     LoadCodes l1 = { codesPtr, idRead.p, (1u << bits[0]) - 1u, bits[0] } ;
     if (nP == 1) part_pass (c, s, l1, H, 1u << bits[0], c->clus.p) ;
     else

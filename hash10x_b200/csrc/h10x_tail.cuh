@@ -232,11 +232,24 @@ struct LoadCodes {
 } ;
 
 /* hist[d * strideBin + job * strideJob] = elements of job `job` with digit d */
+/* Jobs are taken round robin, or - ticket != NULL - in order from a counter: the jobs of P2 are the hash ranges, whose
+   sizes fall linearly from twice the average to nothing (density 2 (1 - x) of min (hash, hashRC)), so a fixed assignment
+   left the CTA holding ranges 0, 592, 1184, 1776 with 30 % more than the average; handing the ranges out largest first
+   as CTAs become free evens that out. */
+__device__ __forceinline__ uint32_t h10x_next_job (unsigned int *ticket, uint32_t prev, bool first, uint32_t *sJob)
+{ if (!ticket) return first ? blockIdx.x : prev + gridDim.x ;
+  __syncthreads () ;
+  if (threadIdx.x == 0) *sJob = atomicAdd (ticket, 1u) ;
+  __syncthreads () ;
+  return *sJob ;
+}
+
 template <class L>
 __global__ void k_part_hist (L ld, const uint64_t *__restrict__ jobStart, uint32_t nJobs, uint32_t nBins,
-			     uint64_t strideBin, uint64_t strideJob, uint32_t *__restrict__ hist)
+			     uint64_t strideBin, uint64_t strideJob, uint32_t *__restrict__ hist, unsigned int *ticket)
 { extern __shared__ uint32_t phist[] ;
-  for (uint32_t job = blockIdx.x ; job < nJobs ; job += gridDim.x)
+  __shared__ uint32_t sJob ;
+  for (uint32_t job = h10x_next_job (ticket, 0, true, &sJob) ; job < nJobs ; job = h10x_next_job (ticket, job, false, &sJob))
     { for (uint32_t d = threadIdx.x ; d < nBins ; d += blockDim.x) phist[d] = 0 ;
       __syncthreads () ;
       const uint64_t a = jobStart[job], b = jobStart[job + 1] ;
@@ -267,8 +280,8 @@ __host__ __device__ inline size_t h10x_part_smem (uint32_t nBins, int nw)
 template <class L, int NW, int ITEMS, int MINB>
 __global__ void __launch_bounds__ (NW * 32, MINB)
 k_part_scatter (L ld, const uint64_t *__restrict__ jobStart, uint32_t nJobs, uint32_t nBins, uint64_t strideBin,
-		uint64_t strideJob, const uint32_t *__restrict__ off, uint64_t *__restrict__ out)
-{ extern __shared__ __align__ (16) unsigned char psmRaw[] ;
+		uint64_t strideJob, const uint32_t *__restrict__ off, uint64_t *__restrict__ out, unsigned int *ticket)
+{ __shared__ uint32_t sJob ; extern __shared__ __align__ (16) unsigned char psmRaw[] ;
   uint64_t *ring = (uint64_t*) psmRaw ;				/* nBins rings */
   uint32_t *cursor = (uint32_t*) (ring + (size_t) nBins * H10X_RING_STRIDE) ;	/* nBins: next output slot of every digit */
   uint32_t *first = cursor + nBins ;				/* nBins: the digit's first slot in this job */
@@ -280,7 +293,7 @@ k_part_scatter (L ld, const uint64_t *__restrict__ jobStart, uint32_t nJobs, uin
   uint32_t *wcWords = (uint32_t*) wc ;
   const uint32_t nWcWords = (NW * nBins + 1u) / 2u ;
   constexpr uint32_t TILE = NW * 32 * ITEMS ;
-  for (uint32_t job = blockIdx.x ; job < nJobs ; job += gridDim.x)
+  for (uint32_t job = h10x_next_job (ticket, 0, true, &sJob) ; job < nJobs ; job = h10x_next_job (ticket, job, false, &sJob))
     { const uint64_t a = jobStart[job], b = jobStart[job + 1] ;
       __syncthreads () ;
       for (uint32_t d = t ; d < nBins ; d += NW * 32)
