@@ -540,19 +540,18 @@ def run_ours(args, wl, wl_name):
                 "traffic_source": "profiles/r02_fused_kernel.json (ncu dram__bytes_read+write of the two fused launches at this workload) x pairs" if traffic else None,
                 "ms_per_launch_group": dom_ms, "share_of_step": dom_ms / ms_step}
     rooflines = [roofline]
-    if alu is not None:
-        # the fused kernel's real bound: the 16-lane-per-scheduler integer ALU pipe (64 lanes per SM and clock)
-        sm_clock = (clocks.get("sm_mhz") or 1965) * 1e6
-        ops = alu["alu_pipe_thread_instructions_per_pair"] * R
-        peak_ops = 148 * 64 * sm_clock
-        ach_ops = ops / (dom_ms * 1e-3)
-        rooflines.append({"bound": "int_alu", "kernel": "fused", "achieved": ach_ops / 1e12, "peak": peak_ops / 1e12,
-                          "unit": "T thread-instructions/s on the ALU pipe", "frac": ach_ops / peak_ops,
-                          "per_pair": alu["alu_pipe_thread_instructions_per_pair"], "source": alu.get("alu_source"),
-                          "note": "SURVEY 8d expected HBM to bind this stage; ncu shows the integer pipes do (ALU %s %%, FMA/IMAD %s %%, "
-                                  "issue %s %%, DRAM %s %%): its 120 R + 8 H bytes would take ~6 ms at the HBM peak"
-                                  % (alu.get("alu_pct"), alu.get("fma_pct"), alu.get("issue_pct"), alu.get("dram_pct"))})
-        roofline["note"] = "bound by the integer ALU pipe, not HBM: see roofline_int_alu"
+    if alu is not None and alu.get("fmaheavy_busy_ns_per_pair"):
+        # the fused kernel's real bound: the half-rate integer multiply ("fmaheavy") pipe.  busy = the pipe's active time per
+        # read pair from the committed ncu capture (pct of cycles active x duration / pairs, whole GPU); it does not depend on
+        # the run, so busy x pairs / live stage time is the fraction of that pipe's peak this run reached
+        busy_ms = alu["fmaheavy_busy_ns_per_pair"] * R * 1e-6
+        rooflines.append({"bound": "int_mul_pipe (fmaheavy)", "kernel": "fused", "achieved": busy_ms, "peak": dom_ms,
+                          "unit": "ms of multiply-pipe work per ms of kernel", "frac": busy_ms / dom_ms,
+                          "busy_ns_per_pair": alu["fmaheavy_busy_ns_per_pair"], "source": alu.get("pipe_capture"),
+                          "note": "SURVEY 8d expected HBM to bind this stage; ncu shows the integer multiply pipe does (fmaheavy %s %%, "
+                                  "ALU %s %%, issue %s %%, DRAM %s %%): its 120 R + 8 M bytes would take ~6 ms at the HBM peak"
+                                  % (alu.get("fmaheavy_pct"), alu.get("alu_pct"), alu.get("issue_pct"), alu.get("dram_pct"))})
+        roofline["note"] = "bound by the integer multiply pipe, not HBM: see roofline_int_pipe"
     pipe_ach = stats["algorithmicBytes"] / (ms_step * 1e-3) / 1e9
     pipeline = {"bound": "hbm", "algorithmic_bytes": stats["algorithmicBytes"],
                 "bytes_per_pair": stats["algorithmicBytes"] / max(1, R), "achieved": pipe_ach, "peak": peak,
@@ -593,7 +592,7 @@ def run_ours(args, wl, wl_name):
             "counts": {"pairs": R, "moshes": M, "block_unique_hashes": H, "bins": D, "blocks": nB,
                        "peak_device_bytes": stats["peakDeviceBytes"]}}
     if len(rooflines) > 1:
-        line["roofline_int_alu"] = rooflines[1]
+        line["roofline_int_pipe"] = rooflines[1]
     if nxt:
         line["next_rows"] = nxt
     if weak_base:
