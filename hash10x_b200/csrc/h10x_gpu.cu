@@ -799,13 +799,13 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     sa.nOver = counters.p ; sa.ticket = counters.p + 1 ; sa.nJobs = counters.p + 2 ; sa.nSub = g.nSub ;
     sa.cap = H10X_SR_CAP ;
     if (const char *e = getenv ("H10X_SR_CAP")) { long v = atol (e) ; if (v >= 1 && v < (long) H10X_SR_CAP) sa.cap = (uint32_t) v ; }	/* tests: force the big-sub-range path */
-    sa.groupCap = std::min<uint32_t> (H10X_SR_GROUP, sa.cap) ; sa.maxLog = (uint32_t) std::min (2, g.p2) ;
+    sa.groupCap = sa.cap ;		/* as large as fits: 3584 cost 2.1 ms more at the 1 Gb workload, no grouping 9.3 ms more */ sa.maxLog = (uint32_t) std::min (2, g.p2) ;
         sa.eShift = g.eShift ; sa.remBits = g.remBits ;
     sa.srCount = srCount.p ; sa.blkDup = blkDup.p ; sa.nDup = nDup.p ; sa.blkMask = blkMask ;
+    if (const char *e = getenv ("H10X_SR_GROUP")) { long v = atol (e) ; if (v >= 1) sa.groupCap = std::min<uint32_t> ((uint32_t) v, sa.cap) ; }
     LAUNCH (c, k_sr_jobs, gridFor (((uint64_t) g.nSub + 3) / 4, 256), 256, 0, s, sa) ;
     int srThreads = H10X_SR_THREADS_DEFAULT ;
     if (const char *e = getenv ("H10X_SR_THREADS")) { long v = atol (e) ; if (v == 256 || v == 512) srThreads = (int) v ; }
-    if (const char *e = getenv ("H10X_SR_GROUP")) { long v = atol (e) ; if (v >= 1) sa.groupCap = std::min<uint32_t> ((uint32_t) v, sa.cap) ; }
     const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (srThreads / 32) * 2 << H10X_SR_DIGIT) + 16 ;
     auto srFn = srThreads == 256 ? k_sr_sort<256> : k_sr_sort<512> ;
     CK (cudaFuncSetAttribute (srFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
@@ -817,20 +817,28 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     CK (cudaMemcpyAsync (&nOver, counters.p, 4, cudaMemcpyDeviceToHost, s)) ;
     CK (cudaStreamSynchronize (s)) ;
     if (nOver)
-      { std::vector<uint32_t> over (nOver), st2 ((size_t) g.nSub + 1) ;
+      { /* one segmented library sort for all of them (one sort + three host round trips per sub-range made a data set
+	   with ~1400 oversized sub-ranges 440 ms slower) */
+	std::vector<uint32_t> over (nOver), st2 ((size_t) g.nSub + 1) ;
 	CK (cudaMemcpyAsync (over.data (), overList.p, 4 * (size_t) nOver, cudaMemcpyDeviceToHost, s)) ;
 	CK (cudaMemcpyAsync (st2.data (), srStart.p, 4 * ((size_t) g.nSub + 1), cudaMemcpyDeviceToHost, s)) ;
 	CK (cudaStreamSynchronize (s)) ;
-	for (uint32_t j : over)
-	  { const uint64_t n = st2[j + 1] - st2[j] ;
-	    DBuf<uint64_t> tmp (n, s, mt) ;
-	    /* the whole word orders a sub-range: q bits, then block, then read (the lowest read of a (hash, block) first) */
-	    cubCall (c, s, [&] (void *t, size_t &b)
-	      { return cub::DeviceRadixSort::SortKeys (t, b, A.p + st2[j], tmp.p, n, 0, g.eShift + g.remBits, s) ; }) ;
-	    CK (cudaMemcpyAsync (A.p + st2[j], tmp.p, 8 * n, cudaMemcpyDeviceToDevice, s)) ;
-	    LAUNCH (c, k_sr_heads_big, 1, 512, 0, s, sa, j) ;
-	  }
-	      }
+	std::sort (over.begin (), over.end ()) ;
+	std::vector<uint64_t> segOff ((size_t) nOver + 1, 0) ;
+	for (uint32_t x = 0 ; x < nOver ; ++x) segOff[x + 1] = segOff[x] + (st2[over[x] + 1] - st2[over[x]]) ;
+	const uint64_t T = segOff[nOver] ;
+	DBuf<uint64_t> cIn (T, s, mt), cOut (T, s, mt), dSegOff ((size_t) nOver + 1, s, mt) ;
+	CK (cudaMemcpyAsync (overList.p, over.data (), 4 * (size_t) nOver, cudaMemcpyHostToDevice, s)) ;
+	CK (cudaMemcpyAsync (dSegOff.p, segOff.data (), 8 * ((size_t) nOver + 1), cudaMemcpyHostToDevice, s)) ;
+	LAUNCH (c, k_over_copy, nOver, 512, 0, s, A.p, srStart.p, overList.p, dSegOff.p, cIn.p, 1) ;
+	/* the whole word orders a sub-range: q bits, then block, then read (the lowest read of a (hash, block) first) */
+	cubCall (c, s, [&] (void *t, size_t &b)
+	  { return cub::DeviceSegmentedSort::SortKeys (t, b, cIn.p, cOut.p, (::cuda::std::int64_t) T, (::cuda::std::int64_t) nOver,
+						       dSegOff.p, dSegOff.p + 1, s) ; }) ;
+	LAUNCH (c, k_over_copy, nOver, 512, 0, s, A.p, srStart.p, overList.p, dSegOff.p, cOut.p, 0) ;
+	LAUNCH (c, k_sr_heads_big, nOver, 512, 0, s, sa, overList.p) ;
+	CK (cudaStreamSynchronize (s)) ;	/* `over` / `segOff` are read by the async copies */
+      }
     unsigned long long dups = 0 ;
     blkDupHost.assign ((size_t) nBlkNumbers + 1, 0) ;
     CK (cudaMemcpyAsync (&dups, nDup.p, 8, cudaMemcpyDeviceToHost, s)) ;

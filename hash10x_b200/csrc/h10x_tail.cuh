@@ -38,8 +38,7 @@
 #define H10X_SR_THREADS_DEFAULT 512
 #define H10X_SR_TARGET 1400.0		/* average sub-range size aimed at; min(hashF, hashR) is not uniform (density 2(1-x)), so the
 					   low sub-ranges hold twice the average and the high ones next to nothing: k_sr_jobs joins
-					   aligned pairs / quads of sub-ranges into sort jobs of up to H10X_SR_GROUP entries */
-#define H10X_SR_GROUP 3584u
+					   aligned pairs / quads of sub-ranges into sort jobs of up to H10X_SR_CAP entries */
 #define H10X_SR_DIGIT 9			/* bits per shared-memory sort pass */
 #define H10X_P1_MAX_RANGES 2304u		/* 64-byte ring + 12 bytes of cursors per range in shared memory */
 #define H10X_PART_MAX_BINS 1024u
@@ -532,9 +531,21 @@ k_sr_sort (SrArgs a)
     }
 }
 
-/* the same scan for a sub-range the library sorted in global memory: one CTA, in chunks */
-__global__ void k_sr_heads_big (SrArgs a, uint32_t j)
+/* sub-ranges too large for shared memory (one hash held by thousands of blocks: repeats) are sorted by the library,
+   all of them in one segmented sort over a compact copy: segment x of the copy is sub-range list[x] */
+__global__ void k_over_copy (uint64_t *__restrict__ A, const uint32_t *__restrict__ srStart, const uint32_t *__restrict__ list,
+			     const uint64_t *__restrict__ segOff, uint64_t *__restrict__ compact, int toCompact)
+{ const uint32_t j = list[blockIdx.x] ;
+  const uint32_t st = srStart[j], n = srStart[j + 1] - st ;
+  uint64_t *c = compact + segOff[blockIdx.x] ;
+  if (toCompact) for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x) c[i] = A[st + i] ;
+  else for (uint32_t i = threadIdx.x ; i < n ; i += blockDim.x) A[st + i] = c[i] ;
+}
+
+/* the same scan for a sub-range the library sorted in global memory: one CTA per listed sub-range, in chunks */
+__global__ void k_sr_heads_big (SrArgs a, const uint32_t *__restrict__ list)
 { __shared__ uint32_t warpTmp[33] ;
+  const uint32_t j = list[blockIdx.x] ;
   const uint32_t st = a.srStart[j], n = a.srStart[j + 1] - st ;
   uint64_t *g = a.A + st ;		/* sorted on the whole word: (hash, block, read) */
   uint32_t doneF = 0, doneH = 0 ;
