@@ -89,3 +89,17 @@ def fastq_from_fqb(recs, read_len):
             q = bytes(b"#I"[x] for x in unpack(rec[o + ws:o + ws + wq], 1, read_len))
             f.append(b"@r%d %s\n" % (r, tag) + s + b"\n+\n" + q + b"\n")
     return b"".join(f1), b"".join(f2)
+
+
+def abandonment_case(n_groups=300, seed=5):
+    """A barcode block with more than 255 sub-clusters (hash10x.c:810-817): block 1 holds n_groups read pairs, and read pair
+    g is also the only read pair of its own barcode block 2 + g, so the moshes of pair g are shared by exactly those two
+    blocks (depth 2).  With --hashDepthRange 2 3 (min <= depth < max) and -ct 1 the second good hash of every pair founds a cluster in block
+    1: the 256th founding abandons the block's clustering.  One more run closes the file (the last run is never hashed)."""
+    rng = np.random.default_rng(seed)
+    words = rng.choice(np.arange(1, 1 << 31, dtype=np.int64), size=n_groups + 2, replace=False)
+    pairs = [(rng.integers(0, 4, 135), rng.integers(0, 4, 151)) for _ in range(n_groups)]
+    out = [make_record(int(words[0]), t, r2) for t, r2 in pairs]
+    out += [make_record(int(words[1 + g]), t, r2) for g, (t, r2) in enumerate(pairs)]
+    out.append(make_record(int(words[n_groups + 1]), rng.integers(0, 4, 135), rng.integers(0, 4, 151)))
+    return np.array(out, dtype=np.uint32).reshape(-1, 30)

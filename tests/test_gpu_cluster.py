@@ -94,6 +94,28 @@ def test_cluster_many_sharing_barcodes_use_the_big_table_and_deep_bins(orc, gpu_
         _same(g.cluster(0, 0, 5), want)
 
 
+def test_cluster_abandons_a_block_with_more_than_255_clusters(orc, gpu_lib):
+    # hash10x.c:810-817 (the case is pinned against the reference binary in tests/test_oracle.py): the 256th founding step
+    # of block 1 wipes its labels; 200 groups stay below the limit and keep theirs
+    import fqbtools
+    seen = set()
+    for groups in (300, 200, 255, 256, 257, 258):          # around the limit: exactly 255 clusters stay, 256 abandon
+        recs = fqbtools.abandonment_case(groups)
+        ix = orc.build(recs, B=20)
+        _w, goff, good = orc.good_hashes(ix, 2, 3)
+        want = orc.cluster(ix, goff, good, 0, 0, 1)
+        seen.add(int(want[1][1]))
+        if groups == 300:
+            assert int(want[1][1]) == 0
+        if groups == 200:
+            assert int(want[1][1]) >= 199
+        with _gpu(B=20) as g:
+            g.build_host(recs)
+            g.depth_range(2, 3)
+            _same(g.cluster(0, 0, 1), want)
+    assert 255 in seen and 0 in seen
+
+
 def test_cluster_argument_checks(orc, gpu_lib):
     import hash10x_b200
     recs = _cluster_case(orc, 37, 120, 20, 80, 40_000, 8_000, 3)

@@ -219,6 +219,30 @@ def test_cluster_equals_reference_binary(orc, tmp_path, seed, nb, pmin, pmax, ge
     assert int(nsub.sum()) > 0 and int(ref.clusSub.max()) > 0          # the case does cluster something
 
 
+def test_cluster_abandons_a_block_with_more_than_255_clusters_like_the_reference(orc, tmp_path):
+    """hash10x.c:810-817: the 256th founding step of a block wipes its labels, sets nSubCluster = 0 and stops; the other
+    blocks (one cluster each here) are not affected.  Reference binary against the oracle, bit for bit."""
+    _need_ref(orc)
+    import subprocess
+    import fqbtools
+    recs = fqbtools.abandonment_case(300)
+    src, dst = str(tmp_path / "o.hash"), str(tmp_path / "r.hash")
+    assert orc.build_and_write(recs, src, B=20) == 0
+    cmd = [orc.ref_binary(), "-B", "20", "-ct", "1", "--readHash", src, "--hashDepthRange", "2", "3", "--cluster", "0", "0",
+           "--writeHash", dst]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "has too many clusters" in r.stderr                     # the reference did abandon block 1
+    ref = hashfile.parse(dst)
+    ix = orc.build(recs, B=20)
+    _within, goff, good = orc.good_hashes(ix, 2, 3)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 1)
+    assert int(nsub[1]) == 0 and int(nsub[2:].sum()) >= 250          # block 1 abandoned, the partners clustered
+    assert np.array_equal(ref.blkNSub, nsub)
+    assert np.array_equal(ref.blkPointToMin.view(np.uint64), ptm.view(np.uint64))
+    assert np.array_equal(ref.clusRaw, clus)
+
+
 def test_cluster_twice_carries_state_like_the_reference(orc, tmp_path):
     """A second --hashDepthRange / --cluster pair works on what the first left behind: within[] flags accumulate
     (hash10x.c:535), only the good entries are wiped (:783) and a block without good hashes is merged again with
