@@ -194,7 +194,9 @@ __global__ void k_owner_merge (uint32_t nSeg, const uint32_t *__restrict__ segSt
    What an owner receives is NR runs (one per source rank), each already ascending in hash.  Instead of radix-sorting
    the concatenation over all 2k bits (6 library passes over 12 B) the runs are MERGED tile by tile:
      - every S-th element of every run is a splitter candidate; the (few) candidates are sorted and every NR-th one is a
-       tile boundary, so a tile [B_t, B_t+1) holds on average NR*S elements and provably fewer than 3 NR S: a run has
+       tile boundary, so a tile [B_t, B_t+1) holds on average NR*S elements and provably fewer than 3 NR S (the host aims at half the
+       shared-memory capacity on average, S = CAP / (2 NR): data whose runs are so differently distributed that a tile
+       overflows sends the whole merge to the library sort instead): a run has
        fewer than S elements between two of its own candidates, a tile holds at most NR candidates plus up to NR - 1 more
        whose value equals its lower boundary, and k candidates of a run inside a tile mean at most k + 1 such stretches
        (rank-distinct hashes: no run holds a value twice);
@@ -203,7 +205,8 @@ __global__ void k_owner_merge (uint32_t nSeg, const uint32_t *__restrict__ segSt
        its index in its own piece plus, for every other piece, the number of smaller elements there (ties: the lower source
        rank first) - binary searches in shared memory; equal hashes then stand side by side: depth = sum, first block =
        min (hash10x.c:178 / :147 seen from the owner), and every received copy learns the number of its bin (segOf).
-   Two launches: COUNT (bins per tile), scan, WRITE.  Everything read or written in global memory is a contiguous piece. */
+   One launch: the tiles are handed out in order from a ticket and the number of bins before a tile comes from a decoupled
+   look-back over the tile words (tileState).  Everything read or written in global memory is a contiguous piece. */
 #define H10X_MERGE_CAP 4096u
 #define H10X_MERGE_THREADS 256
 
@@ -211,7 +214,8 @@ struct MergeArgs {
   const uint64_t *rHash ; const uint32_t *rDepth, *rFirst ;	/* the receive arrays, run r at [recvOff[r], recvOff[r+1]) */
   uint64_t recvOff[H10X_MAX_RANKS + 1] ;
   const uint32_t *bnd ;		/* (nTiles + 1) * nranks: start of tile t inside run r (relative to the run) */
-  uint32_t *tileBins ;		/* COUNT: bins of tile t; WRITE: exclusive scan of it = first bin of tile t */
+  unsigned long long *tileState ;	/* decoupled look-back: flag << 62 | bins of tile t (flag 1) or up to and including it (flag 2) */
+  unsigned int *ticket ;
   uint64_t *gHash ; uint32_t *gDepth, *gFirst, *newCnt, *segOf ;
   unsigned int *overflow ;
   uint32_t nTiles ; int nranks ;
@@ -243,39 +247,43 @@ __global__ void k_merge_bounds (MergeArgs a, const uint64_t *__restrict__ candSo
   bnd[x] = lo ;
 }
 
-static inline size_t h10x_merge_smem (bool write) { return (size_t) H10X_MERGE_CAP * (write ? 18 : 10) ; }
+static inline size_t h10x_merge_smem () { return (size_t) H10X_MERGE_CAP * 18 ; }
 
-template <bool WRITE>
 __global__ void __launch_bounds__ (H10X_MERGE_THREADS)
 k_owner_merge_tiles (MergeArgs a)
 { extern __shared__ __align__ (16) unsigned char mergeRaw[] ;
   uint64_t *hs = (uint64_t*) mergeRaw ;			/* CAP: the pieces, run after run */
   uint16_t *order = (uint16_t*) (hs + H10X_MERGE_CAP) ;	/* CAP: merged position -> slot in hs[] */
-  uint32_t *dep = (uint32_t*) (order + H10X_MERGE_CAP), *fst = dep + H10X_MERGE_CAP ;	/* CAP each, WRITE only */
-  __shared__ uint32_t pStart[H10X_MAX_RANKS + 1], pSrc[H10X_MAX_RANKS], warpTmp[33] ;
+  uint32_t *dep = (uint32_t*) (order + H10X_MERGE_CAP), *fst = dep + H10X_MERGE_CAP ;	/* CAP each */
+  __shared__ uint32_t pStart[H10X_MAX_RANKS + 1], pSrc[H10X_MAX_RANKS], pLen[H10X_MAX_RANKS], warpTmp[33], sTile, sBase ;
   const uint32_t t = threadIdx.x ;
   const int NR = a.nranks ;
   constexpr uint32_t PER = H10X_MERGE_CAP / H10X_MERGE_THREADS ;
-  for (uint32_t tile = blockIdx.x ; tile < a.nTiles ; tile += gridDim.x)
+  for (;;)
     { __syncthreads () ;
+      if (t == 0) sTile = atomicAdd (a.ticket, 1u) ;	/* tiles are taken in order: the chained scan below cannot deadlock */
+      __syncthreads () ;
+      const uint32_t tile = sTile ;
+      if (tile >= a.nTiles) break ;
+      if (t < (uint32_t) NR)		/* the piece lengths in parallel (two dependent global loads each), then a tiny prefix */
+	{ const uint32_t lo = a.bnd[(size_t) tile * NR + t], hi = a.bnd[(size_t) (tile + 1) * NR + t] ;
+	  pSrc[t] = lo ; pLen[t] = hi - lo ;
+	}
+      __syncthreads () ;
       if (t == 0)
 	{ uint32_t run = 0 ;
-	  for (int r = 0 ; r < NR ; ++r)
-	    { const uint32_t lo = a.bnd[(size_t) tile * NR + r], hi = a.bnd[(size_t) (tile + 1) * NR + r] ;
-	      pStart[r] = run ; pSrc[r] = lo ; run += hi - lo ;
-	    }
+	  for (int r = 0 ; r < NR ; ++r) { pStart[r] = run ; run += pLen[r] ; }
 	  pStart[NR] = run ;
 	}
       __syncthreads () ;
-      const uint32_t n = pStart[NR] ;
-      if (n > H10X_MERGE_CAP) { if (t == 0) atomicExch (a.overflow, 1u) ; continue ; }	/* cannot happen (bound above); the host re-runs with the sort */
-      for (int r = 0 ; r < NR ; ++r)
+      uint32_t n = pStart[NR] ;
+      const bool over = n > H10X_MERGE_CAP ;	/* the host re-runs with the library sort; the chain below still gets this tile's word */
+      if (over) { if (t == 0) atomicExch (a.overflow, 1u) ; n = 0 ; }
+      for (int r = 0 ; r < NR && !over ; ++r)
 	{ const uint32_t ps = pStart[r], len = pStart[r + 1] - ps ;
 	  const uint64_t g0 = a.recvOff[r] + pSrc[r] ;
 	  for (uint32_t x = t ; x < len ; x += H10X_MERGE_THREADS)
-	    { hs[ps + x] = a.rHash[g0 + x] ;
-	      if (WRITE) { dep[ps + x] = a.rDepth[g0 + x] ; fst[ps + x] = a.rFirst[g0 + x] ; }
-	    }
+	    { hs[ps + x] = a.rHash[g0 + x] ; dep[ps + x] = a.rDepth[g0 + x] ; fst[ps + x] = a.rFirst[g0 + x] ; }
 	}
       __syncthreads () ;
       for (uint32_t slot = t ; slot < n ; slot += H10X_MERGE_THREADS)
@@ -298,8 +306,35 @@ k_owner_merge_tiles (MergeArgs a)
       for (uint32_t p = p0 ; p < p1 ; ++p) if (p == 0 || hs[order[p]] != hs[order[p - 1]]) ++heads ;
       uint32_t total ;
       uint32_t k = sr_cta_exclusive_scan (heads, warpTmp, total) ;	/* bins before p0 in this tile */
-      if (!WRITE) { if (t == 0) a.tileBins[tile] = total ; continue ; }
-      const uint32_t base = a.tileBins[tile] ;
+      /* bins before this tile: decoupled look-back over the tile words (2 flag bits | count).  A tile publishes its own
+	 count at once (flag 1 = aggregate), warp 0 then walks back 32 tiles at a time adding aggregates until it meets a
+	 word that already holds an inclusive prefix (flag 2), and publishes its own inclusive prefix. */
+      if (t < 32)
+	{ volatile unsigned long long *st = a.tileState ;
+	  if (t == 0) st[tile] = (1ull << 62) | (unsigned long long) total ;
+	  unsigned long long sum = 0 ;
+	  long long idx = (long long) tile - 1 ;
+	  bool done = (tile == 0) ;
+	  while (!done)
+	    { const long long my = idx - (long long) t ;
+	      const unsigned long long w = (my >= 0) ? st[my] : (2ull << 62) ;	/* before tile 0: prefix 0 */
+	      const uint32_t flag = (uint32_t) (w >> 62) ;
+	      const uint32_t ready = __ballot_sync (0xffffffffu, flag != 0), pm = __ballot_sync (0xffffffffu, flag == 2) ;
+	      uint32_t take = 0 ;
+	      if (pm) { const int fp = __ffs (pm) - 1 ; const uint32_t need = (fp == 31) ? 0xffffffffu : ((1u << (fp + 1)) - 1u) ;
+			if ((ready & need) == need) { take = need ; done = true ; } }
+	      else if (ready == 0xffffffffu) { take = 0xffffffffu ; idx -= 32 ; }
+	      if (take)
+		{ unsigned long long v = ((take >> t) & 1u) ? (w & 0x3fffffffffffffffull) : 0ull ;
+#pragma unroll
+		  for (int o = 16 ; o ; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o) ;
+		  sum += v ;
+		}
+	    }
+	  if (t == 0) { sBase = (uint32_t) sum ; st[tile] = (2ull << 62) | (sum + (unsigned long long) total) ; }
+	}
+      __syncthreads () ;
+      const uint32_t base = sBase ;
       for (uint32_t p = p0 ; p < p1 ; ++p)
 	{ const uint32_t slot = order[p] ;
 	  const bool head = (p == 0 || hs[slot] != hs[order[p - 1]]) ;

@@ -1955,19 +1955,25 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
   bool merged = false ;
   if (Ro && !getenv ("H10X_OWNER_SORT"))
     { /* the received runs are sorted: merge them tile by tile (h10x_dist.cuh, "owner merge without a sort") */
-      const uint32_t S = std::max<uint32_t> (16u, H10X_MERGE_CAP / (3u * (uint32_t) NR)) ;
+      uint32_t S = std::max<uint32_t> (16u, H10X_MERGE_CAP / (2u * (uint32_t) NR)) ;
+      if (const char *e = getenv ("H10X_MERGE_S")) { long v = atol (e) ; if (v >= 16 && v <= (long) H10X_MERGE_CAP) S = (uint32_t) v ; }
       std::vector<uint32_t> candOff ((size_t) NR + 1, 0) ;
       for (int r = 0 ; r < NR ; ++r) candOff[r + 1] = candOff[r] + (uint32_t) (recvCnt[r] ? (recvCnt[r] - 1) / S : 0) ;
       const uint32_t nCand = candOff[NR], nTiles = nCand / (uint32_t) NR + 1 ;
-      DBuf<uint32_t> dCandOff ((size_t) NR + 1, s, mt), bnd (((size_t) nTiles + 1) * NR, s, mt), tileBins ((size_t) nTiles + 1, s, mt) ;
-      DBuf<uint64_t> cand (nCand, s, mt), candS (nCand, s, mt) ; DBuf<unsigned int> ovf (1, s, mt) ;
+      DBuf<uint32_t> dCandOff ((size_t) NR + 1, s, mt), bnd (((size_t) nTiles + 1) * NR, s, mt) ;
+      DBuf<unsigned long long> tileState (nTiles, s, mt) ;
+      DBuf<uint64_t> cand (nCand, s, mt), candS (nCand, s, mt) ; DBuf<unsigned int> ovf (2, s, mt) ;
+      /* the number of bins is only known afterwards: sized for the worst case (every received copy its own bin) */
+      gHash.alloc (Ro, s, mt) ; gDepth.alloc (Ro, s, mt) ; gFirst.alloc (Ro, s, mt) ; segOf.alloc (Ro, s, mt) ;
       MergeArgs ma ; memset (&ma, 0, sizeof (ma)) ;
       ma.rHash = rHash.p ; ma.rDepth = rDepth.p ; ma.rFirst = rFirst.p ;
       for (int r = 0 ; r <= NR ; ++r) ma.recvOff[r] = recvOff[r] ;
-      ma.bnd = bnd.p ; ma.tileBins = tileBins.p ; ma.newCnt = newCnt.p ; ma.overflow = ovf.p ; ma.nTiles = nTiles ; ma.nranks = NR ;
+      ma.bnd = bnd.p ; ma.tileState = tileState.p ; ma.newCnt = newCnt.p ; ma.overflow = ovf.p ; ma.ticket = ovf.p + 1 ;
+      ma.nTiles = nTiles ; ma.nranks = NR ;
+      ma.gHash = gHash.p ; ma.gDepth = gDepth.p ; ma.gFirst = gFirst.p ; ma.segOf = segOf.p ;
       CK (cudaMemcpyAsync (dCandOff.p, candOff.data (), 4 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
-      CK (cudaMemsetAsync (ovf.p, 0, 4, s)) ;
-      CK (cudaMemsetAsync (tileBins.p + nTiles, 0, 4, s)) ;
+      CK (cudaMemsetAsync (ovf.p, 0, 8, s)) ;
+      CK (cudaMemsetAsync (tileState.p, 0, 8 * (size_t) nTiles, s)) ;
       if (nCand)
 	{ const uint32_t gx = (uint32_t) std::min<uint64_t> (gridFor (nCand / NR + 1, 256), 1024) ;
 	  k_merge_candidates<<<dim3 (gx, (unsigned) NR), 256, 0, s>>> (ma, S, dCandOff.p, cand.p) ; ++c->launches ;
@@ -1975,21 +1981,20 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	}
       LAUNCH (c, k_merge_bounds, gridFor (((uint64_t) nTiles + 1) * NR, 256), 256, 0, s, ma, candS.p, nCand, bnd.p) ;
       const int nSM = device_sms (c) ;
-      CK (cudaFuncSetAttribute (k_owner_merge_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_merge_smem (false))) ;
-      CK (cudaFuncSetAttribute (k_owner_merge_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_merge_smem (true))) ;
-      LAUNCH (c, k_owner_merge_tiles<false>, std::min<uint32_t> (nTiles, (uint32_t) nSM * 5), H10X_MERGE_THREADS, h10x_merge_smem (false), s, ma) ;
-      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, tileBins.p, tileBins.p, (size_t) nTiles + 1, s) ; }) ;
-      unsigned int over = 0 ;
-      CK (cudaMemcpyAsync (&Do, tileBins.p + nTiles, 4, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaFuncSetAttribute (k_owner_merge_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h10x_merge_smem ())) ;
+      int occ = 1 ;
+      CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_owner_merge_tiles, H10X_MERGE_THREADS, h10x_merge_smem ())) ;
+      /* every CTA of the grid must be resident: a waiting tile's predecessor is then always running or done */
+      LAUNCH (c, k_owner_merge_tiles, std::min<uint32_t> (nTiles, (uint32_t) (nSM * std::max (occ, 1))), H10X_MERGE_THREADS, h10x_merge_smem (), s, ma) ;
+      unsigned int over = 0 ; unsigned long long last = 0 ;
+      CK (cudaMemcpyAsync (&last, tileState.p + (nTiles - 1), 8, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaMemcpyAsync (&over, ovf.p, 4, cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;
-      if (!over)
-	{ gHash.alloc (Do, s, mt) ; gDepth.alloc (Do, s, mt) ; gFirst.alloc (Do, s, mt) ; segOf.alloc (Ro, s, mt) ;
-	  ma.gHash = gHash.p ; ma.gDepth = gDepth.p ; ma.gFirst = gFirst.p ; ma.segOf = segOf.p ;
-	  LAUNCH (c, k_owner_merge_tiles<true>, std::min<uint32_t> (nTiles, (uint32_t) nSM * 3), H10X_MERGE_THREADS, h10x_merge_smem (true), s, ma) ;
-	  merged = true ;
+      if (!over) { Do = (uint32_t) (last & 0x3fffffffffffffffull) ; merged = true ; }
+      else
+	{ Do = 0 ; gHash.release () ; gDepth.release () ; gFirst.release () ; segOf.release () ;
+	  CK (cudaMemsetAsync (newCnt.p, 0, 4 * (size_t) nB2, s)) ;	/* the tiles before the overflow have counted already */
 	}
-      else Do = 0 ;
     }
   if (Ro && !merged)
     { oi.alloc (Ro, s, mt) ; oSegIncl.alloc (Ro, s, mt) ;
