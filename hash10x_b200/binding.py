@@ -36,7 +36,7 @@ class CIndex(C.Structure):
                 ("blkNRead", C.c_void_p), ("blkNHash", C.c_void_p), ("blkOff", C.c_void_p),
                 ("clusHash", C.c_void_p), ("codeOff", C.c_void_p), ("codes", C.c_void_p),
                 ("onDevice", C.c_int32), ("pinned", C.c_int32),
-                ("blkNSubCluster", C.c_void_p), ("blkPointToMin", C.c_void_p)]
+                ("blkNSubCluster", C.c_void_p), ("blkPointToMin", C.c_void_p), ("blkClusterParent", C.c_void_p)]
 
 
 class CStats(C.Structure):
@@ -125,6 +125,7 @@ def load_library():
     L.h10x_gpu_depth_range.argtypes = [vp, C.c_int, C.c_int, C.POINTER(CGood), cp, sz]
     L.h10x_gpu_load_index.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(CClusters), cp, sz]
+    L.h10x_gpu_cluster_split.argtypes = [vp, C.POINTER(CIndex), C.POINTER(C.c_uint32), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -166,6 +167,7 @@ class Index:
         self.codes = _arr(ci.codes, H, np.uint32) if ci.codes else None
         self.blkNSub = _arr(ci.blkNSubCluster, nb, np.uint32) if ci.blkNSubCluster else None
         self.blkPointToMin = _arr(ci.blkPointToMin, nb, np.float64) if ci.blkPointToMin else None
+        self.blkParent = _arr(ci.blkClusterParent, nb, np.uint32) if ci.blkClusterParent else None
         self.status = 0
 
 
@@ -366,13 +368,24 @@ class Hash10xGPU:
         ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
                     tab.ctypes.data if tab is not None else None, keep[0].ctypes.data, keep[1].ctypes.data,
                     keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data, keep[5].ctypes.data,
-                    keep[6].ctypes.data, keep[7].ctypes.data, 0, 0, None, None)
+                    keep[6].ctypes.data, keep[7].ctypes.data, 0, 0, None, None, None)
         nsub, ptm = getattr(ix, "blkNSub", None), getattr(ix, "blkPointToMin", None)
         if nsub is not None and ptm is not None:
             keep += [np.ascontiguousarray(nsub, np.uint32), np.ascontiguousarray(ptm, np.float64)]
             ci.blkNSubCluster, ci.blkPointToMin = keep[-2].ctypes.data, keep[-1].ctypes.data
+        if getattr(ix, "blkParent", None) is not None:
+            keep.append(np.ascontiguousarray(ix.blkParent, np.uint32))
+            ci.blkClusterParent = keep[-1].ctypes.data
         err = C.create_string_buffer(512)
         self._check(self.lib.h10x_gpu_load_index(self.ctx, C.byref(ci), err, len(err)), err)
+
+    def cluster_split(self):
+        """--clusterSplit (clusterSplitCodes, hash10x.c:956-1013) on the resident index -> (Index with blkParent, blocks added)"""
+        ci = CIndex()
+        n_new = C.c_uint32(0)
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_cluster_split(self.ctx, C.byref(ci), C.byref(n_new), err, len(err)), err)
+        return Index(ci, self.lib), int(n_new.value)
 
     def cluster(self, code_min=0, code_max=0, threshold=5, copy=True):
         """--cluster codeMin codeMax (-ct threshold) on the resident index and goodHashes ->
@@ -422,11 +435,14 @@ def write_hash(index_arrays, path):
                                               ix.blkNHash, ix.blkOff, ix.clus)]
     ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
                 keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
-                keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0, None, None)
+                keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0, None, None, None)
     nsub, ptm = getattr(ix, "blkNSub", None), getattr(ix, "blkPointToMin", None)
     if nsub is not None and ptm is not None:
         keep += [np.ascontiguousarray(nsub, np.uint32), np.ascontiguousarray(ptm, np.float64)]
         ci.blkNSubCluster, ci.blkPointToMin = keep[-2].ctypes.data, keep[-1].ctypes.data
+    if getattr(ix, "blkParent", None) is not None:
+        keep.append(np.ascontiguousarray(ix.blkParent, np.uint32))
+        ci.blkClusterParent = keep[-1].ctypes.data
     st = L.h10x_write_hash(C.byref(ci), path.encode())
     if st:
         raise H10xError(st, "write fail")

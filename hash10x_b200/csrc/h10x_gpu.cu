@@ -75,6 +75,7 @@ struct MemTrack {
 	}
     throw SlabFull { cur + bytes } ;
   }
+  size_t largestFree () const { size_t m = 0 ; for (auto &f : freeList) m = std::max (m, f.second) ; return m ; }
   void give (void *p, size_t bytes)
   { bytes = (bytes + 511) & ~(size_t) 511 ;
     size_t off = (size_t) ((char*) p - base) ;
@@ -141,8 +142,8 @@ struct h10x_ctx {
   /* goodHashes of the last --hashDepthRange (hash10x.c:722-766), resident for --cluster; ClusterBlock.nSubCluster /
      .pointToMin (hash10x.c:62-70) once a --cluster command ran */
   DBuf<uint64_t> goodOffD ; DBuf<uint16_t> goodD ; bool haveGood = false ;
-  DBuf<uint32_t> blkNSub ; DBuf<double> blkPtm ;
-  void *clusSlot[2] = { nullptr, nullptr } ; size_t clusCap[2] = { 0, 0 } ;	/* pinned host: nSubCluster, pointToMin */
+  DBuf<uint32_t> blkNSub, blkParent ; DBuf<double> blkPtm ;
+  void *clusSlot[3] = { nullptr, nullptr, nullptr } ; size_t clusCap[3] = { 0, 0, 0 } ;	/* pinned host: nSubCluster, pointToMin, clusterParent */
   void *goodSlot[3] = { nullptr, nullptr, nullptr } ; size_t goodCap[3] = { 0, 0, 0 } ;	/* pinned host: within, goodOff, good */
   struct DistState *dist = nullptr ;
   DBuf<uint32_t> localBinId, localCodeOff, localCodes ;	/* this rank's part of the hash->code lists */
@@ -206,6 +207,7 @@ struct CastU64 { __host__ __device__ uint64_t operator() (uint32_t x) const { re
 #include "h10x_dist.cuh"
 #include "h10x_fq2b.cuh"
 #include "h10x_crib.cuh"
+#include "h10x_split.cuh"
 
 /* ------------------------------------------------------------------ kernels: runs */
 
@@ -559,7 +561,7 @@ static int simulate_chunks (const std::vector<uint32_t> &runStart, const std::ve
 static void reset_result (h10x_ctx *c)
 { c->hashIndex.release () ; c->hashDepth.release () ; c->blkNRead.release () ; c->blkNHash.release () ;
   c->localBinId.release () ; c->localCodeOff.release () ; c->localCodes.release () ; c->within.release () ;
-  c->goodOffD.release () ; c->goodD.release () ; c->haveGood = false ; c->blkNSub.release () ; c->blkPtm.release () ;
+  c->goodOffD.release () ; c->goodD.release () ; c->haveGood = false ; c->blkNSub.release () ; c->blkPtm.release () ; c->blkParent.release () ;
   c->codes.release () ; c->hashValue.release () ; c->blkOff.release () ; c->codeOff.release () ; c->clus.release () ;
   c->hashNumber = 1 ; c->nBlocksMax = 2 ; c->nReads = 0 ; c->nHashes = 0 ; c->haveIndex = false ;
   c->spans.clear () ; c->evUsed = 0 ; c->launches = 0 ; c->mt.peak = c->mt.cur ;
@@ -2270,7 +2272,7 @@ void h10x_gpu_destroy (h10x_ctx *c)
   for (auto e : c->evPool) cudaEventDestroy (e) ;
   for (int i = 0 ; i < 9 ; ++i) if (c->hostSlot[i]) cudaFreeHost (c->hostSlot[i]) ;
   for (int i = 0 ; i < 3 ; ++i) if (c->goodSlot[i]) cudaFreeHost (c->goodSlot[i]) ;
-  for (int i = 0 ; i < 2 ; ++i) if (c->clusSlot[i]) cudaFreeHost (c->clusSlot[i]) ;
+  for (int i = 0 ; i < 3 ; ++i) if (c->clusSlot[i]) cudaFreeHost (c->clusSlot[i]) ;
   if (c->own) { cudaStreamSynchronize (c->own) ; cudaStreamDestroy (c->own) ; }
   delete c ;
 }
@@ -2309,8 +2311,8 @@ void h10x_index_free (h10x_index *ix)
   void *ps[] = { ix->hashIndex, ix->hashValue, ix->hashDepth, ix->blkNRead, ix->blkNHash, ix->blkOff,
 		 ix->clusHash, ix->codeOff, ix->codes } ;
   for (void *p : ps) if (p) { if (ix->pinned) cudaFreeHost (p) ; else free (p) ; }
-  if (!ix->pinned) { free (ix->blkNSubCluster) ; free (ix->blkPointToMin) ; }	/* h10x_read_hash's; otherwise borrowed */
-  ix->blkNSubCluster = nullptr ; ix->blkPointToMin = nullptr ;
+  if (!ix->pinned) { free (ix->blkNSubCluster) ; free (ix->blkPointToMin) ; free (ix->blkClusterParent) ; }	/* h10x_read_hash's; otherwise borrowed */
+  ix->blkNSubCluster = nullptr ; ix->blkPointToMin = nullptr ; ix->blkClusterParent = nullptr ;
   ix->hashIndex = nullptr ; ix->hashValue = nullptr ; ix->hashDepth = nullptr ; ix->blkNRead = nullptr ;
   ix->blkNHash = nullptr ; ix->blkOff = nullptr ; ix->clusHash = nullptr ; ix->codeOff = nullptr ; ix->codes = nullptr ;
 }
@@ -2752,6 +2754,7 @@ int h10x_gpu_load_index (h10x_ctx *c, const h10x_index *h, char *err, size_t err
 	  if (h->codeOff && h->codes) { up (c->codeOff, h->codeOff, hn + 1, 8) ; up (c->codes, h->codes, H, 4) ; }
 	  if (h->blkNSubCluster && h->blkPointToMin)	/* what an earlier --cluster left in the file */
 	    { up (c->blkNSub, h->blkNSubCluster, nb, 4) ; up (c->blkPtm, h->blkPointToMin, nb, 8) ; }
+	  if (h->blkClusterParent) up (c->blkParent, h->blkClusterParent, nb, 4) ;
 	  c->hashNumber = (uint32_t) hn ; c->nBlocksMax = (uint32_t) nb ; c->nReads = h->nReads ; c->nHashes = H ;
 	  CK (cudaStreamSynchronize (s)) ;
 	  c->haveIndex = true ;
@@ -2866,7 +2869,7 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
   if (!codeMax) codeMax = (int) c->nBlocksMax ;
   if (codeMin < 1 || codeMax > (int) c->nBlocksMax)
     { set_err (err, errlen, "code range outside the barcode blocks") ; return H10X_ERR_BAD_PARAM ; }
-  void *scratch = nullptr ;
+  void *scratch = nullptr, *slabWork = nullptr ; size_t slabWorkBytes = 0 ;
   int st = guarded (err, errlen, [&] ()
     { CK (cudaSetDevice (c->P.device)) ;
       cudaStream_t s = c->own ;
@@ -2893,16 +2896,21 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
 	     global-memory versions of the per-step arrays and read labels for blocks that do not fit in shared memory */
 	  const size_t perCta = (size_t) cap * 8 + (size_t) H10X_SC_WARPS * 65536 * 4 + (size_t) 2 * 65536 * 4 + (size_t) 6 * 65536 * 4
 	    + (size_t) 65536 * (2 + 4 + 2 + 1) + (size_t) 65536 * 4 ;
+	  /* the workspace comes out of the context's slab when the build's temporaries have left room there (no driver
+	     call, and the slab may hold nearly all of the device's memory); a driver allocation otherwise */
 	  size_t freeB = 0, totalB = 0 ;
 	  CK (cudaMemGetInfo (&freeB, &totalB)) ;
-	  size_t budget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
-	  uint32_t grid = (uint32_t) std::min<size_t> ((size_t) nSM * occ, (size_t) (codeMax - codeMin)) ;
-	  grid = (uint32_t) std::min<size_t> (grid, budget / perCta) ;
+	  const size_t devBudget = freeB - std::min<size_t> (freeB / 8, (size_t) 1 << 30) ;
+	  const size_t slabBudget = c->mt.largestFree () > 1024 ? c->mt.largestFree () - 1024 : 0 ;
+	  const uint32_t want = (uint32_t) std::min<size_t> ((size_t) nSM * occ, (size_t) (codeMax - codeMin)) ;
+	  const bool fromSlab = slabBudget >= perCta * want + 256 || slabBudget >= devBudget ;
+	  uint32_t grid = (uint32_t) std::min<size_t> (want, (fromSlab ? slabBudget - 256 : devBudget) / perCta) ;
 	  if (grid < 1) throw H10xError (H10X_ERR_NOMEM, "not enough device memory for the cluster workspace") ;
 	  const size_t bytes = perCta * grid + 256 ;
-	  CK (cudaMalloc (&scratch, bytes)) ;
-	  CK (cudaMemsetAsync (scratch, 0, bytes, s)) ;
-	  char *p = (char*) scratch ;
+	  if (fromSlab) { slabWork = c->mt.take (bytes) ; slabWorkBytes = bytes ; }
+	  else CK (cudaMalloc (&scratch, bytes)) ;
+	  char *p = (char*) (fromSlab ? slabWork : scratch) ;
+	  CK (cudaMemsetAsync (p, 0, bytes, s)) ;
 	  SubClusterArgs a ;
 	  a.work = (unsigned int*) p ; p += 256 ;
 	  a.table = (unsigned long long*) p ; p += (size_t) cap * 8 * grid ;
@@ -2943,8 +2951,130 @@ int h10x_gpu_cluster (h10x_ctx *c, int codeMin, int codeMax, int clusterThreshol
       if (codeMax > codeMin) { float ms = 0 ; CK (cudaEventElapsedTime (&ms, evA, evB)) ; out->msKernel = ms ; }
     }) ;
   if (scratch) { cudaStreamSynchronize (c->own) ; cudaFree (scratch) ; }
+  if (slabWork) c->mt.give (slabWork, slabWorkBytes) ;		/* same stream as whatever takes it next */
   if (st != H10X_OK) { cudaGetLastError () ; memset (out, 0, sizeof (*out)) ; }
   return st ;
+}
+
+/* --clusterSplit: see include/h10x_gpu.h and h10x_split.cuh */
+int h10x_gpu_cluster_split (h10x_ctx *c, h10x_index *out, uint32_t *nNew, char *err, size_t errlen)
+{ if (!c || !out || !nNew) { set_err (err, errlen, "bad argument") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->haveIndex || c->dist) { set_err (err, errlen, "no single-GPU index resident") ; return H10X_ERR_BAD_PARAM ; }
+  if (!c->codes.p || !c->codeOff.p) { set_err (err, errlen, "the context was created without the hash->code lists") ; return H10X_ERR_BAD_PARAM ; }
+  *nNew = 0 ;
+  void *scratch = nullptr ; MemTrack scratchMt ;
+  int st = guarded (err, errlen, [&] ()
+    { CK (cudaSetDevice (c->P.device)) ;
+      cudaStream_t s = c->own ;
+      MemTrack *mt = &c->mt ;
+      const uint32_t nbOld = c->nBlocksMax ;
+      const uint64_t H = c->nHashes ;
+      /* new block numbers of every block's first cluster (hash10x.c:963-964,993) */
+      std::vector<uint32_t> nSub (nbOld, 0), nReadOld (nbOld, 0), base (nbOld, 0) ;
+      std::vector<double> ptmOld (nbOld, 0.0) ;
+      if (c->blkNSub.p)
+	{ CK (cudaMemcpyAsync (nSub.data (), c->blkNSub.p, 4 * (size_t) nbOld, cudaMemcpyDeviceToHost, s)) ;
+	  CK (cudaMemcpyAsync (ptmOld.data (), c->blkPtm.p, 8 * (size_t) nbOld, cudaMemcpyDeviceToHost, s)) ;
+	}
+      CK (cudaMemcpyAsync (nReadOld.data (), c->blkNRead.p, 4 * (size_t) nbOld, cudaMemcpyDeviceToHost, s)) ;
+      CK (cudaStreamSynchronize (s)) ;
+      uint64_t add = 0 ;
+      for (uint32_t i = 0 ; i < nbOld ; ++i) { base[i] = (uint32_t) (nbOld + add) ; add += nSub[i] ; }
+      if ((uint64_t) nbOld + add >= 0xffffffffull) throw H10xError (H10X_ERR_UNSUPPORTED, "more than 2^32-2 barcode blocks after the split") ;
+      const uint32_t nbNew = (uint32_t) (nbOld + add) ;
+      std::vector<uint32_t> parent (nbNew, 0), nReadNew (nbNew, 0) ;
+      std::vector<double> ptmNew (nbNew, 0.0) ;
+      for (uint32_t i = 0 ; i < nbOld ; ++i)
+	{ nReadNew[i] = nReadOld[i] ;				/* :991 for a split block, :998 otherwise */
+	  if (!nSub[i]) ptmNew[i] = ptmOld[i] ;			/* a split block starts from a zeroed ClusterBlock */
+	  for (uint32_t j = 0 ; j < nSub[i] ; ++j) parent[base[i] + j] = i + 1 ;	/* :976 */
+	}
+      /* everything that stays is allocated first and swapped in at the end: a full slab leaves the old index intact */
+      DBuf<uint32_t> dNSub (nbOld, s, mt), dBase (nbOld, s, mt), newNHash ((size_t) nbNew + 1, s, mt), newNRead (nbNew, s, mt) ;
+      DBuf<uint32_t> newParent (nbNew, s, mt), newNSub (nbNew, s, mt) ; DBuf<double> newPtm (nbNew, s, mt) ;
+      DBuf<uint64_t> newOff ((size_t) nbNew + 1, s, mt) ;
+      DBuf<uint64_t> newClus (H, s, mt) ;
+      DBuf<unsigned int> ticket (1, s, mt) ;
+      uint32_t maxRead = 1 ;
+      for (uint32_t i = 0 ; i < nbOld ; ++i) maxRead = std::max (maxRead, nReadOld[i]) ;
+      const uint32_t tblSize = std::min<uint32_t> (65536u, maxRead) ;
+      const int nSM = device_sms (c) ;
+      int occ = 1 ;
+      CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, k_split<true>, H10X_SPLIT_WARPS * 32, 0)) ;
+      const uint32_t grid = (uint32_t) std::min<uint64_t> ((uint64_t) nSM * std::max (occ, 1), ((uint64_t) nbOld + H10X_SPLIT_WARPS - 1) / H10X_SPLIT_WARPS) ;
+      /* the temporaries (per-warp read tables, the (bin, block) words of the transposition) come from the slab when it has
+	 room, from one driver allocation otherwise (a context sized for a small build) */
+      const size_t nTbl = (size_t) grid * H10X_SPLIT_WARPS * tblSize ;
+      MemTrack *tm = mt ;
+      if (mt->largestFree () < 8 * nTbl + 16 * (size_t) H + (1u << 20) + (mt->cap - mt->cur) / 4)
+	{ const size_t bytes = 8 * nTbl + 16 * (size_t) H + (4u << 20) ;
+	  CK (cudaMalloc (&scratch, bytes)) ;
+	  scratchMt.base = (char*) scratch ; scratchMt.cap = bytes ; scratchMt.reset () ;
+	  tm = &scratchMt ;
+	}
+      DBuf<uint32_t> first (nTbl, s, tm), number (nTbl, s, tm) ;
+      DBuf<uint64_t> idBlock (H, s, tm), idBlock2 (H, s, tm) ;
+      CK (cudaMemcpyAsync (dNSub.p, nSub.data (), 4 * (size_t) nbOld, cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemcpyAsync (dBase.p, base.data (), 4 * (size_t) nbOld, cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemcpyAsync (newNRead.p, nReadNew.data (), 4 * (size_t) nbNew, cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemcpyAsync (newParent.p, parent.data (), 4 * (size_t) nbNew, cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemcpyAsync (newPtm.p, ptmNew.data (), 8 * (size_t) nbNew, cudaMemcpyHostToDevice, s)) ;
+      CK (cudaMemsetAsync (newNHash.p, 0, 4 * ((size_t) nbNew + 1), s)) ;
+      CK (cudaMemsetAsync (newNSub.p, 0, 4 * (size_t) nbNew, s)) ;
+      SplitArgs a ; memset (&a, 0, sizeof (a)) ;
+      a.clus = (const unsigned long long*) c->clus.p ; a.blkOff = c->blkOff.p ; a.blkNHash = c->blkNHash.p ; a.nSub = dNSub.p ;
+      a.clusterBase = dBase.p ; a.nBlocksOld = nbOld ; a.first = first.p ; a.number = number.p ; a.tblSize = tblSize ;
+      a.newNHash = newNHash.p ; a.newNRead = newNRead.p ; a.newOff = newOff.p ; a.newClus = (unsigned long long*) newClus.p ;
+      a.idBlock = idBlock.p ; a.ticket = ticket.p ;
+      CK (cudaMemsetAsync (ticket.p, 0, 4, s)) ;
+      LAUNCH (c, k_split<false>, grid, H10X_SPLIT_WARPS * 32, 0, s, a) ;
+      cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> nh64 (newNHash.p, CastU64 ()) ;
+      cubCall (c, s, [&] (void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum (t, b, nh64, newOff.p, (size_t) nbNew + 1, s) ; }) ;
+      CK (cudaMemsetAsync (ticket.p, 0, 4, s)) ;
+      LAUNCH (c, k_split<true>, grid, H10X_SPLIT_WARPS * 32, 0, s, a) ;
+      /* fillHashTable again (:1012): stable passes on the bin id turn the block-major (bin, new block) words bin-major,
+	 new blocks ascending inside a bin; hashDepth and therefore codeOff do not change */
+      if (H)
+	{ const int idBits = bits_for (c->hashNumber) ;
+	  const int nP = (idBits + 9) / 10 ;
+	  uint64_t *src = idBlock.p, *dst = idBlock2.p ;
+	  for (int i = 0, left = idBits, shift = 32 ; i < nP ; ++i)
+	    { const int bits = (left + (nP - i) - 1) / (nP - i) ;
+	      LoadWord lw = { src, shift, (1u << bits) - 1u, ~(uint64_t) 0 } ;
+	      part_pass (c, s, lw, H, 1u << bits, dst) ;
+	      shift += bits ; left -= bits ; std::swap (src, dst) ;
+	    }
+	  LAUNCH (c, k_split_codes, gridFor (H, 256), 256, 0, s, H, src, c->codes.p) ;
+	}
+      CK (cudaStreamSynchronize (s)) ;
+      /* the new index replaces the old one (the old arrays leave with the locals) */
+      c->clus.swap (newClus) ; c->blkOff.swap (newOff) ; c->blkNHash.swap (newNHash) ; c->blkNRead.swap (newNRead) ;
+      c->blkNSub.swap (newNSub) ; c->blkPtm.swap (newPtm) ; c->blkParent.swap (newParent) ;
+      c->goodOffD.release () ; c->goodD.release () ; c->haveGood = false ;
+      c->nBlocksMax = nbNew ;
+      *nNew = (uint32_t) add ;
+    }) ;
+  if (scratch) { cudaStreamSynchronize (c->own) ; cudaFree (scratch) ; }
+  if (st != H10X_OK) return st ;
+  st = h10x_gpu_download (c, out, err, errlen) ;
+  if (st != H10X_OK) return st ;
+  return guarded (err, errlen, [&] ()
+    { /* the ClusterBlock fields beside the block table, in the context's pinned cluster slots */
+      const size_t nb = c->nBlocksMax ;
+      auto pull = [&] (int slot, const void *src, size_t bytes) -> void*
+	{ if (c->clusCap[slot] < bytes || !c->clusSlot[slot])
+	    { if (c->clusSlot[slot]) cudaFreeHost (c->clusSlot[slot]) ;
+	      c->clusSlot[slot] = nullptr ; c->clusCap[slot] = 0 ;
+	      c->clusSlot[slot] = pinned_alloc (bytes) ; c->clusCap[slot] = bytes ? bytes : 1 ;
+	    }
+	  if (bytes) CK (cudaMemcpyAsync (c->clusSlot[slot], src, bytes, cudaMemcpyDeviceToHost, c->own)) ;
+	  return c->clusSlot[slot] ;
+	} ;
+      out->blkNSubCluster = (uint32_t*) pull (0, c->blkNSub.p, 4 * nb) ;
+      out->blkPointToMin = (double*) pull (1, c->blkPtm.p, 8 * nb) ;
+      out->blkClusterParent = (uint32_t*) pull (2, c->blkParent.p, 4 * nb) ;
+      CK (cudaStreamSynchronize (c->own)) ;
+    }) ;
 }
 
 int h10x_gpu_stats (h10x_ctx *c, h10x_stats *out)

@@ -70,6 +70,7 @@ int h10x_write_hash (const h10x_index *ix, const char *path)
 	{ cb[8*b] = ix->blkNRead[b] ; cb[8*b + 1] = ix->blkNHash[b] ;
 	  if (ix->blkNSubCluster) cb[8*b + 2] = ix->blkNSubCluster[b] ;
 	  if (ix->blkPointToMin) memcpy (&cb[8*b + 6], &ix->blkPointToMin[b], 8) ;
+	  if (ix->blkClusterParent) cb[8*b + 3] = ix->blkClusterParent[b] ;
 	}
       ok = put_array (f, cb, 32, (int) nb, 1200) ;	/* dim0 = 1200: hash10x.c:1151 */
       free (cb) ;
@@ -149,11 +150,13 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   if (fread (cb, 32, a.dim, f) != (size_t) a.dim) { seterr (err, errlen, "failed to read clusterBlocks array") ; goto fail ; }
   { uint32_t nb = out->nBlocksMax, b ;
     out->blkNRead = calloc (nb, 4) ; out->blkNHash = calloc (nb, 4) ; out->blkOff = calloc ((size_t) nb + 1, 8) ;
-    out->blkNSubCluster = calloc (nb, 4) ; out->blkPointToMin = calloc (nb, 8) ;
-    if (!out->blkNRead || !out->blkNHash || !out->blkOff || !out->blkNSubCluster || !out->blkPointToMin) { st = H10X_ERR_NOMEM ; goto fail ; }
+    out->blkNSubCluster = calloc (nb, 4) ; out->blkPointToMin = calloc (nb, 8) ; out->blkClusterParent = calloc (nb, 4) ;
+    if (!out->blkNRead || !out->blkNHash || !out->blkOff || !out->blkNSubCluster || !out->blkPointToMin || !out->blkClusterParent)
+      { st = H10X_ERR_NOMEM ; goto fail ; }
     for (b = 0 ; b < nb ; ++b)
       { out->blkNRead[b] = cb[8*b] ; out->blkNHash[b] = b ? cb[8*b + 1] : 0 ;
 	out->blkNSubCluster[b] = cb[8*b + 2] ; memcpy (&out->blkPointToMin[b], &cb[8*b + 6], 8) ;
+	out->blkClusterParent[b] = cb[8*b + 3] ;
 	out->blkOff[b] = out->nHashes ;
 	if (b) { out->nReads += out->blkNRead[b] ; out->nHashes += out->blkNHash[b] ; }
       }
@@ -184,7 +187,7 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   free (cb) ;
   fclose (f) ;
   free (out->hashIndex) ; free (out->hashValue) ; free (out->hashDepth) ; free (out->blkNRead) ;
-  free (out->blkNHash) ; free (out->blkOff) ; free (out->clusHash) ; free (out->blkNSubCluster) ; free (out->blkPointToMin) ;
+  free (out->blkNHash) ; free (out->blkOff) ; free (out->clusHash) ; free (out->blkNSubCluster) ; free (out->blkPointToMin) ; free (out->blkClusterParent) ;
   memset (out, 0, sizeof (*out)) ;
   return st ;
 }

@@ -80,6 +80,7 @@ static void usage (void)
   fprintf (stderr, "   --hashDepthRange <min> <max>: set limits for hash counts\n") ;
   fprintf (stderr, "   -ct | --clusterThreshold <clusterThreshold> [%d]\n", params.clusterThreshold) ;
   fprintf (stderr, "   --cluster <codeMin> <codeMax> : cluster this range of barcodes; 0 for codeMax means to end (runs on the GPU)\n") ;
+  fprintf (stderr, "   --clusterSplit : every sub-cluster becomes a barcode block of its own (runs on the GPU)\n") ;
   fprintf (stderr, "   --hashStats : distribution of hash counts and summary info\n") ;
   fprintf (stderr, "   --codeStats : distribution of barcode/cluster sizes and summary info\n") ;
   fprintf (stderr, "   --gpuStats : per-stage device times and roofline bytes of the last --readFQB\n") ;
@@ -324,6 +325,27 @@ static void clusterCodes (int codeMin, int codeMax)
   if (outFile != stdout) printf ("  clustered codes %d to %d\n", codeMin, codeMax) ;
 }
 
+/* ---- --clusterSplit: clusterSplitCodes hash10x.c:956-1013, on the GPU (h10x_gpu_cluster_split) ---- */
+static void clusterSplit (void)
+{ if (!haveIndex) die ("no index to split") ;
+  if (multi || !(ctx && indexFromGpu))
+    die ("--clusterSplit runs on the index resident on one GPU (--readFQB, or --readHash with a GPU present)") ;
+  char err[512] ; h10x_index nx ; uint32_t nNew = 0 ;
+  const int nOld = (int) ix.nBlocksMax ;
+  int st = h10x_gpu_cluster_split (ctx, &nx, &nNew, err, sizeof (err)) ;
+  if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
+  if (ix.pinned == 0) h10x_index_free (&ix) ;		/* an index h10x_read_hash malloc'ed */
+  ix = nx ;
+  /* the reference keeps its goodHashes arrays, indexed by the OLD block numbers (a later --cluster without a new
+     --hashDepthRange walks stale lists there); here they are dropped, hashWithinRange stays (flags only accumulate) */
+  free (goodHashes) ; goodHashes = 0 ; free (nGoodHashes) ; nGoodHashes = 0 ;
+  fprintf (outFile, "  made %d additional new barcodes from clusters in %d original barcodes\n", (int) nNew, nOld) ;
+  if (outFile != stdout) printf ("  made %d additional new barcodes from clusters in %d original barcodes\n", (int) nNew, nOld) ;
+  printf ("  cluster timepoint: ") ; timeUpdate (stdout) ;
+  fprintf (outFile, "  filled hash table: %ld hashes from %d barcodes in %d bins\n",
+	   (long) ix.nHashes, (int) ix.nBlocksMax, (int) ix.hashNumber) ;
+}
+
 /* ---- --cribBuild genome1.fa genome2.fa: cribBuild hash10x.c:426-510, on the GPU (h10x_gpu_crib_build) ---- */
 
 /* readSequence (readseq.c:63-157) as cribAddGenome calls it (dna2indexConv with N -> 0, no id, hash10x.c:433-434),
@@ -463,6 +485,7 @@ int main (int argc, char *argv[])
       else if (ARGMATCH ("--hashDepthRange", 3)) hashDepthRange (atoi (argv[-2]), atoi (argv[-1])) ;
       else if (ARGMATCH ("-ct", 2) || ARGMATCH ("--clusterThreshold", 2)) params.clusterThreshold = atoi (argv[-1]) ;
       else if (ARGMATCH ("--cluster", 3)) clusterCodes (atoi (argv[-2]), atoi (argv[-1])) ;
+      else if (ARGMATCH ("--clusterSplit", 1)) clusterSplit () ;
       else if (ARGMATCH ("--cribBuild", 3))
 	{ FILE *f1, *f2 ;
 	  if (!(f1 = fopen (argv[-2], "r"))) die ("failed to open .fa file %s", argv[-2]) ;
@@ -474,7 +497,7 @@ int main (int argc, char *argv[])
       else if (ARGMATCH ("--gpuStats", 1)) gpuStats () ;
       else if (ARGMATCH ("--help", 1)) usage () ;
       else if (ARGMATCH ("--quit", 1) || ARGMATCH ("--exit", 1)) break ;
-      else if (!strcmp (*argv, "--clusterReport") || !strcmp (*argv, "--clusterSplit")
+      else if (!strcmp (*argv, "--clusterReport")
 	       || !strcmp (*argv, "--cribSummary") || !strcmp (*argv, "--hashInfo")
 	       || !strcmp (*argv, "--hashExplore") || !strcmp (*argv, "--doubleShared") || !strcmp (*argv, "--codeExplore")
 	       || !strcmp (*argv, "--errorFix") || !strcmp (*argv, "--shareScan") || !strcmp (*argv, "--interactive"))

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define H10X_ABI_VERSION 2
+#define H10X_ABI_VERSION 3
 
 /* return codes; the host turns 1 and 2 into the reference's die() texts
    ("hashTableSize is too small" hash10x.c:149, "chunkSize too small" hash10x.c:206) */
@@ -97,6 +97,8 @@ typedef struct h10x_index {
      them only then (pinned == 0); after h10x_gpu_cluster the host points them at h10x_clusters' arrays. */
   uint32_t *blkNSubCluster ;
   double *blkPointToMin ;
+  uint32_t *blkClusterParent ;	/* ClusterBlock.clusterParent (hash10x.c:66), nBlocksMax; NULL = all zero (no --clusterSplit yet);
+				   ownership as the two arrays above */
 } h10x_index ;
 
 /* per-build measurements for the roofline report */
@@ -256,6 +258,17 @@ typedef struct h10x_clusters {
 } h10x_clusters ;
 int h10x_gpu_cluster (h10x_ctx *ctx, int codeMin, int codeMax, int clusterThreshold, h10x_clusters *out,
 		      char *err, size_t errlen) ;
+
+/* `--clusterSplit` (clusterSplitCodes, hash10x.c:956-1013) on the resident single-GPU index after h10x_gpu_cluster: every
+   sub-cluster j of block i becomes a barcode block of its own behind the original ones (the clusters of block i at
+   nBlocksMax + sum of nSubCluster of the blocks before i, in label order) holding the entries with that label in list
+   order, subCluster bytes wiped, reads renumbered in order of first appearance, clusterParent = i + 1; the parent keeps
+   its unclustered entries and its nRead; blocks without sub-clusters are carried over whole.  The hash->code lists are
+   rebuilt over the new blocks (fillHashTable, :1012).  The resident index is replaced and comes back in *out like
+   h10x_gpu_download's (pinned arena of the context; blkNSubCluster is all zero afterwards, blkPointToMin survives only
+   for the blocks that were not split, as in the reference).  *nNew = the number of blocks added.  The good-hash lists are
+   dropped: the reference leaves its own indexed by the old block numbers; run h10x_gpu_depth_range again. */
+int h10x_gpu_cluster_split (h10x_ctx *ctx, h10x_index *out, uint32_t *nNew, char *err, size_t errlen) ;
 
 /* pinned host staging for callers that want the H2D copy to run at full PCIe rate */
 void *h10x_host_alloc (size_t bytes) ;

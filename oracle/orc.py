@@ -310,3 +310,78 @@ def index_digests(ix):
         d["codes"] = digest(ix.codes)
         d["codeOff"] = digest(ix.codeOff)
     return d
+
+
+# ------------------------------------------------------------------ --clusterSplit (hash10x.c:956-1013)
+
+class SplitIndex:
+    """what clusterSplitCodes leaves in clusterBlocks: per-block arrays (nBlocksMax = old + sum of nSubCluster) and the
+    ClusterHash stream (8-byte words: bin id | read << 32, subCluster and flags 0), block after block"""
+    pass
+
+
+def cluster_split(ix, clus, n_sub, point_to_min):
+    """clusterSplitCodes (hash10x.c:956-1013), restated.  TEST INFRASTRUCTURE.  Every sub-cluster j of block i becomes a
+    new block behind the original ones (:963-964: new2 starts at nCodes - 1 and is indexed from 1, so the clusters of
+    block i sit at nCodes + sum of nSubCluster of the blocks before i, in label order) holding the block's entries with
+    that label in list order, subCluster wiped (:981), reads renumbered in order of first appearance (:983-985: ONE
+    readMap per original block, so the number a read gets comes from the counter of the cluster of its FIRST clustered
+    entry); clusterParent = i + 1 (:976).  The parent keeps the unclustered entries and its old nRead (:991) in a fresh,
+    otherwise zero ClusterBlock; blocks without sub-clusters are copied as they are (:998)."""
+    nb = int(ix.nBlocksMax)
+    clus = np.asarray(clus, np.uint64)
+    n_sub = np.asarray(n_sub, np.uint32)
+    off = np.asarray(ix.blkOff, np.uint64).astype(np.int64)
+    nh = np.asarray(ix.blkNHash, np.uint32).astype(np.int64)
+    total_sub = int(n_sub.astype(np.int64).sum())
+    out = SplitIndex()
+    out.nBlocksMax = nb + total_sub
+    out.blkNRead = np.zeros(out.nBlocksMax, np.uint32)
+    out.blkNHash = np.zeros(out.nBlocksMax, np.uint32)
+    out.blkNSub = np.zeros(out.nBlocksMax, np.uint32)
+    out.blkParent = np.zeros(out.nBlocksMax, np.uint32)
+    out.blkPointToMin = np.zeros(out.nBlocksMax, np.float64)
+    lists = [None] * out.nBlocksMax
+    nxt = nb                                             # new2 + 1 in the reference's terms
+    for i in range(nb):
+        e = clus[off[i]:off[i] + nh[i]] if i else clus[0:0]        # block 0 is the dummy
+        ns = int(n_sub[i])
+        if not ns:
+            lists[i] = e.copy()
+            out.blkNRead[i], out.blkNHash[i] = ix.blkNRead[i], nh[i]
+            out.blkPointToMin[i] = point_to_min[i]                  # *new1++ = *old carries every field (:998)
+            continue
+        lab = ((e >> np.uint64(48)) & np.uint64(0xFF)).astype(np.int64)
+        read = ((e >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.int64)
+        base = e & np.uint64(0xFF00FFFFFFFFFFFF)                    # c->subCluster = 0 (:981); the flags byte travels
+        read_map = {}
+        n_read = [0] * (ns + 1)
+        parts = [[] for _ in range(ns + 1)]
+        for j in range(e.size):
+            c = int(lab[j])
+            if c:
+                r = int(read[j])
+                if r not in read_map:
+                    n_read[c] += 1
+                    read_map[r] = n_read[c]
+                w = (int(base[j]) & ~(0xFFFF << 32)) | ((read_map[r] - 1) << 32)
+                parts[c].append(w)
+            else:
+                parts[0].append(int(base[j]))
+        lists[i] = np.array(parts[0], np.uint64)
+        out.blkNRead[i], out.blkNHash[i] = ix.blkNRead[i], len(parts[0])
+        for c in range(1, ns + 1):
+            k = nxt + c - 1
+            lists[k] = np.array(parts[c], np.uint64)
+            out.blkNRead[k], out.blkNHash[k], out.blkParent[k] = n_read[c], len(parts[c]), i + 1
+        nxt += ns
+    out.clus = np.concatenate([x for x in lists if x is not None and x.size] or [np.zeros(0, np.uint64)])
+    out.blkOff = np.zeros(out.nBlocksMax + 1, np.uint64)
+    out.blkOff[1:] = np.cumsum(out.blkNHash.astype(np.uint64))
+    out.nHashes = int(out.clus.size)
+    # fillHashTable (:317-347) over the new blocks: per bin the blocks holding it, ascending
+    ids = (out.clus & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    blk = np.repeat(np.arange(out.nBlocksMax, dtype=np.int64), out.blkNHash.astype(np.int64))
+    order = np.argsort(ids, kind="stable")
+    out.codes = blk[order].astype(np.uint32)
+    return out

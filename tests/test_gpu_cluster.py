@@ -116,6 +116,77 @@ def test_cluster_abandons_a_block_with_more_than_255_clusters(orc, gpu_lib):
     assert 255 in seen and 0 in seen
 
 
+def _split_same(sp_gpu, n_new, want, nsub):
+    assert n_new == int(nsub.sum()) and sp_gpu.nBlocksMax == want.nBlocksMax
+    assert np.array_equal(sp_gpu.blkNRead, want.blkNRead) and np.array_equal(sp_gpu.blkNHash, want.blkNHash)
+    assert np.array_equal(sp_gpu.blkOff, want.blkOff)
+    assert not sp_gpu.blkNSub.any() and np.array_equal(sp_gpu.blkParent, want.blkParent)
+    assert np.array_equal(sp_gpu.blkPointToMin.view(np.uint64), want.blkPointToMin.view(np.uint64))
+    assert np.array_equal(sp_gpu.clus, want.clus)
+
+
+@pytest.mark.parametrize("case", [(31, 200, 40, 160, 60_000, 20_000, 2, 3, 200, 3), (35, 500, 60, 160, 300_000, 15_000, 5, 3, 100, 2),
+                                  (37, 120, 20, 80, 40_000, 8_000, 3, 2, 13, 1)])
+def test_cluster_split_matches_oracle(orc, gpu_lib, case):
+    """--clusterSplit (clusterSplitCodes, hash10x.c:956-1013) on the GPU against the oracle's restatement, which
+    tests/test_oracle.py pins to the reference binary: the new block table, every ClusterHash word with its renumbered
+    read, and the hash->code lists rebuilt over the new blocks; then --hashDepthRange / --cluster go on from the split
+    index like a second clustering round of the reference."""
+    seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr = case
+    recs = _cluster_case(orc, seed, nb, pmin, pmax, genome, mol, mpb)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, dmin, dmax)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, thr)
+    want = orc.cluster_split(ix, clus, nsub, ptm)
+    assert int(nsub.sum()) > 0
+    with _gpu(B=20) as g:
+        g.build_host(recs)
+        g.depth_range(dmin, dmax)
+        g.cluster(0, 0, thr)
+        got, n_new = g.cluster_split()
+        _split_same(got, n_new, want, nsub)
+        coff, codes = g.download_codes()
+        assert np.array_equal(coff, ix.codeOff) and np.array_equal(codes, want.codes)
+        dg = g.digest()
+        assert dg["haveCodes"] and dg["codesMissing"] == 0 and dg["codesUnordered"] == 0
+        import hash10x_b200
+        with pytest.raises(hash10x_b200.H10xError, match="you must set hashDepthRange before cluster"):
+            g.cluster(0, 0, thr)                      # the good lists were indexed by the old blocks: dropped
+        g.depth_range(dmin, dmax)                     # a second round on the split index runs
+        g.cluster(0, 0, thr)
+        again, n2 = g.cluster_split()
+        assert again.nBlocksMax == got.nBlocksMax + n2
+
+
+def test_cli_cluster_split_writes_the_reference_file(orc, gpu_lib, tmp_path):
+    """hash10x-b200 ... --cluster --clusterSplit --writeHash: the block table and ClusterHash stream of the file are the
+    oracle's (= the reference's, tests/test_oracle.py), and the file reads back (--readHash --codeStats)."""
+    import subprocess
+    import hashfile
+    recs = _cluster_case(orc, 34, 300, 100, 250, 200_000, 20_000, 4)
+    fq = tmp_path / "x.fqb"
+    recs.astype(np.uint32).tofile(fq)
+    out = tmp_path / "s.hash"
+    import hash10x_b200
+    exe = os.path.join(os.path.dirname(hash10x_b200.__file__), "bin", "hash10x-b200")
+    r = subprocess.run([exe, "-B", "20", "-ct", "3", "--readFQB", str(fq), "--hashDepthRange", "4", "400", "--cluster", "0", "0",
+                        "--clusterSplit", "--writeHash", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, 4, 400)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 3)
+    want = orc.cluster_split(ix, clus, nsub, ptm)
+    assert "made %d additional new barcodes from clusters in %d original barcodes" % (int(nsub.sum()), ix.nBlocksMax) in r.stdout
+    hf = hashfile.parse(str(out))
+    assert hf.nBlocksMax == want.nBlocksMax
+    assert np.array_equal(hf.blkNRead, want.blkNRead) and np.array_equal(hf.blkNHash, want.blkNHash)
+    assert np.array_equal(hf.blkParent, want.blkParent) and not hf.blkNSub.any()
+    assert np.array_equal(hf.blkPointToMin.view(np.uint64), want.blkPointToMin.view(np.uint64))
+    assert np.array_equal(hf.clusRaw, want.clus)
+    r2 = subprocess.run([exe, "-B", "20", "--readHash", str(out), "--codeStats"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+
+
 def test_cluster_argument_checks(orc, gpu_lib):
     import hash10x_b200
     recs = _cluster_case(orc, 37, 120, 20, 80, 40_000, 8_000, 3)

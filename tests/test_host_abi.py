@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(L, n), n
-    assert L.h10x_abi_version() == 2      # 2: h10x_gpu_cluster, ClusterBlock fields in h10x_index
+    assert L.h10x_abi_version() == 3      # 3: h10x_gpu_cluster_split, clusterParent in h10x_index
 
 
 def test_header_compiles_as_plain_c(tmp_path):

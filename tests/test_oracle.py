@@ -243,6 +243,35 @@ def test_cluster_abandons_a_block_with_more_than_255_clusters_like_the_reference
     assert np.array_equal(ref.clusRaw, clus)
 
 
+@pytest.mark.parametrize("seed,nb,pmin,pmax,genome,mol,mpb,dmin,dmax,thr,cmin,cmax", CLUSTER_CASES[:3] + CLUSTER_CASES[4:])
+def test_cluster_split_equals_reference_binary(orc, tmp_path, seed, nb, pmin, pmax, genome, mol, mpb, dmin, dmax, thr, cmin, cmax):
+    """--clusterSplit (clusterSplitCodes, hash10x.c:956-1013): the reference's --readHash --hashDepthRange --cluster
+    --clusterSplit --writeHash against the oracle's restatement: the whole new block table (nRead, nHash, nSubCluster,
+    clusterParent, pointToMin) and every ClusterHash word, renumbered reads included."""
+    _need_ref(orc)
+    import subprocess
+    recs = _cluster_case(orc, seed, nb, pmin, pmax, genome, mol, mpb)
+    B = 20
+    src, dst = str(tmp_path / "o.hash"), str(tmp_path / "r.hash")
+    assert orc.build_and_write(recs, src, B=B) == 0
+    cmd = [orc.ref_binary(), "-B", str(B), "-ct", str(thr), "--readHash", src, "--hashDepthRange", str(dmin), str(dmax),
+           "--cluster", str(cmin), str(cmax), "--clusterSplit", "--writeHash", dst]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref = hashfile.parse(dst)
+    ix = orc.build(recs, B=B)
+    _within, goff, good = orc.good_hashes(ix, dmin, dmax)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, cmin, cmax, thr)
+    sp = orc.cluster_split(ix, clus, nsub, ptm)
+    assert "made %d additional new barcodes from clusters in %d original barcodes" % (int(nsub.sum()), ix.nBlocksMax) in r.stdout
+    assert ref.nBlocksMax == sp.nBlocksMax == ix.nBlocksMax + int(nsub.sum())
+    assert np.array_equal(ref.blkNRead, sp.blkNRead) and np.array_equal(ref.blkNHash, sp.blkNHash)
+    assert np.array_equal(ref.blkNSub, sp.blkNSub) and np.array_equal(ref.blkParent, sp.blkParent)
+    assert np.array_equal(ref.blkPointToMin.view(np.uint64), sp.blkPointToMin.view(np.uint64))
+    assert np.array_equal(ref.clusRaw, sp.clus)
+    assert int(sp.blkParent.max()) > 0
+
+
 def test_cluster_twice_carries_state_like_the_reference(orc, tmp_path):
     """A second --hashDepthRange / --cluster pair works on what the first left behind: within[] flags accumulate
     (hash10x.c:535), only the good entries are wiped (:783) and a block without good hashes is merged again with
