@@ -104,6 +104,13 @@ struct FusedArgs {
   unsigned long long *moshCount ;	/* selected k-mers of the blocks this path completed (seqhash.c:171,189) */
 } ;
 
+#ifndef H10X_MULSHIFT_R
+#define H10X_MULSHIFT_R 0xffu
+#endif
+#ifndef H10X_MULSHIFT_F
+#define H10X_MULSHIFT_F 0xffu
+#endif
+
 /* CTAs per SM that the shared memory of a size class allows (h10x_gpu.cu, kClasses): the register budget follows it */
 __host__ __device__ constexpr int h10x_fused_ctas_per_sm (int threads)
 { return threads <= 256 ? 5 : threads <= 384 ? 4 : threads <= 512 ? 2 : 1 ; }
@@ -209,13 +216,23 @@ k_fused_block (FusedArgs a, HashParams hp)
 	    { const int c = SH - 2 * j ;		/* (W >> c) & mask: k-mer j, first base on top */
 	      uint32_t hlo = __funnelshift_r (Wlo, Whi, c) & LMASK, hhi ;
 	      uint32_t rlo = __funnelshift_r (WRlo, WRhi, 2 * j) & LMASK, rhi ;
-	      if constexpr (K > 16)	/* the integer ALU pipe is the limiter: take the high fields with a multiply (FMA pipe) + one
-			   shift instead of shift + mask */
-		{ uint32_t tt, uu ;
-		  asm ("mul.lo.u32 %0, %1, %2;" : "=r" (tt) : "r" (WRhi), "r" (1u << (64 - 2 * K - 2 * j))) ;
-		  rhi = tt >> (64 - 2 * K) ;
+	      /* the high fields: shift + mask (two ALU-pipe instructions) or a multiply by a power of two + one shift (one on
+		 the multiply pipe, one on the ALU pipe).  Which pipe has room decides, per k-mer slot j: H10X_MULSHIFT_R /
+		 H10X_MULSHIFT_F are the slots whose reverse / forward field takes the multiply (round 1: all of them, the ALU
+		 pipe was the limiter; since the selection got cheaper the multiply pipe is, ncu 86 % against 60 %).  Measured at
+		 the 1 Gb workload: all multiply 60.6 ms, forward only 61.3, reverse only 61.0, alternate slots 61.2, all shift +
+		 mask 62.6 - the two pipes and the issue slots (72 %) are within a few per cent of each other. */
+	      if constexpr (K > 16)
+		{ if ((H10X_MULSHIFT_R >> j) & 1)
+		    { uint32_t tt ;
+		      asm ("mul.lo.u32 %0, %1, %2;" : "=r" (tt) : "r" (WRhi), "r" (1u << (64 - 2 * K - 2 * j))) ;
+		      rhi = tt >> (64 - 2 * K) ;
+		    }
+		  else rhi = (WRhi >> (2 * j)) & HMASK ;
 		  if (j == 0) hhi = Whi >> c ;	/* c = 64-2K: nothing above the field */
-		  else { asm ("mul.lo.u32 %0, %1, %2;" : "=r" (uu) : "r" (Whi), "r" (1u << (2 * j))) ; hhi = uu >> (64 - 2 * K) ; }
+		  else if ((H10X_MULSHIFT_F >> j) & 1)
+		    { uint32_t uu ; asm ("mul.lo.u32 %0, %1, %2;" : "=r" (uu) : "r" (Whi), "r" (1u << (2 * j))) ; hhi = uu >> (64 - 2 * K) ; }
+		  else hhi = (Whi >> c) & HMASK ;
 		}
 	      else { hhi = (Whi >> c) & HMASK ; rhi = (WRhi >> (2 * j)) & HMASK ; }
 	      if (kk <= 16) { hhi = 0 ; rhi = 0 ; if (c >= 32) hlo = (Whi >> (c - 32)) & LMASK ; }
