@@ -154,6 +154,7 @@ class Index:
 
     def __init__(self, ci, lib, keep_c=False):
         self.B, self.hashNumber, self.nBlocksMax = ci.B, ci.hashNumber, ci.nBlocksMax
+        self.reserved = ci.reserved
         self.nReads, self.nHashes = ci.nReads, ci.nHashes
         hn, nb, H = ci.hashNumber, ci.nBlocksMax, ci.nHashes
         self.hashIndex = _arr(ci.hashIndex, 1 << ci.B, np.uint32) if ci.hashIndex else None
@@ -433,7 +434,7 @@ def write_hash(index_arrays, path):
     ix = index_arrays
     keep = [np.ascontiguousarray(a) for a in (ix.hashIndex, ix.hashValue, ix.hashDepth, ix.blkNRead,
                                               ix.blkNHash, ix.blkOff, ix.clus)]
-    ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, 0, ix.nReads, ix.nHashes,
+    ci = CIndex(ix.B, ix.hashNumber, ix.nBlocksMax, int(getattr(ix, "reserved", 0)), ix.nReads, ix.nHashes,
                 keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
                 keep[4].ctypes.data, keep[5].ctypes.data, keep[6].ctypes.data, None, None, 0, 0, None, None, None)
     nsub, ptm = getattr(ix, "blkNSub", None), getattr(ix, "blkPointToMin", None)

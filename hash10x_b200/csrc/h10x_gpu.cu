@@ -1771,16 +1771,7 @@ static void dist_bins (h10x_ctx *c, cudaStream_t s, uint64_t H, const uint64_t *
 	H10X_FLAT_OWNERS=1 restores the equal-width cut (tests run both). */
   if (NR > H10X_MAX_RANKS) throw H10xError (H10X_ERR_UNSUPPORTED, "more ranks than H10X_MAX_RANKS") ;
   std::vector<uint64_t> thr ((size_t) NR + 1) ;
-  const bool flatOwners = getenv ("H10X_FLAT_OWNERS") != nullptr ;
-  for (int o = 0 ; o <= NR ; ++o)
-    { if (flatOwners || o == 0 || o == NR)
-	{ unsigned __int128 t = ((unsigned __int128) o << (2 * P.k)) + (unsigned) (NR - 1) ; thr[o] = (uint64_t) (t / (unsigned) NR) ; }
-      else
-	{ const long double x = 1.0L - sqrtl (1.0L - (long double) o / (long double) NR) ;
-	  thr[o] = (uint64_t) (x * (long double) ((uint64_t) 1 << (2 * P.k))) ;	/* same bits on every rank: same code, same CPU */
-	  if (thr[o] < thr[o-1]) thr[o] = thr[o-1] ;
-	}
-    }
+  h10x_dist_owner_thresholds (P.k, NR, getenv ("H10X_FLAT_OWNERS") ? 1 : 0, thr.data ()) ;
   CK (cudaMemcpyAsync (dThr.p, thr.data (), 8 * ((size_t) NR + 1), cudaMemcpyHostToDevice, s)) ;
   /* the rank-distinct (hash, local depth, local first block) triples either come ready from the hand-written tail
      (preHash / preDepth / preFirst, hash-ascending) or are read off the library-sorted entries (sh, se, segStart) */
@@ -3073,6 +3064,7 @@ int h10x_gpu_cluster_split (h10x_ctx *c, h10x_index *out, uint32_t *nNew, char *
       out->blkNSubCluster = (uint32_t*) pull (0, c->blkNSub.p, 4 * nb) ;
       out->blkPointToMin = (double*) pull (1, c->blkPtm.p, 8 * nb) ;
       out->blkClusterParent = (uint32_t*) pull (2, c->blkParent.p, 4 * nb) ;
+      out->reserved |= H10X_INDEX_EXACT_BLOCKS ;
       CK (cudaStreamSynchronize (c->own)) ;
     }) ;
 }
@@ -3127,6 +3119,21 @@ void *h10x_host_alloc (size_t bytes)
 { void *p = nullptr ; if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError () ; return nullptr ; } return p ; }
 
 void h10x_host_free (void *p) { if (p) cudaFreeHost (p) ; }
+
+/* thr[o] = first hash of owner o's range, thr[nranks] = 2^(2k): see dist_bins ("owner = hash range") */
+int h10x_dist_owner_thresholds (int k, int nranks, int flat, uint64_t *thr)
+{ if (!thr || nranks < 1 || k < 1 || k > 31) return H10X_ERR_BAD_PARAM ;
+  for (int o = 0 ; o <= nranks ; ++o)
+    { if (flat || o == 0 || o == nranks)
+	{ unsigned __int128 t = ((unsigned __int128) o << (2 * k)) + (unsigned) (nranks - 1) ; thr[o] = (uint64_t) (t / (unsigned) nranks) ; }
+      else
+	{ const long double x = 1.0L - sqrtl (1.0L - (long double) o / (long double) nranks) ;
+	  thr[o] = (uint64_t) (x * (long double) ((uint64_t) 1 << (2 * k))) ;	/* same bits on every rank: same code, same CPU */
+	  if (thr[o] < thr[o-1]) thr[o] = thr[o-1] ;
+	}
+    }
+  return H10X_OK ;
+}
 
 int h10x_dist_unique_id (void *id128, char *err, size_t errlen)
 { if (!id128) return H10X_ERR_BAD_PARAM ;

@@ -31,10 +31,11 @@ static int grown_dim (int dim, int size, int max)
   return dim ;
 }
 
+/* dim0 > 0: the Array grew from dim0 as its elements were touched; dim0 == 0: it was created with exactly max elements */
 static int put_array (FILE *f, const void *data, int size, int max, int dim0)
 { array_header a ;
   memset (&a, 0, sizeof (a)) ;
-  a.magic = ARRAY_MAGIC ; a.size = size ; a.max = max ; a.dim = grown_dim (dim0, size, max) ;
+  a.magic = ARRAY_MAGIC ; a.size = size ; a.max = max ; a.dim = dim0 ? grown_dim (dim0, size, max) : max ;
   if (fwrite (&a, sizeof (a), 1, f) != 1) return 0 ;
   if (max && fwrite (data, size, max, f) != (size_t) max) return 0 ;
   size_t rest = (size_t) (a.dim - max) * size ;
@@ -72,7 +73,9 @@ int h10x_write_hash (const h10x_index *ix, const char *path)
 	  if (ix->blkPointToMin) memcpy (&cb[8*b + 6], &ix->blkPointToMin[b], 8) ;
 	  if (ix->blkClusterParent) cb[8*b + 3] = ix->blkClusterParent[b] ;
 	}
-      ok = put_array (f, cb, 32, (int) nb, 1200) ;	/* dim0 = 1200: hash10x.c:1151 */
+      /* dim0 = 1200: hash10x.c:1151; clusterSplitCodes makes a new Array of exactly the blocks it needs (:961), and
+	 arrayRead keeps whatever dim a file had - H10X_INDEX_EXACT_BLOCKS in `reserved` remembers that */
+      ok = put_array (f, cb, 32, (int) nb, (ix->reserved & H10X_INDEX_EXACT_BLOCKS) ? 0 : 1200) ;
       free (cb) ;
     }
   ok = ok && (!ix->nHashes || fwrite (ix->clusHash, 8, ix->nHashes, f) == ix->nHashes) ;
@@ -146,6 +149,7 @@ int h10x_read_hash (const char *path, int32_t wantB, h10x_index *out, char *err,
   if (fread (&a, sizeof (a), 1, f) != 1 || a.size != 32 || a.dim < a.max || a.max < 1)
     { seterr (err, errlen, "failed to read clusterBlocks array") ; goto fail ; }
   out->nBlocksMax = (uint32_t) a.max ;
+  if (a.dim == a.max) out->reserved |= H10X_INDEX_EXACT_BLOCKS ;
   if (!(cb = malloc ((size_t) a.dim * 32 + 32))) { st = H10X_ERR_NOMEM ; goto fail ; }
   if (fread (cb, 32, a.dim, f) != (size_t) a.dim) { seterr (err, errlen, "failed to read clusterBlocks array") ; goto fail ; }
   { uint32_t nb = out->nBlocksMax, b ;

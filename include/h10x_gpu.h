@@ -73,11 +73,13 @@ typedef struct h10x_cluster_hash {
    the last run has nHash 0 (hash10x.c:209,216).  Block i's ClusterHash list is
    clusHash[blkOff[i] .. blkOff[i]+blkNHash[i]) sorted by bin id; bin x's barcode list
    (hashCodes[x], hash10x.c:317-338) is codes[codeOff[x] .. codeOff[x+1]) ascending. */
+#define H10X_INDEX_EXACT_BLOCKS 1u
 typedef struct h10x_index {
   int32_t B ;
   uint32_t hashNumber ;		/* bins are 1..hashNumber-1 */
   uint32_t nBlocksMax ;		/* arrayMax(clusterBlocks) */
-  uint32_t reserved ;
+  uint32_t reserved ;		/* H10X_INDEX_EXACT_BLOCKS: clusterBlocks holds exactly nBlocksMax elements (after --clusterSplit,
+				   hash10x.c:961), which is the Array size --writeHash puts into the file */
   uint64_t nReads ;		/* records consumed (readFQB's nReads) */
   uint64_t nHashes ;		/* sum of nHash */
   uint32_t *hashIndex ;		/* 2^B, layout identical to the reference's sequential insertion */
@@ -294,6 +296,10 @@ typedef struct h10x_dist_info {
 
 /* rank 0 creates the NCCL unique id; the caller ships the 128 bytes to the other ranks (torch.distributed,
    MPI, a file ...); every rank then joins with h10x_dist_init (collective) */
+/* The hash ranges of the owners in a distributed build (host arithmetic, no device needed): thr[o] = first hash owned by
+   rank o, thr[nranks] = 2^(2k).  flat = 0: cut at the quantiles of the density 2 (1 - x) of min (hash, hashRC), so that
+   every owner numbers about the same count of bins; flat = 1: equal widths.  Any monotone cut gives the reference's ids. */
+int h10x_dist_owner_thresholds (int k, int nranks, int flat, uint64_t *thr) ;
 int h10x_dist_unique_id (void *id128, char *err, size_t errlen) ;
 int h10x_dist_init (h10x_ctx *ctx, int rank, int nranks, const void *id128, char *err, size_t errlen) ;
 /* collective over all ranks; d_fqb holds this rank's records */

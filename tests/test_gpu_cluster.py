@@ -185,6 +185,17 @@ def test_cli_cluster_split_writes_the_reference_file(orc, gpu_lib, tmp_path):
     assert np.array_equal(hf.clusRaw, want.clus)
     r2 = subprocess.run([exe, "-B", "20", "--readHash", str(out), "--codeStats"], capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0, r2.stdout + r2.stderr
+    if orc.ref_binary() is not None:        # the reference's own command chain on the same FQB: the same file
+        ref = tmp_path / "r.hash"
+        r3 = subprocess.run([orc.ref_binary(), "-B", "20", "-ct", "3", "--readFQB", str(fq), "--hashDepthRange", "4", "400",
+                             "--cluster", "0", "0", "--clusterSplit", "--writeHash", str(ref)], capture_output=True, text=True, timeout=600)
+        assert r3.returncode == 0, r3.stderr
+        rf = hashfile.parse(str(ref))
+        assert rf.size == hf.size and rf.nBlocksMax == hf.nBlocksMax
+        assert np.array_equal(rf.blkNRead, hf.blkNRead) and np.array_equal(rf.blkNHash, hf.blkNHash)
+        assert np.array_equal(rf.blkParent, hf.blkParent)
+        # the reference's --readFQB leaves the two spare ClusterHash bytes uninitialised (hash10x.c:175): compare ids and reads
+        assert np.array_equal(rf.clusIdx, hf.clusIdx) and np.array_equal(rf.clusRead, hf.clusRead)
 
 
 def test_cluster_argument_checks(orc, gpu_lib):

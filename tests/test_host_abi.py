@@ -185,3 +185,67 @@ def test_hash_writer_reader_carry_the_cluster_fields(orc, tmp_path):
             o = off2 + 32 + 32 * blk + 16
             buf[o:o + 8] = bytes(8)
     assert a == b
+
+
+def test_owner_thresholds_are_monotone_and_balance_the_mosh_density():
+    """h10x_dist_owner_thresholds (the hash ranges of a multi-GPU build): monotone with the right ends for every rank
+    count; cut at the quantiles of min (hash, hashRC) so that owners hold equal shares (flat = 1: equal widths, where
+    owner 0 of 2 holds three quarters)."""
+    import hash10x_b200
+    L = hash10x_b200.load_library()
+    L.h10x_dist_owner_thresholds.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(11)
+    k = 21
+    top = 1 << (2 * k)
+    moshes = np.minimum(rng.integers(0, top, 2_000_000, dtype=np.int64), rng.integers(0, top, 2_000_000, dtype=np.int64))
+    for nranks in (1, 2, 3, 4, 8, 16):
+        for flat in (0, 1):
+            thr = np.zeros(nranks + 1, np.uint64)
+            assert L.h10x_dist_owner_thresholds(k, nranks, flat, thr.ctypes.data) == 0
+            t = thr.astype(np.int64)
+            assert t[0] == 0 and t[-1] == top and (np.diff(t) >= 0).all()
+            share = np.diff(np.searchsorted(np.sort(moshes), t)) / moshes.size
+            if flat:
+                assert abs(share[0] - (1 - (1 - 1 / nranks) ** 2)) < 0.01
+            else:
+                assert np.abs(share - 1 / nranks).max() < 0.01, (nranks, share)
+    assert L.h10x_dist_owner_thresholds(0, 2, 0, thr.ctypes.data) != 0
+
+
+def test_hash_writer_carries_the_split_index_like_the_reference(orc, tmp_path):
+    """--clusterSplit's result through h10x_write_hash: clusterParent (hash10x.c:66) sits where the reference puts it; the
+    file equals the reference's --clusterSplit --writeHash outside the raw pointers, and reads back."""
+    import hash10x_b200
+    from hash10x_b200 import binding
+    p = orc.synth_params(seed=37, n_barcodes=120, pairs_min=20, pairs_max=80, genome_len=40_000, mol_len=8_000,
+                         mol_per_barcode=3)
+    recs = orc.synth_fqb(p)
+    ix = orc.build(recs, B=20)
+    _w, goff, good = orc.good_hashes(ix, 2, 13)
+    clus, nsub, ptm = orc.cluster(ix, goff, good, 0, 0, 1)
+    sp = orc.cluster_split(ix, clus, nsub, ptm)
+    sp.B, sp.hashNumber, sp.nReads, sp.reserved = ix.B, ix.hashNumber, ix.nReads, 1      # H10X_INDEX_EXACT_BLOCKS
+    sp.hashIndex, sp.hashValue, sp.hashDepth = ix.hashIndex, ix.hashValue, ix.hashDepth
+    ours = str(tmp_path / "ours.hash")
+    binding.write_hash(sp, ours)
+    hf = hashfile.parse(ours)
+    assert np.array_equal(hf.blkParent, sp.blkParent) and int(hf.blkParent.max()) > 0
+    assert np.array_equal(hf.blkNRead, sp.blkNRead) and np.array_equal(hf.clusRaw, sp.clus)
+    L = hash10x_b200.load_library()
+    ci = binding.CIndex()
+    err = C.create_string_buffer(256)
+    assert L.h10x_read_hash(ours.encode(), 20, C.byref(ci), err, 256) == 0, err.value
+    got = binding.Index(ci, L)
+    L.h10x_index_free(C.byref(ci))
+    assert np.array_equal(got.blkParent, sp.blkParent) and np.array_equal(got.clus, sp.clus)
+    if orc.ref_binary() is None:
+        return
+    src, ref = str(tmp_path / "src.hash"), str(tmp_path / "ref.hash")
+    assert orc.build_and_write(recs, src, B=20) == 0
+    r = subprocess.run([orc.ref_binary(), "-B", "20", "-ct", "1", "--readHash", src, "--hashDepthRange", "2", "13",
+                        "--cluster", "0", "0", "--clusterSplit", "--writeHash", ref], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rf = hashfile.parse(ref)
+    assert rf.size == hf.size and np.array_equal(rf.blkParent, hf.blkParent) and np.array_equal(rf.clusRaw, hf.clusRaw)
+    assert np.array_equal(rf.blkNRead, hf.blkNRead) and np.array_equal(rf.blkNHash, hf.blkNHash)
+    assert np.array_equal(rf.blkPointToMin.view(np.uint64), hf.blkPointToMin.view(np.uint64))
