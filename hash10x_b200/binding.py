@@ -126,6 +126,7 @@ def load_library():
     L.h10x_gpu_load_index.argtypes = [vp, C.POINTER(CIndex), cp, sz]
     L.h10x_gpu_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(CClusters), cp, sz]
     L.h10x_gpu_cluster_split.argtypes = [vp, C.POINTER(CIndex), C.POINTER(C.c_uint32), cp, sz]
+    L.h10x_gpu_depth_range_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -360,6 +361,13 @@ class Hash10xGPU:
             return int(cg.nGood)
         return (_arr(cg.within, cg.hashNumber, np.uint8), _arr(cg.goodOff, cg.nBlocksMax + 1, np.uint64),
                 _arr(cg.good, cg.nGood, np.uint16))
+
+    def depth_range_device(self, dmin, dmax):
+        """--hashDepthRange with the lists left on the device (what --cluster reads) -> number of good hashes"""
+        n = C.c_uint64(0)
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_depth_range_device(self.ctx, dmin, dmax, C.byref(n), err, len(err)), err)
+        return int(n.value)
 
     def load_index(self, ix):
         """make a host index (numpy arrays as in Index, with codeOff / codes) the resident one: --readHash's counterpart"""

@@ -19,6 +19,7 @@ struct ClusterArgs {
   const uint32_t *entryId ;	/* bin id of every entry (entry order = block, hash) */
   const uint16_t *eRead ;	/* read index of every entry */
   uint64_t *clus ;		/* out: id | read << 32 */
+  uint16_t *valsOut ;		/* or, when not NULL: only the 16-bit values, in key order (the good-hash lists of --hashDepthRange) */
   unsigned int *work ;		/* ticket counter */
   uint32_t nList ;
   uint32_t cap ;		/* entries per block this launch can hold */
@@ -111,7 +112,8 @@ k_cluster_sort (ClusterArgs a)
 	  uint32_t *tk = src ; src = dst ; dst = tk ;
 	  uint16_t *tv = vsrc ; vsrc = vdst ; vdst = tv ;
 	}
-      for (uint32_t i = t ; i < n ; i += THREADS) a.clus[off + i] = (uint64_t) src[i] | ((uint64_t) vsrc[i] << 32) ;
+      if (a.valsOut) for (uint32_t i = t ; i < n ; i += THREADS) a.valsOut[off + i] = vsrc[i] ;
+      else for (uint32_t i = t ; i < n ; i += THREADS) a.clus[off + i] = (uint64_t) src[i] | ((uint64_t) vsrc[i] << 32) ;
       __syncthreads () ;
     }
 }

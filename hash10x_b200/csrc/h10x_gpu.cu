@@ -1652,7 +1652,7 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
 	  CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) cc.threads, smem)) ;
 	  if (occ < 1) occ = 1 ;
 	  ClusterArgs ca ;
-	  ca.list = dl[ci].p ; ca.blkOff = blkOffProc.p ; ca.entryId = entryId.p ; ca.eRead = eRead.p ; ca.clus = c->clus.p ;
+	  ca.list = dl[ci].p ; ca.blkOff = blkOffProc.p ; ca.entryId = entryId.p ; ca.eRead = eRead.p ; ca.clus = c->clus.p ; ca.valsOut = nullptr ;
 	  ca.work = cwork.p + ci ; ca.nList = (uint32_t) lists[ci].size () ; ca.cap = cc.cap ; ca.digitBits = digitBits ; ca.passes = passes ;
 	  void *args[1] = { (void*) &ca } ;
 	  uint32_t grid = (uint32_t) std::min<size_t> (lists[ci].size (), (size_t) nSM * occ) ;
@@ -2795,7 +2795,7 @@ int h10x_gpu_build_file (h10x_ctx *c, const char *path, h10x_index *out, char *e
   return h10x_gpu_download (c, out, err, errlen) ;
 }
 
-int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen)
+static int depth_range_impl (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out, bool download, char *err, size_t errlen)
 { if (!c || !out || !c->haveIndex || (c->dist && !c->dist->globalCodes))
     { set_err (err, errlen, "no index resident (after a distributed build: h10x_gpu_dist_global_codes first)") ; return H10X_ERR_BAD_PARAM ; }
   memset (out, 0, sizeof (*out)) ;
@@ -2827,8 +2827,57 @@ int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out
       std::vector<uint64_t> hOff ((size_t) nb + 1) ;
       CK (cudaMemcpyAsync (hOff.data (), goodOff.p, 8 * ((size_t) nb + 1), cudaMemcpyDeviceToHost, s)) ;
       CK (cudaStreamSynchronize (s)) ;
-      /* sort by increasing depth inside every block; stable = ties keep list order, as glibc's qsort does */
-      if (nGood) segmented_sort_blocks<uint32_t, uint16_t> (c, s, keyDepth.p, keyS.p, valIdx.p, valS.p, hOff, goodOff.p, true) ;
+      /* sort by increasing depth inside every block; stable = ties keep list order, as glibc's qsort does.  One CTA per
+	 block, LSD radix sort in shared memory on the depth bits (k_cluster_sort: one pass for a range like 30..100);
+	 the library's segmented sort, which took 1.1 s of this command's 1.2 s at the 1 Gb workload, only gets the blocks
+	 with more good hashes than the largest shared-memory class (H10X_GOOD_LIBSORT=1: all of them, for A/B) */
+      if (nGood && getenv ("H10X_GOOD_LIBSORT"))
+	segmented_sort_blocks<uint32_t, uint16_t> (c, s, keyDepth.p, keyS.p, valIdx.p, valS.p, hOff, goodOff.p, true) ;
+      else if (nGood)
+	{ struct ClusClass { uint32_t cap, threads ; } ;
+	  static const ClusClass kCC[3] = { { 1024, 128 }, { 4096, 256 }, { 12288, 512 } } ;
+	  const int keyBits = bits_for (dmax > 1 ? (uint64_t) dmax - 1 : 1) ;
+	  uint32_t digitBits = 8, passes = (keyBits + 7) / 8 ;
+	  for (uint32_t db = 9 ; db <= 10 ; ++db) if ((keyBits + db - 1) / db < passes) { digitBits = db ; passes = (keyBits + db - 1) / db ; }
+	  std::vector<uint32_t> lists[3] ;
+	  std::vector<std::pair<uint32_t, uint32_t>> bigRuns ;
+	  for (uint32_t p = 0 ; p < nb ; ++p)
+	    { const uint64_t n = hOff[p + 1] - hOff[p] ;
+	      if (!n) continue ;
+	      const int ci = n <= kCC[0].cap ? 0 : n <= kCC[1].cap ? 1 : n <= kCC[2].cap ? 2 : -1 ;
+	      if (ci >= 0) lists[ci].push_back (p) ;
+	      else if (!bigRuns.empty () && bigRuns.back ().second == p) bigRuns.back ().second = p + 1 ;
+	      else bigRuns.push_back ({ p, p + 1 }) ;
+	    }
+	  const int nSM = device_sms (c) ;
+	  DBuf<unsigned int> cwork (3, s, mt) ;
+	  CK (cudaMemsetAsync (cwork.p, 0, 12, s)) ;
+	  std::vector<DBuf<uint32_t>> dl (3) ;
+	  for (int ci = 0 ; ci < 3 ; ++ci)
+	    { if (lists[ci].empty ()) continue ;
+	      const ClusClass &cc = kCC[ci] ;
+	      dl[ci].alloc (lists[ci].size (), s, mt) ;
+	      CK (cudaMemcpyAsync (dl[ci].p, lists[ci].data (), 4 * lists[ci].size (), cudaMemcpyHostToDevice, s)) ;
+	      const uint32_t nd = 1u << digitBits ;
+	      const size_t smem = (size_t) cc.cap * 12 + 4 + (size_t) nd * 4 + (size_t) (cc.threads / 32) * nd * 2 + 16 ;
+	      const void *fn = cc.threads == 128 ? (const void*) k_cluster_sort<128> : cc.threads == 256 ? (const void*) k_cluster_sort<256>
+		: (const void*) k_cluster_sort<512> ;
+	      CK (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+	      int occ = 1 ;
+	      CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) cc.threads, smem)) ;
+	      if (occ < 1) occ = 1 ;
+	      ClusterArgs ca ;
+	      ca.list = dl[ci].p ; ca.blkOff = goodOff.p ; ca.entryId = keyDepth.p ; ca.eRead = valIdx.p ; ca.clus = nullptr ; ca.valsOut = valS.p ;
+	      ca.work = cwork.p + ci ; ca.nList = (uint32_t) lists[ci].size () ; ca.cap = cc.cap ; ca.digitBits = digitBits ; ca.passes = passes ;
+	      void *args[1] = { (void*) &ca } ;
+	      const uint32_t grid = (uint32_t) std::min<size_t> (lists[ci].size (), (size_t) nSM * occ) ;
+	      CK (cudaLaunchKernel (fn, dim3 (grid), dim3 (cc.threads), args, smem, s)) ;
+	      ++c->launches ;
+	    }
+	  for (auto &r : bigRuns)
+	    segmented_sort_blocks<uint32_t, uint16_t> (c, s, keyDepth.p, keyS.p, valIdx.p, valS.p, hOff, goodOff.p, true, r.first, r.second) ;
+	  CK (cudaStreamSynchronize (s)) ;	/* the block lists are read by the async copies */
+	}
       auto pull = [&] (int slot, const void *src, size_t bytes) -> void*
 	{ if (c->goodCap[slot] < bytes || !c->goodSlot[slot])
 	    { if (c->goodSlot[slot]) cudaFreeHost (c->goodSlot[slot]) ;
@@ -2838,13 +2887,27 @@ int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out
 	  if (bytes) CK (cudaMemcpyAsync (c->goodSlot[slot], src, bytes, cudaMemcpyDeviceToHost, s)) ;
 	  return c->goodSlot[slot] ;
 	} ;
-      out->within = (uint8_t*) pull (0, c->within.p, hn) ;
-      out->goodOff = (uint64_t*) pull (1, goodOff.p, 8 * ((size_t) nb + 1)) ;
-      out->good = (uint16_t*) pull (2, valS.p, 2 * (size_t) nGood) ;
+      if (download)
+	{ out->within = (uint8_t*) pull (0, c->within.p, hn) ;
+	  out->goodOff = (uint64_t*) pull (1, goodOff.p, 8 * ((size_t) nb + 1)) ;
+	  out->good = (uint16_t*) pull (2, valS.p, 2 * (size_t) nGood) ;
+	}
       out->nGood = nGood ; out->hashNumber = hn ; out->nBlocksMax = nb ;
       CK (cudaStreamSynchronize (s)) ;
       c->haveGood = true ;
     }) ;
+}
+
+int h10x_gpu_depth_range (h10x_ctx *c, int dmin, int dmax, h10x_good_hashes *out, char *err, size_t errlen)
+{ return depth_range_impl (c, dmin, dmax, out, true, err, errlen) ; }
+
+/* the same, the lists staying where h10x_gpu_cluster reads them: no pinned host copies (2.7 GB of them at the 1 Gb
+   workload, whose first cudaHostAlloc alone takes a second) */
+int h10x_gpu_depth_range_device (h10x_ctx *c, int dmin, int dmax, uint64_t *nGood, char *err, size_t errlen)
+{ h10x_good_hashes g ;
+  int st = depth_range_impl (c, dmin, dmax, &g, false, err, errlen) ;
+  if (st == H10X_OK && nGood) *nGood = g.nGood ;
+  return st ;
 }
 
 /* --cluster codeMin codeMax (hash10x.c:1241-1256) on the resident index and goodHashes: h10x_subcluster.cuh */

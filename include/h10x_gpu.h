@@ -239,6 +239,8 @@ typedef struct h10x_good_hashes {
   uint16_t *good ;		/* nGood */
 } h10x_good_hashes ;
 int h10x_gpu_depth_range (h10x_ctx *ctx, int min, int max, h10x_good_hashes *out, char *err, size_t errlen) ;
+/* the same without the host copies: the lists stay on the device, where h10x_gpu_cluster reads them; *nGood = their total length */
+int h10x_gpu_depth_range_device (h10x_ctx *ctx, int min, int max, uint64_t *nGood, char *err, size_t errlen) ;
 void h10x_index_free (h10x_index *ix) ;
 
 /* "next" row: `--cluster codeMin codeMax` (hash10x.c:1241-1256) on the index and the goodHashes
