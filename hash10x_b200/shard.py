@@ -51,6 +51,16 @@ def job_time_and_units(dist, torch, ms_local, units_local, device=None):
     return float(t[0]), float(u[0])
 
 
-def owner_thresholds(k, world):
-    """hash-range owners (h10x_dist.cuh step 2): owner o takes hashes in [thr[o], thr[o+1])."""
-    return [((o << (2 * k)) + world - 1) // world for o in range(world + 1)]
+def owner_thresholds(k, world, flat=False):
+    """hash-range owners (dist_bins step 2): owner o takes hashes in [thr[o], thr[o+1]).  The native function itself
+    (h10x_dist_owner_thresholds: host arithmetic, runs without a device), so that models of the exchange cut exactly
+    where the library does: at the quantiles of the mosh density, or - flat - into equal widths."""
+    import ctypes as C
+    from .binding import load_library
+    L = load_library()
+    L.h10x_dist_owner_thresholds.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    thr = np.zeros(world + 1, np.uint64)
+    st = L.h10x_dist_owner_thresholds(k, world, 1 if flat else 0, thr.ctypes.data)
+    if st:
+        raise ValueError("bad k / world")
+    return [int(x) for x in thr]

@@ -44,8 +44,13 @@ def test_plan_shards_properties():
 def test_owner_thresholds_cover_the_hash_space():
     for k in (13, 21, 31):
         for world in (1, 2, 3, 8):
-            thr = shard.owner_thresholds(k, world)
-            assert thr[0] == 0 and thr[-1] == 1 << (2 * k) and all(a < b for a, b in zip(thr, thr[1:]))
+            for flat in (False, True):
+                thr = shard.owner_thresholds(k, world, flat)
+                assert thr[0] == 0 and thr[-1] == 1 << (2 * k) and all(a < b for a, b in zip(thr, thr[1:]))
+            # the quantile cut gives the low owners narrower ranges (the density of min (hash, hashRC) falls with the hash)
+            q = shard.owner_thresholds(k, world)
+            if world > 1:
+                assert q[1] - q[0] < q[-1] - q[-2]
 
 
 def _alltoallv(send, recv, rank, world):
