@@ -127,6 +127,7 @@ def load_library():
     L.h10x_gpu_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(CClusters), cp, sz]
     L.h10x_gpu_cluster_split.argtypes = [vp, C.POINTER(CIndex), C.POINTER(C.c_uint32), cp, sz]
     L.h10x_gpu_depth_range_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), cp, sz]
+    L.h10x_gpu_block_keys.argtypes = [vp, vp, u64, vp, vp, vp, u64, C.POINTER(C.c_uint32), C.POINTER(C.c_int), cp, sz]
     L.h10x_write_hash.argtypes = [C.POINTER(CIndex), cp]
     L.h10x_read_hash.argtypes = [cp, C.c_int32, C.POINTER(CIndex), cp, sz]
     _lib = L
@@ -421,6 +422,20 @@ class Hash10xGPU:
         self._check(self.lib.h10x_gpu_index_digest(self.ctx, block_base, entry_base, 1 if with_block_zero else 0,
                                                    C.byref(d), err, len(err)), err)
         return {f: int(getattr(d, f)) for f, _ in CDigest._fields_ if f != "reserved"}
+
+    def block_keys(self, recs):
+        """what the fused kernel stored per block -> (offsets[nBlocks+1], hashes u64, reads u32, lean)"""
+        recs = np.ascontiguousarray(recs, dtype=np.uint32).reshape(-1)
+        n = recs.size // 30
+        cap = max(1, n * 240)
+        off = np.zeros(n + 2, np.uint64)
+        hs, rd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        nb, lean = C.c_uint32(0), C.c_int(0)
+        err = C.create_string_buffer(512)
+        self._check(self.lib.h10x_gpu_block_keys(self.ctx, recs.ctypes.data, n, off.ctypes.data, hs.ctypes.data, rd.ctypes.data,
+                                                 cap, C.byref(nb), C.byref(lean), err, len(err)), err)
+        m = int(off[nb.value])
+        return off[:nb.value + 1].copy(), hs[:m].copy(), rd[:m].copy(), bool(lean.value)
 
     def record_moshes(self, recs):
         """K1 alone: per-record mosh hashes in generation order -> (offsets[n+1], hashes)."""

@@ -143,6 +143,9 @@ struct h10x_ctx {
      .pointToMin (hash10x.c:62-70) once a --cluster command ran */
   DBuf<uint64_t> goodOffD ; DBuf<uint16_t> goodD ; bool haveGood = false ;
   DBuf<uint32_t> blkNSub, blkParent ; DBuf<double> blkPtm ;
+  /* tests: the key lists the mosh stage left per block, kept when dbgKeys is set (h10x_gpu_block_keys) */
+  bool dbgKeys = false, dbgLean = false ; uint32_t dbgNBlk = 0 ; uint64_t dbgScratchLen = 0 ;
+  std::vector<uint64_t> dbgSrcOff, dbgScratch ; std::vector<uint32_t> dbgBlkCnt ;
   void *clusSlot[3] = { nullptr, nullptr, nullptr } ; size_t clusCap[3] = { 0, 0, 0 } ;	/* pinned host: nSubCluster, pointToMin, clusterParent */
   void *goodSlot[3] = { nullptr, nullptr, nullptr } ; size_t goodCap[3] = { 0, 0, 0 } ;	/* pinned host: within, goodOff, good */
   struct DistState *dist = nullptr ;
@@ -1416,6 +1419,17 @@ static void build_device_impl (h10x_ctx *c, const uint32_t *fqb, uint64_t nFile,
   else if (!bucketed && !tail2) { eHash.alloc (H, s, mt) ; eBR.alloc (H, s, mt) ; }
   { StageTimer tm (c, s, ST_DEDUP) ;
     CK (cudaMemcpyAsync (blkOffProc.p, hBlkOff.data (), 8 * ((size_t) nProcBlk + 1), cudaMemcpyHostToDevice, s)) ;
+    if (c->dbgKeys)
+      { unsigned long long used = 0 ;
+	CK (cudaMemcpyAsync (&used, eng.cursor.p, 8, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+	c->dbgNBlk = nProcBlk ; c->dbgLean = lean ; c->dbgScratchLen = used ;
+	c->dbgSrcOff.assign (nProcBlk, 0) ; c->dbgBlkCnt.assign (nProcBlk, 0) ; c->dbgScratch.assign ((size_t) used, 0) ;
+	CK (cudaMemcpyAsync (c->dbgSrcOff.data (), srcOff.p, 8 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaMemcpyAsync (c->dbgBlkCnt.data (), blkCnt.p, 4 * (size_t) nProcBlk, cudaMemcpyDeviceToHost, s)) ;
+	if (used) CK (cudaMemcpyAsync (c->dbgScratch.data (), scratch.p, 8 * (size_t) used, cudaMemcpyDeviceToHost, s)) ;
+	CK (cudaStreamSynchronize (s)) ;
+      }
     if (tail2)
       { TailSrc in = { nProcBlk, blkBase, srcOff.p, blkCnt.p, scratch.p, gHash.p, gRec.p, dBlkStart.p, wInvFull, wDiv } ;
 	tail_p1 (c, s, tg, in, H, tailB, tailRangeStart) ;
@@ -3580,6 +3594,43 @@ int h10x_gpu_memcpy_d2h (h10x_ctx *c, void *dst, const void *src, size_t bytes)
 { if (!c || (!dst && bytes) || (!src && bytes)) return H10X_ERR_BAD_PARAM ;
   if (cudaSetDevice (c->P.device) != cudaSuccess) return H10X_ERR_CUDA ;
   if (bytes && cudaMemcpy (dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError () ; return H10X_ERR_CUDA ; }
+  return H10X_OK ;
+}
+
+/* tests: what the FUSED kernel itself selected.  Builds the index of the host records and hands back, per processed
+   block, the keys the fused kernel stored for it (hash, read index within the block) before any grouping: in lean mode
+   (*lean = 1: the hand-written tail follows) that is every mosh of the block in no particular order, duplicates included
+   - directly comparable with seqAddHashes / moshRCnext (hash10x.c:123-132, seqhash.c:154-195) record by record; in
+   classic mode the sorted unique list.  A block the generic path took has outOff[b+1] == outOff[b]. */
+int h10x_gpu_block_keys (h10x_ctx *c, const void *fqb, uint64_t nRecords, uint64_t *outOff, uint64_t *outHash, uint32_t *outRead,
+			 uint64_t cap, uint32_t *nBlocks, int *lean, char *err, size_t errlen)
+{ if (!c || !outOff || !nBlocks || (!fqb && nRecords)) { set_err (err, errlen, "null argument") ; return H10X_ERR_BAD_PARAM ; }
+  h10x_index ix ;
+  c->dbgKeys = true ;
+  int st = h10x_gpu_build_host (c, fqb, nRecords, &ix, err, errlen) ;
+  c->dbgKeys = false ;
+  if (st != H10X_OK) return st ;
+  uint64_t n = 0 ;
+  outOff[0] = 0 ;
+  for (uint32_t b = 0 ; b < c->dbgNBlk ; ++b)
+    { const uint64_t so = c->dbgSrcOff[b] ;
+      const uint32_t cnt = c->dbgBlkCnt[b] ;
+      if (!(so >> 63) && cnt != 0xffffffffu)
+	{ const int sh = (int) (so >> 56) ;
+	  const uint64_t o = so & 0x00ffffffffffffffull, rmask = ((uint64_t) 1 << sh) - 1 ;
+	  if (n + cnt > cap || o + cnt > c->dbgScratchLen) { set_err (err, errlen, "block_keys: output capacity too small") ; return H10X_ERR_BAD_PARAM ; }
+	  for (uint32_t i = 0 ; i < cnt ; ++i)
+	    { const uint64_t key = c->dbgScratch[o + i] ;
+	      if (outHash) outHash[n] = key >> sh ;
+	      if (outRead) outRead[n] = (uint32_t) (key & rmask) ;
+	      ++n ;
+	    }
+	}
+      outOff[b + 1] = n ;
+    }
+  *nBlocks = c->dbgNBlk ;
+  if (lean) *lean = c->dbgLean ? 1 : 0 ;
+  c->dbgSrcOff.clear () ; c->dbgScratch.clear () ; c->dbgBlkCnt.clear () ;
   return H10X_OK ;
 }
 

@@ -342,6 +342,10 @@ int h10x_gpu_memcpy_d2h (h10x_ctx *ctx, void *dst, const void *src, size_t bytes
 /* moshes of each record without the index build (the K1 stage alone), for parity tests of
    seqhash.c:154-195: outCount[i] = number of moshes of record i in generation order, written to
    outHash[outOff[i]..]; arrays are HOST memory, outOff has nRecords+1 entries. */
+/* tests: the keys the FUSED kernel stored per processed block of a host FQB, before any grouping (see the definition):
+   outOff[nBlocks+1], outHash / outRead [cap].  *lean = 1 when the kernel ran lean (every mosh, unsorted, duplicates in). */
+int h10x_gpu_block_keys (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, uint64_t *outOff, uint64_t *outHash,
+			 uint32_t *outRead, uint64_t cap, uint32_t *nBlocks, int *lean, char *err, size_t errlen) ;
 int h10x_gpu_record_moshes (h10x_ctx *ctx, const void *fqb, uint64_t nRecords, uint64_t *outOff,
 			    uint64_t *outHash, uint64_t cap, char *err, size_t errlen) ;
 
