@@ -268,23 +268,27 @@ static void hashDepthRange (int min, int max)
 { if (!haveIndex) die ("cluster code called without setting hashDepthRange") ;
   uint32_t c ;
   if ((ctx || multi) && indexFromGpu)	/* the index is resident on the GPU(s): build the lists there */
-    { char err[512] ; h10x_good_hashes g ;
+    { char err[512] ; h10x_good_hashes g ; uint64_t nGood = 0 ;
+      /* one GPU: the lists stay on the device, where --cluster reads them (no command of this program reads them on the
+	 host; copying them would first pin 2 bytes per good hash of host memory, a second at the 1 Gb scale) */
       int st = multi ? h10x_multi_depth_range (multi, min, max, &g, err, sizeof (err))
-	: h10x_gpu_depth_range (ctx, min, max, &g, err, sizeof (err)) ;
+	: h10x_gpu_depth_range_device (ctx, min, max, &nGood, err, sizeof (err)) ;
       if (st) die ("%s", *err ? err : h10x_strerror (st)) ;
       if (!hashWithinRange) hashWithinRange = calloc (ix.hashNumber, 1) ;
       if (!hashWithinRange) die ("myalloc failure") ;
-      memcpy (hashWithinRange, g.within, ix.hashNumber) ;
+      if (multi) memcpy (hashWithinRange, g.within, ix.hashNumber) ;
       hashRangeMin = min ; hashRangeMax = max ;
       free (goodHashes) ; free (nGoodHashes) ;		/* the tables of an earlier --hashDepthRange (the lists are the context's) */
-      goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;
+      goodHashes = calloc (ix.nBlocksMax, sizeof (uint16_t*)) ;		/* non-NULL = "--hashDepthRange has run" (hash10x.c:1258) */
       nGoodHashes = calloc (ix.nBlocksMax, sizeof (int)) ;
       if (!hashWithinRange || !goodHashes || !nGoodHashes) die ("myalloc failure") ;
       for (c = 0 ; c < ix.nBlocksMax ; ++c)
 	{ if (c && ix.blkNHash[c] > 65535)
 	    fprintf (stderr, "ignoring barcode %d - too many hashes %d > %d\n", (int) c, (int) ix.blkNHash[c], 65535) ;
-	  goodHashes[c] = g.good + g.goodOff[c] ;		/* slab owned by the context */
-	  nGoodHashes[c] = (int) (g.goodOff[c+1] - g.goodOff[c]) ;
+	  if (multi)
+	    { goodHashes[c] = g.good + g.goodOff[c] ;		/* stitched lists owned by the session */
+	      nGoodHashes[c] = (int) (g.goodOff[c+1] - g.goodOff[c]) ;
+	    }
 	}
       printf ("  made goodHashes arrays for hash range %d to %d\n  ", hashRangeMin, hashRangeMax) ;
       timeUpdate (outFile) ; fflush (outFile) ;
