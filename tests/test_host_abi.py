@@ -61,6 +61,24 @@ def test_no_device_means_loud_failure_not_fallback():
         fq = os.path.join(ROOT, "tests", "golden", "synth_small.fqb")
         r = subprocess.run([cli, "-B", "20", "--readFQB", fq], capture_output=True, text=True)
         assert r.returncode != 0 and "FATAL ERROR: no CUDA device" in r.stderr
+        # the commands after the build have no CPU version either: a host index (--readHash) without a device dies loudly
+        from oracle import orc
+        import tempfile
+        recs = np.fromfile(fq, dtype=np.uint32).reshape(-1, 30)
+        with tempfile.TemporaryDirectory() as d:
+            h = os.path.join(d, "x.hash")
+            assert orc.build_and_write(recs, h, B=20) == 0
+            for cmd, text in ((["--hashDepthRange", "2", "40"], "--hashDepthRange runs on the GPU-resident index"),
+                              (["--clusterSplit"], "--clusterSplit runs on the index resident on one GPU")):
+                r = subprocess.run([cli, "-B", "20", "--readHash", h] + cmd, capture_output=True, text=True)
+                assert r.returncode != 0 and text in r.stderr, r.stderr
+    # entry points that need a context refuse a NULL one instead of doing anything on the host
+    err = C.create_string_buffer(256)
+    n = C.c_uint64(0)
+    L.h10x_gpu_depth_range_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t]
+    assert L.h10x_gpu_depth_range_device(None, 2, 40, C.byref(n), err, 256) != 0
+    L.h10x_gpu_cluster_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
+    assert L.h10x_gpu_cluster_split(None, None, None, err, 256) != 0
 
 
 def test_product_never_imports_the_oracle():
