@@ -809,10 +809,9 @@ static uint32_t tail_rest (h10x_ctx *c, cudaStream_t s, const TailGeom &g, uint6
     sa.srCount = srCount.p ; sa.blkDup = blkDup.p ; sa.nDup = nDup.p ; sa.blkMask = blkMask ;
     if (const char *e = getenv ("H10X_SR_GROUP")) { long v = atol (e) ; if (v >= 1) sa.groupCap = std::min<uint32_t> ((uint32_t) v, sa.cap) ; }
     LAUNCH (c, k_sr_jobs, gridFor (((uint64_t) g.nSub + 3) / 4, 256), 256, 0, s, sa) ;
-    int srThreads = H10X_SR_THREADS_DEFAULT ;
-    if (const char *e = getenv ("H10X_SR_THREADS")) { long v = atol (e) ; if (v == 256 || v == 512) srThreads = (int) v ; }
+    const int srThreads = H10X_SR_THREADS_DEFAULT ;
     const size_t smem = (size_t) 2 * sa.cap * 8 + ((size_t) 4 << H10X_SR_DIGIT) + ((size_t) (srThreads / 32) * 2 << H10X_SR_DIGIT) + 16 ;
-    auto srFn = srThreads == 256 ? k_sr_sort<256> : k_sr_sort<512> ;
+    auto srFn = k_sr_sort<H10X_SR_THREADS_DEFAULT> ;	/* 256-thread CTAs (four per SM) were tried: the per-thread step arrays no longer fit the register budget */
     CK (cudaFuncSetAttribute (srFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
     int occ = 1 ;
     CK (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, srFn, srThreads, smem)) ;
