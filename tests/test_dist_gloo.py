@@ -172,3 +172,47 @@ def test_protocol_model_over_gloo(world):
         pr.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
     assert sum(r[2] for r in res) == 41
+
+
+def test_owner_merge_tiling_model():
+    """The owner's merge of its received runs (h10x_dist.cuh "owner merge without a sort"), restated in numpy: every S-th
+    element of every run is a splitter candidate, every NR-th sorted candidate a tile boundary, a tile takes from each run
+    the elements in [B_t, B_t+1).  Checked here: the tiles partition every run, no tile reaches 3 NR S elements whatever
+    the runs look like (disjoint ranges, one run dense and the others sparse, shared values), and merging tile after tile
+    with ties in source order is the stable sort of the concatenation - which is what the sort path computes."""
+    rng = np.random.default_rng(3)
+    for nr, S, shape in [(2, 16, "uniform"), (8, 8, "uniform"), (8, 8, "disjoint"), (5, 4, "skewed"), (8, 8, "shared"), (3, 8, "empty")]:
+        runs = []
+        for r in range(nr):
+            n = int(rng.integers(200, 2000))
+            if shape == "disjoint":
+                v = rng.choice(np.arange(r * 100_000, (r + 1) * 100_000), n, replace=False)
+            elif shape == "skewed":
+                v = rng.choice(np.arange(0, 1_000_000), n * (20 if r == 0 else 1) // (1 if r == 0 else 4), replace=False)
+            elif shape == "shared":
+                v = rng.choice(np.arange(0, 3000), min(n, 2500), replace=False)     # most values held by several runs
+            elif shape == "empty" and r == 1:
+                v = np.zeros(0, np.int64)
+            else:
+                v = rng.choice(np.arange(0, 1_000_000), n, replace=False)
+            runs.append(np.sort(v.astype(np.int64)))                                 # rank-distinct: no value twice in a run
+        cand = np.sort(np.concatenate([run[S::S][:(run.size - 1) // S] if run.size else run for run in runs]))
+        n_tiles = cand.size // nr + 1
+        bounds = [None] + [int(cand[t * nr - 1]) for t in range(1, n_tiles)] + [None]
+        start = [[0 if bounds[t] is None and t == 0 else (run.size if bounds[t] is None else int(np.searchsorted(run, bounds[t], "left")))
+                  for run in runs] for t in range(n_tiles + 1)]
+        merged_val, merged_src = [], []
+        for t in range(n_tiles):
+            pieces = [runs[r][start[t][r]:start[t + 1][r]] for r in range(nr)]
+            size = sum(p.size for p in pieces)
+            assert size < 3 * nr * S, (shape, nr, S, size)
+            vals = np.concatenate(pieces)
+            src = np.concatenate([np.full(p.size, r) for r, p in enumerate(pieces)])
+            order = np.lexsort((src, vals))                                          # ties: the lower source rank first
+            merged_val.append(vals[order])
+            merged_src.append(src[order])
+        mv, ms = np.concatenate(merged_val), np.concatenate(merged_src)
+        allv = np.concatenate(runs)
+        alls = np.concatenate([np.full(run.size, r) for r, run in enumerate(runs)])
+        order = np.lexsort((alls, allv))
+        assert np.array_equal(mv, allv[order]) and np.array_equal(ms, alls[order]), shape
